@@ -1,0 +1,152 @@
+/*
+ * matcouply_b200 — C ABI of the B200-native AO-ADMM engine (libmatcouply_b200.so).
+ *
+ * The reference (MarieRoald/matcouply, pure Python) has no FFI: its boundary is the Python call surface
+ * `matcouply.decomposition.cmf_aoadmm` (decomposition.py:662) and the `ADMMPenalty` protocol (penalties.py:21).
+ * This header is the seam underneath our Python mirror of that surface (`matcouply_b200/decomposition.py`,
+ * `matcouply_b200/penalties.py`): every numerical step of the reference hot path maps onto one entry point below;
+ * each entry cites the reference lines it replaces.  INTEGRATION.md shows the ctypes binding a maintainer would add
+ * on the reference side.
+ *
+ * Conventions
+ *   - all pointers are DEVICE pointers unless the name ends in `_host`; the caller owns every buffer;
+ *   - all calls are asynchronous on `stream` (a cudaStream_t passed as void*), no hidden allocation, no host sync;
+ *   - return value: 0 = B2_OK, otherwise an error code; `b2_last_error()` returns a thread-local message;
+ *   - dtype: B2_F32 / B2_F64 for every floating-point buffer of a call (scalars in `double`);
+ *   - matrices are dense row-major; "packed" means the vertical concatenation of the per-slice matrices
+ *     (np.concatenate(list, axis=0)) addressed through `row_off[G+1]` (int64 prefix sum of the J_i);
+ *   - reference symbols: I slices X_i (J_i x K), A (I x R), B_i (J_i x R), C (K x R); N = sum_i J_i.
+ */
+#ifndef MATCOUPLY_B200_H
+#define MATCOUPLY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { B2_OK = 0, B2_ERR_INVALID = 1, B2_ERR_CUDA = 2 };
+enum { B2_F32 = 0, B2_F64 = 1 };
+enum { B2_VARIANT_AUTO = 0, B2_VARIANT_FMA = 1, B2_VARIANT_DMMA = 2 };
+
+/* penalty kinds (penalties.py: Parafac2 :1018, Unimodality :983, L2Ball :844, L1Penalty :545, Box :511,
+ * NonNegativity :488) */
+enum { B2_PEN_NONNEG = 0, B2_PEN_BOX = 1, B2_PEN_L1 = 2, B2_PEN_L2BALL = 3, B2_PEN_UNIMODAL = 4, B2_PEN_PARAFAC2 = 5 };
+
+/* how a row of an ADMM state matrix finds its group (slice) */
+enum { B2_GROUP_SINGLE = 0 /* every row -> group 0 (C-mode) */,
+       B2_GROUP_INDEXED = 1 /* group_of_row[row]     (B-mode) */,
+       B2_GROUP_IDENTITY = 2 /* group = row           (A-mode) */ };
+
+typedef struct {
+    int32_t kind;           /* B2_PEN_* */
+    int32_t non_negativity; /* L1 / L2Ball / Unimodality flag */
+    double p0;              /* L1: reg_strength; Box: min_val; L2Ball: norm_bound */
+    double p1;              /* Box: max_val */
+    void* aux;              /* n x R auxiliary variable; PARAFAC2: the product P_i*Delta ("aux as matrix") */
+    void* dual;             /* n x R scaled dual variable */
+} b2_penalty_desc;
+
+const char* b2_last_error(void);
+int b2_version(void);
+int b2_device_sm_count(void);
+
+/* ---- X-stream contractions (the HBM-bound hot kernels) ------------------------------------------------------
+ * X: packed data, n_rows x K, row stride ldx elements (ldx*sizeof % 16 == 0, pad columns zero).
+ * b2_xstream_y:  Y (n_rows x R) = X * C.              decomposition.py:242 (X_i (C*a_i) = (X_i C)*a_i), :148-152.
+ * b2_xstream_z:  Z (K x R) = X^T * W, W n_rows x R,   decomposition.py:312-315 with W_i = B_i * a_i.
+ *                W must be allocated with n_rows rounded up to a multiple of 16 rows, zero tail.
+ * ws: scratch of at least b2_xstream_workspace_bytes(K, R, dtype) bytes, 16-byte aligned.
+ * variant: B2_VARIANT_FMA (fp32/fp64 FMA pipes) or B2_VARIANT_DMMA (fp64 tensor cores, DMMA.8x8x4); AUTO picks.
+ * max_ctas: 0 = one CTA per SM. */
+int b2_xstream_y(const void* X, long long n_rows, int K, int ldx, const void* C, int R, void* Y, int dtype, void* ws,
+                 size_t ws_bytes, int variant, int max_ctas, void* stream);
+int b2_xstream_z(const void* X, long long n_rows, int K, int ldx, const void* W, int R, void* Z, int dtype, void* ws,
+                 size_t ws_bytes, int variant, int max_ctas, void* stream);
+size_t b2_xstream_workspace_bytes(int K, int R, int dtype);
+/* out[0] = sum(X**2) in double (decomposition.py:906, _root_sum_squared_list :347). ws >= 8*4*SMs bytes. */
+int b2_sumsq(const void* X, long long n_rows, int K, int ldx, int dtype, double* out, void* ws, size_t ws_bytes,
+             void* stream);
+
+/* ---- small dense / batched per-slice math --------------------------------------------------------------------*/
+/* G (R x R) = M^T M for a dense n x R matrix (C^T C :138,:240 ; sum_i (B_i a_i)^T (B_i a_i) :314). ws >= 8*R*R*SMs. */
+int b2_gram(const void* M, long long n, int R, void* G, int dtype, void* ws, size_t ws_bytes, void* stream);
+/* lhs[g] = G o (a_g a_g^T), g < n_groups  (decomposition.py:243). */
+int b2_scale_gram(const void* G, const void* A, int n_groups, int R, void* lhs, int dtype, void* stream);
+/* rho[g] = 0.5 * trace(lhs[g]) * scale ; rho_max[0] = max_g rho[g]  (decomposition.py:162-165, 247-250, 319). */
+int b2_rho_from_trace(const void* lhs, int n_groups, int R, double scale, void* rho, void* rho_max, int dtype,
+                      void* stream);
+/* If rho_max != NULL every rho[g] is first overwritten by rho_max[0] (constant_feasibility_penalty).
+ * Minv[g] = inverse(lhs[g] + (rho[g]*n_reg + l2) * I) via Cholesky; replaces the SVD solve of :168-172, :252-256,
+ * :320-321 (x (U/s) Uh == x lhs^-1 for symmetric positive definite lhs). */
+int b2_factor_batch(const void* lhs, int n_groups, int R, void* rho, const void* rho_max, int n_reg, double l2,
+                    void* Minv, int dtype, void* stream);
+/* Per slice g: rhs[g][r] = sum_j B[j][r]*Y[j][r] (= diag(B_i^T X_i C), :158) and
+ * cross[g] = (B_g^T B_g) o CtC (:155).  rhs may be NULL; CtC may be NULL (then cross = B^T B, used for PARAFAC2). */
+int b2_slice_cross(const void* B, const void* Y, const int64_t* row_off, int n_groups, int R, const void* CtC,
+                   void* cross, void* rhs, int dtype, void* stream);
+/* W[row] = B[row] o A[group_of_row[row]]  (B_i * a_i, :313). */
+int b2_rowscale(const void* B, const void* A, const int32_t* group_of_row, long long n, int R, void* W, int dtype,
+                void* stream);
+
+/* ---- fused ADMM step ------------------------------------------------------------------------------------------
+ * For every row:  s = rhs[row] o rhs_scale[g] + rho[g] * sum_p (aux_p[row] - dual_p[row])      (:261-273,:328-331,:179-195)
+ *                 x[row] = s * Minv[g]
+ *   then per penalty p:  v = x[row] + dual_p[row]
+ *        elementwise kinds (NONNEG, BOX, L1):  aux_p[row] = prox(v, rho[g]); dual_p[row] = v - aux_p[row]   (:275-285)
+ *        column-coupled kinds (L2BALL, UNIMODAL, PARAFAC2): dual_p[row] = v  (finished by the b2_prox_* / b2_pf2_* calls)
+ * rhs_scale (n_groups x R) may be NULL. group_of_row is used when group_mode == B2_GROUP_INDEXED. */
+int b2_admm_solve(long long n, int R, const void* rhs, const void* rhs_scale, int group_mode,
+                  const int32_t* group_of_row, const void* rho, const void* Minv, const b2_penalty_desc* pens_host,
+                  int n_pen, void* x, int dtype, void* stream);
+
+/* ---- column-coupled proximal operators (V arrives in `dual`, see b2_admm_solve) --------------------------------*/
+/* L2Ball (penalties.py:920-925): per group and column  aux = clip(V)*bound/max(||clip(V)_col||, bound); dual = V - aux. */
+int b2_prox_l2ball(void* aux, void* dual, const int64_t* row_off, int n_groups, int R, double bound, int non_negativity,
+                   int dtype, void* stream);
+/* Unimodality (penalties.py:1014-1015 -> _unimodal_regression.py:24-141): per group and column aux = unimodal
+ * regression of V (PAVA prefix/suffix isotonic fits, `<=` pooling, first strict minimum peak); dual = V - aux.
+ * peaks (may be NULL): n_groups x R int32 peak indices t*.  ws >= b2_unimodal_workspace_bytes(). fp64 arithmetic. */
+int b2_prox_unimodal(void* aux, void* dual, const int64_t* row_off, int n_groups, int R, int max_rows,
+                     int non_negativity, int32_t* peaks, int dtype, void* ws, size_t ws_bytes, void* stream);
+size_t b2_unimodal_workspace_bytes(int n_groups, int R, int max_rows);
+
+/* PARAFAC2 (penalties.py:1224-1250).  With V_i = B_i + dual_i (in `dual`) and S_i = V_i^T V_i (b2_slice_cross):
+ *   b2_pf2_polar:  W_i such that P_i = V_i W_i = polar(V_i Delta^T)   (R x R Jacobi eigen-decomposition of
+ *                  Delta S_i Delta^T instead of the J_i x R SVD of :1234-1235), and
+ *                  num_part[g] = rho_i W_i^T S_i = rho_i P_i^T V_i (summand of :1244).
+ *   b2_pf2_delta:  Delta_new = sum_g num_part[g] / sum_g rho[g]  in fixed order (:1240-1245); also writes the
+ *                  un-normalised sums to `sums` (R*R + 1 values: numerator, then sum rho) for a cross-rank all-reduce;
+ *                  with `sums_in` != NULL it only normalises those (already reduced) sums.
+ *   b2_pf2_apply:  pd[row] = V[row] W_g Delta_new (= P_i Delta) ; dual[row] = V[row] - pd[row] (:282-285);
+ *                  optionally basis[row] = V[row] W_g (= P_i). */
+int b2_pf2_polar(const void* S, const void* Delta, const void* rho, int n_groups, int R, void* Wmat, void* num_part,
+                 int dtype, void* stream);
+int b2_pf2_delta(const void* num_part, const void* rho, int n_groups, int R, void* Delta_new, void* sums,
+                 const void* sums_in, int dtype, void* stream);
+int b2_pf2_apply(void* pd, void* dual, void* basis, const void* Wmat, const void* Delta_new,
+                 const int32_t* group_of_row, long long n, int R, int dtype, void* stream);
+
+/* ---- fused reductions for feasibility gaps / loss (decomposition.py:351-452, 617-627; penalties.py:589-592) ------
+ * out[0] = sum((x-y)^2), out[1] = sum(x^2), out[2] = sum(|x|) over n elements (y may be NULL -> out[0] = 0). double. */
+int b2_reduce_stats(const void* x, const void* y, long long n, double* out, int dtype, void* ws, size_t ws_bytes,
+                    void* stream);
+/* out[0] = sum_i rhs_i . a_i ; out[1] = sum_i a_i^T cross_i a_i   (decomposition.py:446-449). */
+int b2_fit_terms(const void* rhs, const void* cross, const void* A, int n_groups, int R, double* out, int dtype,
+                 void* ws, size_t ws_bytes, void* stream);
+
+/* ---- standalone elementwise prox (ADMMPenalty.factor_matrix_update for NONNEG/BOX/L1 with a scalar rho) ---------*/
+int b2_prox_elementwise(const void* v, void* out, long long n, int kind, int non_negativity, double p0, double p1,
+                        double rho, int dtype, void* stream);
+
+/* ---- measurement helpers (bench.py / DESIGN.md roofline denominators) -------------------------------------------
+ * kind 0: fp64 FMA pipe, 1: DMMA.8x8x4, 2: fp32 FMA. Runs `iters` dependent-chain-free iterations on every SM and
+ * writes the number of floating-point operations issued to flops_host. Time it with CUDA events around the call. */
+int b2_microbench_flops(int kind, int iters, double* flops_host, void* sink, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MATCOUPLY_B200_H */

@@ -1,0 +1,365 @@
+"""Device-resident AO-ADMM engine: owns the packed data, the factor/aux/dual state in HBM and sequences the CUDA
+kernels of one outer iteration (reference decomposition.py:945-988 -> admm_update_B :222, admm_update_C :295,
+admm_update_A :120).  Host Python only launches kernels (through the C ABI) and reads back one small scalar pack per
+outer iteration for the stopping rule.
+
+Data layout in HBM (reference symbols: I slices X_i of J_i x K, N = sum J_i):
+  X          N x ldx   packed row-major, ldx = K rounded up to 16 bytes (zero padded)  — read twice per outer iteration
+  B, Y, W    N x R     packed per-slice factor, cached product Y = X C, scaled factor W = B o a (W has a 16-row zero tail)
+  aux/dual   N x R     one pair per B-mode penalty (PARAFAC2: `pd` = P_i Delta in the aux slot, plus Delta R x R, W_i R x R)
+  A, C       I x R, K x R with their aux/dual pairs
+  per slice  rho (I), Minv (I x R x R), cross (I x R x R), rhsA (I x R)
+
+X-stream schedule (exact Gauss-Seidel order of the reference, two passes instead of its three):
+  Y = X C^(t)   (after the C-update; serves the A-update of iteration t and the B-update of iteration t+1)
+  Z = X^T W     (after the B-update; serves the C-update)
+
+Sharding: with a process group, every rank holds a contiguous range of slices (X, B-state, A rows are rank-local);
+C, Delta and all scalars are replicated through a few small all-reduces per outer iteration.
+"""
+import numpy as np
+import torch
+
+from . import _lib, _ops
+
+
+class PackedMatrices:
+    """Ragged list of J_i x K matrices packed along rows (``np.concatenate(matrices, 0)``) on the device."""
+
+    def __init__(self, X, row_offsets, K):
+        self.X = X  # (N, ldx) CUDA tensor
+        self.row_offsets = np.asarray(row_offsets, dtype=np.int64)
+        self.K = int(K)
+        self.N = int(self.row_offsets[-1])
+        self.n_slices = len(self.row_offsets) - 1
+        assert X.shape[0] >= self.N and X.shape[1] == _ops.padded_ld(self.K, X.dtype)
+
+    @property
+    def shapes(self):
+        return [(int(j), self.K) for j in np.diff(self.row_offsets)]
+
+    @classmethod
+    def from_list(cls, matrices, dtype, device):
+        K = int(matrices[0].shape[1])
+        sizes = [int(m.shape[0]) for m in matrices]
+        for m in matrices:
+            if len(m.shape) != 2 or int(m.shape[1]) != K:
+                raise ValueError("All matrices must be two-dimensional with the same number of columns")
+        N = int(sum(sizes))
+        ld = _ops.padded_ld(K, dtype)
+        X = torch.zeros((N, ld), dtype=dtype, device=device)
+        if all(isinstance(m, np.ndarray) for m in matrices):
+            host = torch.empty((N, K), dtype=dtype, pin_memory=torch.cuda.is_available())
+            r = 0
+            for m in matrices:
+                host[r:r + m.shape[0]] = torch.from_numpy(np.ascontiguousarray(m))
+                r += m.shape[0]
+            X[:, :K].copy_(host, non_blocking=True)
+        else:
+            r = 0
+            for m in matrices:
+                X[r:r + m.shape[0], :K] = torch.as_tensor(m).to(device=device, dtype=dtype)
+                r += m.shape[0]
+        return cls(X, np.concatenate([[0], np.cumsum(sizes)]), K)
+
+
+class _ModeState:
+    """Factor matrix + per-penalty aux/dual of one mode, all flat (n x R) device tensors."""
+
+    def __init__(self):
+        self.x = None
+        self.regs = []  # penalty objects (descriptors)
+        self.desc = []  # (kind, nn, p0, p1)
+        self.aux = []   # device tensors (PARAFAC2: P*Delta)
+        self.dual = []
+        self.descs_c = None
+
+
+class AOADMMEngine:
+    def __init__(self, packed, rank, regs, l2_penalty=(0, 0, 0), feasibility_penalty_scale=1.0, constant_A=False,
+                 constant_B=False, inner_n_iter_max=5, update=(True, True, True), group=None, xstream_variant=None):
+        _lib.load()
+        self.p = packed
+        self.dev = packed.X.device
+        self.dtype = packed.X.dtype
+        self.R = int(rank)
+        if not (1 <= self.R <= _lib.MAX_RANK):
+            raise ValueError(f"matcouply_b200 supports rank 1..{_lib.MAX_RANK}, got {rank}")
+        self.I, self.K, self.N = packed.n_slices, packed.K, packed.N
+        self.l2 = [float(v) for v in l2_penalty]
+        self.scale = float(feasibility_penalty_scale)
+        self.const_A, self.const_B = bool(constant_A), bool(constant_B)
+        self.n_inner = int(inner_n_iter_max)
+        self.update_A, self.update_B, self.update_C = update
+        self.group = group
+        self.world = 1 if group is None else torch.distributed.get_world_size(group)
+        self.variant = _lib.VARIANT_AUTO if xstream_variant is None else xstream_variant
+        R, I, K, N, dt, dev = self.R, self.I, self.K, self.N, self.dtype, self.dev
+
+        self.row_off = torch.as_tensor(packed.row_offsets, dtype=torch.int64).to(dev)
+        sizes = torch.as_tensor(np.diff(packed.row_offsets), dtype=torch.int64).to(dev)
+        self.gor = torch.repeat_interleave(torch.arange(I, dtype=torch.int32, device=dev), sizes)
+        self.max_rows = int(np.diff(packed.row_offsets).max()) if I else 0
+        self.off_single_K = torch.tensor([0, K], dtype=torch.int64, device=dev)
+        self.off_single_I = torch.tensor([0, I], dtype=torch.int64, device=dev)
+
+        self.modes = [_ModeState(), _ModeState(), _ModeState()]
+        for m in range(3):
+            st = self.modes[m]
+            st.regs = list(regs[m])
+            if len(st.regs) > _lib.MAX_PENALTIES_PER_MODE:
+                raise ValueError(f"at most {_lib.MAX_PENALTIES_PER_MODE} penalties per mode are supported")
+            st.desc = [r._descriptor() for r in st.regs]
+        for kind, *_ in self.modes[0].desc:
+            if kind in (_lib.PEN_L2BALL, _lib.PEN_UNIMODAL):
+                if not self.const_A:
+                    raise AttributeError(
+                        "Matrix-wise penalties (L2Ball, Unimodality) on mode 0 have no row update: "
+                        "use constant_feasibility_penalty=True (or 'A'), as with the reference"
+                    )
+                if self.world > 1:
+                    raise NotImplementedError("column-coupled penalties on mode 0 are not sharded yet")
+            if kind == _lib.PEN_PARAFAC2:
+                raise ValueError("PARAFAC2 constraint can only be imposed with mode=1")
+        for kind, *_ in self.modes[2].desc:
+            if kind == _lib.PEN_PARAFAC2:
+                raise ValueError("PARAFAC2 constraint can only be imposed with mode=1")
+
+        z = lambda *s: torch.zeros(s, dtype=dt, device=dev)  # noqa: E731
+        self.Y = z(N, R)
+        self.Wpad = z((N + 15) // 16 * 16, R)  # zero tail required by b2_xstream_z
+        self.ZL = z(K * R + R * R)             # Z (K x R) followed by lhs_C (R x R): one all-reduce buffer
+        self.Z = self.ZL[: K * R].view(K, R)
+        self.lhsC = self.ZL[K * R:].view(R, R)
+        self.CtC = z(R, R)
+        self.lhsB, self.MinvB, self.rhoB = z(I, R, R), z(I, R, R), z(I)
+        self.cross, self.MinvA, self.rhoA, self.rhsA = z(I, R, R), z(I, R, R), z(I), z(I, R)
+        self.MinvC, self.rhoC = z(1, R, R), z(1)
+        self.rho_max = z(1)
+        self.has_pf2 = any(d[0] == _lib.PEN_PARAFAC2 for d in self.modes[1].desc)
+        if self.has_pf2:
+            self.Delta = z(R, R)
+            self.S, self.Wmat = z(I, R, R), z(I, R, R)
+            self.num_part = torch.zeros(I, R, R, dtype=torch.float64, device=dev)
+            self.pf2_sums = torch.zeros(R * R + 1, dtype=torch.float64, device=dev)
+            self.pf2_basis0 = None   # initial basis matrices (host) until the first B-update replaces them
+            self.pf2_fresh = False
+        self.scal = torch.zeros(64, dtype=torch.float64, device=dev)
+        self.normX_sq = None
+        uni = None
+        if any(d[0] == _lib.PEN_UNIMODAL for d in self.modes[1].desc):
+            uni = (I, R, self.max_rows)
+        self.ws = _ops.Workspace(dev, K, R, dt, unimodal_shape=uni)
+        self.n_xstream_launches = 0
+
+    # ------------------------------------------------------------------------------------------------------
+    # state upload / download (host NumPy float64 <-> device)
+    # ------------------------------------------------------------------------------------------------------
+    def _up(self, a):
+        return _ops.to_device(np.asarray(a), self.dtype, self.dev)
+
+    def load_state(self, A, B_is, C, auxes, duals):
+        """A: I x R, B_is: list of J_i x R (or packed N x R), C: K x R; auxes/duals: 3 lists as in ADMMVars."""
+        st = self.modes
+        st[0].x = self._up(A)
+        st[1].x = self._up(B_is if isinstance(B_is, np.ndarray) else np.concatenate(B_is, 0))
+        st[2].x = self._up(C)
+        for m in range(3):
+            st[m].aux, st[m].dual = [], []
+            for p, (kind, *_rest) in enumerate(st[m].desc):
+                aux, dual = auxes[m][p], duals[m][p]
+                if kind == _lib.PEN_PARAFAC2:
+                    basis, delta = aux
+                    self.pf2_basis0 = [np.asarray(b, dtype=np.float64) for b in basis]
+                    self.pf2_fresh = False
+                    self.Delta.copy_(self._up(delta))
+                    pd = np.concatenate([np.asarray(b) @ np.asarray(delta) for b in basis], 0)
+                    st[m].aux.append(self._up(pd))
+                elif m == 1:
+                    st[m].aux.append(self._up(np.concatenate(aux, 0) if not isinstance(aux, np.ndarray) else aux))
+                else:
+                    st[m].aux.append(self._up(aux))
+                if m == 1:
+                    st[m].dual.append(self._up(np.concatenate(dual, 0) if not isinstance(dual, np.ndarray) else dual))
+                else:
+                    st[m].dual.append(self._up(dual))
+            st[m].descs_c = _ops.make_descs(
+                [(d[0], d[1], d[2], d[3], a, u) for d, a, u in zip(st[m].desc, st[m].aux, st[m].dual)])
+        for m, n in ((0, self.I), (1, self.N), (2, self.K)):
+            assert tuple(st[m].x.shape) == (n, self.R), (m, st[m].x.shape, (n, self.R))
+
+    def _split(self, t):
+        host = t.detach().to(torch.float64).cpu().numpy()
+        return [host[a:b].copy() for a, b in zip(self.p.row_offsets[:-1], self.p.row_offsets[1:])]
+
+    def factors(self):
+        st = self.modes
+        f64 = lambda t: t.detach().to(torch.float64).cpu().numpy()  # noqa: E731
+        return f64(st[0].x), self._split(st[1].x), f64(st[2].x)
+
+    def admm_vars(self):
+        """(auxes, duals) in the reference's ADMMVars layout (decomposition.py:1077-1081)."""
+        f64 = lambda t: t.detach().to(torch.float64).cpu().numpy()  # noqa: E731
+        auxes, duals = ([], [], []), ([], [], [])
+        for m in range(3):
+            st = self.modes[m]
+            for p, (kind, *_r) in enumerate(st.desc):
+                if kind == _lib.PEN_PARAFAC2:
+                    if self.pf2_fresh:
+                        # P_i = V_i W_i with V = dual + P Delta (the pre-image of the last prox call)
+                        V = (st.dual[p] + st.aux[p]).contiguous()
+                        basis, tmp = torch.empty_like(V), torch.empty_like(V)
+                        _ops.pf2_apply(tmp, V, basis, self.Wmat, self.Delta, self.gor, self.N, self.R)
+                        bases = self._split(basis)
+                    else:
+                        bases = self.pf2_basis0
+                    auxes[m].append((bases, f64(self.Delta)))
+                elif m == 1:
+                    auxes[m].append(self._split(st.aux[p]))
+                else:
+                    auxes[m].append(f64(st.aux[p]))
+                duals[m].append(self._split(st.dual[p]) if m == 1 else f64(st.dual[p]))
+        return auxes, duals
+
+    # ------------------------------------------------------------------------------------------------------
+    # collectives (no-ops on a single GPU)
+    # ------------------------------------------------------------------------------------------------------
+    def _allreduce(self, t, op="sum"):
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.all_reduce(t, op=dist.ReduceOp.SUM if op == "sum" else dist.ReduceOp.MAX, group=self.group)
+
+    # ------------------------------------------------------------------------------------------------------
+    # pieces of one outer iteration
+    # ------------------------------------------------------------------------------------------------------
+    def _column_coupled(self, st, row_off, n_groups, max_rows, rho, gor, n_rows):
+        """Finish the prox + dual update of the column-coupled penalties (V = x + dual is stored in `dual`)."""
+        R = self.R
+        for p, (kind, nn, p0, _p1) in enumerate(st.desc):
+            if kind == _lib.PEN_L2BALL:
+                _ops.prox_l2ball(st.aux[p], st.dual[p], row_off, n_groups, R, p0, nn)
+            elif kind == _lib.PEN_UNIMODAL:
+                _ops.prox_unimodal(st.aux[p], st.dual[p], row_off, n_groups, R, max_rows, nn, self.ws)
+            elif kind == _lib.PEN_PARAFAC2:
+                _ops.slice_cross(st.dual[p], None, row_off, n_groups, R, None, self.S, None)
+                _ops.pf2_polar(self.S, self.Delta, rho, n_groups, R, self.Wmat, self.num_part)
+                if self.world > 1:
+                    _ops.pf2_delta(self.num_part, rho, n_groups, R, self.Delta, self.pf2_sums)
+                    self._allreduce(self.pf2_sums)
+                    _ops.pf2_delta(self.num_part, rho, n_groups, R, self.Delta, None, self.pf2_sums)
+                else:
+                    _ops.pf2_delta(self.num_part, rho, n_groups, R, self.Delta, self.pf2_sums)
+                _ops.pf2_apply(st.aux[p], st.dual[p], None, self.Wmat, self.Delta, gor, n_rows, R)
+                self.pf2_fresh = True
+
+    def step_B(self):
+        """admm_update_B (decomposition.py:222-292); rhs_i = Y_i o a_i with the cached Y = X C."""
+        st, R, I = self.modes[1], self.R, self.I
+        A, C = self.modes[0].x, self.modes[2].x
+        _ops.gram(C, self.K, self.CtC, self.ws)
+        _ops.scale_gram(self.CtC, A, self.lhsB)
+        _ops.rho_from_trace(self.lhsB, I, R, self.scale, self.rhoB, self.rho_max if self.const_B else None)
+        if self.const_B:
+            self._allreduce(self.rho_max, "max")
+        _ops.factor_batch(self.lhsB, I, R, self.rhoB, self.rho_max if self.const_B else None, len(st.desc), self.l2[1],
+                          self.MinvB)
+        for _ in range(self.n_inner):
+            _ops.admm_solve(self.N, R, self.Y, A, _lib.GROUP_INDEXED, self.gor, self.rhoB, self.MinvB, st.descs_c,
+                            len(st.desc), st.x)
+            self._column_coupled(st, self.row_off, I, self.max_rows, self.rhoB, self.gor, self.N)
+
+    def step_C(self):
+        """admm_update_C (decomposition.py:295-344); one X pass: Z = X^T (B o a)."""
+        st, R, K = self.modes[2], self.R, self.K
+        W = self.Wpad[: self.N]
+        _ops.rowscale(self.modes[1].x, self.modes[0].x, self.gor, self.N, R, W)
+        _ops.xstream_z(self.p.X, self.N, K, self.Wpad, self.Z, self.ws, self.variant)
+        self.n_xstream_launches += 1
+        _ops.gram(W, self.N, self.lhsC, self.ws)
+        self._allreduce(self.ZL)
+        _ops.rho_from_trace(self.lhsC, 1, R, self.scale, self.rhoC, None)
+        _ops.factor_batch(self.lhsC, 1, R, self.rhoC, None, len(st.desc), self.l2[2], self.MinvC)
+        for _ in range(self.n_inner):
+            _ops.admm_solve(K, R, self.Z, None, _lib.GROUP_SINGLE, None, self.rhoC, self.MinvC, st.descs_c,
+                            len(st.desc), st.x)
+            self._column_coupled(st, self.off_single_K, 1, K, self.rhoC, None, K)
+
+    def refresh_products(self):
+        """Y = X C (one X pass), CtC, cross_i = (B_i^T B_i) o CtC, rhsA_i = colsum(B_i o Y_i)
+        (decomposition.py:138-158).  Also what the fit term needs (:446-449)."""
+        C, B = self.modes[2].x, self.modes[1].x
+        _ops.xstream_y(self.p.X, self.N, self.K, C, self.Y, self.ws, self.variant)
+        self.n_xstream_launches += 1
+        _ops.gram(C, self.K, self.CtC, self.ws)
+        _ops.slice_cross(B, self.Y, self.row_off, self.I, self.R, self.CtC, self.cross, self.rhsA)
+
+    def step_A(self):
+        """admm_update_A (decomposition.py:120-219) after refresh_products()."""
+        st, R, I = self.modes[0], self.R, self.I
+        _ops.rho_from_trace(self.cross, I, R, self.scale, self.rhoA, self.rho_max if self.const_A else None)
+        if self.const_A:
+            self._allreduce(self.rho_max, "max")
+        _ops.factor_batch(self.cross, I, R, self.rhoA, self.rho_max if self.const_A else None, len(st.desc), self.l2[0],
+                          self.MinvA)
+        for _ in range(self.n_inner):
+            _ops.admm_solve(I, R, self.rhsA, None, _lib.GROUP_IDENTITY, None, self.rhoA, self.MinvA, st.descs_c,
+                            len(st.desc), st.x)
+            self._column_coupled(st, self.off_single_I, 1, I, self.rhoA, None, I)
+
+    def prepare(self):
+        """Before the first iteration: ||X||^2 and the products for the initial fit (decomposition.py:906-913)."""
+        out = self.scal[60:61]
+        _ops.sumsq(self.p.X, self.N, self.K, out, self.ws)
+        self._allreduce(out)
+        self.normX_sq = float(out.item())
+        self.refresh_products()
+
+    def outer_iteration(self):
+        """One pass of decomposition.py:945-988."""
+        if self.update_B:
+            self.step_B()
+        if self.update_C:
+            self.step_C()
+        if self.update_B or self.update_C:
+            self.refresh_products()
+        if self.update_A:
+            self.step_A()
+
+    # ------------------------------------------------------------------------------------------------------
+    # diagnostics: one fused scalar pack, one device->host copy
+    # ------------------------------------------------------------------------------------------------------
+    def diagnostics(self):
+        """Returns dict(gaps=(A_gaps, B_gaps, C_gaps), sse_terms=(inner, quad), sq=[|A|^2,|B|^2,|C|^2],
+        l1=[[...],[...],[...]] sums of |x| per penalty) — everything the host loss/stopping logic needs
+        (decomposition.py:351-417, 420-452, 617-627, 1016-1023)."""
+        scal = self.scal
+        scal.zero_()
+        slot = 2  # [0:2] fit terms
+        _ops.fit_terms(self.rhsA, self.cross, self.modes[0].x, self.I, self.R, scal[0:2], self.ws)
+        layout = []
+        sizes = (self.I * self.R, self.N * self.R, self.K * self.R)
+        # sharded modes first (A, B), replicated mode (C) last
+        for m in (0, 1, 2):
+            st = self.modes[m]
+            if m == 2:
+                shard_end = slot
+            if len(st.desc) == 0:
+                _ops.reduce_stats(st.x, None, sizes[m], scal[slot:slot + 3], self.ws)
+                layout.append((m, -1, slot))
+                slot += 3
+            for p in range(len(st.desc)):
+                _ops.reduce_stats(st.x, st.aux[p], sizes[m], scal[slot:slot + 3], self.ws)
+                layout.append((m, p, slot))
+                slot += 3
+        if self.world > 1:
+            self._allreduce(scal[:shard_end])
+        host = scal[:slot].cpu().numpy()
+        gaps, sq, l1 = ([], [], []), [0.0, 0.0, 0.0], ([], [], [])
+        for m, p, s in layout:
+            d2, x2, ab = host[s:s + 3]
+            sq[m] = x2
+            if p >= 0:
+                gaps[m].append(np.sqrt(d2) / np.sqrt(x2))
+                l1[m].append(ab)
+        return dict(gaps=gaps, fit=(host[0], host[1]), sq=sq, l1=l1)

@@ -1,0 +1,188 @@
+"""Operator-level wrappers: torch CUDA tensors in, C-ABI kernel launches on torch's current stream.
+
+torch is plumbing only (device memory + stream); every computation below is a hand-written sm_100a kernel from
+``matcouply_b200/csrc``.  All functions require CUDA tensors and raise otherwise (no CPU fallback).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import PenaltyDesc, call, dtype_code
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("matcouply_b200 kernels need CUDA tensors (there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("matcouply_b200 kernels need contiguous tensors")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def padded_ld(K, dtype):
+    """Row stride (elements) of the packed data matrix: rows must be multiples of 16 bytes for TMA."""
+    q = 16 // torch.empty((), dtype=dtype).element_size()
+    return (K + q - 1) // q * q
+
+
+class Workspace:
+    """Caller-owned scratch buffers handed to the C ABI (which never allocates)."""
+
+    def __init__(self, device, K, R, dtype, unimodal_shape=None):
+        lib = _lib.load()
+        self.xs_bytes = int(lib.b2_xstream_workspace_bytes(K, R, dtype_code(dtype)))
+        self.xs = torch.empty(self.xs_bytes, dtype=torch.uint8, device=device)
+        sms = int(lib.b2_device_sm_count())
+        self.red_bytes = 8 * max(3 * 4 * sms, 2 * R * R * sms, 4096)
+        self.red = torch.empty(self.red_bytes, dtype=torch.uint8, device=device)
+        self.uni = None
+        self.uni_bytes = 0
+        if unimodal_shape is not None:
+            self.ensure_unimodal(*unimodal_shape)
+
+    def ensure_unimodal(self, n_groups, R, max_rows):
+        need = int(_lib.load().b2_unimodal_workspace_bytes(n_groups, R, max_rows))
+        if need > self.uni_bytes:
+            self.uni = torch.empty(need, dtype=torch.uint8, device=self.xs.device)
+            self.uni_bytes = need
+
+
+def xstream_y(X, n_rows, K, C, Y, ws, variant=_lib.VARIANT_AUTO, max_ctas=0):
+    R = C.shape[1]
+    call("b2_xstream_y", _ptr(X), n_rows, K, X.shape[1], _ptr(C), R, _ptr(Y), dtype_code(X.dtype), _ptr(ws.xs),
+         ws.xs_bytes, resolve_variant(variant, X.dtype), max_ctas, _stream())
+
+
+def xstream_z(X, n_rows, K, W, Z, ws, variant=_lib.VARIANT_AUTO, max_ctas=0):
+    R = Z.shape[1]
+    call("b2_xstream_z", _ptr(X), n_rows, K, X.shape[1], _ptr(W), R, _ptr(Z), dtype_code(X.dtype), _ptr(ws.xs),
+         ws.xs_bytes, resolve_variant(variant, X.dtype), max_ctas, _stream())
+
+
+_DEFAULT_VARIANT = {"f64": _lib.VARIANT_FMA}
+
+
+def set_default_fp64_variant(variant):
+    """Select the fp64 X-stream kernel flavour (FMA pipes or DMMA tensor cores) used for VARIANT_AUTO."""
+    _DEFAULT_VARIANT["f64"] = variant
+
+
+def resolve_variant(variant, dtype):
+    if variant != _lib.VARIANT_AUTO:
+        return variant
+    return _DEFAULT_VARIANT["f64"] if dtype == torch.float64 else _lib.VARIANT_FMA
+
+
+def sumsq(X, n_rows, K, out, ws):
+    call("b2_sumsq", _ptr(X), n_rows, K, X.shape[1], dtype_code(X.dtype), _ptr(out), _ptr(ws.red), ws.red_bytes,
+         _stream())
+
+
+def gram(M, n, G, ws):
+    call("b2_gram", _ptr(M), n, G.shape[0], _ptr(G), dtype_code(M.dtype), _ptr(ws.red), ws.red_bytes, _stream())
+
+
+def scale_gram(G, A, lhs):
+    call("b2_scale_gram", _ptr(G), _ptr(A), A.shape[0], A.shape[1], _ptr(lhs), dtype_code(G.dtype), _stream())
+
+
+def rho_from_trace(lhs, n_groups, R, scale, rho, rho_max=None):
+    call("b2_rho_from_trace", _ptr(lhs), n_groups, R, float(scale), _ptr(rho), _ptr(rho_max), dtype_code(lhs.dtype),
+         _stream())
+
+
+def factor_batch(lhs, n_groups, R, rho, rho_max, n_reg, l2, Minv):
+    call("b2_factor_batch", _ptr(lhs), n_groups, R, _ptr(rho), _ptr(rho_max), int(n_reg), float(l2), _ptr(Minv),
+         dtype_code(lhs.dtype), _stream())
+
+
+def slice_cross(B, Y, row_off, n_groups, R, CtC, cross, rhs):
+    call("b2_slice_cross", _ptr(B), _ptr(Y), _ptr(row_off), n_groups, R, _ptr(CtC), _ptr(cross), _ptr(rhs),
+         dtype_code(B.dtype), _stream())
+
+
+def rowscale(B, A, group_of_row, n, R, W):
+    call("b2_rowscale", _ptr(B), _ptr(A), _ptr(group_of_row), n, R, _ptr(W), dtype_code(B.dtype), _stream())
+
+
+def make_descs(entries):
+    """entries: list of (kind, non_negativity, p0, p1, aux_tensor, dual_tensor) -> ctypes array (host)."""
+    arr = (PenaltyDesc * max(len(entries), 1))()
+    for i, (kind, nn, p0, p1, aux, dual) in enumerate(entries):
+        arr[i].kind = kind
+        arr[i].non_negativity = int(bool(nn))
+        arr[i].p0 = float(p0)
+        arr[i].p1 = float(p1)
+        arr[i].aux = aux.data_ptr()
+        arr[i].dual = dual.data_ptr()
+    return arr
+
+
+def admm_solve(n, R, rhs, rhs_scale, group_mode, group_of_row, rho, Minv, descs, n_pen, x):
+    call("b2_admm_solve", n, R, _ptr(rhs), _ptr(rhs_scale), group_mode, _ptr(group_of_row), _ptr(rho), _ptr(Minv),
+         descs, n_pen, _ptr(x), dtype_code(x.dtype), _stream())
+
+
+def prox_l2ball(aux, dual, row_off, n_groups, R, bound, nn):
+    call("b2_prox_l2ball", _ptr(aux), _ptr(dual), _ptr(row_off), n_groups, R, float(bound), int(bool(nn)),
+         dtype_code(aux.dtype), _stream())
+
+
+def prox_unimodal(aux, dual, row_off, n_groups, R, max_rows, nn, ws, peaks=None):
+    ws.ensure_unimodal(n_groups, R, max_rows)
+    call("b2_prox_unimodal", _ptr(aux), _ptr(dual), _ptr(row_off), n_groups, R, max_rows, int(bool(nn)), _ptr(peaks),
+         dtype_code(aux.dtype), _ptr(ws.uni), ws.uni_bytes, _stream())
+
+
+def pf2_polar(S, Delta, rho, n_groups, R, Wmat, num_part):
+    call("b2_pf2_polar", _ptr(S), _ptr(Delta), _ptr(rho), n_groups, R, _ptr(Wmat), _ptr(num_part),
+         dtype_code(S.dtype), _stream())
+
+
+def pf2_delta(num_part, rho, n_groups, R, Delta_new, sums, sums_in=None):
+    call("b2_pf2_delta", _ptr(num_part), _ptr(rho), n_groups, R, _ptr(Delta_new), _ptr(sums), _ptr(sums_in),
+         dtype_code(Delta_new.dtype), _stream())
+
+
+def pf2_apply(pd, dual, basis, Wmat, Delta_new, group_of_row, n, R):
+    call("b2_pf2_apply", _ptr(pd), _ptr(dual), _ptr(basis), _ptr(Wmat), _ptr(Delta_new), _ptr(group_of_row), n, R,
+         dtype_code(pd.dtype), _stream())
+
+
+def reduce_stats(x, y, n, out, ws):
+    call("b2_reduce_stats", _ptr(x), _ptr(y), n, _ptr(out), dtype_code(x.dtype), _ptr(ws.red), ws.red_bytes, _stream())
+
+
+def fit_terms(rhs, cross, A, n_groups, R, out, ws):
+    call("b2_fit_terms", _ptr(rhs), _ptr(cross), _ptr(A), n_groups, R, _ptr(out), dtype_code(A.dtype), _ptr(ws.red),
+         ws.red_bytes, _stream())
+
+
+def prox_elementwise(v, out, kind, nn, p0, p1, rho):
+    call("b2_prox_elementwise", _ptr(v), _ptr(out), v.numel(), kind, int(bool(nn)), float(p0), float(p1), float(rho),
+         dtype_code(v.dtype), _stream())
+
+
+def microbench_flops(kind, iters):
+    """Returns (flops_issued, milliseconds) for one launch of the peak micro-benchmark (CUDA-event timed)."""
+    sink = torch.zeros(8, dtype=torch.float64, device="cuda")
+    flops = ctypes.c_double(0.0)
+    call("b2_microbench_flops", kind, 16, ctypes.byref(flops), _ptr(sink), _stream())  # warm-up
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    call("b2_microbench_flops", kind, iters, ctypes.byref(flops), _ptr(sink), _stream())
+    e1.record()
+    torch.cuda.synchronize()
+    return flops.value, e0.elapsed_time(e1)
+
+
+def to_device(a, dtype, device):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(device)

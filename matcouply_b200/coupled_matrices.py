@@ -1,0 +1,141 @@
+"""Result container of the decomposition: same behaviour as ``matcouply.coupled_matrices.CoupledMatrixFactorization``
+(reference src/matcouply/coupled_matrices.py:8-240) for the parts the AO-ADMM path returns and consumes: tuple-like
+``(weights, (A, B_is, C))``, ``.shape``, ``.rank``, validation (``_validate_cmf`` :243-362) and dense reconstruction
+(``cmf_to_matrix`` :365-428, ``cmf_to_matrices`` :441-504).  Host-side convenience on NumPy arrays (or torch tensors);
+the TensorLy conversions (``from_CPTensor``, ``to_tensor`` ...) are out of scope.
+"""
+import numpy as np
+
+__all__ = ["CoupledMatrixFactorization", "cmf_to_matrix", "cmf_to_matrices", "cmf_to_slice", "cmf_to_slices"]
+
+
+def _is_array(x):
+    if isinstance(x, np.ndarray):
+        return True
+    try:
+        import torch
+
+        return isinstance(x, torch.Tensor)
+    except ImportError:  # pragma: no cover
+        return False
+
+
+def _validate_cmf(cmf):
+    weights, (A, B_is, C) = cmf
+    if not (_is_array(weights) or weights is None):
+        raise TypeError("Weights should be a first order tensor of length rank, not {}".format(type(weights)))
+    elif weights is not None and len(weights.shape) != 1:
+        raise ValueError(
+            "Weights should be a first order tensor. However weights has shape {}".format(tuple(weights.shape))
+        )
+    for label, position, sizes, M in (("A", "first", "(I, rank)", A), ("C", "last", "(K, rank)", C)):
+        if not _is_array(M):
+            raise TypeError(
+                "The {} factor matrix, {}, should be a second order tensor of size {}), not {}".format(
+                    position, label, sizes, type(M)
+                )
+            )
+        elif len(M.shape) != 2:
+            raise ValueError(
+                "The {} factor matrix, {}, should be a second order tensor. However {} has shape {}".format(
+                    position, label, label, tuple(M.shape)
+                )
+            )
+    rank = int(A.shape[1])
+    if C.shape[1] != rank:
+        raise ValueError(
+            "All the factors of a coupled matrix factorization should have the same number of columns."
+            "However, A.shape[1]={} but C.shape[1]={}.".format(rank, C.shape[1])
+        )
+    shape = []
+    for i, B_i in enumerate(B_is):
+        if not _is_array(B_i):
+            raise TypeError(
+                "The B_is[{}] factor matrix should be second order tensor of size (J_i, rank)), not {}".format(
+                    i, type(B_i)
+                )
+            )
+        elif len(B_i.shape) != 2:
+            raise ValueError(
+                "The B_is[{}] factor matrix should be second order tensor. However B_is[{}] has shape {}".format(
+                    i, i, tuple(B_i.shape)
+                )
+            )
+        if B_i.shape[1] != rank:
+            raise ValueError(
+                "All the factors of a coupled matrix factorization should have the same number of columns."
+                "However, A.shape[1]={} but B_is[{}].shape[1]={}.".format(rank, i, B_i.shape[1])
+            )
+        shape.append((B_i.shape[0], C.shape[0]))
+    if weights is not None and weights.shape[0] != rank:
+        raise ValueError(
+            "Given factors for a rank-{} coupled matrix factorization but len(weights)={}.".format(
+                rank, weights.shape[0]
+            )
+        )
+    if A.shape[0] != len(B_is):
+        raise ValueError(
+            "The number of rows in A should be the same as the number of B_i matrices"
+            "However, tl.shape(A)[0]={}, but len(B_is)={}".format(A.shape[0], len(B_is))
+        )
+    return tuple(shape), rank
+
+
+class CoupledMatrixFactorization:
+    """``(weights, (A, B_is, C))`` with ``X_i ~ B_i diag(a_i) C^T``; indexable and iterable like a 2-tuple."""
+
+    def __init__(self, cmf_matrices):
+        shape, rank = _validate_cmf(cmf_matrices)
+        self.weights, self.factors = cmf_matrices
+        self.shape = shape
+        self.rank = rank
+
+    def __getitem__(self, item):
+        if item == 0:
+            return self.weights
+        elif item == 1:
+            return self.factors
+        raise IndexError(
+            "You tried to access index {} of a coupled matrix factorization.\n"
+            "You can only access index 0 and 1 of a coupled matrix factorization"
+            "(corresponding respectively to the weights and factors)".format(item)
+        )
+
+    def __iter__(self):
+        yield self.weights
+        yield self.factors
+
+    def __len__(self):
+        return 2
+
+    def __repr__(self):  # pragma: nocover
+        return "(weights, factors) : rank-{} CoupledMatrixFactorization of shape {}".format(self.rank, self.shape)
+
+    def to_matrices(self):
+        return cmf_to_matrices(self)
+
+    def to_matrix(self, matrix_idx):
+        return cmf_to_matrix(self, matrix_idx)
+
+
+def cmf_to_matrix(cmf, matrix_idx, validate=True):
+    if validate:
+        cmf = CoupledMatrixFactorization(cmf)
+    weights, (A, B_is, C) = cmf
+    a = A[matrix_idx]
+    if weights is not None:
+        a = a * weights
+    return (B_is[matrix_idx] * a) @ C.T
+
+
+def cmf_to_matrices(cmf, validate=True):
+    if validate:
+        cmf = CoupledMatrixFactorization(cmf)
+    weights, (A, B_is, C) = cmf
+    if weights is not None:
+        A = A * weights
+    return [cmf_to_matrix((None, (A, B_is, C)), i, validate=False) for i in range(A.shape[0])]
+
+
+cmf_to_slice = cmf_to_matrix
+cmf_to_slices = cmf_to_matrices

@@ -1,0 +1,541 @@
+// Small dense and batched per-slice math of the AO-ADMM sub-solvers: Gram matrices, feasibility penalties rho,
+// Cholesky-based R x R inverses (one warp per slice), per-slice cross products, and the PARAFAC2 Procrustes step
+// as an R x R Jacobi eigen-decomposition (one warp per slice, matrices in shared memory).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------
+// G = M^T M for n x R (n arbitrary): blocks own row ranges, partial Grams -> fixed-order final reduction
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kGramRows = 32;  // rows staged per step
+
+template <typename T>
+__global__ void gram_partial_kernel(const T* __restrict__ M, long long n, int R, double* __restrict__ part) {
+    __shared__ T tile[kGramRows * B2_MAX_RANK];
+    const int RR = R * R;
+    // each thread owns outputs e = tid, tid + blockDim, ... (at most 4 for R=32, 256 threads)
+    double acc[4] = {0, 0, 0, 0};
+    const long long rows_per_block = (n + gridDim.x - 1) / gridDim.x;
+    const long long r_begin = (long long)blockIdx.x * rows_per_block;
+    long long r_end = r_begin + rows_per_block;
+    if (r_end > n) r_end = n;
+    for (long long r0 = r_begin; r0 < r_end; r0 += kGramRows) {
+        const int nr = (int)((r_end - r0) < kGramRows ? (r_end - r0) : kGramRows);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nr * R; i += blockDim.x) tile[i] = M[r0 * R + i];
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = threadIdx.x + u * blockDim.x;
+            if (e < RR) {
+                const int a = e / R, b = e - a * R;
+                double s = 0.0;
+                for (int j = 0; j < nr; ++j) s += (double)tile[j * R + a] * (double)tile[j * R + b];
+                acc[u] += s;
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int e = threadIdx.x + u * blockDim.x;
+        if (e < RR) part[(size_t)blockIdx.x * RR + e] = acc[u];
+    }
+}
+
+template <typename T>
+__global__ void gram_final_kernel(const double* __restrict__ part, int blocks, int RR, T* __restrict__ G) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= RR) return;
+    double s = 0.0;
+    for (int b = 0; b < blocks; ++b) s += part[(size_t)b * RR + e];
+    G[e] = (T)s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void scale_gram_kernel(const T* __restrict__ G, const T* __restrict__ A, int n_groups, int R,
+                                  T* __restrict__ lhs) {
+    const int RR = R * R;
+    const long long total = (long long)n_groups * RR;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i / RR), e = (int)(i - (long long)g * RR);
+        const int r = e / R, s = e - r * R;
+        // (CtC[r][s] * a[s]) * a[r]   — same association as transpose(transpose(CtC * a) * a)
+        lhs[i] = (G[e] * A[(size_t)g * R + s]) * A[(size_t)g * R + r];
+    }
+}
+
+// rho[g] = 0.5*trace*scale ; rho_max via one block (n_groups up to ~1e5: grid-stride inside a single block pass 2)
+template <typename T>
+__global__ void rho_trace_kernel(const T* __restrict__ lhs, int n_groups, int R, double scale, T* __restrict__ rho) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const T* L = lhs + (size_t)g * R * R;
+    T tr = T(0);
+    for (int r = 0; r < R; ++r) tr += L[r * R + r];
+    rho[g] = (T)(T(0.5) * tr * (T)scale);
+}
+
+template <typename T>
+__global__ void max_kernel(const T* __restrict__ v, int n, T* __restrict__ out) {
+    __shared__ T scratch[32];
+    T m = -INFINITY;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = v[i] > m ? v[i] : m;
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        T u = threadIdx.x < (blockDim.x >> 5) ? scratch[threadIdx.x] : (T)-INFINITY;
+        u = warp_max(u);
+        if (threadIdx.x == 0) out[0] = u;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Batched SPD inverse by Cholesky, one warp per matrix (lane = column). fp64 internally.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kFactorWarps = 4;
+
+template <typename T>
+__global__ void factor_batch_kernel(const T* __restrict__ lhs, int n_groups, int R, T* __restrict__ rho,
+                                    const T* __restrict__ rho_max, int n_reg, double l2, T* __restrict__ Minv) {
+    extern __shared__ double fsm[];  // per warp: L (R*R) + Z (R*R)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = blockIdx.x * kFactorWarps + warp;
+    if (g >= n_groups) return;
+    double* L = fsm + (size_t)warp * 2 * R * R;
+    double* Z = L + R * R;
+    double rho_g = rho_max ? (double)rho_max[0] : (double)rho[g];
+    if (rho_max && lane == 0) rho[g] = (T)rho_g;
+    const double shift = rho_g * n_reg + l2;
+    const T* src = lhs + (size_t)g * R * R;
+    for (int e = lane; e < R * R; e += 32) {
+        const int r = e / R, c = e - r * R;
+        L[e] = (double)src[e] + (r == c ? shift : 0.0);
+    }
+    __syncwarp();
+    // in-place Cholesky (lower), right-looking; lane owns row `lane`
+    for (int k = 0; k < R; ++k) {
+        const double d = sqrt(L[k * R + k]);
+        __syncwarp();
+        if (lane == k) L[k * R + k] = d;
+        if (lane > k && lane < R) L[lane * R + k] /= d;
+        __syncwarp();
+        if (lane > k && lane < R) {
+            const double lik = L[lane * R + k];
+            for (int j = k + 1; j <= lane; ++j) L[lane * R + j] -= lik * L[j * R + k];
+        }
+        __syncwarp();
+    }
+    // Z = L^-1 (lower): lane = column c, forward substitution
+    if (lane < R) {
+        const int c = lane;
+        for (int i = 0; i < R; ++i) {
+            double s = (i == c) ? 1.0 : 0.0;
+            for (int j = c; j < i; ++j) s -= L[i * R + j] * Z[j * R + c];
+            Z[i * R + c] = (i < c) ? 0.0 : s / L[i * R + i];
+        }
+    }
+    __syncwarp();
+    // Minv = Z^T Z ; lane = column s
+    if (lane < R) {
+        const int s = lane;
+        T* dst = Minv + (size_t)g * R * R;
+        for (int r = 0; r < R; ++r) {
+            double acc = 0.0;
+            const int k0 = r > s ? r : s;
+            for (int k = k0; k < R; ++k) acc += Z[k * R + r] * Z[k * R + s];
+            dst[r * R + s] = (T)acc;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// per-slice cross products: CTA per slice.  cross[g] = (B_g^T B_g) [o CtC], rhs[g][r] = sum_j B[j][r] Y[j][r]
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kCrossRows = 32;
+
+template <typename T>
+__global__ void slice_cross_kernel(const T* __restrict__ B, const T* __restrict__ Y, const int64_t* __restrict__ row_off,
+                                   int R, const T* __restrict__ CtC, T* __restrict__ cross, T* __restrict__ rhs) {
+    __shared__ T tb[kCrossRows * B2_MAX_RANK];
+    __shared__ T ty[kCrossRows * B2_MAX_RANK];
+    const int g = blockIdx.x;
+    const long long r_begin = row_off[g], r_end = row_off[g + 1];
+    const int RR = R * R;
+    double acc[4] = {0, 0, 0, 0};
+    double racc = 0.0;  // threads < R accumulate rhs column
+    for (long long r0 = r_begin; r0 < r_end; r0 += kCrossRows) {
+        const int nr = (int)((r_end - r0) < kCrossRows ? (r_end - r0) : kCrossRows);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nr * R; i += blockDim.x) {
+            tb[i] = B[r0 * R + i];
+            if (Y) ty[i] = Y[r0 * R + i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int e = threadIdx.x + u * blockDim.x;
+            if (e < RR) {
+                const int a = e / R, b = e - a * R;
+                double s = 0.0;
+                for (int j = 0; j < nr; ++j) s += (double)tb[j * R + a] * (double)tb[j * R + b];
+                acc[u] += s;
+            }
+        }
+        if (Y && threadIdx.x < R) {
+            double s = 0.0;
+            for (int j = 0; j < nr; ++j) s += (double)tb[j * R + threadIdx.x] * (double)ty[j * R + threadIdx.x];
+            racc += s;
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int e = threadIdx.x + u * blockDim.x;
+        if (e < RR) {
+            double v = acc[u];
+            if (CtC) v *= (double)CtC[e];
+            cross[(size_t)g * RR + e] = (T)v;
+        }
+    }
+    if (rhs && Y && threadIdx.x < R) rhs[(size_t)g * R + threadIdx.x] = (T)racc;
+}
+
+template <typename T>
+__global__ void rowscale_kernel(const T* __restrict__ B, const T* __restrict__ A, const int32_t* __restrict__ gor,
+                                long long n, int R, T* __restrict__ W) {
+    const long long total = n * R;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / R;
+        const int c = (int)(i - row * R);
+        W[i] = B[i] * A[(size_t)gor[row] * R + c];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// PARAFAC2 Procrustes via the R x R Gram route, one warp per slice, fp64 in shared memory.
+//   G = Delta S Delta^T = Q Lam Q^T (cyclic Jacobi);  W = Delta^T Q Lam^-1/2 Q^T ;  num = rho * W^T S
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kPolarWarps = 2;
+
+__device__ __forceinline__ void warp_matmul(const double* A, const double* Bm, double* Cm, int R, int lane, bool transA,
+                                            bool transB) {
+    // C = op(A) op(B), all R x R row-major in shared memory; lane strides over output elements
+    for (int e = lane; e < R * R; e += 32) {
+        const int i = e / R, j = e - i * R;
+        double s = 0.0;
+        for (int k = 0; k < R; ++k) {
+            const double a = transA ? A[k * R + i] : A[i * R + k];
+            const double b = transB ? Bm[j * R + k] : Bm[k * R + j];
+            s += a * b;
+        }
+        Cm[e] = s;
+    }
+}
+
+template <typename T>
+__global__ void pf2_polar_kernel(const T* __restrict__ S, const T* __restrict__ Delta, const T* __restrict__ rho,
+                                 int n_groups, int R, T* __restrict__ Wmat, double* __restrict__ num_part) {
+    extern __shared__ double psm[];  // per warp: 4 matrices R*R : Sg, G (->work), Q, Tm ; plus shared Delta
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int RR = R * R;
+    double* D = psm;  // Delta, shared by the block
+    double* Sg = psm + RR + (size_t)warp * 4 * RR;
+    double* G = Sg + RR;
+    double* Q = G + RR;
+    double* Tm = Q + RR;
+    for (int e = threadIdx.x; e < RR; e += blockDim.x) D[e] = (double)Delta[e];
+    __syncthreads();
+    const int g = blockIdx.x * kPolarWarps + warp;
+    if (g >= n_groups) return;
+    for (int e = lane; e < RR; e += 32) {
+        Sg[e] = (double)S[(size_t)g * RR + e];
+        Q[e] = (e / R == e % R) ? 1.0 : 0.0;
+    }
+    __syncwarp();
+    warp_matmul(D, Sg, Tm, R, lane, false, false);  // Tm = Delta S
+    __syncwarp();
+    warp_matmul(Tm, D, G, R, lane, false, true);  // G = Delta S Delta^T
+    __syncwarp();
+    // symmetrise (round-off) and take the scale
+    for (int e = lane; e < RR; e += 32) {
+        const int i = e / R, j = e - i * R;
+        if (i < j) {
+            const double v = 0.5 * (G[i * R + j] + G[j * R + i]);
+            G[i * R + j] = v;
+            G[j * R + i] = v;
+        }
+    }
+    __syncwarp();
+    // cyclic Jacobi sweeps; lane k updates row/column entry k of the rotated pair
+    for (int sweep = 0; sweep < 30; ++sweep) {
+        double off = 0.0, dg = 0.0;
+        for (int e = lane; e < RR; e += 32) {
+            const int i = e / R, j = e - i * R;
+            const double v = G[e];
+            if (i == j) dg += v * v; else off += v * v;
+        }
+        off = warp_sum(off);
+        dg = warp_sum(dg);
+        if (off <= 1e-30 * dg || off == 0.0) break;
+        for (int p = 0; p < R - 1; ++p) {
+            for (int q = p + 1; q < R; ++q) {
+                const double apq = G[p * R + q];
+                const double app = G[p * R + p], aqq = G[q * R + q];
+                __syncwarp();
+                if (fabs(apq) <= 1e-300 || fabs(apq) <= 1e-20 * sqrt(fabs(app * aqq))) continue;  // warp-uniform
+                const double tau = (aqq - app) / (2.0 * apq);
+                const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                const double c = 1.0 / sqrt(1.0 + t * t), s = t * c;
+                // columns p,q of G (rows k) and of Q
+                if (lane < R) {
+                    const int k = lane;
+                    const double gkp = G[k * R + p], gkq = G[k * R + q];
+                    G[k * R + p] = c * gkp - s * gkq;
+                    G[k * R + q] = s * gkp + c * gkq;
+                    const double qkp = Q[k * R + p], qkq = Q[k * R + q];
+                    Q[k * R + p] = c * qkp - s * qkq;
+                    Q[k * R + q] = s * qkp + c * qkq;
+                }
+                __syncwarp();
+                // rows p,q of G (columns k)
+                if (lane < R) {
+                    const int k = lane;
+                    const double gpk = G[p * R + k], gqk = G[q * R + k];
+                    G[p * R + k] = c * gpk - s * gqk;
+                    G[q * R + k] = s * gpk + c * gqk;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    G[p * R + q] = 0.0;
+                    G[q * R + p] = 0.0;
+                }
+                __syncwarp();
+            }
+        }
+    }
+    __syncwarp();
+    // lam_k = G[k][k]; Tm = Q diag(lam^-1/2)   (directions with lam <= eps*lam_max are dropped)
+    double lam = lane < R ? G[lane * R + lane] : 0.0;
+    const double lmax = warp_max(lam);
+    const double isq = (lane < R && lam > 1e-28 * lmax && lam > 0.0) ? 1.0 / sqrt(lam) : 0.0;
+    __syncwarp();
+    if (lane < R) G[lane] = isq;  // G is free now: reuse its first row for lam^-1/2
+    __syncwarp();
+    for (int e = lane; e < RR; e += 32) Tm[e] = Q[e] * G[e % R];
+    __syncwarp();
+    warp_matmul(Tm, Q, G, R, lane, false, true);  // G = Q lam^-1/2 Q^T   (symmetric)
+    __syncwarp();
+    warp_matmul(D, G, Tm, R, lane, true, false);  // Tm = Delta^T G = W
+    __syncwarp();
+    for (int e = lane; e < RR; e += 32) Wmat[(size_t)g * RR + e] = (T)Tm[e];
+    warp_matmul(Tm, Sg, G, R, lane, true, false);  // G = W^T S
+    __syncwarp();
+    const double rg = (double)rho[g];
+    for (int e = lane; e < RR; e += 32) num_part[(size_t)g * RR + e] = rg * G[e];
+}
+
+// Delta_new = (sum_g num_part[g]) / (sum_g rho[g]); one block, fixed order per element (pairwise over thread chunks)
+template <typename T>
+__global__ void pf2_delta_kernel(const double* __restrict__ num_part, const T* __restrict__ rho, int n_groups, int RR,
+                                 T* __restrict__ Delta_new, double* __restrict__ sums, const double* __restrict__ sums_in) {
+    __shared__ double scratch[32];
+    __shared__ double tot[B2_MAX_RANK * B2_MAX_RANK + 1];
+    if (sums_in) {
+        for (int e = threadIdx.x; e <= RR; e += blockDim.x) tot[e] = sums_in[e];
+        __syncthreads();
+    } else {
+        for (int e = 0; e <= RR; ++e) {
+            double acc = 0.0;
+            if (e < RR)
+                for (int g = threadIdx.x; g < n_groups; g += blockDim.x) acc += num_part[(size_t)g * RR + e];
+            else
+                for (int g = threadIdx.x; g < n_groups; g += blockDim.x) acc += (double)rho[g];
+            acc = block_sum(acc, scratch);
+            if (threadIdx.x == 0) tot[e] = acc;
+        }
+        __syncthreads();
+        if (sums)
+            for (int e = threadIdx.x; e <= RR; e += blockDim.x) sums[e] = tot[e];
+    }
+    for (int e = threadIdx.x; e < RR; e += blockDim.x) Delta_new[e] = (T)(tot[e] / tot[RR]);
+}
+
+template <typename T, int RM>
+__global__ void pf2_apply_kernel(T* __restrict__ pd, T* __restrict__ dual, T* __restrict__ basis,
+                                 const T* __restrict__ Wmat, const T* __restrict__ Delta_new,
+                                 const int32_t* __restrict__ gor, long long n, int R) {
+    // one thread per row: p = v W_g ; pdrow = p Delta_new   (RM = compile-time bound on R: arrays stay in registers)
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const int g = gor[row];
+    const T* Wg = Wmat + (size_t)g * R * R;
+    T v[RM], p[RM];
+#pragma unroll
+    for (int r = 0; r < RM; ++r) v[r] = r < R ? dual[row * R + r] : T(0);
+#pragma unroll
+    for (int c = 0; c < RM; ++c) {
+        T s = T(0);
+        if (c < R) {
+#pragma unroll
+            for (int r = 0; r < RM; ++r)
+                if (r < R) s = fma(v[r], __ldg(Wg + r * R + c), s);
+        }
+        p[c] = s;
+    }
+    if (basis) {
+#pragma unroll
+        for (int c = 0; c < RM; ++c)
+            if (c < R) basis[row * R + c] = p[c];
+    }
+#pragma unroll
+    for (int c = 0; c < RM; ++c) {
+        if (c < R) {
+            T s = T(0);
+#pragma unroll
+            for (int r = 0; r < RM; ++r)
+                if (r < R) s = fma(p[r], __ldg(Delta_new + r * R + c), s);
+            pd[row * R + c] = s;
+            dual[row * R + c] = v[c] - s;
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int b2_gram(const void* M, long long n, int R, void* G, int dtype, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
+    int blocks = (int)((n + 1023) / 1024);
+    const int cap = b2_num_sms() * 2;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    B2_REQUIRE(ws_bytes >= (size_t)blocks * R * R * sizeof(double), "b2_gram workspace too small");
+    B2_DISPATCH_DTYPE(dtype, {
+        gram_partial_kernel<T><<<blocks, 256, 0, st>>>((const T*)M, n, R, (double*)ws);
+        B2_LAUNCH_CHECK();
+        gram_final_kernel<T><<<(R * R + 255) / 256, 256, 0, st>>>((const double*)ws, blocks, R * R, (T*)G);
+        B2_LAUNCH_CHECK();
+    });
+    return B2_OK;
+}
+
+int b2_scale_gram(const void* G, const void* A, int n_groups, int R, void* lhs, int dtype, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_groups == 0) return B2_OK;
+    const long long total = (long long)n_groups * R * R;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > b2_num_sms() * 8) blocks = b2_num_sms() * 8;
+    B2_DISPATCH_DTYPE(dtype, {
+        scale_gram_kernel<T><<<blocks, 256, 0, st>>>((const T*)G, (const T*)A, n_groups, R, (T*)lhs);
+        B2_LAUNCH_CHECK();
+    });
+    return B2_OK;
+}
+
+int b2_rho_from_trace(const void* lhs, int n_groups, int R, double scale, void* rho, void* rho_max, int dtype,
+                      void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_groups == 0) return B2_OK;
+    B2_DISPATCH_DTYPE(dtype, {
+        rho_trace_kernel<T><<<(n_groups + 127) / 128, 128, 0, st>>>((const T*)lhs, n_groups, R, scale, (T*)rho);
+        B2_LAUNCH_CHECK();
+        if (rho_max) {
+            max_kernel<T><<<1, 1024, 0, st>>>((const T*)rho, n_groups, (T*)rho_max);
+            B2_LAUNCH_CHECK();
+        }
+    });
+    return B2_OK;
+}
+
+int b2_factor_batch(const void* lhs, int n_groups, int R, void* rho, const void* rho_max, int n_reg, double l2,
+                    void* Minv, int dtype, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
+    if (n_groups == 0) return B2_OK;
+    const size_t smem = (size_t)kFactorWarps * 2 * R * R * sizeof(double);
+    B2_DISPATCH_DTYPE(dtype, {
+        auto kern = factor_batch_kernel<T>;
+        B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(n_groups + kFactorWarps - 1) / kFactorWarps, kFactorWarps * 32, smem, st>>>(
+            (const T*)lhs, n_groups, R, (T*)rho, (const T*)rho_max, n_reg, l2, (T*)Minv);
+        B2_LAUNCH_CHECK();
+    });
+    return B2_OK;
+}
+
+int b2_slice_cross(const void* B, const void* Y, const int64_t* row_off, int n_groups, int R, const void* CtC,
+                   void* cross, void* rhs, int dtype, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
+    if (n_groups == 0) return B2_OK;
+    B2_DISPATCH_DTYPE(dtype, {
+        slice_cross_kernel<T><<<n_groups, 256, 0, st>>>((const T*)B, (const T*)Y, row_off, R, (const T*)CtC, (T*)cross,
+                                                        (T*)rhs);
+        B2_LAUNCH_CHECK();
+    });
+    return B2_OK;
+}
+
+int b2_rowscale(const void* B, const void* A, const int32_t* group_of_row, long long n, int R, void* W, int dtype,
+                void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) return B2_OK;
+    long long blocks = (n * R + 255) / 256;
+    if (blocks > b2_num_sms() * 16) blocks = b2_num_sms() * 16;
+    B2_DISPATCH_DTYPE(dtype, {
+        rowscale_kernel<T><<<(int)blocks, 256, 0, st>>>((const T*)B, (const T*)A, group_of_row, n, R, (T*)W);
+        B2_LAUNCH_CHECK();
+    });
+    return B2_OK;
+}
+
+int b2_pf2_polar(const void* S, const void* Delta, const void* rho, int n_groups, int R, void* Wmat, void* num_part,
+                 int dtype, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
+    if (n_groups == 0) return B2_OK;
+    const size_t smem = (size_t)(1 + 4 * kPolarWarps) * R * R * sizeof(double);
+    B2_DISPATCH_DTYPE(dtype, {
+        auto kern = pf2_polar_kernel<T>;
+        B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<(n_groups + kPolarWarps - 1) / kPolarWarps, kPolarWarps * 32, smem, st>>>(
+            (const T*)S, (const T*)Delta, (const T*)rho, n_groups, R, (T*)Wmat, (double*)num_part);
+        B2_LAUNCH_CHECK();
+    });
+    return B2_OK;
+}
+
+int b2_pf2_delta(const void* num_part, const void* rho, int n_groups, int R, void* Delta_new, void* sums,
+                 const void* sums_in, int dtype, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    B2_DISPATCH_DTYPE(dtype, {
+        pf2_delta_kernel<T><<<1, 1024, 0, st>>>((const double*)num_part, (const T*)rho, n_groups, R * R, (T*)Delta_new,
+                                                (double*)sums, (const double*)sums_in);
+        B2_LAUNCH_CHECK();
+    });
+    return B2_OK;
+}
+
+int b2_pf2_apply(void* pd, void* dual, void* basis, const void* Wmat, const void* Delta_new,
+                 const int32_t* group_of_row, long long n, int R, int dtype, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) return B2_OK;
+    B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
+    const int grid = (int)((n + 127) / 128);
+    B2_DISPATCH_DTYPE(dtype, B2_DISPATCH_RANK(R, {
+        pf2_apply_kernel<T, RM><<<grid, 128, 0, st>>>((T*)pd, (T*)dual, (T*)basis, (const T*)Wmat,
+                                                      (const T*)Delta_new, group_of_row, n, R);
+        B2_LAUNCH_CHECK();
+    }));
+    return B2_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,587 @@
+// X-stream contractions over the packed varlen data matrix X (N = sum_i J_i rows, K columns, row-major, ldx >= K):
+//
+//   b2_xstream_y : Y = X * C           (N x R)   — serves rhs of the B-update  X_i (C*a_i) = Y_i*a_i  (decomposition.py:242)
+//                                                  and of the A-update  diag(B_i^T X_i C) = colsum(B_i o Y_i) (:145-158)
+//   b2_xstream_z : Z = X^T * W         (K x R)   — W = B o a (row-scaled), rhs of the C-update  sum_i X_i^T (B_i*a_i) (:312-315)
+//   b2_sumsq     : sum(X**2)                      — ||X||^2 for the fit term (:906)
+//
+// Both contractions are HBM-streaming tall-skinny products (R << K, J_i): X is read exactly once per launch through
+// TMA (cp.async.bulk.tensor, SWIZZLE_128B boxes) into an mbarrier-synchronised shared-memory ring filled by a
+// dedicated producer warp; consumer warps contract from shared memory with FP64/FP32 FMAs or, for fp64, with
+// DMMA.8x8x4 tensor-core instructions.  Grids are persistent (<= one CTA per SM, static tile striding).
+#include "common.cuh"
+
+namespace {
+
+constexpr int kConsumerThreads = 256;
+constexpr int kThreads = kConsumerThreads + 32;  // + producer warp
+
+// ---------------------------------------------------------------------------------------------------------
+// Y = X * C
+// ---------------------------------------------------------------------------------------------------------
+// Stage layout (1024-byte aligned): NBOX swizzled boxes [TM rows x 128 B] of X, then the C chunk [KC x LDC].
+template <typename T>
+struct YCfg {
+    static constexpr int TM = 128;                    // rows per tile
+    static constexpr int EPB = 128 / (int)sizeof(T);  // elements per 128-byte box row
+    static constexpr int NBOX = 2;
+    static constexpr int KC = NBOX * EPB;  // K-chunk per stage (32 fp64 / 64 fp32)
+    static constexpr int BOX_BYTES = TM * 128;
+    static constexpr int X_BYTES = NBOX * BOX_BYTES;
+};
+
+// pad/copy C (K x R, ld R) into Cp (Kp x LDC), zero filled, so that a K-chunk is one contiguous 16B-aligned bulk copy
+template <typename T>
+__global__ void pad_c_kernel(const T* __restrict__ C, T* __restrict__ Cp, int K, int R, int Kp, int LDC) {
+    const int n = Kp * LDC;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int k = i / LDC, c = i - k * LDC;
+        Cp[i] = (k < K && c < R) ? C[(size_t)k * R + c] : T(0);
+    }
+}
+
+// CT = columns per thread in the FMA path (thread tile 2 rows x CT cols, 4 column groups) ; LDC = 4*CT.
+// DMMA path (fp64): warp w owns rows [16w,16w+16) = 2 m-blocks, NBLK = LDC_used/8 n-blocks; LDC = 8 (mod 16).
+template <typename T, int CT, bool DMMA, int NBLK>
+__global__ void __launch_bounds__(kThreads, 1)
+xstream_y_kernel(const __grid_constant__ CUtensorMap tmap_x, const T* __restrict__ Cp, T* __restrict__ Y, long long N,
+                 int R, int Kp, int LDC, int num_tiles, int stages) {
+    using Cfg = YCfg<T>;
+    constexpr int TM = Cfg::TM, EPB = Cfg::EPB, NBOX = Cfg::NBOX, KC = Cfg::KC;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    // carve: [stages x (X boxes | C chunk)] | full[stages] | empty[stages]
+    const uint32_t c_bytes = (uint32_t)(KC * LDC * sizeof(T));
+    const uint32_t stage_bytes = (Cfg::X_BYTES + c_bytes + 1023u) & ~1023u;
+    unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = (uint64_t*)(base + (size_t)stages * stage_bytes);
+    uint64_t* empty = full + stages;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumerThreads / 32);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int kchunks = Kp / KC;
+
+    if (warp == kConsumerThreads / 32) {
+        // ===== producer warp: one elected lane issues all TMA traffic =====
+        if (lane == 0) {
+            prefetch_tmap(&tmap_x);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int row0 = tile * TM;
+                for (int kc = 0; kc < kchunks; ++kc) {
+                    mbar_wait(&empty[s], ph ^ 1);
+                    unsigned char* st = base + (size_t)s * stage_bytes;
+                    mbar_arrive_expect_tx(&full[s], Cfg::X_BYTES + c_bytes);
+#pragma unroll
+                    for (int b = 0; b < NBOX; ++b)
+                        tma_load_2d(st + b * Cfg::BOX_BYTES, &tmap_x, kc * KC + b * EPB, row0, &full[s]);
+                    bulk_load_1d(st + Cfg::X_BYTES, Cp + (size_t)kc * KC * LDC, c_bytes, &full[s]);
+                    if (++s == stages) {
+                        s = 0;
+                        ph ^= 1;
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ===== consumers =====
+    int s = 0;
+    uint32_t ph = 0;
+    if constexpr (!DMMA) {
+        const int tc = tid & 3, tr = tid >> 2;  // 4 column groups x 64 row pairs (rows tr, tr+64)
+        constexpr int EPC = 16 / (int)sizeof(T);  // elements per 16-byte chunk
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            T acc0[CT], acc1[CT];
+#pragma unroll
+            for (int c = 0; c < CT; ++c) acc0[c] = acc1[c] = T(0);
+            for (int kc = 0; kc < kchunks; ++kc) {
+                mbar_wait(&full[s], ph);
+                const unsigned char* st = base + (size_t)s * stage_bytes;
+                const T* Cs = (const T*)(st + Cfg::X_BYTES) + tc * CT;
+#pragma unroll
+                for (int b = 0; b < NBOX; ++b) {
+                    const unsigned char* box = st + b * Cfg::BOX_BYTES;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        T x0[EPC], x1[EPC];
+                        *(int4*)x0 = *(const int4*)(box + swz128(tr, q));
+                        *(int4*)x1 = *(const int4*)(box + swz128(tr + 64, q));
+#pragma unroll
+                        for (int e = 0; e < EPC; ++e) {
+                            const T* crow = Cs + (size_t)(b * EPB + q * EPC + e) * LDC;
+                            T cv[CT];
+                            if constexpr ((CT * sizeof(T)) % 16 == 0) {
+#pragma unroll
+                                for (int v = 0; v < (int)(CT * sizeof(T) / 16); ++v)
+                                    *((int4*)cv + v) = *((const int4*)crow + v);
+                            } else if constexpr ((CT * sizeof(T)) % 8 == 0) {
+#pragma unroll
+                                for (int v = 0; v < (int)(CT * sizeof(T) / 8); ++v)
+                                    *((int2*)cv + v) = *((const int2*)crow + v);
+                            } else {
+#pragma unroll
+                                for (int c = 0; c < CT; ++c) cv[c] = crow[c];
+                            }
+#pragma unroll
+                            for (int c = 0; c < CT; ++c) {
+                                acc0[c] = fma(x0[e], cv[c], acc0[c]);
+                                acc1[c] = fma(x1[e], cv[c], acc1[c]);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+                if (++s == stages) {
+                    s = 0;
+                    ph ^= 1;
+                }
+            }
+            const long long r0 = (long long)tile * TM + tr, r1 = r0 + 64;
+#pragma unroll
+            for (int c = 0; c < CT; ++c) {
+                const int col = tc * CT + c;
+                if (col < R) {
+                    if (r0 < N) Y[r0 * R + col] = acc0[c];
+                    if (r1 < N) Y[r1 * R + col] = acc1[c];
+                }
+            }
+        }
+    } else {
+        // fp64 tensor-core path. lane = 4g + t. A frag: X[16w + 8m + g][k0 + t]; B frag: C[k0 + t][8n + g].
+        const int g = lane >> 2, t = lane & 3;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            double acc[2][NBLK][2];
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int n = 0; n < NBLK; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
+            for (int kc = 0; kc < kchunks; ++kc) {
+                mbar_wait(&full[s], ph);
+                const unsigned char* st = base + (size_t)s * stage_bytes;
+                const double* Cs = (const double*)(st + Cfg::X_BYTES);
+#pragma unroll
+                for (int b = 0; b < NBOX; ++b) {
+                    const unsigned char* box = st + b * Cfg::BOX_BYTES;
+#pragma unroll
+                    for (int k4 = 0; k4 < EPB / 4; ++k4) {
+                        const int kk = k4 * 4 + t;  // column inside the box (0..15)
+                        double a[2], bf[NBLK];
+#pragma unroll
+                        for (int m = 0; m < 2; ++m) {
+                            const uint32_t row = warp * 16 + m * 8 + g;
+                            a[m] = *(const double*)(box + swz128(row, kk >> 1) + (kk & 1) * 8);
+                        }
+                        const double* crow = Cs + (size_t)(b * EPB + kk) * LDC + g;
+#pragma unroll
+                        for (int n = 0; n < NBLK; ++n) bf[n] = crow[n * 8];
+#pragma unroll
+                        for (int m = 0; m < 2; ++m)
+#pragma unroll
+                            for (int n = 0; n < NBLK; ++n) dmma884(acc[m][n][0], acc[m][n][1], a[m], bf[n]);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+                if (++s == stages) {
+                    s = 0;
+                    ph ^= 1;
+                }
+            }
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const long long row = (long long)tile * TM + warp * 16 + m * 8 + g;
+                if (row < N) {
+#pragma unroll
+                    for (int n = 0; n < NBLK; ++n) {
+                        const int col = n * 8 + 2 * t;
+                        if (col < R) Y[row * R + col] = (T)acc[m][n][0];
+                        if (col + 1 < R) Y[row * R + col + 1] = (T)acc[m][n][1];
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Z = X^T * W   (FMA path: thread owns 2 consecutive k's x all R columns; grid = row-groups x k-blocks)
+// ---------------------------------------------------------------------------------------------------------
+// Stage layout: KZB swizzled boxes [TMZ rows x 128 B] of X (KZB = KZ / EPB), then the W tile [TMZ x R] (contiguous rows).
+template <typename T>
+struct ZCfg {
+    static constexpr int TMZ = 16;
+    static constexpr int EPB = 128 / (int)sizeof(T);
+    static constexpr int EPC = 16 / (int)sizeof(T);  // k's per thread (one 16-byte chunk)
+    static constexpr int BOX_BYTES = TMZ * 128;
+};
+
+template <typename T, int RP>
+__global__ void __launch_bounds__(kThreads, 1)
+xstream_z_kernel(const __grid_constant__ CUtensorMap tmap_x, const T* __restrict__ W, T* __restrict__ part, int K, int R,
+                 int KZ, int num_tiles, int stages) {
+    using Cfg = ZCfg<T>;
+    constexpr int TMZ = Cfg::TMZ, EPB = Cfg::EPB, EPC = Cfg::EPC;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const int kzb = KZ / EPB;
+    const uint32_t x_bytes = (uint32_t)kzb * Cfg::BOX_BYTES;
+    const uint32_t w_bytes = (uint32_t)(TMZ * R * sizeof(T));
+    const uint32_t stage_bytes = (x_bytes + w_bytes + 1023u) & ~1023u;
+    unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = (uint64_t*)(base + (size_t)stages * stage_bytes);
+    uint64_t* empty = full + stages;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n_cons_warps = (blockDim.x >> 5) - 1;
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], n_cons_warps);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int k_base = blockIdx.y * KZ;
+
+    if (warp == n_cons_warps) {
+        if (lane == 0) {
+            prefetch_tmap(&tmap_x);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int row0 = tile * TMZ;
+                mbar_wait(&empty[s], ph ^ 1);
+                unsigned char* st = base + (size_t)s * stage_bytes;
+                mbar_arrive_expect_tx(&full[s], x_bytes + w_bytes);
+                for (int b = 0; b < kzb; ++b)
+                    tma_load_2d(st + b * Cfg::BOX_BYTES, &tmap_x, k_base + b * EPB, row0, &full[s]);
+                bulk_load_1d(st + x_bytes, W + (size_t)row0 * R, w_bytes, &full[s]);
+                if (++s == stages) {
+                    s = 0;
+                    ph ^= 1;
+                }
+            }
+        }
+        return;
+    }
+
+    // consumer thread `tid` owns k's [k_base + EPC*tid, +EPC) for all RP (>= R) columns
+    T acc[EPC][RP];
+#pragma unroll
+    for (int e = 0; e < EPC; ++e)
+#pragma unroll
+        for (int c = 0; c < RP; ++c) acc[e][c] = T(0);
+    const int box_id = tid / 8, chunk = tid & 7;  // 8 chunks of 16 B per 128-byte box row
+    const bool active = tid * EPC < KZ;           // consumer count is rounded up to whole warps
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&full[s], ph);
+        const unsigned char* st = base + (size_t)s * stage_bytes;
+        const unsigned char* box = st + (size_t)box_id * Cfg::BOX_BYTES;
+        const T* Ws = (const T*)(st + x_bytes);
+#pragma unroll 4
+        for (int r = 0; r < (active ? TMZ : 0); ++r) {
+            T x[EPC];
+            *(int4*)x = *(const int4*)(box + swz128(r, chunk));
+            const T* wr = Ws + r * R;
+#pragma unroll
+            for (int c = 0; c < RP; ++c) {
+                const T w = (c < R) ? wr[c] : T(0);
+#pragma unroll
+                for (int e = 0; e < EPC; ++e) acc[e][c] = fma(x[e], w, acc[e][c]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (++s == stages) {
+            s = 0;
+            ph ^= 1;
+        }
+    }
+    // partials: part[blockIdx.x][k][c]
+    T* out = part + (size_t)blockIdx.x * K * R;
+#pragma unroll
+    for (int e = 0; e < EPC; ++e) {
+        const int k = k_base + tid * EPC + e;
+        if (k < K) {
+#pragma unroll
+            for (int c = 0; c < RP; ++c)
+                if (c < R) out[(size_t)k * R + c] = acc[e][c];
+        }
+    }
+}
+
+// fixed-order reduction of the per-row-group partials: Z[i] = sum_g part[g][i]
+template <typename T>
+__global__ void reduce_partials_kernel(const T* __restrict__ part, T* __restrict__ out, int n, int groups) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    T s = T(0);
+    for (int g = 0; g < groups; ++g) s += part[(size_t)g * n + i];
+    out[i] = s;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// sum of squares of X (only the K valid columns of each ldx-strided row)
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void sumsq_kernel(const T* __restrict__ X, long long N, int K, int ldx, double* __restrict__ part) {
+    __shared__ double scratch[32];
+    double acc = 0.0;
+    const long long total = N * (long long)ldx;
+    constexpr int V = 16 / (int)sizeof(T);
+    // ldx is a multiple of V and padding columns are zero, so the padded buffer can be summed as a flat vector
+    const long long nvec = total / V;
+    const int4* Xv = (const int4*)X;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+        int4 raw = __ldg(Xv + i);
+        const T* v = (const T*)&raw;
+#pragma unroll
+        for (int e = 0; e < V; ++e) acc += (double)v[e] * (double)v[e];
+    }
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+
+__global__ void reduce_double_kernel(const double* __restrict__ part, int n, double* __restrict__ out) {
+    __shared__ double scratch[32];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += part[i];
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0) out[0] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host: tensor-map encoding through the driver entry point (no link-time dependency on libcuda)
+// ---------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+int encode_x_map(CUtensorMap* map, const void* X, long long N, int K, int ldx, int dtype, int box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    B2_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available from the driver");
+    const size_t es = dtype == B2_F64 ? 8 : 4;
+    B2_REQUIRE(((size_t)ldx * es) % 16 == 0, "X row stride (%d elements) must be a multiple of 16 bytes", ldx);
+    B2_REQUIRE(((uintptr_t)X) % 16 == 0, "X must be 16-byte aligned");
+    cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    cuuint64_t gstr[1] = {(cuuint64_t)ldx * es};
+    cuuint32_t box[2] = {(cuuint32_t)(128 / es), (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, dtype == B2_F64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                    const_cast<void*>(X), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    B2_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return B2_OK;
+}
+
+template <typename T, int CT>
+int launch_y_fma(const CUtensorMap& map, const T* Cp, T* Y, long long N, int R, int Kp, int num_tiles, int grid,
+                 int stages, size_t smem, cudaStream_t st) {
+    auto kern = xstream_y_kernel<T, CT, false, 1>;
+    B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, st>>>(map, Cp, Y, N, R, Kp, 4 * CT, num_tiles, stages);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+template <int NBLK>
+int launch_y_dmma(const CUtensorMap& map, const double* Cp, double* Y, long long N, int R, int Kp, int LDC, int num_tiles,
+                  int grid, int stages, size_t smem, cudaStream_t st) {
+    auto kern = xstream_y_kernel<double, 1, true, NBLK>;
+    B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, st>>>(map, Cp, Y, N, R, Kp, LDC, num_tiles, stages);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+
+template <typename T>
+int xstream_y_impl(const void* X, long long N, int K, int ldx, const void* C, int R, void* Y, void* ws, size_t ws_bytes,
+                   int variant, int max_ctas, cudaStream_t st) {
+    using Cfg = YCfg<T>;
+    const int dtype = sizeof(T) == 8 ? B2_F64 : B2_F32;
+    const bool dmma = (variant == B2_VARIANT_DMMA);
+    B2_REQUIRE(!dmma || dtype == B2_F64, "the DMMA variant exists for fp64 only");
+    B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
+    if (N == 0) return B2_OK;
+    const int Kp = ((K + Cfg::KC - 1) / Cfg::KC) * Cfg::KC;
+    int CT = (R + 3) / 4, LDC = 4 * CT, NBLK = (R + 7) / 8;
+    if (dmma) LDC = (NBLK <= 1) ? 8 : (NBLK <= 3 ? 24 : 40);  // == 8 (mod 16): conflict-free B-fragment reads
+    const size_t cp_bytes = (size_t)Kp * LDC * sizeof(T);
+    B2_REQUIRE(ws_bytes >= cp_bytes, "xstream_y workspace too small: need %zu bytes, got %zu", cp_bytes, ws_bytes);
+    B2_REQUIRE(((uintptr_t)ws) % 16 == 0, "workspace must be 16-byte aligned");
+    pad_c_kernel<T><<<(Kp * LDC + 255) / 256, 256, 0, st>>>((const T*)C, (T*)ws, K, R, Kp, LDC);
+    B2_LAUNCH_CHECK();
+
+    alignas(64) CUtensorMap map;
+    int rc = encode_x_map(&map, X, N, K, ldx, dtype, Cfg::TM);
+    if (rc != B2_OK) return rc;
+    const int num_tiles = (int)((N + Cfg::TM - 1) / Cfg::TM);
+    const uint32_t c_bytes = (uint32_t)(Cfg::KC * LDC * sizeof(T));
+    const uint32_t stage_bytes = (Cfg::X_BYTES + c_bytes + 1023u) & ~1023u;
+    int stages = (int)((220 * 1024 - 1024 - 256) / stage_bytes);
+    if (stages > 6) stages = 6;
+    B2_REQUIRE(stages >= 2, "xstream_y: stage does not fit shared memory");
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + 2 * stages * sizeof(uint64_t);
+    int grid = b2_num_sms();
+    if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
+    if (grid > num_tiles) grid = num_tiles;
+
+    if (dmma) {
+        const double* Cp = (const double*)ws;
+        double* Yd = (double*)Y;
+        switch (NBLK) {
+            case 1: return launch_y_dmma<1>(map, Cp, Yd, N, R, Kp, LDC, num_tiles, grid, stages, smem, st);
+            case 2: return launch_y_dmma<2>(map, Cp, Yd, N, R, Kp, LDC, num_tiles, grid, stages, smem, st);
+            case 3: return launch_y_dmma<3>(map, Cp, Yd, N, R, Kp, LDC, num_tiles, grid, stages, smem, st);
+            default: return launch_y_dmma<4>(map, Cp, Yd, N, R, Kp, LDC, num_tiles, grid, stages, smem, st);
+        }
+    }
+    const T* Cp = (const T*)ws;
+    T* Yt = (T*)Y;
+    switch (CT) {
+        case 1: return launch_y_fma<T, 1>(map, Cp, Yt, N, R, Kp, num_tiles, grid, stages, smem, st);
+        case 2: return launch_y_fma<T, 2>(map, Cp, Yt, N, R, Kp, num_tiles, grid, stages, smem, st);
+        case 3: return launch_y_fma<T, 3>(map, Cp, Yt, N, R, Kp, num_tiles, grid, stages, smem, st);
+        case 4: return launch_y_fma<T, 4>(map, Cp, Yt, N, R, Kp, num_tiles, grid, stages, smem, st);
+        case 5: return launch_y_fma<T, 5>(map, Cp, Yt, N, R, Kp, num_tiles, grid, stages, smem, st);
+        case 6: return launch_y_fma<T, 6>(map, Cp, Yt, N, R, Kp, num_tiles, grid, stages, smem, st);
+        case 7: return launch_y_fma<T, 7>(map, Cp, Yt, N, R, Kp, num_tiles, grid, stages, smem, st);
+        default: return launch_y_fma<T, 8>(map, Cp, Yt, N, R, Kp, num_tiles, grid, stages, smem, st);
+    }
+}
+
+template <typename T, int RP>
+int launch_z(const CUtensorMap& map, const T* W, T* part, int K, int R, int KZ, int num_tiles, dim3 grid, int threads,
+             int stages, size_t smem, cudaStream_t st) {
+    auto kern = xstream_z_kernel<T, RP>;
+    B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, threads, smem, st>>>(map, W, part, K, R, KZ, num_tiles, stages);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+
+template <typename T>
+int xstream_z_impl(const void* X, long long N, int K, int ldx, const void* W, int R, void* Z, void* ws, size_t ws_bytes,
+                   int variant, int max_ctas, cudaStream_t st) {
+    using Cfg = ZCfg<T>;
+    (void)variant;
+    const int dtype = sizeof(T) == 8 ? B2_F64 : B2_F32;
+    B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
+    B2_REQUIRE(((size_t)Cfg::TMZ * R * sizeof(T)) % 16 == 0, "internal: W tile not 16-byte sized");
+    if (N == 0) {
+        B2_CHECK_CUDA(cudaMemsetAsync(Z, 0, (size_t)K * R * sizeof(T), st));
+        return B2_OK;
+    }
+    // k-block per CTA: up to 256 consumer threads x EPC k's; rounded to whole 128-byte boxes
+    const int kmax = kConsumerThreads * Cfg::EPC;
+    const int Kbox = ((K + Cfg::EPB - 1) / Cfg::EPB) * Cfg::EPB;
+    const int kblocks = (Kbox + kmax - 1) / kmax;
+    int KZ = (Kbox + kblocks - 1) / kblocks;
+    KZ = ((KZ + Cfg::EPB - 1) / Cfg::EPB) * Cfg::EPB;
+    // consumer threads: one per 16-byte chunk, rounded up to whole warps
+    const int cons = ((KZ / Cfg::EPC + 31) / 32) * 32;
+    const int threads = cons + 32;
+    const int num_tiles = (int)((N + Cfg::TMZ - 1) / Cfg::TMZ);
+    int groups = b2_num_sms() / kblocks;
+    if (max_ctas > 0 && max_ctas / kblocks < groups) groups = max_ctas / kblocks;
+    if (groups < 1) groups = 1;
+    if (groups > num_tiles) groups = num_tiles;
+    const size_t part_bytes = (size_t)groups * K * R * sizeof(T);
+    B2_REQUIRE(ws_bytes >= part_bytes, "xstream_z workspace too small: need %zu bytes, got %zu", part_bytes, ws_bytes);
+
+    alignas(64) CUtensorMap map;
+    int rc = encode_x_map(&map, X, N, K, ldx, dtype, Cfg::TMZ);
+    if (rc != B2_OK) return rc;
+    const uint32_t x_bytes = (uint32_t)(KZ / Cfg::EPB) * Cfg::BOX_BYTES;
+    const uint32_t w_bytes = (uint32_t)(Cfg::TMZ * R * sizeof(T));
+    const uint32_t stage_bytes = (x_bytes + w_bytes + 1023u) & ~1023u;
+    int stages = (int)((200 * 1024) / stage_bytes);
+    if (stages > 8) stages = 8;
+    B2_REQUIRE(stages >= 2, "xstream_z: stage does not fit shared memory");
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + 2 * stages * sizeof(uint64_t);
+    dim3 grid(groups, kblocks);
+    const T* Wt = (const T*)W;
+    T* part = (T*)ws;
+    const int RP = ((R + 3) / 4) * 4;
+    switch (RP) {
+        case 4: rc = launch_z<T, 4>(map, Wt, part, K, R, KZ, num_tiles, grid, threads, stages, smem, st); break;
+        case 8: rc = launch_z<T, 8>(map, Wt, part, K, R, KZ, num_tiles, grid, threads, stages, smem, st); break;
+        case 12: rc = launch_z<T, 12>(map, Wt, part, K, R, KZ, num_tiles, grid, threads, stages, smem, st); break;
+        case 16: rc = launch_z<T, 16>(map, Wt, part, K, R, KZ, num_tiles, grid, threads, stages, smem, st); break;
+        case 20: rc = launch_z<T, 20>(map, Wt, part, K, R, KZ, num_tiles, grid, threads, stages, smem, st); break;
+        case 24: rc = launch_z<T, 24>(map, Wt, part, K, R, KZ, num_tiles, grid, threads, stages, smem, st); break;
+        case 28: rc = launch_z<T, 28>(map, Wt, part, K, R, KZ, num_tiles, grid, threads, stages, smem, st); break;
+        default: rc = launch_z<T, 32>(map, Wt, part, K, R, KZ, num_tiles, grid, threads, stages, smem, st); break;
+    }
+    if (rc != B2_OK) return rc;
+    const int n = K * R;
+    reduce_partials_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(part, (T*)Z, n, groups);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b2_xstream_y(const void* X, long long n_rows, int K, int ldx, const void* C, int R, void* Y, int dtype, void* ws,
+                 size_t ws_bytes, int variant, int max_ctas, void* stream) {
+    B2_DISPATCH_DTYPE(dtype, return xstream_y_impl<T>(X, n_rows, K, ldx, C, R, Y, ws, ws_bytes, variant, max_ctas,
+                                                      (cudaStream_t)stream));
+}
+
+int b2_xstream_z(const void* X, long long n_rows, int K, int ldx, const void* W, int R, void* Z, int dtype, void* ws,
+                 size_t ws_bytes, int variant, int max_ctas, void* stream) {
+    B2_DISPATCH_DTYPE(dtype, return xstream_z_impl<T>(X, n_rows, K, ldx, W, R, Z, ws, ws_bytes, variant, max_ctas,
+                                                      (cudaStream_t)stream));
+}
+
+size_t b2_xstream_workspace_bytes(int K, int R, int dtype) {
+    const size_t es = dtype == B2_F64 ? 8 : 4;
+    const size_t kp = (size_t)((K + 63) / 64) * 64;
+    const size_t y = kp * 40 * es;
+    const size_t z = (size_t)b2_num_sms() * K * R * es;
+    return (y > z ? y : z) + 256;
+}
+
+int b2_sumsq(const void* X, long long n_rows, int K, int ldx, int dtype, double* out, void* ws, size_t ws_bytes,
+             void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = b2_num_sms() * 4;
+    B2_REQUIRE(ws_bytes >= blocks * sizeof(double), "b2_sumsq workspace too small");
+    (void)K;
+    if (dtype == B2_F64)
+        sumsq_kernel<double><<<blocks, 256, 0, st>>>((const double*)X, n_rows, K, ldx, (double*)ws);
+    else if (dtype == B2_F32)
+        sumsq_kernel<float><<<blocks, 256, 0, st>>>((const float*)X, n_rows, K, ldx, (double*)ws);
+    else
+        B2_REQUIRE(false, "unknown dtype %d", dtype);
+    B2_LAUNCH_CHECK();
+    reduce_double_kernel<<<1, 256, 0, st>>>((const double*)ws, blocks, out);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+
+}  // extern "C"

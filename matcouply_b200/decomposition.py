@@ -1,0 +1,465 @@
+"""AO-ADMM for coupled matrix factorization / PARAFAC2 with the call surface of ``matcouply.decomposition``
+(reference src/matcouply/decomposition.py): :func:`cmf_aoadmm` (:662), :func:`parafac2_aoadmm` (:1103),
+:func:`compute_feasibility_gaps` (:351), :class:`ADMMVars` (:643), :class:`DiagnosticMetrics` (:648).
+
+The host side keeps what must stay on the host for parity — NumPy ``RandomState`` initialisation in the reference's
+draw order (:31-39, :78-89), keyword -> penalty parsing (:455-614) and the stopping rule with all its quirks
+(:990-1059) — and drives :class:`matcouply_b200._engine.AOADMMEngine`, which runs every numerical step as CUDA
+kernels on the B200.  There is no CPU path: without the compiled library / a CUDA device the call raises.
+"""
+from copy import copy
+from typing import NamedTuple, Optional
+
+import numpy as np
+
+from . import penalties
+from .coupled_matrices import CoupledMatrixFactorization
+
+__all__ = ["compute_feasibility_gaps", "ADMMVars", "DiagnosticMetrics", "cmf_aoadmm", "parafac2_aoadmm"]
+
+_UNSUPPORTED_INITS = {"svd", "threshold_svd", "parafac2_als", "cp_als", "parafac_als", "cp_hals", "parafac_hals"}
+
+
+class ADMMVars(NamedTuple):
+    auxes: tuple  #: Length three tuple containing a list of auxiliary factor matrices for each mode
+    duals: tuple  #: Length three tuple containing a list of dual variables for each mode
+
+
+class DiagnosticMetrics(NamedTuple):
+    rec_errors: list  #: relative reconstruction errors, one per evaluated iteration plus the initial one
+    feasibility_gaps: list  #: feasibility gaps, same length convention
+    regularized_loss: list  #: regularized loss, same length convention
+    satisfied_stopping_condition: Optional[bool]  #: None if no tolerance is set
+    satisfied_feasibility_condition: Optional[bool]  #: None if no feasibility tolerance is set
+    n_iter: int  #: Number of iterations ran
+    message: str  #: Convergence message
+
+
+def is_iterable(x):
+    try:
+        iter(x)
+    except TypeError:
+        return False
+    return True
+
+
+def _listify(input_value, param_name):  # decomposition.py:455-467
+    if hasattr(input_value, "get"):
+        return [input_value.get(i, None) for i in range(3)]
+    if not is_iterable(input_value):
+        return [input_value] * 3
+    out = list(input_value)
+    if len(out) != 3:
+        raise ValueError(
+            "All parameters must be a dictionary, non-iterable value or non-dictionary iterable of length 3."
+            f" {param_name} is iterable of length {len(out)}."
+        )
+    return out
+
+
+def _parse_mode_penalties(non_negative, lower_bound, upper_bound, l2_norm_bound, unimodal, parafac2, l1_penalty,
+                          tv_penalty, generalized_l2_penalty, svd, dual_init, aux_init):
+    """Fixed per-mode order Parafac2, Unimodality, GeneralizedL2, L2Ball, TV, L1, Box, NonNegativity; non_negative is
+    folded into the penalties that support it (decomposition.py:549-614)."""
+    init = dict(aux_init=aux_init, dual_init=dual_init)
+    l1_penalty = l1_penalty if l1_penalty else 0
+    regs, nn_handled = [], False
+    if parafac2:
+        regs.append(penalties.Parafac2(svd=svd, **init))
+    if unimodal:
+        regs.append(penalties.Unimodality(non_negativity=non_negative, **init))
+        nn_handled = True
+    if generalized_l2_penalty is not None and generalized_l2_penalty is not False:
+        regs.append(penalties.GeneralizedL2Penalty(generalized_l2_penalty, svd=svd, **init))
+    if l2_norm_bound:
+        regs.append(penalties.L2Ball(l2_norm_bound, non_negativity=non_negative, **init))
+        nn_handled = True
+    if tv_penalty:
+        regs.append(penalties.TotalVariationPenalty(tv_penalty, l1_strength=l1_penalty, **init))
+        l1_penalty = 0
+    if l1_penalty:
+        regs.append(penalties.L1Penalty(l1_penalty, non_negativity=non_negative, **init))
+        nn_handled = True
+    if lower_bound is not None or upper_bound is not None:
+        if lower_bound is None:
+            lower_bound = -float("inf")
+        if non_negative:
+            lower_bound = max(lower_bound, 0)
+        regs.append(penalties.Box(lower_bound, upper_bound, **init))
+        nn_handled = True
+    if non_negative and not nn_handled:
+        regs.append(penalties.NonNegativity(**init))
+    return regs
+
+
+def _parse_all_penalties(non_negative, lower_bound, upper_bound, l2_norm_bound, unimodal, parafac2, l1_penalty,
+                         tv_penalty, generalized_l2_penalty, svd, regs, dual_init, aux_init, verbose):
+    """decomposition.py:470-546."""
+    if regs is None:
+        regs = [[], [], []]
+    elif is_iterable(regs):
+        for modereg in regs:
+            if not is_iterable(modereg):
+                raise TypeError(
+                    "regs should contain an iterable of iterables containting "
+                    "matcouply.penalties.ADMMMPenalty instances at least one of the"
+                    f"elements in regs were not iterable (regs={regs})"
+                )
+            for reg in modereg:
+                if not isinstance(reg, penalties.ADMMPenalty):
+                    raise TypeError(
+                        "regs should contain an iterable of iterables containting "
+                        "matcouply.penalties.ADMMMPenalty instances at least one of the"
+                        f"elements in regs contained something other than an ADMMPenalty (regs={regs})"
+                    )
+    regs = [copy(reg_list) for reg_list in regs]  # the caller's lists are never modified
+
+    per_mode = dict(
+        non_negative=_listify(non_negative, "non_negative"),
+        upper_bound=_listify(upper_bound, "upper_bound"),
+        lower_bound=_listify(lower_bound, "lower_bound"),
+        l2_norm_bound=_listify(l2_norm_bound, "l2_norm_bound"),
+        unimodal=_listify(unimodal, "unimodal"),
+        parafac2=[False, bool(parafac2), False],
+        l1_penalty=_listify(l1_penalty, "l1_penalty"),
+        generalized_l2_penalty=_listify(generalized_l2_penalty, "generalized_l2_penalty"),
+        tv_penalty=_listify(tv_penalty, "tv_penalty"),
+    )
+    for mode in range(3):
+        parsed = _parse_mode_penalties(svd=svd, dual_init=dual_init, aux_init=aux_init,
+                                       **{k: v[mode] for k, v in per_mode.items()})
+        regs[mode] = parsed + list(regs[mode])
+
+    if verbose:
+        print("All regularization penalties (including regs list):")
+        for mode, reg in enumerate(regs):
+            print(f"* Mode {mode}:")
+            if len(reg) == 0:
+                print("   - (no regularization added)")
+            for single_reg in reg:
+                print(f"   - {single_reg}")
+    return regs
+
+
+class _ShapeOnly:
+    """Stand-in for a data matrix when only its shape is needed (random init of device-resident inputs)."""
+
+    def __init__(self, shape):
+        self.shape = tuple(shape)
+
+
+def initialize_cmf(matrices, rank, init, random_state=None):
+    """decomposition.py:18-75: a given factorization is used as is, "random" draws A, C, B_0..B_{I-1} (in this
+    order) uniformly from one RandomState."""
+    random_state = penalties._check_random_state(random_state)
+    if isinstance(init, (tuple, list, CoupledMatrixFactorization)):
+        weights, (A, B_is, C) = init
+        if weights is not None:
+            return CoupledMatrixFactorization((None, (weights * A, B_is, C)))
+        return CoupledMatrixFactorization(init)
+    if init == "random":
+        n_slices, n_cols = len(matrices), matrices[0].shape[1]
+        A = random_state.uniform(size=(n_slices, rank))
+        C = random_state.uniform(size=(n_cols, rank))
+        B_is = [random_state.uniform(size=(m.shape[0], rank)) for m in matrices]
+        return CoupledMatrixFactorization((None, [A, B_is, C]))
+    if init in _UNSUPPORTED_INITS:
+        raise NotImplementedError(
+            f'init="{init}" needs TensorLy decompositions / batched tall SVDs that are not on the B200 hot path yet '
+            '(SURVEY.md §8f); use init="random" or pass a factorization'
+        )
+    raise ValueError('Initialization method "{}" not recognized'.format(init))
+
+
+def _check_feasibility(feasibility_gaps, feasibility_tol):  # decomposition.py:630-640
+    worst = -float("inf")
+    for mode_gaps in feasibility_gaps:
+        if len(mode_gaps):
+            worst = max(max(mode_gaps), worst)
+    return worst < feasibility_tol
+
+
+def compute_feasibility_gaps(cmf, regs, A_aux_list, B_aux_list, C_aux_list):
+    """Relative distance between every factor and each of its auxiliary variables (decomposition.py:351-417),
+    evaluated with the fused CUDA reduction ``b2_reduce_stats``."""
+    import torch
+
+    from . import _ops
+
+    weights, (A, B_is, C) = cmf
+
+    def dev(x):
+        return torch.as_tensor(np.ascontiguousarray(x), dtype=torch.float64).cuda()
+
+    ws = _ops.Workspace("cuda", 1, 1, torch.float64)
+    out = torch.zeros(3, dtype=torch.float64, device="cuda")
+
+    def gap(x, z):
+        xd = dev(x)
+        _ops.reduce_stats(xd, dev(z), xd.numel(), out, ws)
+        d2, x2, _ = out.cpu().numpy()
+        return np.sqrt(d2) / np.sqrt(x2)
+
+    B_flat = np.concatenate([np.asarray(b) for b in B_is], 0)
+    A_gaps = [gap(A, reg.aux_as_matrix(aux)) for reg, aux in zip(regs[0], A_aux_list)]
+    B_gaps = [gap(B_flat, np.concatenate([np.asarray(z) for z in reg.auxes_as_matrices(aux)], 0))
+              for reg, aux in zip(regs[1], B_aux_list)]
+    C_gaps = [gap(C, reg.aux_as_matrix(aux)) for reg, aux in zip(regs[2], C_aux_list)]
+    return A_gaps, B_gaps, C_gaps
+
+
+def _loss(diag, norm_X_sq, l2_penalty, regs):
+    """0.5*rel_err^2 + 0.5*sum_m lambda_m ||factor_m||^2 + sum penalties (decomposition.py:1013-1023)."""
+    inner, quad = diag["fit"]
+    rec_error = np.sqrt(max(0, norm_X_sq - 2 * inner + quad)) / np.sqrt(norm_X_sq)
+    l2reg = 0
+    for m in range(3):
+        if l2_penalty[m]:
+            l2reg += 0.5 * l2_penalty[m] * diag["sq"][m]
+    reg_penalty = 0
+    for m in range(3):
+        for p, reg in enumerate(regs[m]):
+            if isinstance(reg, penalties.L1Penalty):
+                reg_penalty += diag["l1"][m][p] * reg.reg_strength
+    return rec_error, 0.5 * rec_error ** 2 + l2reg + reg_penalty
+
+
+def cmf_aoadmm(
+    matrices,
+    rank,
+    init="random",
+    n_iter_max=1000,
+    l2_penalty=None,
+    tv_penalty=None,
+    l1_penalty=None,
+    non_negative=None,
+    unimodal=None,
+    generalized_l2_penalty=None,
+    l2_norm_bound=None,
+    lower_bound=None,
+    upper_bound=None,
+    parafac2=None,
+    regs=None,
+    feasibility_penalty_scale=1,
+    constant_feasibility_penalty=False,
+    aux_init="random_uniform",
+    dual_init="random_uniform",
+    svd="truncated_svd",
+    init_params=None,
+    random_state=None,
+    tol=1e-8,
+    absolute_tol=1e-10,
+    feasibility_tol=1e-4,
+    inner_tol=None,
+    inner_n_iter_max=5,
+    update_A=True,
+    update_B_is=True,
+    update_C=True,
+    return_admm_vars=False,
+    return_errors=False,
+    verbose=False,
+    device=None,
+    process_group=None,
+):
+    """Fit a regularized coupled matrix factorization with AO-ADMM on a B200 (same signature and semantics as the
+    reference ``matcouply.decomposition.cmf_aoadmm``, decomposition.py:662-1100).
+
+    ``matrices`` is a list of ``J_i x K`` arrays (NumPy, or torch tensors), a 3-D array iterated along axis 0, or a
+    device-resident :class:`matcouply_b200.PackedMatrices`.  float32 inputs run the fp32 kernels, everything else fp64.
+    Extra keywords: ``device`` (CUDA device, default current) and ``process_group`` (slices of ``matrices`` are then
+    this rank's shard; see ``matcouply_b200.distributed``).
+    """
+    import torch
+
+    from ._engine import AOADMMEngine, PackedMatrices
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("matcouply_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    if inner_tol:
+        raise NotImplementedError("inner_tol (inner-loop convergence checks) is not on the fused path yet")
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+
+    random_state = penalties._check_random_state(random_state)
+    if isinstance(matrices, PackedMatrices):
+        packed = matrices
+        shape_view = [_ShapeOnly(s) for s in packed.shapes]
+    else:
+        matrices = list(matrices)
+        all_f32 = all(getattr(m, "dtype", None) in (np.float32, torch.float32) for m in matrices)
+        packed = PackedMatrices.from_list(matrices, torch.float32 if all_f32 else torch.float64, device)
+        shape_view = matrices
+    cmf = initialize_cmf(shape_view, rank, init, random_state=random_state)
+
+    l2_penalty = [l2 if l2 is not None else 0 for l2 in _listify(l2_penalty, "l2_penalty")]
+    regs = _parse_all_penalties(
+        non_negative=non_negative, lower_bound=lower_bound, upper_bound=upper_bound, l2_norm_bound=l2_norm_bound,
+        unimodal=unimodal, parafac2=parafac2, l1_penalty=l1_penalty, tv_penalty=tv_penalty,
+        generalized_l2_penalty=generalized_l2_penalty, svd=svd, regs=regs, dual_init=dual_init, aux_init=aux_init,
+        verbose=verbose,
+    )
+    if not update_A:
+        regs[0] = []
+    if not update_B_is:
+        regs[1] = []
+    if not update_C:
+        regs[2] = []
+
+    # aux first, then dual, each in mode order from the same RandomState (decomposition.py:78-89)
+    auxes = [[reg.init_aux(shape_view, rank, m, random_state=random_state) for reg in regs[m]] for m in range(3)]
+    duals = [[reg.init_dual(shape_view, rank, m, random_state=random_state) for reg in regs[m]] for m in range(3)]
+
+    if isinstance(constant_feasibility_penalty, str) and constant_feasibility_penalty not in {"A", "B"}:
+        raise ValueError(
+            f"If `constant_feasibility_penalty` is a string, it must be 'A' or 'B', not {constant_feasibility_penalty}"
+        )
+    both = constant_feasibility_penalty and not isinstance(constant_feasibility_penalty, str)
+    constant_A = bool(both or constant_feasibility_penalty == "A")
+    constant_B = bool(both or constant_feasibility_penalty == "B")
+
+    engine = AOADMMEngine(packed, rank, regs, l2_penalty=l2_penalty,
+                          feasibility_penalty_scale=feasibility_penalty_scale, constant_A=constant_A,
+                          constant_B=constant_B, inner_n_iter_max=inner_n_iter_max,
+                          update=(update_A, update_B_is, update_C), group=process_group)
+    _, (A0, B0, C0) = cmf
+    engine.load_state(np.asarray(A0), [np.asarray(b) for b in B0], np.asarray(C0), auxes, duals)
+    engine.prepare()
+    norm_X_sq = engine.normX_sq
+
+    diag = engine.diagnostics()
+    rec_error, loss = _loss(diag, norm_X_sq, l2_penalty, regs)
+    rec_errors, losses, feasibility_gaps = [rec_error], [loss], [diag["gaps"]]
+    if verbose and verbose > 0:
+        print("Feasibility gaps for A: {}".format(diag["gaps"][0]))
+        print("Feasibility gaps for the Bi-matrices: {}".format(diag["gaps"][1]))
+        print("Feasibility gaps for C: {}".format(diag["gaps"][2]))
+
+    satisfied_stopping_condition = False
+    feasibility_criterion = None
+    message = "MAXIMUM NUMBER OF ITERATIONS REACHED"
+    it = -1
+    for it in range(n_iter_max):
+        engine.outer_iteration()
+
+        if tol or absolute_tol or return_errors:
+            diag = engine.diagnostics()
+            curr_gaps = diag["gaps"]
+            feasibility_gaps.append(curr_gaps)
+            if tol or absolute_tol:
+                feasibility_criterion = feasibility_tol and _check_feasibility(curr_gaps, feasibility_tol)
+                if not feasibility_criterion and not return_errors:
+                    # the loss is NOT appended on infeasible iterations (decomposition.py:996-1011)
+                    if verbose and it % verbose == 0 and verbose > 0:
+                        print(
+                            "Coupled matrix factorization iteration={}, ".format(it)
+                            + "reconstruction error=NOT COMPUTED, "
+                            + "regularized loss=NOT COMPUTED, "
+                            + "regularized loss variation=NOT COMPUTED."
+                        )
+                        print("Feasibility gaps for A: {}".format(curr_gaps[0]))
+                        print("Feasibility gaps for the Bi-matrices: {}".format(curr_gaps[1]))
+                        print("Feasibility gaps for C: {}".format(curr_gaps[2]))
+                    continue
+
+            rec_error, loss = _loss(diag, norm_X_sq, l2_penalty, regs)
+            rec_errors.append(rec_error)
+            losses.append(loss)
+            if verbose and it % verbose == 0 and verbose > 0:
+                print(
+                    "Coupled matrix factorization iteration={}, ".format(it)
+                    + "reconstruction error={}, ".format(rec_errors[-1])
+                    + "regularized loss={} ".format(losses[-1])
+                    + "regularized loss variation={}.".format(abs(losses[-2] - losses[-1]) / losses[-2])
+                )
+                print("Feasibility gaps for A: {}".format(curr_gaps[0]))
+                print("Feasibility gaps for the Bi-matrices: {}".format(curr_gaps[1]))
+                print("Feasibility gaps for C: {}".format(curr_gaps[2]))
+
+            if tol:
+                rel_loss_criterion = abs(losses[-2] - losses[-1]) < (tol * losses[-2])
+                abs_loss_criterion = losses[-1] < absolute_tol
+                if feasibility_criterion and rel_loss_criterion:
+                    satisfied_stopping_condition = True
+                    message = "FEASIBILITY GAP CRITERION AND RELATIVE LOSS CRITERION SATISFIED"
+                    if verbose:
+                        print("converged in {} iterations: {}".format(it, message))
+                    break
+                elif feasibility_criterion and abs_loss_criterion:
+                    satisfied_stopping_condition = True
+                    message = "FEASIBILITY GAP CRITERION AND ABSOLUTE LOSS CRITERION SATISFIED"
+                    if verbose:
+                        print("converged in {} iterations: {}".format(it, message))
+                    break
+        elif verbose and it % verbose == 0 and verbose > 0:
+            print("Coupled matrix factorization iteration={}".format(it))
+    else:
+        if verbose:
+            print("REACHED MAXIMUM NUMBER OF ITERATIONS")
+
+    if feasibility_tol and return_errors:  # decomposition.py:1065-1070
+        feasibility_criterion = _check_feasibility(engine.diagnostics()["gaps"], feasibility_tol)
+    elif not feasibility_tol:
+        feasibility_criterion = None
+
+    A, B_is, C = engine.factors()
+    out = [CoupledMatrixFactorization((None, [A, B_is, C]))]
+    if return_admm_vars:
+        aux_out, dual_out = engine.admm_vars()
+        out.append(ADMMVars(auxes=tuple(aux_out), duals=tuple(dual_out)))
+    if return_errors:
+        if not satisfied_stopping_condition and not (tol or absolute_tol):
+            satisfied_stopping_condition = None
+        out.append(DiagnosticMetrics(
+            rec_errors=rec_errors, feasibility_gaps=feasibility_gaps, regularized_loss=losses,
+            satisfied_stopping_condition=satisfied_stopping_condition,
+            satisfied_feasibility_condition=feasibility_criterion, message=message, n_iter=it + 1,
+        ))
+    return out[0] if len(out) == 1 else tuple(out)
+
+
+def parafac2_aoadmm(
+    matrices,
+    rank,
+    init="random",
+    n_iter_max=1000,
+    l2_penalty=0,
+    tv_penalty=None,
+    l1_penalty=None,
+    non_negative=None,
+    unimodal=None,
+    generalized_l2_penalty=None,
+    l2_norm_bound=None,
+    lower_bound=None,
+    upper_bound=None,
+    regs=None,
+    feasibility_penalty_scale=1,
+    constant_feasibility_penalty=False,
+    aux_init="random_uniform",
+    dual_init="random_uniform",
+    svd="truncated_svd",
+    init_params=None,
+    random_state=None,
+    tol=1e-8,
+    absolute_tol=1e-10,
+    feasibility_tol=1e-4,
+    inner_tol=None,
+    inner_n_iter_max=5,
+    update_A=True,
+    update_B_is=True,
+    update_C=True,
+    return_errors=False,
+    return_admm_vars=False,
+    verbose=False,
+    **extra,
+):
+    """Alias of :func:`cmf_aoadmm` with the PARAFAC2 constraint on mode 1 (decomposition.py:1103-1179)."""
+    return cmf_aoadmm(
+        matrices=matrices, rank=rank, init=init, n_iter_max=n_iter_max, l2_penalty=l2_penalty, tv_penalty=tv_penalty,
+        l1_penalty=l1_penalty, non_negative=non_negative, unimodal=unimodal,
+        generalized_l2_penalty=generalized_l2_penalty, l2_norm_bound=l2_norm_bound, lower_bound=lower_bound,
+        upper_bound=upper_bound, parafac2=True, regs=regs, feasibility_penalty_scale=feasibility_penalty_scale,
+        constant_feasibility_penalty=constant_feasibility_penalty, aux_init=aux_init, dual_init=dual_init, svd=svd,
+        init_params=init_params, random_state=random_state, tol=tol, absolute_tol=absolute_tol,
+        feasibility_tol=feasibility_tol, inner_tol=inner_tol, inner_n_iter_max=inner_n_iter_max, update_A=update_A,
+        update_B_is=update_B_is, update_C=update_C, return_errors=return_errors, return_admm_vars=return_admm_vars,
+        verbose=verbose, **extra,
+    )

@@ -1,0 +1,169 @@
+"""End-to-end parity of ``matcouply_b200.cmf_aoadmm`` (CUDA path, called like the reference) against
+
+* golden trajectories produced by the UNMODIFIED reference (tests/golden/traj_*.npz, recipe: oracle/gen_golden.py),
+* the oracle run live on fresh seeded inputs.
+
+Tolerances (BASELINE.json north_star): factor matrices within 1e-8 relative per iteration for the first 50
+iterations in fp64, final relative loss within 1e-6, same stopping iteration.
+"""
+import glob
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CASES = sorted(os.path.basename(p)[5:-4] for p in glob.glob(os.path.join(HERE, "golden", "traj_*.npz")))
+
+
+def load_case(name):
+    g = np.load(os.path.join(HERE, "golden", f"traj_{name}.npz"), allow_pickle=False)
+    off = g["row_offsets"]
+    X = [g["X"][a:b] for a, b in zip(off[:-1], off[1:])]
+    kw = json.loads(str(g["kwargs"]))
+    for key in ("l1_penalty", "non_negative", "unimodal", "l2_norm_bound", "lower_bound", "upper_bound"):
+        if isinstance(kw.get(key), dict):
+            kw[key] = {int(k): v for k, v in kw[key].items()}
+    return g, X, int(g["rank"]), kw
+
+
+def rel(a, b):
+    return np.linalg.norm(np.asarray(a) - np.asarray(b)) / max(np.linalg.norm(b), 1e-300)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_trajectory_matches_reference(name):
+    """Per-iteration factors for the first 50 outer iterations: chain 1-iteration... no: run k iterations from the
+    same seed (the run is deterministic) at a few checkpoints and compare with the reference trajectory."""
+    from matcouply_b200 import cmf_aoadmm
+
+    g, X, rank, kw = load_case(name)
+    n_traj = g["A_traj"].shape[0] if g["A_traj"].ndim == 3 else 0
+    if n_traj == 0:
+        pytest.skip("no trajectory stored")
+    kw = dict(kw)
+    kw.pop("n_iter_max", None)
+    worst = 0.0
+    for k in sorted({1, 2, 3, 5, 10, 20, 35, min(50, n_traj)}):
+        if k > n_traj:
+            continue
+        cmf = cmf_aoadmm(X, rank, n_iter_max=k, tol=None, absolute_tol=None, **kw)
+        _, (A, B_is, C) = cmf
+        errs = (rel(A, g["A_traj"][k - 1]), rel(np.concatenate(B_is, 0), g["B_traj"][k - 1]),
+                rel(C, g["C_traj"][k - 1]))
+        worst = max(worst, *errs)
+        assert max(errs) < 1e-8, (name, k, errs)
+    print(f"{name}: worst relative factor difference over checkpoints = {worst:.3e}")
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_full_run_matches_reference(name):
+    """Same stopping iteration and message, final loss within 1e-6 relative, diagnostics lists element-wise close."""
+    from matcouply_b200 import cmf_aoadmm
+
+    g, X, rank, kw = load_case(name)
+    cmf, admm, diag = cmf_aoadmm(X, rank, return_errors=True, return_admm_vars=True, **kw)
+    assert diag.n_iter == int(g["n_iter"]), (diag.n_iter, int(g["n_iter"]))
+    assert diag.message == str(g["message"])
+    assert str(diag.satisfied_stopping_condition) == str(g["satisfied_stopping_condition"])
+    assert str(diag.satisfied_feasibility_condition) == str(g["satisfied_feasibility_condition"])
+    ref_loss = g["regularized_loss"]
+    assert len(diag.regularized_loss) == len(ref_loss)
+    assert abs(diag.regularized_loss[-1] - ref_loss[-1]) <= 1e-6 * abs(ref_loss[-1])
+    np.testing.assert_allclose(diag.regularized_loss[:51], ref_loss[:51], rtol=1e-8)
+    np.testing.assert_allclose(diag.rec_errors[:51], g["rec_errors"][:51], rtol=1e-8)
+    gaps = np.array([[v for mode in it for v in mode] for it in diag.feasibility_gaps], dtype=np.float64)
+    assert gaps.shape == g["feasibility_gaps"].shape
+    if gaps.size:
+        np.testing.assert_allclose(gaps[:51], g["feasibility_gaps"][:51], rtol=1e-6, atol=1e-12)
+    _, (A, B_is, C) = cmf
+    if diag.n_iter <= 130:  # short runs stay within round-off of the reference up to the end
+        assert rel(A, g["A"]) < 1e-7 and rel(C, g["C"]) < 1e-7 and rel(np.concatenate(B_is, 0), g["B"]) < 1e-7
+        # ADMM variables in the reference's ADMMVars layout
+        for m in range(3):
+            for n, (aux, dual) in enumerate(zip(admm.auxes[m], admm.duals[m])):
+                key = f"m{m}_r{n}"
+                d = np.concatenate(dual, 0) if m == 1 else dual
+                assert rel(d, g["dual_" + key]) < 1e-6, key
+                if isinstance(aux, tuple):
+                    assert rel(aux[1], g["aux_" + key + "_coord"]) < 1e-6
+                    assert rel(np.concatenate(aux[0], 0), g["aux_" + key + "_basis"]) < 1e-6
+                else:
+                    a = np.concatenate(aux, 0) if m == 1 else aux
+                    assert rel(a, g["aux_" + key]) < 1e-6, key
+
+
+def test_return_errors_false_skips_loss_like_reference():
+    """Stopping iteration with return_errors=False (loss skipped on infeasible iterations) equals the oracle's."""
+    from matcouply_b200 import cmf_aoadmm
+    from oracle import aoadmm_oracle as O
+
+    rs = np.random.RandomState(5)
+    X = [rs.uniform(size=(J, 9)) for J in (7, 9, 8, 12, 6)]
+    kw = dict(non_negative=True, parafac2=True, random_state=3, n_iter_max=400, tol=1e-6)
+    o = O.ao_admm(X, 2, return_errors=False, **kw)
+    cmf, diag = cmf_aoadmm(X, 2, return_errors=False, return_admm_vars=False, **kw), None
+    o2 = O.ao_admm(X, 2, return_errors=True, **kw)
+    cmf2, diag2 = cmf_aoadmm(X, 2, return_errors=True, **kw)
+    assert diag2.n_iter == o2["n_iter"]
+    assert rel(cmf2[1][0], o2["A"]) < 1e-6
+    assert rel(cmf[1][0], o["A"]) < 1e-6
+
+
+def test_live_oracle_ragged_fp64_and_fp32():
+    """Fresh seeded ragged problem (scaled-down twin of BASELINE config 2): fp64 within 1e-8 after 30 iterations,
+    fp32 within single-precision tolerance of the fp64 oracle on fp32-rounded inputs."""
+    from matcouply_b200 import cmf_aoadmm
+    from oracle import aoadmm_oracle as O
+
+    rs = np.random.RandomState(42)
+    I, K, R = 24, 40, 6
+    Js = rs.randint(R, 70, size=I)
+    A, C = rs.uniform(0.1, 1.1, size=(I, R)), rs.uniform(size=(K, R))
+    X = []
+    for i, J in enumerate(Js):
+        M = (rs.uniform(size=(J, R)) * A[i]) @ C.T
+        X.append(M + 0.1 * rs.standard_normal(size=M.shape))
+    kw = dict(non_negative=True, parafac2=True, l1_penalty={2: 0.1}, random_state=0, n_iter_max=30, tol=None,
+              absolute_tol=None)
+    o = O.ao_admm(X, R, **kw)
+    _, (Ag, Bg, Cg) = cmf_aoadmm(X, R, **kw)
+    assert rel(Ag, o["A"]) < 1e-8 and rel(Cg, o["C"]) < 1e-8
+    assert rel(np.concatenate(Bg, 0), np.concatenate(o["B_is"], 0)) < 1e-8
+    X32 = [x.astype(np.float32) for x in X]
+    o32 = O.ao_admm([x.astype(np.float64) for x in X32], R, **kw)
+    _, (A32, B32, C32) = cmf_aoadmm(X32, R, **kw)
+    assert rel(A32, o32["A"]) < 5e-3 and rel(C32, o32["C"]) < 5e-3
+
+
+def test_edge_cases_and_api_errors():
+    from matcouply_b200 import cmf_aoadmm, parafac2_aoadmm
+    from matcouply_b200.penalties import NonNegativity
+    from oracle import aoadmm_oracle as O
+
+    rs = np.random.RandomState(1)
+    X = [rs.uniform(size=(J, 6)) for J in (5, 1, 9, 3)]  # includes a single-row slice
+    cmf, diag = cmf_aoadmm(X, 2, n_iter_max=0, non_negative=True, return_errors=True, random_state=0)
+    o = O.ao_admm(X, 2, n_iter_max=0, non_negative=True, random_state=0)
+    assert diag.n_iter == 0 and len(diag.regularized_loss) == 1
+    assert abs(diag.regularized_loss[0] - o["regularized_loss"][0]) < 1e-12
+    # 3-D array input, explicit regs list, zero iterations produce the init
+    T = rs.uniform(size=(4, 7, 5))
+    cmf2 = cmf_aoadmm(T, 3, n_iter_max=3, regs=[[NonNegativity()], [], []], random_state=1)
+    o2 = O.ao_admm(list(T), 3, n_iter_max=3, regs=[[O.NonNeg()], [], []], random_state=1, tol=None, absolute_tol=None)
+    assert rel(cmf2[1][0], o2["A"]) < 1e-9
+    with pytest.raises(TypeError):
+        cmf_aoadmm(X, 2, regs=[[1], [], []])
+    with pytest.raises(ValueError):
+        cmf_aoadmm(X, 2, constant_feasibility_penalty="C")
+    with pytest.raises(ValueError):
+        cmf_aoadmm(X, 2, l1_penalty=[1, 2])
+    with pytest.raises(ValueError):
+        cmf_aoadmm(X, 2, init="nonsense")
+    out = parafac2_aoadmm(X, 2, n_iter_max=2, non_negative=True, random_state=0, return_admm_vars=True)
+    assert len(out) == 2 and isinstance(out[1].auxes[1][0], tuple)

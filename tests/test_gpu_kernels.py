@@ -1,0 +1,376 @@
+"""Operator-level parity of every CUDA kernel (called through the C ABI) against NumPy float64 / the oracle."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _imports():
+    from matcouply_b200 import _lib, _ops
+    from oracle import aoadmm_oracle as O
+
+    return _lib, _ops, O
+
+
+def dev(a, dtype=None):
+    return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype or torch.float64).cuda()
+
+
+def packed_x(N, K, dtype, rs):
+    from matcouply_b200 import _ops
+
+    ld = _ops.padded_ld(K, dtype)
+    Xh = rs.standard_normal(size=(N, K))
+    X = torch.zeros((N, ld), dtype=dtype, device="cuda")
+    X[:, :K] = dev(Xh, dtype)
+    return Xh if dtype == torch.float64 else Xh.astype(np.float32).astype(np.float64), X
+
+
+XSTREAM_SHAPES = [(1, 1, 1), (37, 15, 3), (128, 32, 4), (300, 33, 5), (1000, 512, 16), (2500, 100, 20), (777, 70, 32),
+                  (513, 1030, 8), (5000, 256, 12)]
+
+
+@pytest.mark.parametrize("N,K,R", XSTREAM_SHAPES)
+@pytest.mark.parametrize("variant", ["fma", "dmma"])
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_xstream_y(N, K, R, variant, dtype):
+    _lib, _ops, _ = _imports()
+    if dtype == "f32" and variant == "dmma":
+        pytest.skip("DMMA is fp64 only")
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    rs = np.random.RandomState(N * 7 + K)
+    Xh, X = packed_x(N, K, tdt, rs)
+    C = rs.standard_normal(size=(K, R))
+    Cd = dev(C, tdt)
+    Y = torch.full((N, R), float("nan"), dtype=tdt, device="cuda")
+    ws = _ops.Workspace("cuda", K, R, tdt)
+    _ops.xstream_y(X, N, K, Cd, Y, ws, _lib.VARIANT_FMA if variant == "fma" else _lib.VARIANT_DMMA)
+    ref = Xh @ Cd.double().cpu().numpy()
+    got = Y.double().cpu().numpy()
+    scale = np.abs(Xh) @ np.abs(C) + 1e-300
+    tol = 1e-13 if dtype == "f64" else 2e-5
+    assert np.all(np.isfinite(got))
+    assert np.max(np.abs(got - ref) / scale) < tol, np.max(np.abs(got - ref) / scale)
+
+
+@pytest.mark.parametrize("N,K,R", XSTREAM_SHAPES)
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_xstream_z(N, K, R, dtype):
+    _lib, _ops, _ = _imports()
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    rs = np.random.RandomState(N * 11 + K)
+    Xh, X = packed_x(N, K, tdt, rs)
+    W = rs.standard_normal(size=(N, R))
+    Wpad = torch.zeros(((N + 15) // 16 * 16, R), dtype=tdt, device="cuda")
+    Wpad[:N] = dev(W, tdt)
+    Z = torch.full((K, R), float("nan"), dtype=tdt, device="cuda")
+    ws = _ops.Workspace("cuda", K, R, tdt)
+    _ops.xstream_z(X, N, K, Wpad, Z, ws, _lib.VARIANT_FMA)
+    Wh = Wpad[:N].double().cpu().numpy()
+    ref = Xh.T @ Wh
+    got = Z.double().cpu().numpy()
+    scale = np.abs(Xh).T @ np.abs(Wh) + 1e-300
+    tol = 1e-13 if dtype == "f64" else 5e-5
+    assert np.all(np.isfinite(got))
+    assert np.max(np.abs(got - ref) / scale) < tol, np.max(np.abs(got - ref) / scale)
+
+
+def test_xstream_linearity_large():
+    """Size-independent property at a streaming size (X larger than L2): Y(X, C1 + C2) = Y(X, C1) + Y(X, C2) and
+    Z/Y adjointness <X C, W> = <C, X^T W>."""
+    _lib, _ops, _ = _imports()
+    N, K, R = 200_000, 512, 16  # 0.8 GB
+    g = torch.Generator(device="cuda").manual_seed(0)
+    X = torch.randn((N, K), dtype=torch.float64, device="cuda", generator=g)
+    C1 = torch.randn((K, R), dtype=torch.float64, device="cuda", generator=g)
+    C2 = torch.randn((K, R), dtype=torch.float64, device="cuda", generator=g)
+    W = torch.randn((N, R), dtype=torch.float64, device="cuda", generator=g)
+    ws = _ops.Workspace("cuda", K, R, torch.float64)
+    Ys = []
+    for variant in (_lib.VARIANT_FMA, _lib.VARIANT_DMMA):
+        Y1, Y2, Y12 = (torch.empty((N, R), dtype=torch.float64, device="cuda") for _ in range(3))
+        _ops.xstream_y(X, N, K, C1, Y1, ws, variant)
+        _ops.xstream_y(X, N, K, C2, Y2, ws, variant)
+        _ops.xstream_y(X, N, K, (C1 + C2).contiguous(), Y12, ws, variant)
+        assert torch.max(torch.abs(Y12 - (Y1 + Y2))).item() < 1e-10
+        Ys.append(Y1)
+    assert torch.max(torch.abs(Ys[0] - Ys[1])).item() < 1e-10
+    Z = torch.empty((K, R), dtype=torch.float64, device="cuda")
+    _ops.xstream_z(X, N, K, W, Z, ws, _lib.VARIANT_FMA)
+    lhs = torch.sum(Ys[0] * W).item()
+    rhs = torch.sum(C1 * Z).item()
+    assert abs(lhs - rhs) < 1e-9 * max(1.0, abs(lhs))
+    out = torch.zeros(1, dtype=torch.float64, device="cuda")
+    _ops.sumsq(X, N, K, out, ws)
+    assert abs(out.item() - torch.sum(X * X).item()) < 1e-9 * out.item()
+
+
+@pytest.mark.parametrize("n,R", [(1, 1), (50, 3), (1000, 16), (4097, 20), (300, 32)])
+def test_gram_and_scale_gram(n, R):
+    _lib, _ops, _ = _imports()
+    rs = np.random.RandomState(n + R)
+    M = rs.standard_normal(size=(n, R))
+    G = torch.empty((R, R), dtype=torch.float64, device="cuda")
+    ws = _ops.Workspace("cuda", 8, R, torch.float64)
+    _ops.gram(dev(M), n, G, ws)
+    np.testing.assert_allclose(G.cpu().numpy(), M.T @ M, rtol=1e-12, atol=1e-12 * n)
+    A = rs.uniform(size=(7, R))
+    lhs = torch.empty((7, R, R), dtype=torch.float64, device="cuda")
+    _ops.scale_gram(G, dev(A), lhs)
+    Gh = G.cpu().numpy()
+    ref = np.stack([np.transpose(np.transpose(Gh * a) * a) for a in A])
+    np.testing.assert_allclose(lhs.cpu().numpy(), ref, rtol=1e-14)
+    rho = torch.empty(7, dtype=torch.float64, device="cuda")
+    rmax = torch.empty(1, dtype=torch.float64, device="cuda")
+    _ops.rho_from_trace(lhs, 7, R, 1.7, rho, rmax)
+    ref_rho = np.array([0.5 * np.trace(L) * 1.7 for L in ref])
+    np.testing.assert_allclose(rho.cpu().numpy(), ref_rho, rtol=1e-13)
+    assert abs(rmax.item() - ref_rho.max()) < 1e-13 * ref_rho.max()
+
+
+@pytest.mark.parametrize("R", [1, 2, 3, 8, 16, 20, 32])
+@pytest.mark.parametrize("constant", [False, True])
+def test_factor_batch(R, constant):
+    _lib, _ops, _ = _imports()
+    rs = np.random.RandomState(R)
+    G = 9
+    Ms = rs.standard_normal(size=(G, 3 * R + 2, R))
+    lhs = np.stack([m.T @ m for m in Ms])
+    rho = np.array([0.5 * np.trace(L) for L in lhs])
+    rho_d, rmax = dev(rho), dev(np.array([rho.max()]))
+    Minv = torch.empty((G, R, R), dtype=torch.float64, device="cuda")
+    _ops.factor_batch(dev(lhs), G, R, rho_d, rmax if constant else None, 2, 0.3, Minv)
+    eff = np.full(G, rho.max()) if constant else rho
+    np.testing.assert_allclose(rho_d.cpu().numpy(), eff, rtol=1e-15)
+    for g in range(G):
+        full = lhs[g] + np.eye(R) * (eff[g] * 2 + 0.3)
+        U, s, Uh = np.linalg.svd(full)  # the reference applies x (U/s) Uh  (decomposition.py:172,194)
+        ref = (U / s) @ Uh
+        np.testing.assert_allclose(Minv[g].cpu().numpy(), ref, rtol=1e-11, atol=1e-13 * np.abs(ref).max())
+
+
+def ragged(rs, G, lo, hi, R):
+    sizes = rs.randint(lo, hi + 1, size=G)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    return sizes, off, rs.standard_normal(size=(int(off[-1]), R))
+
+
+@pytest.mark.parametrize("R", [3, 16, 20, 32])
+def test_slice_cross_and_rowscale(R):
+    _lib, _ops, _ = _imports()
+    rs = np.random.RandomState(R)
+    G = 13
+    sizes, off, B = ragged(rs, G, 1, 150, R)
+    Y = rs.standard_normal(size=B.shape)
+    CtC = rs.standard_normal(size=(R, R))
+    cross = torch.empty((G, R, R), dtype=torch.float64, device="cuda")
+    rhs = torch.empty((G, R), dtype=torch.float64, device="cuda")
+    _ops.slice_cross(dev(B), dev(Y), dev(off, torch.int64), G, R, dev(CtC), cross, rhs)
+    for g in range(G):
+        Bg, Yg = B[off[g]:off[g + 1]], Y[off[g]:off[g + 1]]
+        np.testing.assert_allclose(cross[g].cpu().numpy(), (Bg.T @ Bg) * CtC, rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(rhs[g].cpu().numpy(), np.diag(Bg.T @ Yg), rtol=1e-12, atol=1e-12)
+    A = rs.uniform(size=(G, R))
+    gor = np.repeat(np.arange(G), sizes).astype(np.int32)
+    W = torch.empty(B.shape, dtype=torch.float64, device="cuda")
+    _ops.rowscale(dev(B), dev(A), dev(gor, torch.int32), B.shape[0], R, W)
+    np.testing.assert_array_equal(W.cpu().numpy(), B * A[gor])
+
+
+def _penalty_cases(O):
+    return [
+        ("nonneg", O.NonNeg(), 0, False, 0.0, 0.0),
+        ("box", O.BoxP(-0.3, 0.6), 1, False, -0.3, 0.6),
+        ("l1", O.L1P(0.25), 2, False, 0.25, 0.0),
+        ("l1nn", O.L1P(0.25, non_negativity=True), 2, True, 0.25, 0.0),
+    ]
+
+
+@pytest.mark.parametrize("mode", ["single", "indexed", "identity"])
+@pytest.mark.parametrize("R", [3, 16, 20])
+def test_admm_solve_elementwise(mode, R):
+    """x-update + prox + dual update for all elementwise penalties at once vs the reference formulas."""
+    _lib, _ops, O = _imports()
+    rs = np.random.RandomState(R + len(mode))
+    G = 6
+    sizes, off, rhs = ragged(rs, G, 2, 40, R)
+    n = rhs.shape[0]
+    if mode == "single":
+        gor, ngroups, gmode = np.zeros(n, dtype=np.int32), 1, _lib.GROUP_SINGLE
+    elif mode == "indexed":
+        gor, ngroups, gmode = np.repeat(np.arange(G), sizes).astype(np.int32), G, _lib.GROUP_INDEXED
+    else:
+        gor, ngroups, gmode = np.arange(n, dtype=np.int32), n, _lib.GROUP_IDENTITY
+    rho = rs.uniform(0.5, 2.0, size=ngroups)
+    Ms = rs.standard_normal(size=(ngroups, 2 * R, R))
+    Minv = np.stack([np.linalg.inv(m.T @ m + np.eye(R)) for m in Ms])
+    scale = rs.uniform(0.5, 1.5, size=(ngroups, R))
+    cases = _penalty_cases(O)
+    aux = [rs.standard_normal(size=(n, R)) for _ in cases]
+    dual = [rs.standard_normal(size=(n, R)) for _ in cases]
+    aux_d, dual_d = [dev(a) for a in aux], [dev(d) for d in dual]
+    descs = _ops.make_descs([(c[2], c[3], c[4], c[5], a, d) for c, a, d in zip(cases, aux_d, dual_d)])
+    x = torch.empty((n, R), dtype=torch.float64, device="cuda")
+    _ops.admm_solve(n, R, dev(rhs), dev(scale), gmode, dev(gor, torch.int32), dev(rho), dev(Minv), descs, len(cases), x)
+    # reference
+    shifted = sum(a - d for a, d in zip(aux, dual))
+    s = rho[gor][:, None] * shifted + rhs * scale[gor]
+    x_ref = np.einsum("nr,nrc->nc", s, Minv[gor])
+    np.testing.assert_allclose(x.cpu().numpy(), x_ref, rtol=1e-11, atol=1e-12)
+    for (name, pen, *_), a_d, d_d, d0 in zip(cases, aux_d, dual_d, dual):
+        v = x_ref + d0
+        z_ref = np.stack([pen.prox(v[i], rho[gor[i]], None) for i in range(n)])
+        np.testing.assert_allclose(a_d.cpu().numpy(), z_ref, rtol=1e-10, atol=1e-11, err_msg=name)
+        np.testing.assert_allclose(d_d.cpu().numpy(), v - z_ref, rtol=1e-10, atol=1e-11, err_msg=name)
+
+
+def test_prox_golden_vectors(golden_dir):
+    """Stand-alone penalty objects (the reference's ADMMPenalty protocol) against vectors produced by the reference."""
+    from matcouply_b200 import penalties as P
+
+    g = np.load(os.path.join(golden_dir, "operators.npz"))
+    M = g["prox_in"]
+    np.testing.assert_array_equal(P.NonNegativity().factor_matrix_update(M, 1.3, None), g["prox_nonneg"])
+    np.testing.assert_array_equal(P.Box(-0.5, 0.7).factor_matrix_update(M, 1.3, None), g["prox_box"])
+    np.testing.assert_allclose(P.L1Penalty(0.4).factor_matrix_update(M, 1.3, None), g["prox_l1"], rtol=1e-15,
+                               atol=1e-16)
+    np.testing.assert_allclose(P.L1Penalty(0.4, non_negativity=True).factor_matrix_update(M, 1.3, None),
+                               g["prox_l1_nn"], rtol=1e-15, atol=1e-16)
+    np.testing.assert_allclose(P.L2Ball(1.5).factor_matrix_update(M, 1.3, None), g["prox_l2ball"], rtol=1e-14)
+    np.testing.assert_allclose(P.L2Ball(1.5, non_negativity=True).factor_matrix_update(M, 1.3, None),
+                               g["prox_l2ball_nn"], rtol=1e-14)
+    row = P.L1Penalty(0.4).factor_matrix_row_update(M[3], 1.3, None)
+    np.testing.assert_allclose(row, g["prox_l1"][3], rtol=1e-15, atol=1e-16)
+    assert abs(P.L1Penalty(0.4).penalty(M) - 0.4 * np.abs(M).sum()) < 1e-12
+    assert P.NonNegativity().penalty(M) == 0
+
+
+def test_l2ball_groups():
+    _lib, _ops, O = _imports()
+    rs = np.random.RandomState(3)
+    for R in (1, 5, 16, 32):
+        for nn in (False, True):
+            sizes, off, V = ragged(rs, 9, 1, 300, R)
+            V *= 3
+            aux = torch.empty(V.shape, dtype=torch.float64, device="cuda")
+            dual = dev(V)
+            _ops.prox_l2ball(aux, dual, dev(off, torch.int64), 9, R, 1.25, nn)
+            pen = O.L2BallP(1.25, non_negativity=nn)
+            ref = np.concatenate([pen.prox(V[off[g]:off[g + 1]], 1.0, None) for g in range(9)], 0)
+            np.testing.assert_allclose(aux.cpu().numpy(), ref, rtol=1e-13, atol=1e-15)
+            np.testing.assert_allclose(dual.cpu().numpy(), V - ref, rtol=1e-12, atol=1e-14)
+
+
+def test_unimodal_golden_bit_exact(golden_dir):
+    """Unimodal regression: fits AND peak indices bit-identical to the reference on its own golden vectors."""
+    _lib, _ops, O = _imports()
+    g = np.load(os.path.join(golden_dir, "operators.npz"))
+    ws = _ops.Workspace("cuda", 1, 4, torch.float64)
+    for k in range(int(g["uni_count"])):
+        y, fit, peaks, nn = g[f"uni{k}_y"], g[f"uni{k}_fit"], g[f"uni{k}_peaks"], bool(g[f"uni{k}_nn"])
+        n, R = y.shape
+        aux = torch.empty((n, R), dtype=torch.float64, device="cuda")
+        dual = dev(y)
+        pk = torch.zeros(R, dtype=torch.int32, device="cuda")
+        _ops.prox_unimodal(aux, dual, dev(np.array([0, n]), torch.int64), 1, R, n, nn, ws, pk)
+        assert np.array_equal(pk.cpu().numpy(), peaks), (k, pk.cpu().numpy(), peaks)
+        assert np.array_equal(aux.cpu().numpy(), fit), (k, np.abs(aux.cpu().numpy() - fit).max())
+        np.testing.assert_array_equal(dual.cpu().numpy(), y - fit)
+
+
+def test_unimodal_ragged_groups_vs_oracle_and_sklearn():
+    _lib, _ops, O = _imports()
+    from sklearn.isotonic import IsotonicRegression
+
+    rs = np.random.RandomState(11)
+    R, G = 6, 40
+    sizes, off, V = ragged(rs, G, 1, 260, R)
+    ws = _ops.Workspace("cuda", 1, R, torch.float64)
+    for nn in (False, True):
+        aux = torch.empty(V.shape, dtype=torch.float64, device="cuda")
+        dual = dev(V)
+        pk = torch.zeros(G * R, dtype=torch.int32, device="cuda")
+        _ops.prox_unimodal(aux, dual, dev(off, torch.int64), G, R, int(sizes.max()), nn, ws, pk)
+        got, pk = aux.cpu().numpy(), pk.cpu().numpy().reshape(G, R)
+        for g in range(G):
+            ref, peaks = O.unimodal_regression(V[off[g]:off[g + 1]], nn, return_peaks=True)
+            assert np.array_equal(pk[g], peaks)
+            assert np.array_equal(got[off[g]:off[g + 1]], ref)
+        # independent check of optimality on one column: best split of two isotonic fits (sklearn)
+        g = int(np.argmax(sizes))
+        y = V[off[g]:off[g + 1], 0]
+        n = len(y)
+        best = np.inf
+        for t in range(n + 1):
+            left = IsotonicRegression(y_min=0 if nn else None).fit_transform(np.arange(t), y[:t]) if t else np.zeros(0)
+            right = (IsotonicRegression(increasing=False, y_min=0 if nn else None).fit_transform(np.arange(n - t), y[t:])
+                     if n - t else np.zeros(0))
+            best = min(best, np.sum((np.concatenate([left, right]) - y) ** 2))
+        assert abs(np.sum((got[off[g]:off[g + 1], 0] - y) ** 2) - best) < 1e-9 * max(best, 1.0)
+
+
+def test_parafac2_prox_golden(golden_dir):
+    """Parafac2.factor_matrices_update (R x R Jacobi polar route) vs the reference's thin-SVD route."""
+    from matcouply_b200 import penalties as P
+
+    g = np.load(os.path.join(golden_dir, "operators.npz"))
+    off = g["pf2_off"]
+    fms = [g["pf2_in"][a:b] for a, b in zip(off[:-1], off[1:])]
+    R = g["pf2_delta_in"].shape[0]
+    bases, delta = P.Parafac2().factor_matrices_update(fms, list(g["pf2_rhos"]),
+                                                       ([np.eye(f.shape[0], R) for f in fms], g["pf2_delta_in"]))
+    np.testing.assert_allclose(np.concatenate(bases, 0), g["pf2_basis"], rtol=0, atol=1e-11)
+    np.testing.assert_allclose(delta, g["pf2_delta_out"], rtol=0, atol=1e-11)
+    for b in bases:
+        np.testing.assert_allclose(b.T @ b, np.eye(R), atol=1e-12)
+
+
+@pytest.mark.parametrize("R", [2, 8, 20, 32])
+def test_parafac2_polar_random(R):
+    from matcouply_b200 import penalties as P
+    from oracle import aoadmm_oracle as O
+
+    rs = np.random.RandomState(R)
+    Js = [R, R + 1, 3 * R, 200, 57 + R]
+    fms = [rs.standard_normal(size=(J, R)) for J in Js]
+    rhos = list(rs.uniform(0.5, 2, size=len(Js)))
+    delta = rs.uniform(size=(R, R)) + 0.5 * np.eye(R)
+    bases, new_delta = P.Parafac2().factor_matrices_update(fms, rhos, (None, delta))
+    ob, od = O.Parafac2P().prox_list(fms, rhos, (None, delta))
+    for b, o in zip(bases, ob):
+        np.testing.assert_allclose(b, o, atol=1e-9)
+    np.testing.assert_allclose(new_delta, od, atol=1e-9)
+
+
+def test_reduce_stats_and_fit_terms():
+    _lib, _ops, O = _imports()
+    rs = np.random.RandomState(0)
+    n = 100_003
+    x, y = rs.standard_normal(size=n), rs.standard_normal(size=n)
+    ws = _ops.Workspace("cuda", 1, 4, torch.float64)
+    out = torch.zeros(3, dtype=torch.float64, device="cuda")
+    _ops.reduce_stats(dev(x), dev(y), n, out, ws)
+    np.testing.assert_allclose(out.cpu().numpy(), [np.sum((x - y) ** 2), np.sum(x ** 2), np.sum(np.abs(x))], rtol=1e-12)
+    G, R = 500, 7
+    rhs, A = rs.standard_normal(size=(G, R)), rs.standard_normal(size=(G, R))
+    cross = rs.standard_normal(size=(G, R, R))
+    out2 = torch.zeros(2, dtype=torch.float64, device="cuda")
+    _ops.fit_terms(dev(rhs), dev(cross), dev(A), G, R, out2, ws)
+    ref = [np.sum(rhs * A), sum(a @ c @ a for a, c in zip(A, cross))]
+    np.testing.assert_allclose(out2.cpu().numpy(), ref, rtol=1e-11)
+
+
+def test_errors_are_reported_not_swallowed():
+    _lib, _ops, _ = _imports()
+    X = torch.zeros((4, 4), dtype=torch.float64, device="cuda")
+    C = torch.zeros((4, 40), dtype=torch.float64, device="cuda")
+    Y = torch.zeros((4, 40), dtype=torch.float64, device="cuda")
+    ws = _ops.Workspace("cuda", 4, 32, torch.float64)
+    with pytest.raises(RuntimeError, match="rank"):
+        _ops.xstream_y(X, 4, 4, C, Y, ws)
+    with pytest.raises(RuntimeError, match="CUDA tensors"):
+        _ops.xstream_y(X.cpu(), 4, 4, C, Y, ws)

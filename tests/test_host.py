@@ -1,0 +1,156 @@
+"""CPU tests of the host logic and of the C-ABI shared library (load + exported symbols; no kernel is launched)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from matcouply_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "matcouply_b200.h")).read()
+    declared = set(re.findall(r"\b(b2_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTED_SYMBOLS), declared ^ set(_lib.EXPORTED_SYMBOLS)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    nm = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    for name in declared:
+        assert re.search(rf"\bT {name}\b", nm), name
+    assert lib.b2_version() >= 100
+
+
+def test_no_product_import_of_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "matcouply_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), f
+
+
+def test_penalty_parsing_order_and_repr():
+    from matcouply_b200 import penalties as P
+    from matcouply_b200.decomposition import _listify, _parse_all_penalties
+
+    regs = _parse_all_penalties(non_negative=True, lower_bound=None, upper_bound=None, l2_norm_bound=[1, 1, 0],
+                                unimodal={1: True}, parafac2=True, l1_penalty={2: 0.1}, tv_penalty=None,
+                                generalized_l2_penalty=None, svd="truncated_svd", regs=None,
+                                dual_init="random_uniform", aux_init="random_uniform", verbose=False)
+    assert [type(r).__name__ for r in regs[0]] == ["L2Ball"]
+    assert [type(r).__name__ for r in regs[1]] == ["Parafac2", "Unimodality", "L2Ball"]
+    assert [type(r).__name__ for r in regs[2]] == ["L1Penalty"]
+    assert regs[1][1].non_negativity and regs[2][0].non_negativity and regs[0][0].non_negativity
+    # exact repr text as asserted by the reference's tests (tests/test_decomposition.py:479-491)
+    assert repr(P.NonNegativity()) == (
+        "<'matcouply_b200.penalties.NonNegativity' with aux_init='random_uniform', dual_init='random_uniform')>")
+    assert repr(P.Box(0, 1, aux_init=np.zeros((2, 2)))).endswith(
+        "with min_val=0, max_val=1, aux_init=given_init, dual_init='random_uniform')>")
+    assert _listify({0: 1, 2: 3}, "x") == [1, None, 3] and _listify(2, "x") == [2, 2, 2]
+    with pytest.raises(ValueError, match="x is iterable of length 2"):
+        _listify([1, 2], "x")
+    user = [[], [P.NonNegativity()], []]
+    out = _parse_all_penalties(non_negative=None, lower_bound=0, upper_bound=None, l2_norm_bound=None, unimodal=None,
+                               parafac2=None, l1_penalty=None, tv_penalty=None, generalized_l2_penalty=None,
+                               svd="truncated_svd", regs=user, dual_init="zeros", aux_init="zeros", verbose=False)
+    assert len(user[1]) == 1 and [type(r).__name__ for r in out[1]] == ["Box", "NonNegativity"]
+    with pytest.raises(TypeError):
+        _parse_all_penalties(None, None, None, None, None, None, None, None, None, "truncated_svd", [[1], [], []],
+                             "zeros", "zeros", False)
+    with pytest.raises(ValueError):
+        P.L1Penalty(-1)
+    with pytest.raises(ValueError):
+        P.L2Ball(0)
+    with pytest.raises(NotImplementedError):
+        P.UnitSimplex()
+
+
+def test_aux_dual_init_draw_order_matches_oracle():
+    """RandomState draw order of factors/aux/dual is what makes trajectories comparable (decomposition.py:31-39,78-89)."""
+    from matcouply_b200 import penalties as P
+    from matcouply_b200.decomposition import initialize_cmf
+    from oracle import aoadmm_oracle as O
+
+    mats = [np.zeros((J, 6)) for J in (4, 7, 5)]
+    rs1, rs2 = np.random.RandomState(3), np.random.RandomState(3)
+    cmf = initialize_cmf(mats, 2, "random", random_state=rs1)
+    regs = [[P.NonNegativity()], [P.Parafac2(), P.L2Ball(1.0)], [P.L1Penalty(0.1, aux_init="random_standard_normal")]]
+    aux = [[r.init_aux(mats, 2, m, random_state=rs1) for r in regs[m]] for m in range(3)]
+    dual = [[r.init_dual(mats, 2, m, random_state=rs1) for r in regs[m]] for m in range(3)]
+    A = rs2.uniform(size=(3, 2)); C = rs2.uniform(size=(6, 2)); Bs = [rs2.uniform(size=(m.shape[0], 2)) for m in mats]
+    oregs = [[O.NonNeg()], [O.Parafac2P(), O.L2BallP(1.0)], [O.L1P(0.1, aux_init="random_standard_normal")]]
+    oaux = [[r.init_aux(mats, 2, m, rs2) for r in oregs[m]] for m in range(3)]
+    odual = [[r.init_dual(mats, 2, m, rs2) for r in oregs[m]] for m in range(3)]
+    np.testing.assert_array_equal(cmf[1][0], A)
+    np.testing.assert_array_equal(cmf[1][2], C)
+    np.testing.assert_array_equal(np.concatenate(cmf[1][1]), np.concatenate(Bs))
+    np.testing.assert_array_equal(aux[1][0][1], oaux[1][0][1])
+    np.testing.assert_array_equal(aux[1][0][0][1], np.eye(7, 2))
+    np.testing.assert_array_equal(np.concatenate(aux[1][1]), np.concatenate(oaux[1][1]))
+    np.testing.assert_array_equal(aux[2][0], oaux[2][0])
+    np.testing.assert_array_equal(np.concatenate(dual[1][0]), np.concatenate(odual[1][0]))
+    np.testing.assert_array_equal(dual[2][0], odual[2][0])
+
+
+def test_init_validation_errors():
+    from matcouply_b200 import penalties as P
+
+    mats = [np.zeros((4, 6)), np.zeros((5, 6))]
+    with pytest.raises(TypeError):
+        P.NonNegativity().init_aux(mats, 2.0, 0)
+    with pytest.raises(ValueError):
+        P.NonNegativity().init_aux(mats, 2, 3)
+    with pytest.raises(ValueError):
+        P.NonNegativity(aux_init=np.zeros((3, 2))).init_aux(mats, 2, 0)
+    with pytest.raises(TypeError):
+        P.NonNegativity(aux_init=[np.zeros((4, 2))]).init_aux(mats, 2, 0)
+    with pytest.raises(TypeError):
+        P.NonNegativity(aux_init=np.zeros((4, 2))).init_aux(mats, 2, 1)
+    with pytest.raises(ValueError):
+        P.NonNegativity(dual_init=[np.zeros((4, 2)), np.zeros((4, 2))]).init_dual(mats, 2, 1)
+    with pytest.raises(ValueError):
+        P.NonNegativity(aux_init="bogus").init_aux(mats, 2, 0)
+    with pytest.raises(ValueError):
+        P.Parafac2().init_aux(mats, 2, 0)
+    with pytest.raises(ValueError, match="orthogonal"):
+        P.Parafac2(aux_init=([np.ones((4, 2)), np.ones((5, 2))], np.eye(2))).init_aux(mats, 2, 1)
+    ok = P.Parafac2(aux_init=([np.eye(4, 2), np.eye(5, 2)], np.eye(2))).init_aux(mats, 2, 1)
+    assert isinstance(ok, tuple)
+
+
+def test_coupled_matrix_factorization_container():
+    from matcouply_b200 import CoupledMatrixFactorization
+    from matcouply_b200.coupled_matrices import cmf_to_matrices
+
+    rs = np.random.RandomState(0)
+    A, C = rs.uniform(size=(3, 2)), rs.uniform(size=(5, 2))
+    Bs = [rs.uniform(size=(J, 2)) for J in (4, 6, 2)]
+    cmf = CoupledMatrixFactorization((None, (A, Bs, C)))
+    assert cmf.rank == 2 and cmf.shape == ((4, 5), (6, 5), (2, 5)) and len(cmf) == 2
+    w, (a, b, c) = cmf
+    assert w is None and a is A
+    with pytest.raises(IndexError):
+        cmf[2]
+    Ms = cmf.to_matrices()
+    np.testing.assert_allclose(Ms[1], (Bs[1] * A[1]) @ C.T)
+    np.testing.assert_allclose(cmf_to_matrices((np.array([2.0, 3.0]), (A, Bs, C)))[0], (Bs[0] * (A[0] * [2, 3])) @ C.T)
+    with pytest.raises(ValueError):
+        CoupledMatrixFactorization((None, (A, Bs[:2], C)))
+    with pytest.raises(ValueError):
+        CoupledMatrixFactorization((None, (A, Bs, C[:, :1])))
+    with pytest.raises(TypeError):
+        CoupledMatrixFactorization((None, (A, [1, 2, 3], C)))
+
+
+def test_cpu_call_fails_loudly():
+    import torch
+
+    from matcouply_b200 import cmf_aoadmm
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        cmf_aoadmm([np.ones((3, 3))], 1)

@@ -1,0 +1,125 @@
+"""CPU tests that PIN the oracle: against the golden vectors generated from the unmodified reference
+(oracle/gen_golden.py), against scikit-learn for the isotonic building block, and — when /root/reference is mounted
+(build container only) — against the reference run live."""
+import glob
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import aoadmm_oracle as O
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CASES = sorted(os.path.basename(p)[5:-4] for p in glob.glob(os.path.join(HERE, "golden", "traj_*.npz")))
+
+
+@pytest.fixture(scope="session", autouse=True)
+def build_oracle_c():
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle")], check=True)
+
+
+def load_case(name):
+    g = np.load(os.path.join(HERE, "golden", f"traj_{name}.npz"))
+    off = g["row_offsets"]
+    X = [g["X"][a:b] for a, b in zip(off[:-1], off[1:])]
+    kw = json.loads(str(g["kwargs"]))
+    for key in ("l1_penalty", "non_negative", "unimodal", "l2_norm_bound", "lower_bound", "upper_bound"):
+        if isinstance(kw.get(key), dict):
+            kw[key] = {int(k): v for k, v in kw[key].items()}
+    return g, X, int(g["rank"]), kw
+
+
+@pytest.mark.parametrize("name", [c for c in CASES if c != "c0_readme"])
+def test_oracle_reproduces_reference_goldens(name):
+    g, X, rank, kw = load_case(name)
+    traj = []
+    o = O.ao_admm(X, rank, trajectory=traj, **kw)
+    assert o["n_iter"] == int(g["n_iter"]) and o["message"] == str(g["message"])
+    np.testing.assert_allclose(o["regularized_loss"], g["regularized_loss"], rtol=1e-11)
+    np.testing.assert_allclose(o["rec_errors"], g["rec_errors"], rtol=1e-10)
+    for k in range(g["A_traj"].shape[0] if g["A_traj"].ndim == 3 else 0):
+        np.testing.assert_allclose(traj[k]["A"], g["A_traj"][k], rtol=1e-9, atol=1e-13)
+        np.testing.assert_allclose(np.concatenate(traj[k]["B_is"], 0), g["B_traj"][k], rtol=1e-9, atol=1e-13)
+        np.testing.assert_allclose(traj[k]["C"], g["C_traj"][k], rtol=1e-9, atol=1e-13)
+    np.testing.assert_allclose(o["A"], g["A"], rtol=1e-8, atol=1e-12)
+
+
+def test_oracle_readme_first_iterations():
+    g, X, rank, kw = load_case("c0_readme")
+    traj = []
+    o = O.ao_admm(X, rank, trajectory=traj, n_iter_max=50, **kw)
+    np.testing.assert_allclose(o["regularized_loss"], g["regularized_loss"][:51], rtol=1e-11)
+    for k in range(50):
+        np.testing.assert_allclose(np.concatenate(traj[k]["B_is"], 0), g["B_traj"][k], rtol=1e-9, atol=1e-13)
+
+
+def test_unimodal_oracle_c_and_python_twin_bit_exact():
+    g = np.load(os.path.join(HERE, "golden", "operators.npz"))
+    assert O._load_c(), "oracle/_build/liboracle.so missing"
+    for k in range(int(g["uni_count"])):
+        y, fit, peaks, nn = g[f"uni{k}_y"], g[f"uni{k}_fit"], g[f"uni{k}_peaks"], bool(g[f"uni{k}_nn"])
+        f1, p1 = O.unimodal_regression(y, nn, return_peaks=True)
+        assert np.array_equal(f1, fit) and np.array_equal(p1, peaks)
+        if y.shape[0] <= 60:
+            f2, p2 = O.unimodal_regression(y, nn, return_peaks=True, force_python=True)
+            assert np.array_equal(f2, fit) and np.array_equal(p2, peaks)
+
+
+def test_prefix_isotonic_vs_sklearn():
+    """Every prefix of the PAVA fit equals scikit-learn's isotonic regression of that prefix
+    (same check as the reference's tests/test_unimodal_regression.py:21-41)."""
+    from sklearn.isotonic import IsotonicRegression
+
+    rs = np.random.RandomState(0)
+    for n in (5, 31, 120):
+        for nn in (False, True):
+            y = rs.standard_normal(n)
+            level, start, err = O._prefix_isotonic_py(y, nn)
+            for end in range(1, n + 1):
+                fit = O._expand_blocks(end, level, start)
+                sk = IsotonicRegression(y_min=0 if nn else None).fit_transform(np.arange(end), y[:end])
+                np.testing.assert_allclose(fit, sk, atol=1e-12)
+                assert abs(err[end] - np.sum((fit - y[:end]) ** 2)) < 1e-9
+
+
+def test_closed_form_l2_update():
+    """With l2_penalty=1 and no constraint one C-update equals solve(Gram + I, rhs)
+    (reference tests/test_decomposition.py:1423-1443)."""
+    rs = np.random.RandomState(2)
+    A, C = rs.uniform(size=(5, 3)), rs.uniform(size=(8, 3))
+    Bs = [rs.uniform(size=(J, 3)) for J in (6, 7, 9, 4, 5)]
+    X = [(B * a) @ C.T for B, a in zip(Bs, A)]
+    Cn, _, _ = O.solve_mode_C(X, [], A, Bs, C, [], [], 1.0, 5, 1)
+    lhs = sum((B * a).T @ (B * a) for B, a in zip(Bs, A)) + np.eye(3)
+    rhs = sum(x.T @ (B * a) for x, B, a in zip(X, Bs, A))
+    np.testing.assert_allclose(Cn, np.linalg.solve(lhs, rhs.T).T, rtol=1e-10)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/src/matcouply"), reason="reference only in the build container")
+def test_oracle_vs_live_reference():
+    code = r"""
+import sys, os
+sys.dont_write_bytecode = True
+os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/nbcache_test")
+sys.path[:0] = [%r, "/root/reference/src", %r]
+import numpy as np
+from matcouply.decomposition import cmf_aoadmm
+from oracle.aoadmm_oracle import ao_admm
+rs = np.random.RandomState(9)
+X = [rs.uniform(size=(J, 11)) for J in (8, 13, 9, 10, 21, 7)]
+kw = dict(non_negative=True, parafac2=True, unimodal={1: True}, l1_penalty={2: 0.05}, l2_norm_bound=[0.0, 2.0, 0],
+          random_state=4, n_iter_max=40)
+cmf, d = cmf_aoadmm(X, 3, return_errors=True, **kw)
+o = ao_admm(X, 3, **kw)
+assert d.n_iter == o["n_iter"]
+np.testing.assert_allclose(o["regularized_loss"], d.regularized_loss, rtol=1e-11)
+np.testing.assert_allclose(o["A"], cmf[1][0], rtol=1e-9, atol=1e-13)
+print("OK")
+""" % (os.path.join(ROOT, "oracle", "_tl_standin"), ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
+                         env=dict(os.environ, PYTHONDONTWRITEBYTECODE="1"))
+    assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-2000:]
