@@ -517,7 +517,7 @@ int xstream_z_impl(const void* X, long long N, int K, int ldx, const void* W, in
     const uint32_t x_bytes = (uint32_t)(KZ / Cfg::EPB) * Cfg::BOX_BYTES;
     const uint32_t w_bytes = (uint32_t)(Cfg::TMZ * R * sizeof(T));
     const uint32_t stage_bytes = (x_bytes + w_bytes + 1023u) & ~1023u;
-    int stages = (int)((200 * 1024) / stage_bytes);
+    int stages = (int)((224 * 1024) / stage_bytes);
     if (stages > 8) stages = 8;
     B2_REQUIRE(stages >= 2, "xstream_z: stage does not fit shared memory");
     const size_t smem = (size_t)stages * stage_bytes + 1024 + 2 * stages * sizeof(uint64_t);

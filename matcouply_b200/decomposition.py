@@ -285,7 +285,7 @@ def cmf_aoadmm(
         shape_view = [_ShapeOnly(s) for s in packed.shapes]
     else:
         matrices = list(matrices)
-        all_f32 = all(getattr(m, "dtype", None) in (np.float32, torch.float32) for m in matrices)
+        all_f32 = all(str(getattr(m, "dtype", "")).endswith("float32") for m in matrices)
         packed = PackedMatrices.from_list(matrices, torch.float32 if all_f32 else torch.float64, device)
         shape_view = matrices
     cmf = initialize_cmf(shape_view, rank, init, random_state=random_state)
