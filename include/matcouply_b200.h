@@ -52,27 +52,32 @@ typedef struct {
 const char* b2_last_error(void);
 int b2_version(void);
 int b2_device_sm_count(void);
+/* number of CUDA kernels this library has launched so far in the calling process */
+unsigned long long b2_launch_count(void);
 
 /* ---- X-stream contractions (the HBM-bound hot kernels) ------------------------------------------------------
  * X: packed data, n_rows x K, row stride ldx elements (ldx*sizeof % 16 == 0, pad columns zero).
  * b2_xstream_y:  Y (n_rows x R) = X * C.              decomposition.py:242 (X_i (C*a_i) = (X_i C)*a_i), :148-152.
- * b2_xstream_z:  Z (K x R) = X^T * W, W n_rows x R,   decomposition.py:312-315 with W_i = B_i * a_i.
- *                W must be allocated with n_rows rounded up to a multiple of 16 rows, zero tail.
+ * b2_xstream_z:  Z (K x R) = X^T * W, W n_rows x R (row stride ldw = b2_xstream_z_ldw(R, dtype, variant), pad columns
+ *                zero), decomposition.py:312-315 with W_i = B_i * a_i.
+ *                W must be allocated with n_rows rounded up to a multiple of 32 rows, zero tail.
  * ws: scratch of at least b2_xstream_workspace_bytes(K, R, dtype) bytes, 16-byte aligned.
  * variant: B2_VARIANT_FMA (fp32/fp64 FMA pipes) or B2_VARIANT_DMMA (fp64 tensor cores, DMMA.8x8x4); AUTO picks.
  * max_ctas: 0 = one CTA per SM. */
 int b2_xstream_y(const void* X, long long n_rows, int K, int ldx, const void* C, int R, void* Y, int dtype, void* ws,
                  size_t ws_bytes, int variant, int max_ctas, void* stream);
-int b2_xstream_z(const void* X, long long n_rows, int K, int ldx, const void* W, int R, void* Z, int dtype, void* ws,
-                 size_t ws_bytes, int variant, int max_ctas, void* stream);
+int b2_xstream_z(const void* X, long long n_rows, int K, int ldx, const void* W, int ldw, int R, void* Z, int dtype,
+                 void* ws, size_t ws_bytes, int variant, int max_ctas, void* stream);
+int b2_xstream_z_ldw(int R, int dtype, int variant);
 size_t b2_xstream_workspace_bytes(int K, int R, int dtype);
 /* out[0] = sum(X**2) in double (decomposition.py:906, _root_sum_squared_list :347). ws >= 8*4*SMs bytes. */
 int b2_sumsq(const void* X, long long n_rows, int K, int ldx, int dtype, double* out, void* ws, size_t ws_bytes,
              void* stream);
 
 /* ---- small dense / batched per-slice math --------------------------------------------------------------------*/
-/* G (R x R) = M^T M for a dense n x R matrix (C^T C :138,:240 ; sum_i (B_i a_i)^T (B_i a_i) :314). ws >= 8*R*R*SMs. */
-int b2_gram(const void* M, long long n, int R, void* G, int dtype, void* ws, size_t ws_bytes, void* stream);
+/* G (R x R) = M^T M for a dense n x R matrix with row stride ld >= R (C^T C :138,:240 ; sum_i (B_i a_i)^T (B_i a_i)
+ * :314). ws >= 16*R*R*SMs bytes. */
+int b2_gram(const void* M, long long n, int R, int ld, void* G, int dtype, void* ws, size_t ws_bytes, void* stream);
 /* lhs[g] = G o (a_g a_g^T), g < n_groups  (decomposition.py:243). */
 int b2_scale_gram(const void* G, const void* A, int n_groups, int R, void* lhs, int dtype, void* stream);
 /* rho[g] = 0.5 * trace(lhs[g]) * scale ; rho_max[0] = max_g rho[g]  (decomposition.py:162-165, 247-250, 319). */
@@ -87,9 +92,9 @@ int b2_factor_batch(const void* lhs, int n_groups, int R, void* rho, const void*
  * cross[g] = (B_g^T B_g) o CtC (:155).  rhs may be NULL; CtC may be NULL (then cross = B^T B, used for PARAFAC2). */
 int b2_slice_cross(const void* B, const void* Y, const int64_t* row_off, int n_groups, int R, const void* CtC,
                    void* cross, void* rhs, int dtype, void* stream);
-/* W[row] = B[row] o A[group_of_row[row]]  (B_i * a_i, :313). */
-int b2_rowscale(const void* B, const void* A, const int32_t* group_of_row, long long n, int R, void* W, int dtype,
-                void* stream);
+/* W[row][0:R] = B[row] o A[group_of_row[row]]  (B_i * a_i, :313); W has row stride ldw >= R. */
+int b2_rowscale(const void* B, const void* A, const int32_t* group_of_row, long long n, int R, void* W, int ldw,
+                int dtype, void* stream);
 
 /* ---- fused ADMM step ------------------------------------------------------------------------------------------
  * For every row:  s = rhs[row] o rhs_scale[g] + rho[g] * sum_p (aux_p[row] - dual_p[row])      (:261-273,:328-331,:179-195)
@@ -101,6 +106,14 @@ int b2_rowscale(const void* B, const void* A, const int32_t* group_of_row, long 
 int b2_admm_solve(long long n, int R, const void* rhs, const void* rhs_scale, int group_mode,
                   const int32_t* group_of_row, const void* rho, const void* Minv, const b2_penalty_desc* pens_host,
                   int n_pen, void* x, int dtype, void* stream);
+
+/* Whole inner ADMM loop in one pass for modes whose penalties are all row-local (NONNEG, BOX, L1; n_pen <= 2):
+ * `n_inner` iterations of the update above with the row state held in registers (decomposition.py:259-289, 325-342,
+ * 176-217).  If w_out != NULL also writes w_out[row][0:R] = x[row] o rhs_scale[g] (row stride ldw) — the scaled
+ * factor B_i * a_i consumed by b2_xstream_z. */
+int b2_admm_local(long long n, int R, const void* rhs, const void* rhs_scale, int group_mode,
+                  const int32_t* group_of_row, const void* rho, const void* Minv, const b2_penalty_desc* pens_host,
+                  int n_pen, int n_inner, void* x, void* w_out, int ldw, int dtype, void* stream);
 
 /* ---- column-coupled proximal operators (V arrives in `dual`, see b2_admm_solve) --------------------------------*/
 /* L2Ball (penalties.py:920-925): per group and column  aux = clip(V)*bound/max(||clip(V)_col||, bound); dual = V - aux. */

@@ -77,7 +77,8 @@ class _ModeState:
 
 class AOADMMEngine:
     def __init__(self, packed, rank, regs, l2_penalty=(0, 0, 0), feasibility_penalty_scale=1.0, constant_A=False,
-                 constant_B=False, inner_n_iter_max=5, update=(True, True, True), group=None, xstream_variant=None):
+                 constant_B=False, inner_n_iter_max=5, update=(True, True, True), group=None, xstream_variant=None,
+                 fuse_local=True):
         _lib.load()
         self.p = packed
         self.dev = packed.X.device
@@ -94,6 +95,8 @@ class AOADMMEngine:
         self.group = group
         self.world = 1 if group is None else torch.distributed.get_world_size(group)
         self.variant = _lib.VARIANT_AUTO if xstream_variant is None else xstream_variant
+        self.fuse_local = bool(fuse_local)
+        self.w_fresh = False
         R, I, K, N, dt, dev = self.R, self.I, self.K, self.N, self.dtype, self.dev
 
         self.row_off = torch.as_tensor(packed.row_offsets, dtype=torch.int64).to(dev)
@@ -127,7 +130,7 @@ class AOADMMEngine:
 
         z = lambda *s: torch.zeros(s, dtype=dt, device=dev)  # noqa: E731
         self.Y = z(N, R)
-        self.Wpad = z((N + 15) // 16 * 16, R)  # zero tail required by b2_xstream_z
+        self.Wpad = _ops.alloc_w(N, R, dt, dev, self.variant)  # zero tail / pad columns required by b2_xstream_z
         self.ZL = z(K * R + R * R)             # Z (K x R) followed by lhs_C (R x R): one all-reduce buffer
         self.Z = self.ZL[: K * R].view(K, R)
         self.lhsC = self.ZL[K * R:].view(R, R)
@@ -151,6 +154,7 @@ class AOADMMEngine:
             uni = (I, R, self.max_rows)
         self.ws = _ops.Workspace(dev, K, R, dt, unimodal_shape=uni)
         self.n_xstream_launches = 0
+        self.xstream_events = None  # set to {"y": [], "z": []} to record (start, end) CUDA events per launch
 
     # ------------------------------------------------------------------------------------------------------
     # state upload / download (host NumPy float64 <-> device)
@@ -187,6 +191,32 @@ class AOADMMEngine:
                 [(d[0], d[1], d[2], d[3], a, u) for d, a, u in zip(st[m].desc, st[m].aux, st[m].dual)])
         for m, n in ((0, self.I), (1, self.N), (2, self.K)):
             assert tuple(st[m].x.shape) == (n, self.R), (m, st[m].x.shape, (n, self.R))
+
+    def load_state_device(self, seed=0):
+        """Benchmark helper: uniform [0,1) factors / aux / dual drawn ON THE DEVICE (no host round trip of N x R
+        arrays, no RNG parity with the reference — parity runs go through load_state)."""
+        gen = torch.Generator(device=self.dev).manual_seed(int(seed))
+        rnd = lambda *s: torch.rand(s, dtype=self.dtype, device=self.dev, generator=gen)  # noqa: E731
+        st, R = self.modes, self.R
+        st[0].x, st[1].x, st[2].x = rnd(self.I, R), rnd(self.N, R), rnd(self.K, R)
+        for m, n in ((0, self.I), (1, self.N), (2, self.K)):
+            st[m].aux, st[m].dual = [], []
+            for kind, *_r in st[m].desc:
+                if kind == _lib.PEN_PARAFAC2:
+                    self.Delta.copy_(rnd(R, R))
+                    pd = torch.zeros((n, R), dtype=self.dtype, device=self.dev)
+                    # P_i = eye(J_i, R): row j < R of slice i is Delta[j]
+                    starts = self.row_off[:-1]
+                    for j in range(R):
+                        ok = (self.row_off[1:] - starts) > j
+                        pd[(starts + j)[ok]] = self.Delta[j]
+                    st[m].aux.append(pd)
+                    self.pf2_basis0, self.pf2_fresh = None, False
+                else:
+                    st[m].aux.append(rnd(n, R))
+                st[m].dual.append(rnd(n, R))
+            st[m].descs_c = _ops.make_descs(
+                [(d[0], d[1], d[2], d[3], a, u) for d, a, u in zip(st[m].desc, st[m].aux, st[m].dual)])
 
     def _split(self, t):
         host = t.detach().to(torch.float64).cpu().numpy()
@@ -253,6 +283,16 @@ class AOADMMEngine:
                 _ops.pf2_apply(st.aux[p], st.dual[p], None, self.Wmat, self.Delta, gor, n_rows, R)
                 self.pf2_fresh = True
 
+    def _timed(self, key, fn):
+        self.n_xstream_launches += 1
+        if self.xstream_events is None:
+            return fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        self.xstream_events[key].append((e0, e1))
+
     def step_B(self):
         """admm_update_B (decomposition.py:222-292); rhs_i = Y_i o a_i with the cached Y = X C."""
         st, R, I = self.modes[1], self.R, self.I
@@ -264,22 +304,38 @@ class AOADMMEngine:
             self._allreduce(self.rho_max, "max")
         _ops.factor_batch(self.lhsB, I, R, self.rhoB, self.rho_max if self.const_B else None, len(st.desc), self.l2[1],
                           self.MinvB)
+        self.w_fresh = False
+        if self._row_local(st):  # whole inner loop in one fused pass, W = B o a emitted for the Z pass
+            # W = B o a stays valid for the C-step: A only changes after the C-step (decomposition.py:948-988)
+            _ops.admm_local(self.N, R, self.Y, A, _lib.GROUP_INDEXED, self.gor, self.rhoB, self.MinvB, st.descs_c,
+                            len(st.desc), self.n_inner, st.x, self.Wpad)
+            self.w_fresh = True
+            return
         for _ in range(self.n_inner):
             _ops.admm_solve(self.N, R, self.Y, A, _lib.GROUP_INDEXED, self.gor, self.rhoB, self.MinvB, st.descs_c,
                             len(st.desc), st.x)
             self._column_coupled(st, self.row_off, I, self.max_rows, self.rhoB, self.gor, self.N)
 
+    def _row_local(self, st):
+        """True when every penalty of the mode is elementwise (the fused b2_admm_local path applies)."""
+        return self.fuse_local and self.n_inner > 0 and len(st.desc) <= 2 and all(
+            d[0] in (_lib.PEN_NONNEG, _lib.PEN_BOX, _lib.PEN_L1) for d in st.desc)
+
     def step_C(self):
         """admm_update_C (decomposition.py:295-344); one X pass: Z = X^T (B o a)."""
         st, R, K = self.modes[2], self.R, self.K
-        W = self.Wpad[: self.N]
-        _ops.rowscale(self.modes[1].x, self.modes[0].x, self.gor, self.N, R, W)
-        _ops.xstream_z(self.p.X, self.N, K, self.Wpad, self.Z, self.ws, self.variant)
-        self.n_xstream_launches += 1
-        _ops.gram(W, self.N, self.lhsC, self.ws)
+        if not getattr(self, "w_fresh", False):
+            _ops.rowscale(self.modes[1].x, self.modes[0].x, self.gor, self.N, R, self.Wpad)
+        self.w_fresh = False
+        self._timed("z", lambda: _ops.xstream_z(self.p.X, self.N, K, self.Wpad, self.Z, self.ws, self.variant))
+        _ops.gram(self.Wpad, self.N, self.lhsC, self.ws)
         self._allreduce(self.ZL)
         _ops.rho_from_trace(self.lhsC, 1, R, self.scale, self.rhoC, None)
         _ops.factor_batch(self.lhsC, 1, R, self.rhoC, None, len(st.desc), self.l2[2], self.MinvC)
+        if self._row_local(st):
+            _ops.admm_local(K, R, self.Z, None, _lib.GROUP_SINGLE, None, self.rhoC, self.MinvC, st.descs_c,
+                            len(st.desc), self.n_inner, st.x)
+            return
         for _ in range(self.n_inner):
             _ops.admm_solve(K, R, self.Z, None, _lib.GROUP_SINGLE, None, self.rhoC, self.MinvC, st.descs_c,
                             len(st.desc), st.x)
@@ -289,8 +345,7 @@ class AOADMMEngine:
         """Y = X C (one X pass), CtC, cross_i = (B_i^T B_i) o CtC, rhsA_i = colsum(B_i o Y_i)
         (decomposition.py:138-158).  Also what the fit term needs (:446-449)."""
         C, B = self.modes[2].x, self.modes[1].x
-        _ops.xstream_y(self.p.X, self.N, self.K, C, self.Y, self.ws, self.variant)
-        self.n_xstream_launches += 1
+        self._timed("y", lambda: _ops.xstream_y(self.p.X, self.N, self.K, C, self.Y, self.ws, self.variant))
         _ops.gram(C, self.K, self.CtC, self.ws)
         _ops.slice_cross(B, self.Y, self.row_off, self.I, self.R, self.CtC, self.cross, self.rhsA)
 
@@ -302,6 +357,10 @@ class AOADMMEngine:
             self._allreduce(self.rho_max, "max")
         _ops.factor_batch(self.cross, I, R, self.rhoA, self.rho_max if self.const_A else None, len(st.desc), self.l2[0],
                           self.MinvA)
+        if self._row_local(st):
+            _ops.admm_local(I, R, self.rhsA, None, _lib.GROUP_IDENTITY, None, self.rhoA, self.MinvA, st.descs_c,
+                            len(st.desc), self.n_inner, st.x)
+            return
         for _ in range(self.n_inner):
             _ops.admm_solve(I, R, self.rhsA, None, _lib.GROUP_IDENTITY, None, self.rhoA, self.MinvA, st.descs_c,
                             len(st.desc), st.x)

@@ -35,15 +35,16 @@ _vp, _i, _ll, _sz, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_longlong, ctypes
 # name -> argtypes ; every function returns int status except the ones listed in _OTHER_RESTYPE
 _SIGNATURES = {
     "b2_xstream_y": [_vp, _ll, _i, _i, _vp, _i, _vp, _i, _vp, _sz, _i, _i, _vp],
-    "b2_xstream_z": [_vp, _ll, _i, _i, _vp, _i, _vp, _i, _vp, _sz, _i, _i, _vp],
+    "b2_xstream_z": [_vp, _ll, _i, _i, _vp, _i, _i, _vp, _i, _vp, _sz, _i, _i, _vp],
     "b2_sumsq": [_vp, _ll, _i, _i, _i, _vp, _vp, _sz, _vp],
-    "b2_gram": [_vp, _ll, _i, _vp, _i, _vp, _sz, _vp],
+    "b2_gram": [_vp, _ll, _i, _i, _vp, _i, _vp, _sz, _vp],
     "b2_scale_gram": [_vp, _vp, _i, _i, _vp, _i, _vp],
     "b2_rho_from_trace": [_vp, _i, _i, _d, _vp, _vp, _i, _vp],
     "b2_factor_batch": [_vp, _i, _i, _vp, _vp, _i, _d, _vp, _i, _vp],
     "b2_slice_cross": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp],
-    "b2_rowscale": [_vp, _vp, _vp, _ll, _i, _vp, _i, _vp],
+    "b2_rowscale": [_vp, _vp, _vp, _ll, _i, _vp, _i, _i, _vp],
     "b2_admm_solve": [_ll, _i, _vp, _vp, _i, _vp, _vp, _vp, ctypes.POINTER(PenaltyDesc), _i, _vp, _i, _vp],
+    "b2_admm_local": [_ll, _i, _vp, _vp, _i, _vp, _vp, _vp, ctypes.POINTER(PenaltyDesc), _i, _i, _vp, _vp, _i, _i, _vp],
     "b2_prox_l2ball": [_vp, _vp, _vp, _i, _i, _d, _i, _i, _vp],
     "b2_prox_unimodal": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _sz, _vp],
     "b2_pf2_polar": [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp],
@@ -58,7 +59,9 @@ _OTHER = {
     "b2_last_error": ([], ctypes.c_char_p),
     "b2_version": ([], _i),
     "b2_device_sm_count": ([], _i),
+    "b2_launch_count": ([], ctypes.c_ulonglong),
     "b2_xstream_workspace_bytes": ([_i, _i, _i], _sz),
+    "b2_xstream_z_ldw": ([_i, _i, _i], _i),
     "b2_unimodal_workspace_bytes": ([_i, _i, _i], _sz),
 }
 EXPORTED_SYMBOLS = sorted(list(_SIGNATURES) + list(_OTHER))

@@ -61,12 +61,22 @@ def xstream_y(X, n_rows, K, C, Y, ws, variant=_lib.VARIANT_AUTO, max_ctas=0):
 
 
 def xstream_z(X, n_rows, K, W, Z, ws, variant=_lib.VARIANT_AUTO, max_ctas=0):
+    """W: (n_rows rounded up to 32, z_ldw(R, dtype, variant)) with zero padding (see alloc_w)."""
     R = Z.shape[1]
-    call("b2_xstream_z", _ptr(X), n_rows, K, X.shape[1], _ptr(W), R, _ptr(Z), dtype_code(X.dtype), _ptr(ws.xs),
-         ws.xs_bytes, resolve_variant(variant, X.dtype), max_ctas, _stream())
+    call("b2_xstream_z", _ptr(X), n_rows, K, X.shape[1], _ptr(W), W.shape[1], R, _ptr(Z), dtype_code(X.dtype),
+         _ptr(ws.xs), ws.xs_bytes, resolve_variant(variant, X.dtype), max_ctas, _stream())
 
 
-_DEFAULT_VARIANT = {"f64": _lib.VARIANT_FMA}
+def z_ldw(R, dtype, variant=_lib.VARIANT_AUTO):
+    return int(_lib.load().b2_xstream_z_ldw(R, dtype_code(dtype), resolve_variant(variant, dtype)))
+
+
+def alloc_w(n_rows, R, dtype, device, variant=_lib.VARIANT_AUTO):
+    """Zero-initialised W buffer in the layout b2_xstream_z expects for this variant."""
+    return torch.zeros(((n_rows + 31) // 32 * 32, z_ldw(R, dtype, variant)), dtype=dtype, device=device)
+
+
+_DEFAULT_VARIANT = {"f64": _lib.VARIANT_DMMA}
 
 
 def set_default_fp64_variant(variant):
@@ -86,7 +96,8 @@ def sumsq(X, n_rows, K, out, ws):
 
 
 def gram(M, n, G, ws):
-    call("b2_gram", _ptr(M), n, G.shape[0], _ptr(G), dtype_code(M.dtype), _ptr(ws.red), ws.red_bytes, _stream())
+    call("b2_gram", _ptr(M), n, G.shape[0], M.shape[1], _ptr(G), dtype_code(M.dtype), _ptr(ws.red), ws.red_bytes,
+         _stream())
 
 
 def scale_gram(G, A, lhs):
@@ -109,7 +120,8 @@ def slice_cross(B, Y, row_off, n_groups, R, CtC, cross, rhs):
 
 
 def rowscale(B, A, group_of_row, n, R, W):
-    call("b2_rowscale", _ptr(B), _ptr(A), _ptr(group_of_row), n, R, _ptr(W), dtype_code(B.dtype), _stream())
+    call("b2_rowscale", _ptr(B), _ptr(A), _ptr(group_of_row), n, R, _ptr(W), W.shape[1], dtype_code(B.dtype),
+         _stream())
 
 
 def make_descs(entries):
@@ -186,3 +198,9 @@ def microbench_flops(kind, iters):
 
 def to_device(a, dtype, device):
     return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(device)
+
+
+def admm_local(n, R, rhs, rhs_scale, group_mode, group_of_row, rho, Minv, descs, n_pen, n_inner, x, w_out=None):
+    call("b2_admm_local", n, R, _ptr(rhs), _ptr(rhs_scale), group_mode, _ptr(group_of_row), _ptr(rho), _ptr(Minv),
+         descs, n_pen, n_inner, _ptr(x), _ptr(w_out), 0 if w_out is None else w_out.shape[1], dtype_code(x.dtype),
+         _stream())

@@ -1,39 +1,9 @@
 // Fused ADMM step (x-update + elementwise prox + dual update), the L2-ball column projection and the fused
 // reductions behind the feasibility gaps / loss.  One thread owns one row of the packed (n x R) state, so the whole
 // row stays in registers between the solve, the prox of every penalty and the dual update.
-#include <math.h>
-
-#include "common.cuh"
+#include "admm_common.cuh"
 
 namespace {
-
-constexpr int kMaxPen = 4;
-
-struct PenArgs {
-    int n_pen;
-    int kind[kMaxPen];
-    int nn[kMaxPen];
-    double p0[kMaxPen], p1[kMaxPen];
-    void* aux[kMaxPen];
-    void* dual[kMaxPen];
-};
-
-template <typename T>
-__device__ __forceinline__ T prox_elem(T v, int kind, int nn, T p0, T p1, T rho) {
-    // penalties.py:503-508 (NonNegativity), :537-542 (Box), :573-586 (L1)
-    if (kind == B2_PEN_NONNEG) return v > T(0) ? v : T(0);
-    if (kind == B2_PEN_BOX) return v < p0 ? p0 : (v > p1 ? p1 : v);
-    // L1
-    const T thr = p0 / rho;
-    if (nn) {
-        const T u = v - thr;
-        return u > T(0) ? u : T(0);
-    }
-    const T a = fabs(v) - thr;
-    const T m = a > T(0) ? a : T(0);
-    const T sgn = v > T(0) ? T(1) : (v < T(0) ? T(-1) : T(0));
-    return sgn * m;
-}
 
 template <typename T, int RM>
 __global__ void __launch_bounds__(128)
@@ -233,21 +203,12 @@ int b2_admm_solve(long long n, int R, const void* rhs, const void* rhs_scale, in
                   void* x, int dtype, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
-    B2_REQUIRE(n_pen >= 0 && n_pen <= kMaxPen, "at most %d penalties per mode are supported (got %d)", kMaxPen, n_pen);
     B2_REQUIRE(group_mode != B2_GROUP_INDEXED || group_of_row != nullptr, "group_of_row required");
     if (n == 0) return B2_OK;
     PenArgs pa;
-    pa.n_pen = n_pen;
-    for (int p = 0; p < n_pen; ++p) {
-        pa.kind[p] = pens[p].kind;
-        pa.nn[p] = pens[p].non_negativity;
-        pa.p0[p] = pens[p].p0;
-        pa.p1[p] = pens[p].p1;
-        pa.aux[p] = pens[p].aux;
-        pa.dual[p] = pens[p].dual;
-        B2_REQUIRE(pens[p].kind >= B2_PEN_NONNEG && pens[p].kind <= B2_PEN_PARAFAC2, "unknown penalty kind %d",
-                   pens[p].kind);
-        B2_REQUIRE(pens[p].aux && pens[p].dual, "penalty %d: aux/dual pointers must be set", p);
+    {
+        const int rc = b2_pack_penalties(pens, n_pen, &pa);
+        if (rc != B2_OK) return rc;
     }
     const int grid = (int)((n + 127) / 128);
     B2_DISPATCH_DTYPE(dtype, B2_DISPATCH_RANK(R, {

@@ -1,0 +1,150 @@
+// Fully fused ADMM sub-solver for modes whose penalties are all row-local (NonNegativity, Box, L1 — or none):
+// the whole inner loop of admm_update_B / _C / _A (decomposition.py:259-289, 325-342, 176-217) runs in registers,
+// one pass over the state: read rhs, aux, dual once; iterate  x = (rho*sum(aux-dual) + rhs) Minv ; aux = prox(x+dual);
+// dual = x + dual - aux  `n_inner` times; write x, aux, dual once (and W = x o a for the following X^T W pass).
+//
+// Thread mapping: 4 lanes per row, each lane owns CPL = ceil(R/4) consecutive columns, so a warp touches 8
+// consecutive rows = one contiguous, fully coalesced 8*R-element segment per array.  The R x R solve needs the whole
+// vector s: it is exchanged between the 4 lanes of a row with warp shuffles (no shared memory, no block barrier).
+#include "admm_common.cuh"
+
+namespace {
+
+template <typename T, int CPL, int NP>
+__global__ void __launch_bounds__(256)
+admm_local_kernel(long long n, int R, const T* __restrict__ rhs, const T* __restrict__ rhs_scale, int group_mode,
+                  const int32_t* __restrict__ gor, const T* __restrict__ rho, const T* __restrict__ Minv, PenArgs pa,
+                  int n_inner, T* __restrict__ x, T* __restrict__ w_out, int ldw) {
+    const int lane = threadIdx.x & 31, l4 = lane & 3;
+    const long long rowid = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    const bool valid = rowid < n;
+    const long long row = valid ? rowid : n - 1;  // clamp: all lanes stay in the shuffles, stores are masked
+    const int g = group_mode == B2_GROUP_SINGLE ? 0 : (group_mode == B2_GROUP_INDEXED ? gor[row] : (int)row);
+    const T rg = rho[g];
+    const int c0 = l4 * CPL;
+    const size_t base = (size_t)row * R + c0;
+    T r_[CPL], xv[CPL], sc[CPL];
+    T a_[NP > 0 ? NP : 1][CPL], d_[NP > 0 ? NP : 1][CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+        const bool in = c0 + j < R;
+        sc[j] = (in && rhs_scale) ? rhs_scale[(size_t)g * R + c0 + j] : T(1);
+        r_[j] = in ? rhs[base + j] * sc[j] : T(0);
+        xv[j] = T(0);
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            a_[p][j] = in ? ((const T*)pa.aux[p])[base + j] : T(0);
+            d_[p][j] = in ? ((const T*)pa.dual[p])[base + j] : T(0);
+        }
+    }
+    const T* Mg = Minv + (size_t)g * R * R + c0;
+    const int iters = NP == 0 ? 1 : n_inner;
+    for (int it = 0; it < iters; ++it) {
+        T s_[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            T sh = T(0);
+#pragma unroll
+            for (int p = 0; p < NP; ++p) sh += a_[p][j] - d_[p][j];
+            s_[j] = NP > 0 ? rg * sh + r_[j] : r_[j];
+            xv[j] = T(0);
+        }
+#pragma unroll
+        for (int rr = 0; rr < 4 * CPL; ++rr) {
+            const T sr = __shfl_sync(0xffffffffu, s_[rr % CPL], (lane & ~3) | (rr / CPL));
+            if (rr < R) {
+#pragma unroll
+                for (int j = 0; j < CPL; ++j)
+                    if (c0 + j < R) xv[j] = fma(sr, __ldg(Mg + (size_t)rr * R + j), xv[j]);
+            }
+        }
+#pragma unroll
+        for (int p = 0; p < NP; ++p) {
+            const int kind = pa.kind[p], nn = pa.nn[p];
+            const T p0 = (T)pa.p0[p], p1 = (T)pa.p1[p];
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                const T v = xv[j] + d_[p][j];
+                const T z = prox_elem<T>(v, kind, nn, p0, p1, rg);
+                a_[p][j] = z;
+                d_[p][j] = v - z;
+            }
+        }
+    }
+    if (!valid) return;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+        if (c0 + j < R) {
+            x[base + j] = xv[j];
+#pragma unroll
+            for (int p = 0; p < NP; ++p) {
+                ((T*)pa.aux[p])[base + j] = a_[p][j];
+                ((T*)pa.dual[p])[base + j] = d_[p][j];
+            }
+            if (w_out) w_out[(size_t)row * ldw + c0 + j] = xv[j] * sc[j];
+        }
+    }
+}
+
+template <typename T, int CPL>
+int launch_local(int n_pen, long long n, int R, const void* rhs, const void* rhs_scale, int group_mode,
+                 const int32_t* gor, const void* rho, const void* Minv, const PenArgs& pa, int n_inner, void* x,
+                 void* w_out, int ldw, cudaStream_t st) {
+    const long long threads = n * 4;
+    const int grid = (int)((threads + 255) / 256);
+#define B2_LAUNCH_LOCAL(NP)                                                                                       \
+    admm_local_kernel<T, CPL, NP><<<grid, 256, 0, st>>>(n, R, (const T*)rhs, (const T*)rhs_scale, group_mode, gor, \
+                                                        (const T*)rho, (const T*)Minv, pa, n_inner, (T*)x,        \
+                                                        (T*)w_out, ldw)
+    switch (n_pen) {
+        case 0: B2_LAUNCH_LOCAL(0); break;
+        case 1: B2_LAUNCH_LOCAL(1); break;
+        default: B2_LAUNCH_LOCAL(2); break;
+    }
+#undef B2_LAUNCH_LOCAL
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b2_admm_local(long long n, int R, const void* rhs, const void* rhs_scale, int group_mode,
+                  const int32_t* group_of_row, const void* rho, const void* Minv, const b2_penalty_desc* pens, int n_pen,
+                  int n_inner, void* x, void* w_out, int ldw, int dtype, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
+    B2_REQUIRE(n_pen >= 0 && n_pen <= 2, "b2_admm_local fuses at most 2 penalties (got %d)", n_pen);
+    B2_REQUIRE(group_mode != B2_GROUP_INDEXED || group_of_row != nullptr, "group_of_row required");
+    B2_REQUIRE(w_out == nullptr || rhs_scale != nullptr, "w_out needs rhs_scale (W = x o a)");
+    if (n == 0) return B2_OK;
+    PenArgs pa;
+    {
+        const int rc = b2_pack_penalties(pens, n_pen, &pa);
+        if (rc != B2_OK) return rc;
+    }
+    for (int p = 0; p < n_pen; ++p)
+        B2_REQUIRE(pa.kind[p] == B2_PEN_NONNEG || pa.kind[p] == B2_PEN_BOX || pa.kind[p] == B2_PEN_L1,
+                   "b2_admm_local handles row-local penalties only (penalty %d has kind %d)", p, pa.kind[p]);
+    const int CPL = (R + 3) / 4;
+#define B2_CASE_CPL(C)                                                                                            \
+    case C:                                                                                                       \
+        B2_DISPATCH_DTYPE(dtype, return launch_local<T, C>(n_pen, n, R, rhs, rhs_scale, group_mode, group_of_row, \
+                                                           rho, Minv, pa, n_inner, x, w_out, ldw, st));           \
+        break
+    switch (CPL) {
+        B2_CASE_CPL(1);
+        B2_CASE_CPL(2);
+        B2_CASE_CPL(3);
+        B2_CASE_CPL(4);
+        B2_CASE_CPL(5);
+        B2_CASE_CPL(6);
+        B2_CASE_CPL(7);
+        B2_CASE_CPL(8);
+    }
+#undef B2_CASE_CPL
+    return B2_OK;
+}
+
+}  // extern "C"

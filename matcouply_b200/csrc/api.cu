@@ -6,6 +6,7 @@
 #include "common.cuh"
 
 static thread_local char g_err[512] = "";
+unsigned long long g_b2_launches = 0;
 
 void b2_set_error(const char* fmt, ...) {
     va_list ap;
@@ -79,6 +80,7 @@ extern "C" {
 const char* b2_last_error(void) { return g_err; }
 int b2_version(void) { return 100; }
 int b2_device_sm_count(void) { return b2_num_sms(); }
+unsigned long long b2_launch_count(void) { return g_b2_launches; }
 
 int b2_microbench_flops(int kind, int iters, double* flops_host, void* sink, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;

@@ -13,7 +13,7 @@ namespace {
 constexpr int kGramRows = 32;  // rows staged per step
 
 template <typename T>
-__global__ void gram_partial_kernel(const T* __restrict__ M, long long n, int R, double* __restrict__ part) {
+__global__ void gram_partial_kernel(const T* __restrict__ M, long long n, int R, int ld, double* __restrict__ part) {
     __shared__ T tile[kGramRows * B2_MAX_RANK];
     const int RR = R * R;
     // each thread owns outputs e = tid, tid + blockDim, ... (at most 4 for R=32, 256 threads)
@@ -25,7 +25,7 @@ __global__ void gram_partial_kernel(const T* __restrict__ M, long long n, int R,
     for (long long r0 = r_begin; r0 < r_end; r0 += kGramRows) {
         const int nr = (int)((r_end - r0) < kGramRows ? (r_end - r0) : kGramRows);
         __syncthreads();
-        for (int i = threadIdx.x; i < nr * R; i += blockDim.x) tile[i] = M[r0 * R + i];
+        for (int i = threadIdx.x; i < nr * R; i += blockDim.x) tile[i] = M[(r0 + i / R) * ld + i % R];
         __syncthreads();
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -207,13 +207,13 @@ __global__ void slice_cross_kernel(const T* __restrict__ B, const T* __restrict_
 
 template <typename T>
 __global__ void rowscale_kernel(const T* __restrict__ B, const T* __restrict__ A, const int32_t* __restrict__ gor,
-                                long long n, int R, T* __restrict__ W) {
+                                long long n, int R, T* __restrict__ W, int ldw) {
     const long long total = n * R;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const long long row = i / R;
         const int c = (int)(i - row * R);
-        W[i] = B[i] * A[(size_t)gor[row] * R + c];
+        W[row * ldw + c] = B[i] * A[(size_t)gor[row] * R + c];  // pad columns [R, ldw) stay zero
     }
 }
 
@@ -410,7 +410,7 @@ __global__ void pf2_apply_kernel(T* __restrict__ pd, T* __restrict__ dual, T* __
 
 extern "C" {
 
-int b2_gram(const void* M, long long n, int R, void* G, int dtype, void* ws, size_t ws_bytes, void* stream) {
+int b2_gram(const void* M, long long n, int R, int ld, void* G, int dtype, void* ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
     int blocks = (int)((n + 1023) / 1024);
@@ -419,7 +419,7 @@ int b2_gram(const void* M, long long n, int R, void* G, int dtype, void* ws, siz
     if (blocks < 1) blocks = 1;
     B2_REQUIRE(ws_bytes >= (size_t)blocks * R * R * sizeof(double), "b2_gram workspace too small");
     B2_DISPATCH_DTYPE(dtype, {
-        gram_partial_kernel<T><<<blocks, 256, 0, st>>>((const T*)M, n, R, (double*)ws);
+        gram_partial_kernel<T><<<blocks, 256, 0, st>>>((const T*)M, n, R, ld, (double*)ws);
         B2_LAUNCH_CHECK();
         gram_final_kernel<T><<<(R * R + 255) / 256, 256, 0, st>>>((const double*)ws, blocks, R * R, (T*)G);
         B2_LAUNCH_CHECK();
@@ -484,14 +484,14 @@ int b2_slice_cross(const void* B, const void* Y, const int64_t* row_off, int n_g
     return B2_OK;
 }
 
-int b2_rowscale(const void* B, const void* A, const int32_t* group_of_row, long long n, int R, void* W, int dtype,
-                void* stream) {
+int b2_rowscale(const void* B, const void* A, const int32_t* group_of_row, long long n, int R, void* W, int ldw,
+                int dtype, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) return B2_OK;
     long long blocks = (n * R + 255) / 256;
     if (blocks > b2_num_sms() * 16) blocks = b2_num_sms() * 16;
     B2_DISPATCH_DTYPE(dtype, {
-        rowscale_kernel<T><<<(int)blocks, 256, 0, st>>>((const T*)B, (const T*)A, group_of_row, n, R, (T*)W);
+        rowscale_kernel<T><<<(int)blocks, 256, 0, st>>>((const T*)B, (const T*)A, group_of_row, n, R, (T*)W, ldw);
         B2_LAUNCH_CHECK();
     });
     return B2_OK;

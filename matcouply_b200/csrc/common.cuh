@@ -31,7 +31,12 @@ void b2_set_error(const char* fmt, ...);
         }                                                                                               \
     } while (0)
 
-#define B2_LAUNCH_CHECK() B2_CHECK_CUDA(cudaGetLastError())
+extern unsigned long long g_b2_launches;  // kernels launched through this library (bench.py's gpu_launches claim)
+#define B2_LAUNCH_CHECK()                     \
+    do {                                      \
+        ++g_b2_launches;                      \
+        B2_CHECK_CUDA(cudaGetLastError());    \
+    } while (0)
 
 int b2_num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
 

@@ -227,14 +227,14 @@ struct ZCfg {
 
 template <typename T, int RP>
 __global__ void __launch_bounds__(kThreads, 1)
-xstream_z_kernel(const __grid_constant__ CUtensorMap tmap_x, const T* __restrict__ W, T* __restrict__ part, int K, int R,
-                 int KZ, int num_tiles, int stages) {
+xstream_z_kernel(const __grid_constant__ CUtensorMap tmap_x, const T* __restrict__ W, int ldw, T* __restrict__ part, int K,
+                 int R, int KZ, int num_tiles, int stages) {
     using Cfg = ZCfg<T>;
     constexpr int TMZ = Cfg::TMZ, EPB = Cfg::EPB, EPC = Cfg::EPC;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const int kzb = KZ / EPB;
     const uint32_t x_bytes = (uint32_t)kzb * Cfg::BOX_BYTES;
-    const uint32_t w_bytes = (uint32_t)(TMZ * R * sizeof(T));
+    const uint32_t w_bytes = (uint32_t)(TMZ * ldw * sizeof(T));
     const uint32_t stage_bytes = (x_bytes + w_bytes + 1023u) & ~1023u;
     unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* full = (uint64_t*)(base + (size_t)stages * stage_bytes);
@@ -264,7 +264,7 @@ xstream_z_kernel(const __grid_constant__ CUtensorMap tmap_x, const T* __restrict
                 mbar_arrive_expect_tx(&full[s], x_bytes + w_bytes);
                 for (int b = 0; b < kzb; ++b)
                     tma_load_2d(st + b * Cfg::BOX_BYTES, &tmap_x, k_base + b * EPB, row0, &full[s]);
-                bulk_load_1d(st + x_bytes, W + (size_t)row0 * R, w_bytes, &full[s]);
+                bulk_load_1d(st + x_bytes, W + (size_t)row0 * ldw, w_bytes, &full[s]);
                 if (++s == stages) {
                     s = 0;
                     ph ^= 1;
@@ -293,7 +293,7 @@ xstream_z_kernel(const __grid_constant__ CUtensorMap tmap_x, const T* __restrict
         for (int r = 0; r < (active ? TMZ : 0); ++r) {
             T x[EPC];
             *(int4*)x = *(const int4*)(box + swz128(r, chunk));
-            const T* wr = Ws + r * R;
+            const T* wr = Ws + r * ldw;
 #pragma unroll
             for (int c = 0; c < RP; ++c) {
                 const T w = (c < R) ? wr[c] : T(0);
@@ -313,10 +313,118 @@ xstream_z_kernel(const __grid_constant__ CUtensorMap tmap_x, const T* __restrict
 #pragma unroll
     for (int e = 0; e < EPC; ++e) {
         const int k = k_base + tid * EPC + e;
-        if (k < K) {
+        if (active && k < K) {  // inactive (warp-rounding) threads would alias the next k-block's rows
 #pragma unroll
             for (int c = 0; c < RP; ++c)
                 if (c < R) out[(size_t)k * R + c] = acc[e][c];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Z = X^T * W, fp64 tensor-core path.  CTA = (row group, k-block of 128 columns); stage = 8 swizzled boxes
+// [32 rows x 16 doubles] of X plus the W tile [32 x ldw].  Warp w owns the 16 k's of box w (2 m-blocks).
+// MMA roles: M = k index (8), N = factor column (8), K = data rows (4, taken as r0+h+2t so that the swizzled
+// A-fragment reads and the ldw = 4 (mod 8) strided B-fragment reads are bank-conflict free).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kZdTM = 32;
+constexpr int kZdKZ = 128;
+constexpr int kZdBoxBytes = kZdTM * 128;
+constexpr int kZdXBytes = (kZdKZ / 16) * kZdBoxBytes;
+
+template <int NBLK>
+__global__ void __launch_bounds__(kThreads, 1)
+xstream_z_dmma_kernel(const __grid_constant__ CUtensorMap tmap_x, const double* __restrict__ W, int ldw,
+                      double* __restrict__ part, int K, int R, int num_tiles, int stages) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    const uint32_t w_bytes = (uint32_t)(kZdTM * ldw * sizeof(double));
+    const uint32_t stage_bytes = (kZdXBytes + w_bytes + 1023u) & ~1023u;
+    unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* full = (uint64_t*)(base + (size_t)stages * stage_bytes);
+    uint64_t* empty = full + stages;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kConsumerThreads / 32);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    const int k_base = blockIdx.y * kZdKZ;
+    if (warp == kConsumerThreads / 32) {
+        if (lane == 0) {
+            prefetch_tmap(&tmap_x);
+            int s = 0;
+            uint32_t ph = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int row0 = tile * kZdTM;
+                mbar_wait(&empty[s], ph ^ 1);
+                unsigned char* st = base + (size_t)s * stage_bytes;
+                mbar_arrive_expect_tx(&full[s], kZdXBytes + w_bytes);
+#pragma unroll
+                for (int b = 0; b < kZdKZ / 16; ++b)
+                    tma_load_2d(st + b * kZdBoxBytes, &tmap_x, k_base + b * 16, row0, &full[s]);
+                bulk_load_1d(st + kZdXBytes, W + (size_t)row0 * ldw, w_bytes, &full[s]);
+                if (++s == stages) {
+                    s = 0;
+                    ph ^= 1;
+                }
+            }
+        }
+        return;
+    }
+    const int g = lane >> 2, t = lane & 3;
+    double acc[2][NBLK][2];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int n = 0; n < NBLK; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
+    int s = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&full[s], ph);
+        const unsigned char* st = base + (size_t)s * stage_bytes;
+        const unsigned char* box = st + (size_t)warp * kZdBoxBytes;
+        const double* Ws = (const double*)(st + kZdXBytes);
+#pragma unroll
+        for (int rg = 0; rg < kZdTM / 8; ++rg) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const uint32_t row = rg * 8 + h + 2 * t;
+                double a[2], bf[NBLK];
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    const uint32_t kk = 8 * m + g;
+                    a[m] = *(const double*)(box + swz128(row, kk >> 1) + (kk & 1) * 8);
+                }
+                const double* wrow = Ws + row * ldw + g;
+#pragma unroll
+                for (int n = 0; n < NBLK; ++n) bf[n] = wrow[n * 8];
+#pragma unroll
+                for (int m = 0; m < 2; ++m)
+#pragma unroll
+                    for (int n = 0; n < NBLK; ++n) dmma884(acc[m][n][0], acc[m][n][1], a[m], bf[n]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        if (++s == stages) {
+            s = 0;
+            ph ^= 1;
+        }
+    }
+    double* out = part + (size_t)blockIdx.x * K * R;
+#pragma unroll
+    for (int m = 0; m < 2; ++m) {
+        const int k = k_base + warp * 16 + m * 8 + g;
+        if (k < K) {
+#pragma unroll
+            for (int n = 0; n < NBLK; ++n) {
+                const int col = n * 8 + 2 * t;
+                if (col < R) out[(size_t)k * R + col] = acc[m][n][0];
+                if (col + 1 < R) out[(size_t)k * R + col + 1] = acc[m][n][1];
+            }
         }
     }
 }
@@ -473,27 +581,85 @@ int xstream_y_impl(const void* X, long long N, int K, int ldx, const void* C, in
 }
 
 template <typename T, int RP>
-int launch_z(const CUtensorMap& map, const T* W, T* part, int K, int R, int KZ, int num_tiles, dim3 grid, int threads,
-             int stages, size_t smem, cudaStream_t st) {
+int launch_z(const CUtensorMap& map, const T* W, int ldw, T* part, int K, int R, int KZ, int num_tiles, dim3 grid,
+             int threads, int stages, size_t smem, cudaStream_t st) {
     auto kern = xstream_z_kernel<T, RP>;
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, threads, smem, st>>>(map, W, part, K, R, KZ, num_tiles, stages);
+    kern<<<grid, threads, smem, st>>>(map, W, ldw, part, K, R, KZ, num_tiles, stages);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+
+template <int NBLK>
+int launch_z_dmma(const CUtensorMap& map, const double* W, int ldw, double* part, int K, int R, int num_tiles, dim3 grid,
+                  int stages, size_t smem, cudaStream_t st) {
+    auto kern = xstream_z_dmma_kernel<NBLK>;
+    B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, st>>>(map, W, ldw, part, K, R, num_tiles, stages);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+
+int z_ldw_for(int R, int dtype, int variant) {
+    if (variant == B2_VARIANT_DMMA && dtype == B2_F64) {
+        const int nblk = (R + 7) / 8;
+        return 8 * nblk + 4;  // == 4 (mod 8): B-fragment rows r0+2t land in alternating 64-byte bank halves
+    }
+    return R;
+}
+
+int xstream_z_dmma_impl(const void* X, long long N, int K, int ldx, const void* W, int ldw, int R, void* Z, void* ws,
+                        size_t ws_bytes, int max_ctas, cudaStream_t st) {
+    const int NBLK = (R + 7) / 8;
+    B2_REQUIRE(ldw == z_ldw_for(R, B2_F64, B2_VARIANT_DMMA), "xstream_z (DMMA): W row stride must be %d, got %d",
+               z_ldw_for(R, B2_F64, B2_VARIANT_DMMA), ldw);
+    const int kblocks = (K + kZdKZ - 1) / kZdKZ;
+    const int num_tiles = (int)((N + kZdTM - 1) / kZdTM);
+    int groups = b2_num_sms() / kblocks;
+    if (max_ctas > 0 && max_ctas / kblocks < groups) groups = max_ctas / kblocks;
+    if (groups < 1) groups = 1;
+    if (groups > num_tiles) groups = num_tiles;
+    const size_t part_bytes = (size_t)groups * K * R * sizeof(double);
+    B2_REQUIRE(ws_bytes >= part_bytes, "xstream_z workspace too small: need %zu bytes, got %zu", part_bytes, ws_bytes);
+    alignas(64) CUtensorMap map;
+    int rc = encode_x_map(&map, X, N, K, ldx, B2_F64, kZdTM);
+    if (rc != B2_OK) return rc;
+    const uint32_t w_bytes = (uint32_t)(kZdTM * ldw * sizeof(double));
+    const uint32_t stage_bytes = (kZdXBytes + w_bytes + 1023u) & ~1023u;
+    int stages = (int)((224 * 1024) / stage_bytes);
+    if (stages > 8) stages = 8;
+    const size_t smem = (size_t)stages * stage_bytes + 1024 + 2 * stages * sizeof(uint64_t);
+    dim3 grid(groups, kblocks);
+    const double* Wd = (const double*)W;
+    double* part = (double*)ws;
+    switch (NBLK) {
+        case 1: rc = launch_z_dmma<1>(map, Wd, ldw, part, K, R, num_tiles, grid, stages, smem, st); break;
+        case 2: rc = launch_z_dmma<2>(map, Wd, ldw, part, K, R, num_tiles, grid, stages, smem, st); break;
+        case 3: rc = launch_z_dmma<3>(map, Wd, ldw, part, K, R, num_tiles, grid, stages, smem, st); break;
+        default: rc = launch_z_dmma<4>(map, Wd, ldw, part, K, R, num_tiles, grid, stages, smem, st); break;
+    }
+    if (rc != B2_OK) return rc;
+    const int n = K * R;
+    reduce_partials_kernel<double><<<(n + 255) / 256, 256, 0, st>>>(part, (double*)Z, n, groups);
     B2_LAUNCH_CHECK();
     return B2_OK;
 }
 
 template <typename T>
-int xstream_z_impl(const void* X, long long N, int K, int ldx, const void* W, int R, void* Z, void* ws, size_t ws_bytes,
-                   int variant, int max_ctas, cudaStream_t st) {
+int xstream_z_impl(const void* X, long long N, int K, int ldx, const void* W, int ldw, int R, void* Z, void* ws,
+                   size_t ws_bytes, int variant, int max_ctas, cudaStream_t st) {
     using Cfg = ZCfg<T>;
-    (void)variant;
     const int dtype = sizeof(T) == 8 ? B2_F64 : B2_F32;
     B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
-    B2_REQUIRE(((size_t)Cfg::TMZ * R * sizeof(T)) % 16 == 0, "internal: W tile not 16-byte sized");
     if (N == 0) {
         B2_CHECK_CUDA(cudaMemsetAsync(Z, 0, (size_t)K * R * sizeof(T), st));
         return B2_OK;
     }
+    if (variant == B2_VARIANT_DMMA) {
+        B2_REQUIRE(dtype == B2_F64, "the DMMA variant exists for fp64 only");
+        return xstream_z_dmma_impl(X, N, K, ldx, W, ldw, R, Z, ws, ws_bytes, max_ctas, st);
+    }
+    B2_REQUIRE(ldw >= R && ((size_t)Cfg::TMZ * ldw * sizeof(T)) % 16 == 0, "xstream_z: bad W row stride %d", ldw);
     // k-block per CTA: up to 256 consumer threads x EPC k's; rounded to whole 128-byte boxes
     const int kmax = kConsumerThreads * Cfg::EPC;
     const int Kbox = ((K + Cfg::EPB - 1) / Cfg::EPB) * Cfg::EPB;
@@ -515,7 +681,7 @@ int xstream_z_impl(const void* X, long long N, int K, int ldx, const void* W, in
     int rc = encode_x_map(&map, X, N, K, ldx, dtype, Cfg::TMZ);
     if (rc != B2_OK) return rc;
     const uint32_t x_bytes = (uint32_t)(KZ / Cfg::EPB) * Cfg::BOX_BYTES;
-    const uint32_t w_bytes = (uint32_t)(Cfg::TMZ * R * sizeof(T));
+    const uint32_t w_bytes = (uint32_t)(Cfg::TMZ * ldw * sizeof(T));
     const uint32_t stage_bytes = (x_bytes + w_bytes + 1023u) & ~1023u;
     int stages = (int)((224 * 1024) / stage_bytes);
     if (stages > 8) stages = 8;
@@ -526,14 +692,14 @@ int xstream_z_impl(const void* X, long long N, int K, int ldx, const void* W, in
     T* part = (T*)ws;
     const int RP = ((R + 3) / 4) * 4;
     switch (RP) {
-        case 4: rc = launch_z<T, 4>(map, Wt, part, K, R, KZ, num_tiles, grid, threads, stages, smem, st); break;
-        case 8: rc = launch_z<T, 8>(map, Wt, part, K, R, KZ, num_tiles, grid, threads, stages, smem, st); break;
-        case 12: rc = launch_z<T, 12>(map, Wt, part, K, R, KZ, num_tiles, grid, threads, stages, smem, st); break;
-        case 16: rc = launch_z<T, 16>(map, Wt, part, K, R, KZ, num_tiles, grid, threads, stages, smem, st); break;
-        case 20: rc = launch_z<T, 20>(map, Wt, part, K, R, KZ, num_tiles, grid, threads, stages, smem, st); break;
-        case 24: rc = launch_z<T, 24>(map, Wt, part, K, R, KZ, num_tiles, grid, threads, stages, smem, st); break;
-        case 28: rc = launch_z<T, 28>(map, Wt, part, K, R, KZ, num_tiles, grid, threads, stages, smem, st); break;
-        default: rc = launch_z<T, 32>(map, Wt, part, K, R, KZ, num_tiles, grid, threads, stages, smem, st); break;
+        case 4: rc = launch_z<T, 4>(map, Wt, ldw, part, K, R, KZ, num_tiles, grid, threads, stages, smem, st); break;
+        case 8: rc = launch_z<T, 8>(map, Wt, ldw, part, K, R, KZ, num_tiles, grid, threads, stages, smem, st); break;
+        case 12: rc = launch_z<T, 12>(map, Wt, ldw, part, K, R, KZ, num_tiles, grid, threads, stages, smem, st); break;
+        case 16: rc = launch_z<T, 16>(map, Wt, ldw, part, K, R, KZ, num_tiles, grid, threads, stages, smem, st); break;
+        case 20: rc = launch_z<T, 20>(map, Wt, ldw, part, K, R, KZ, num_tiles, grid, threads, stages, smem, st); break;
+        case 24: rc = launch_z<T, 24>(map, Wt, ldw, part, K, R, KZ, num_tiles, grid, threads, stages, smem, st); break;
+        case 28: rc = launch_z<T, 28>(map, Wt, ldw, part, K, R, KZ, num_tiles, grid, threads, stages, smem, st); break;
+        default: rc = launch_z<T, 32>(map, Wt, ldw, part, K, R, KZ, num_tiles, grid, threads, stages, smem, st); break;
     }
     if (rc != B2_OK) return rc;
     const int n = K * R;
@@ -552,11 +718,13 @@ int b2_xstream_y(const void* X, long long n_rows, int K, int ldx, const void* C,
                                                       (cudaStream_t)stream));
 }
 
-int b2_xstream_z(const void* X, long long n_rows, int K, int ldx, const void* W, int R, void* Z, int dtype, void* ws,
-                 size_t ws_bytes, int variant, int max_ctas, void* stream) {
-    B2_DISPATCH_DTYPE(dtype, return xstream_z_impl<T>(X, n_rows, K, ldx, W, R, Z, ws, ws_bytes, variant, max_ctas,
+int b2_xstream_z(const void* X, long long n_rows, int K, int ldx, const void* W, int ldw, int R, void* Z, int dtype,
+                 void* ws, size_t ws_bytes, int variant, int max_ctas, void* stream) {
+    B2_DISPATCH_DTYPE(dtype, return xstream_z_impl<T>(X, n_rows, K, ldx, W, ldw, R, Z, ws, ws_bytes, variant, max_ctas,
                                                       (cudaStream_t)stream));
 }
+
+int b2_xstream_z_ldw(int R, int dtype, int variant) { return z_ldw_for(R, dtype, variant); }
 
 size_t b2_xstream_workspace_bytes(int K, int R, int dtype) {
     const size_t es = dtype == B2_F64 ? 8 : 4;

@@ -57,20 +57,24 @@ def test_xstream_y(N, K, R, variant, dtype):
     assert np.max(np.abs(got - ref) / scale) < tol, np.max(np.abs(got - ref) / scale)
 
 
-@pytest.mark.parametrize("N,K,R", XSTREAM_SHAPES)
+@pytest.mark.parametrize("N,K,R", XSTREAM_SHAPES + [(513, 1024, 8), (64, 1030, 16), (700, 2048, 32), (3000, 1024, 20)])
+@pytest.mark.parametrize("variant", ["fma", "dmma"])
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
-def test_xstream_z(N, K, R, dtype):
+def test_xstream_z(N, K, R, variant, dtype):
     _lib, _ops, _ = _imports()
+    if dtype == "f32" and variant == "dmma":
+        pytest.skip("DMMA is fp64 only")
     tdt = torch.float64 if dtype == "f64" else torch.float32
+    var = _lib.VARIANT_FMA if variant == "fma" else _lib.VARIANT_DMMA
     rs = np.random.RandomState(N * 11 + K)
     Xh, X = packed_x(N, K, tdt, rs)
     W = rs.standard_normal(size=(N, R))
-    Wpad = torch.zeros(((N + 15) // 16 * 16, R), dtype=tdt, device="cuda")
-    Wpad[:N] = dev(W, tdt)
+    Wpad = _ops.alloc_w(N, R, tdt, "cuda", var)
+    Wpad[:N, :R] = dev(W, tdt)
     Z = torch.full((K, R), float("nan"), dtype=tdt, device="cuda")
     ws = _ops.Workspace("cuda", K, R, tdt)
-    _ops.xstream_z(X, N, K, Wpad, Z, ws, _lib.VARIANT_FMA)
-    Wh = Wpad[:N].double().cpu().numpy()
+    _ops.xstream_z(X, N, K, Wpad, Z, ws, var)
+    Wh = Wpad[:N, :R].double().cpu().numpy()
     ref = Xh.T @ Wh
     got = Z.double().cpu().numpy()
     scale = np.abs(Xh).T @ np.abs(Wh) + 1e-300
@@ -90,6 +94,15 @@ def test_xstream_linearity_large():
     C2 = torch.randn((K, R), dtype=torch.float64, device="cuda", generator=g)
     W = torch.randn((N, R), dtype=torch.float64, device="cuda", generator=g)
     ws = _ops.Workspace("cuda", K, R, torch.float64)
+    Zs = []
+    for variant in (_lib.VARIANT_FMA, _lib.VARIANT_DMMA):
+        Wp = _ops.alloc_w(N, R, torch.float64, "cuda", variant)
+        Wp[:N, :R] = W
+        Zv = torch.empty((K, R), dtype=torch.float64, device="cuda")
+        _ops.xstream_z(X, N, K, Wp, Zv, ws, variant)
+        Zs.append(Zv)
+    assert torch.max(torch.abs(Zs[0] - Zs[1])).item() < 1e-8
+    Z = Zs[1]
     Ys = []
     for variant in (_lib.VARIANT_FMA, _lib.VARIANT_DMMA):
         Y1, Y2, Y12 = (torch.empty((N, R), dtype=torch.float64, device="cuda") for _ in range(3))
@@ -99,8 +112,6 @@ def test_xstream_linearity_large():
         assert torch.max(torch.abs(Y12 - (Y1 + Y2))).item() < 1e-10
         Ys.append(Y1)
     assert torch.max(torch.abs(Ys[0] - Ys[1])).item() < 1e-10
-    Z = torch.empty((K, R), dtype=torch.float64, device="cuda")
-    _ops.xstream_z(X, N, K, W, Z, ws, _lib.VARIANT_FMA)
     lhs = torch.sum(Ys[0] * W).item()
     rhs = torch.sum(C1 * Z).item()
     assert abs(lhs - rhs) < 1e-9 * max(1.0, abs(lhs))
@@ -176,9 +187,13 @@ def test_slice_cross_and_rowscale(R):
         np.testing.assert_allclose(rhs[g].cpu().numpy(), np.diag(Bg.T @ Yg), rtol=1e-12, atol=1e-12)
     A = rs.uniform(size=(G, R))
     gor = np.repeat(np.arange(G), sizes).astype(np.int32)
-    W = torch.empty(B.shape, dtype=torch.float64, device="cuda")
+    W = torch.zeros((B.shape[0], R + 4), dtype=torch.float64, device="cuda")
     _ops.rowscale(dev(B), dev(A), dev(gor, torch.int32), B.shape[0], R, W)
-    np.testing.assert_array_equal(W.cpu().numpy(), B * A[gor])
+    np.testing.assert_array_equal(W[:, :R].cpu().numpy(), B * A[gor])
+    assert float(W[:, R:].abs().max()) == 0.0
+    G = torch.empty((R, R), dtype=torch.float64, device="cuda")
+    _ops.gram(W, B.shape[0], G, _ops.Workspace("cuda", 8, R, torch.float64))
+    np.testing.assert_allclose(G.cpu().numpy(), (B * A[gor]).T @ (B * A[gor]), rtol=1e-12, atol=1e-12)
 
 
 def _penalty_cases(O):
@@ -226,6 +241,43 @@ def test_admm_solve_elementwise(mode, R):
         z_ref = np.stack([pen.prox(v[i], rho[gor[i]], None) for i in range(n)])
         np.testing.assert_allclose(a_d.cpu().numpy(), z_ref, rtol=1e-10, atol=1e-11, err_msg=name)
         np.testing.assert_allclose(d_d.cpu().numpy(), v - z_ref, rtol=1e-10, atol=1e-11, err_msg=name)
+
+
+@pytest.mark.parametrize("R", [1, 3, 8, 16, 20, 32])
+@pytest.mark.parametrize("n_pen", [0, 1, 2])
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_admm_local_equals_iterated_admm_solve(R, n_pen, dtype):
+    """The fused whole-inner-loop kernel must reproduce 5 launches of the one-iteration kernel (and W = x o a)."""
+    _lib, _ops, O = _imports()
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    rs = np.random.RandomState(R * 10 + n_pen)
+    G = 7
+    sizes, off, rhs = ragged(rs, G, 1, 50, R)
+    n = rhs.shape[0]
+    gor = dev(np.repeat(np.arange(G), sizes).astype(np.int32), torch.int32)
+    rho = dev(rs.uniform(0.5, 2.0, size=G), tdt)
+    Ms = rs.standard_normal(size=(G, 2 * R, R))
+    Minv = dev(np.stack([np.linalg.inv(m.T @ m + np.eye(R)) for m in Ms]), tdt)
+    scale = dev(rs.uniform(0.5, 1.5, size=(G, R)), tdt)
+    cases = [(_lib.PEN_L1, False, 0.2, 0.0), (_lib.PEN_BOX, False, -0.1, 0.8)][:n_pen]
+    aux0 = [rs.standard_normal(size=(n, R)) for _ in cases]
+    dual0 = [rs.standard_normal(size=(n, R)) for _ in cases]
+    results = []
+    for fused in (False, True):
+        aux, dual = [dev(a, tdt) for a in aux0], [dev(d, tdt) for d in dual0]
+        descs = _ops.make_descs([(c[0], c[1], c[2], c[3], a, d) for c, a, d in zip(cases, aux, dual)])
+        x = torch.zeros((n, R), dtype=tdt, device="cuda")
+        W = torch.zeros((n, R + 4), dtype=tdt, device="cuda")
+        if fused:
+            _ops.admm_local(n, R, dev(rhs, tdt), scale, _lib.GROUP_INDEXED, gor, rho, Minv, descs, n_pen, 5, x, W)
+        else:
+            for _ in range(5):
+                _ops.admm_solve(n, R, dev(rhs, tdt), scale, _lib.GROUP_INDEXED, gor, rho, Minv, descs, n_pen, x)
+            _ops.rowscale(x, scale, gor, n, R, W)
+        results.append([t.double().cpu().numpy() for t in [x, W] + aux + dual])
+    tol = 1e-11 if dtype == "f64" else 2e-4
+    for a, b in zip(*results):
+        np.testing.assert_allclose(a, b, rtol=tol, atol=tol)
 
 
 def test_prox_golden_vectors(golden_dir):

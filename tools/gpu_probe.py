@@ -55,7 +55,9 @@ for (N, K, R, tag) in ((4096 * 256, 512, 16, "c1"), (2048 * 1024, 1024, 20, "c2s
                        (4096 * 512, 256, 8, "c3slice")):
     X = torch.empty((N, K), dtype=torch.float64, device="cuda").normal_()
     C = torch.rand((K, R), dtype=torch.float64, device="cuda")
-    W = torch.rand(((N + 15) // 16 * 16, R), dtype=torch.float64, device="cuda")
+    Wv = {v: _ops.alloc_w(N, R, torch.float64, "cuda", v) for v in (_lib.VARIANT_FMA, _lib.VARIANT_DMMA)}
+    for v in Wv:
+        Wv[v][:N, :R] = torch.rand((N, R), dtype=torch.float64, device="cuda")
     Y = torch.empty((N, R), dtype=torch.float64, device="cuda")
     Z = torch.empty((K, R), dtype=torch.float64, device="cuda")
     ws = _ops.Workspace("cuda", K, R, torch.float64)
@@ -64,9 +66,10 @@ for (N, K, R, tag) in ((4096 * 256, 512, 16, "c1"), (2048 * 1024, 1024, 20, "c2s
         med, mn = ev_time(lambda: _ops.xstream_y(X, N, K, C, Y, ws, variant))
         out[f"y_{tag}_{vn}_gbs"] = xb / med / 1e6
         print(f"xstream_y {tag} {vn}: {med:.3f} ms  {xb / med / 1e6:.0f} GB/s", flush=True)
-    med, mn = ev_time(lambda: _ops.xstream_z(X, N, K, W, Z, ws, _lib.VARIANT_FMA))
-    out[f"z_{tag}_fma_gbs"] = xb / med / 1e6
-    print(f"xstream_z {tag} fma: {med:.3f} ms  {xb / med / 1e6:.0f} GB/s", flush=True)
+    for variant, vn in ((_lib.VARIANT_FMA, "fma"), (_lib.VARIANT_DMMA, "dmma")):
+        med, mn = ev_time(lambda: _ops.xstream_z(X, N, K, Wv[variant], Z, ws, variant))
+        out[f"z_{tag}_{vn}_gbs"] = xb / med / 1e6
+        print(f"xstream_z {tag} {vn}: {med:.3f} ms  {xb / med / 1e6:.0f} GB/s", flush=True)
     o = torch.zeros(1, dtype=torch.float64, device="cuda")
     med, mn = ev_time(lambda: _ops.sumsq(X, N, K, o, ws))
     out[f"sumsq_{tag}_gbs"] = xb / med / 1e6
@@ -79,11 +82,13 @@ for (N, K, R, tag) in ((4096 * 256, 512, 16, "c1"), (2048 * 1024, 1024, 20, "c2s
         med, _ = ev_time(lambda: _ops.xstream_y(X32, N, K, C.float(), Y32, ws32, _lib.VARIANT_FMA))
         print(f"xstream_y f32 {tag}: {med:.3f} ms {xb / 2 / med / 1e6:.0f} GB/s", flush=True)
         out[f"y_{tag}_f32_gbs"] = xb / 2 / med / 1e6
-        med, _ = ev_time(lambda: _ops.xstream_z(X32, N, K, W.float(), Z32, ws32, _lib.VARIANT_FMA))
+        W32 = _ops.alloc_w(N, R, torch.float32, "cuda", _lib.VARIANT_FMA)
+        W32[:N, :R] = torch.rand((N, R), dtype=torch.float32, device="cuda")
+        med, _ = ev_time(lambda: _ops.xstream_z(X32, N, K, W32, Z32, ws32, _lib.VARIANT_FMA))
         print(f"xstream_z f32 {tag}: {med:.3f} ms {xb / 2 / med / 1e6:.0f} GB/s", flush=True)
         out[f"z_{tag}_f32_gbs"] = xb / 2 / med / 1e6
         del X32
-    del X, C, W, Y, Z
+    del X, C, Wv, Y, Z
 
 # outer iteration at config 1 (NN-CMF) through the engine, device-generated data
 from matcouply_b200._engine import AOADMMEngine, PackedMatrices  # noqa: E402
