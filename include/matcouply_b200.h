@@ -137,6 +137,16 @@ size_t b2_unimodal_workspace_bytes(int n_groups, int R, int max_rows);
  *                  optionally basis[row] = V[row] W_g (= P_i). */
 int b2_pf2_polar(const void* S, const void* Delta, const void* rho, int n_groups, int R, void* Wmat, void* num_part,
                  int dtype, void* stream);
+/* Fused row pass of one B-mode inner iteration when pens[0] is PARAFAC2 (one CTA per slice):
+ *   deferred != 0: pens[0].dual holds the pre-image V of the previous prox; P Delta = V (W_g Delta) and
+ *                  dual = V - P Delta are formed on the fly (pens[0].aux is not read);
+ *   deferred == 0: pens[0].aux = P Delta and pens[0].dual are read as stored.
+ *   x = (rho_g * sum_p (aux_p - dual_p) + Y o a_g) Minv_g ; pens[0].dual <- V' = x + dual_pf2 ; S_out[g] = V'^T V' ;
+ *   other penalties: elementwise kinds are finished (aux = prox, dual update), column-coupled kinds get dual <- x + dual.
+ * x / w_out (= x o a_g, row stride ldw) are written only when non-NULL (last inner iteration). */
+int b2_pf2_rowpass(const int64_t* row_off, int n_groups, int R, const void* Y, const void* A, const void* rho,
+                   const void* Minv, const b2_penalty_desc* pens_host, int n_pen, int deferred, const void* Wmat,
+                   const void* Delta, void* x, void* w_out, int ldw, void* S_out, int dtype, void* stream);
 int b2_pf2_delta(const void* num_part, const void* rho, int n_groups, int R, void* Delta_new, void* sums,
                  const void* sums_in, int dtype, void* stream);
 int b2_pf2_apply(void* pd, void* dual, void* basis, const void* Wmat, const void* Delta_new,

@@ -23,6 +23,10 @@ import torch
 from . import _lib, _ops
 
 
+# Kernel-fusion switches (tests flip them to cross-check the fused kernels against the one-kernel-per-step path).
+FUSION_DEFAULTS = {"local": True, "pf2": True}
+
+
 class PackedMatrices:
     """Ragged list of J_i x K matrices packed along rows (``np.concatenate(matrices, 0)``) on the device."""
 
@@ -78,7 +82,7 @@ class _ModeState:
 class AOADMMEngine:
     def __init__(self, packed, rank, regs, l2_penalty=(0, 0, 0), feasibility_penalty_scale=1.0, constant_A=False,
                  constant_B=False, inner_n_iter_max=5, update=(True, True, True), group=None, xstream_variant=None,
-                 fuse_local=True):
+                 fuse_local=None, fuse_pf2=None):
         _lib.load()
         self.p = packed
         self.dev = packed.X.device
@@ -95,7 +99,8 @@ class AOADMMEngine:
         self.group = group
         self.world = 1 if group is None else torch.distributed.get_world_size(group)
         self.variant = _lib.VARIANT_AUTO if xstream_variant is None else xstream_variant
-        self.fuse_local = bool(fuse_local)
+        self.fuse_local = FUSION_DEFAULTS["local"] if fuse_local is None else bool(fuse_local)
+        self.fuse_pf2 = FUSION_DEFAULTS["pf2"] if fuse_pf2 is None else bool(fuse_pf2)
         self.w_fresh = False
         R, I, K, N, dt, dev = self.R, self.I, self.K, self.N, self.dtype, self.dev
 
@@ -311,10 +316,36 @@ class AOADMMEngine:
                             len(st.desc), self.n_inner, st.x, self.Wpad)
             self.w_fresh = True
             return
+        if self.fuse_pf2 and self.n_inner > 0 and st.desc and st.desc[0][0] == _lib.PEN_PARAFAC2:
+            return self._step_B_pf2_fused()
         for _ in range(self.n_inner):
             _ops.admm_solve(self.N, R, self.Y, A, _lib.GROUP_INDEXED, self.gor, self.rhoB, self.MinvB, st.descs_c,
                             len(st.desc), st.x)
             self._column_coupled(st, self.row_off, I, self.max_rows, self.rhoB, self.gor, self.N)
+
+    def _step_B_pf2_fused(self):
+        """PARAFAC2 B-mode inner loop with the fused row pass (csrc/pf2_fused.cu): per inner iteration one pass over
+        the B-state (deferred prox of the previous iteration + solve + other penalties + Gram), the CTA-parallel polar
+        step and the Delta reduction; P Delta / dual are materialised once at the end."""
+        st, R, I = self.modes[1], self.R, self.I
+        A = self.modes[0].x
+        for it in range(self.n_inner):
+            last = it == self.n_inner - 1
+            _ops.pf2_rowpass(self.row_off, I, R, self.Y, A, self.rhoB, self.MinvB, st.descs_c, len(st.desc), it > 0,
+                             self.Wmat, self.Delta, st.x if last else None, self.Wpad if last else None, self.S)
+            for p, (kind, nn, p0, _p1) in enumerate(st.desc):  # column-coupled companions (V is in their dual slot)
+                if kind == _lib.PEN_L2BALL:
+                    _ops.prox_l2ball(st.aux[p], st.dual[p], self.row_off, I, R, p0, nn)
+                elif kind == _lib.PEN_UNIMODAL:
+                    _ops.prox_unimodal(st.aux[p], st.dual[p], self.row_off, I, R, self.max_rows, nn, self.ws)
+            _ops.pf2_polar(self.S, self.Delta, self.rhoB, I, R, self.Wmat, self.num_part)
+            _ops.pf2_delta(self.num_part, self.rhoB, I, R, self.Delta, self.pf2_sums)
+            if self.world > 1:
+                self._allreduce(self.pf2_sums)
+                _ops.pf2_delta(self.num_part, self.rhoB, I, R, self.Delta, None, self.pf2_sums)
+        _ops.pf2_apply(st.aux[0], st.dual[0], None, self.Wmat, self.Delta, self.gor, self.N, R)
+        self.pf2_fresh = True
+        self.w_fresh = True
 
     def _row_local(self, st):
         """True when every penalty of the mode is elementwise (the fused b2_admm_local path applies)."""

@@ -204,3 +204,9 @@ def admm_local(n, R, rhs, rhs_scale, group_mode, group_of_row, rho, Minv, descs,
     call("b2_admm_local", n, R, _ptr(rhs), _ptr(rhs_scale), group_mode, _ptr(group_of_row), _ptr(rho), _ptr(Minv),
          descs, n_pen, n_inner, _ptr(x), _ptr(w_out), 0 if w_out is None else w_out.shape[1], dtype_code(x.dtype),
          _stream())
+
+
+def pf2_rowpass(row_off, n_groups, R, Y, A, rho, Minv, descs, n_pen, deferred, Wmat, Delta, x, w_out, S_out):
+    call("b2_pf2_rowpass", _ptr(row_off), n_groups, R, _ptr(Y), _ptr(A), _ptr(rho), _ptr(Minv), descs, n_pen,
+         int(bool(deferred)), _ptr(Wmat), _ptr(Delta), _ptr(x), _ptr(w_out), 0 if w_out is None else w_out.shape[1],
+         _ptr(S_out), dtype_code(Y.dtype), _stream())

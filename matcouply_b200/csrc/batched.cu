@@ -1,6 +1,6 @@
 // Small dense and batched per-slice math of the AO-ADMM sub-solvers: Gram matrices, feasibility penalties rho,
 // Cholesky-based R x R inverses (one warp per slice), per-slice cross products, and the PARAFAC2 Procrustes step
-// as an R x R Jacobi eigen-decomposition (one warp per slice, matrices in shared memory).
+// materialisation pass (the Procrustes step itself lives in pf2_fused.cu).
 #include <math.h>
 
 #include "common.cuh"
@@ -217,155 +217,7 @@ __global__ void rowscale_kernel(const T* __restrict__ B, const T* __restrict__ A
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------
-// PARAFAC2 Procrustes via the R x R Gram route, one warp per slice, fp64 in shared memory.
-//   G = Delta S Delta^T = Q Lam Q^T (cyclic Jacobi);  W = Delta^T Q Lam^-1/2 Q^T ;  num = rho * W^T S
-// ---------------------------------------------------------------------------------------------------------
-constexpr int kPolarWarps = 2;
-
-__device__ __forceinline__ void warp_matmul(const double* A, const double* Bm, double* Cm, int R, int lane, bool transA,
-                                            bool transB) {
-    // C = op(A) op(B), all R x R row-major in shared memory; lane strides over output elements
-    for (int e = lane; e < R * R; e += 32) {
-        const int i = e / R, j = e - i * R;
-        double s = 0.0;
-        for (int k = 0; k < R; ++k) {
-            const double a = transA ? A[k * R + i] : A[i * R + k];
-            const double b = transB ? Bm[j * R + k] : Bm[k * R + j];
-            s += a * b;
-        }
-        Cm[e] = s;
-    }
-}
-
-template <typename T>
-__global__ void pf2_polar_kernel(const T* __restrict__ S, const T* __restrict__ Delta, const T* __restrict__ rho,
-                                 int n_groups, int R, T* __restrict__ Wmat, double* __restrict__ num_part) {
-    extern __shared__ double psm[];  // per warp: 4 matrices R*R : Sg, G (->work), Q, Tm ; plus shared Delta
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int RR = R * R;
-    double* D = psm;  // Delta, shared by the block
-    double* Sg = psm + RR + (size_t)warp * 4 * RR;
-    double* G = Sg + RR;
-    double* Q = G + RR;
-    double* Tm = Q + RR;
-    for (int e = threadIdx.x; e < RR; e += blockDim.x) D[e] = (double)Delta[e];
-    __syncthreads();
-    const int g = blockIdx.x * kPolarWarps + warp;
-    if (g >= n_groups) return;
-    for (int e = lane; e < RR; e += 32) {
-        Sg[e] = (double)S[(size_t)g * RR + e];
-        Q[e] = (e / R == e % R) ? 1.0 : 0.0;
-    }
-    __syncwarp();
-    warp_matmul(D, Sg, Tm, R, lane, false, false);  // Tm = Delta S
-    __syncwarp();
-    warp_matmul(Tm, D, G, R, lane, false, true);  // G = Delta S Delta^T
-    __syncwarp();
-    // symmetrise (round-off) and take the scale
-    for (int e = lane; e < RR; e += 32) {
-        const int i = e / R, j = e - i * R;
-        if (i < j) {
-            const double v = 0.5 * (G[i * R + j] + G[j * R + i]);
-            G[i * R + j] = v;
-            G[j * R + i] = v;
-        }
-    }
-    __syncwarp();
-    // cyclic Jacobi sweeps; lane k updates row/column entry k of the rotated pair
-    for (int sweep = 0; sweep < 30; ++sweep) {
-        double off = 0.0, dg = 0.0;
-        for (int e = lane; e < RR; e += 32) {
-            const int i = e / R, j = e - i * R;
-            const double v = G[e];
-            if (i == j) dg += v * v; else off += v * v;
-        }
-        off = warp_sum(off);
-        dg = warp_sum(dg);
-        if (off <= 1e-30 * dg || off == 0.0) break;
-        for (int p = 0; p < R - 1; ++p) {
-            for (int q = p + 1; q < R; ++q) {
-                const double apq = G[p * R + q];
-                const double app = G[p * R + p], aqq = G[q * R + q];
-                __syncwarp();
-                if (fabs(apq) <= 1e-300 || fabs(apq) <= 1e-20 * sqrt(fabs(app * aqq))) continue;  // warp-uniform
-                const double tau = (aqq - app) / (2.0 * apq);
-                const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
-                const double c = 1.0 / sqrt(1.0 + t * t), s = t * c;
-                // columns p,q of G (rows k) and of Q
-                if (lane < R) {
-                    const int k = lane;
-                    const double gkp = G[k * R + p], gkq = G[k * R + q];
-                    G[k * R + p] = c * gkp - s * gkq;
-                    G[k * R + q] = s * gkp + c * gkq;
-                    const double qkp = Q[k * R + p], qkq = Q[k * R + q];
-                    Q[k * R + p] = c * qkp - s * qkq;
-                    Q[k * R + q] = s * qkp + c * qkq;
-                }
-                __syncwarp();
-                // rows p,q of G (columns k)
-                if (lane < R) {
-                    const int k = lane;
-                    const double gpk = G[p * R + k], gqk = G[q * R + k];
-                    G[p * R + k] = c * gpk - s * gqk;
-                    G[q * R + k] = s * gpk + c * gqk;
-                }
-                __syncwarp();
-                if (lane == 0) {
-                    G[p * R + q] = 0.0;
-                    G[q * R + p] = 0.0;
-                }
-                __syncwarp();
-            }
-        }
-    }
-    __syncwarp();
-    // lam_k = G[k][k]; Tm = Q diag(lam^-1/2)   (directions with lam <= eps*lam_max are dropped)
-    double lam = lane < R ? G[lane * R + lane] : 0.0;
-    const double lmax = warp_max(lam);
-    const double isq = (lane < R && lam > 1e-28 * lmax && lam > 0.0) ? 1.0 / sqrt(lam) : 0.0;
-    __syncwarp();
-    if (lane < R) G[lane] = isq;  // G is free now: reuse its first row for lam^-1/2
-    __syncwarp();
-    for (int e = lane; e < RR; e += 32) Tm[e] = Q[e] * G[e % R];
-    __syncwarp();
-    warp_matmul(Tm, Q, G, R, lane, false, true);  // G = Q lam^-1/2 Q^T   (symmetric)
-    __syncwarp();
-    warp_matmul(D, G, Tm, R, lane, true, false);  // Tm = Delta^T G = W
-    __syncwarp();
-    for (int e = lane; e < RR; e += 32) Wmat[(size_t)g * RR + e] = (T)Tm[e];
-    warp_matmul(Tm, Sg, G, R, lane, true, false);  // G = W^T S
-    __syncwarp();
-    const double rg = (double)rho[g];
-    for (int e = lane; e < RR; e += 32) num_part[(size_t)g * RR + e] = rg * G[e];
-}
-
-// Delta_new = (sum_g num_part[g]) / (sum_g rho[g]); one block, fixed order per element (pairwise over thread chunks)
-template <typename T>
-__global__ void pf2_delta_kernel(const double* __restrict__ num_part, const T* __restrict__ rho, int n_groups, int RR,
-                                 T* __restrict__ Delta_new, double* __restrict__ sums, const double* __restrict__ sums_in) {
-    __shared__ double scratch[32];
-    __shared__ double tot[B2_MAX_RANK * B2_MAX_RANK + 1];
-    if (sums_in) {
-        for (int e = threadIdx.x; e <= RR; e += blockDim.x) tot[e] = sums_in[e];
-        __syncthreads();
-    } else {
-        for (int e = 0; e <= RR; ++e) {
-            double acc = 0.0;
-            if (e < RR)
-                for (int g = threadIdx.x; g < n_groups; g += blockDim.x) acc += num_part[(size_t)g * RR + e];
-            else
-                for (int g = threadIdx.x; g < n_groups; g += blockDim.x) acc += (double)rho[g];
-            acc = block_sum(acc, scratch);
-            if (threadIdx.x == 0) tot[e] = acc;
-        }
-        __syncthreads();
-        if (sums)
-            for (int e = threadIdx.x; e <= RR; e += blockDim.x) sums[e] = tot[e];
-    }
-    for (int e = threadIdx.x; e < RR; e += blockDim.x) Delta_new[e] = (T)(tot[e] / tot[RR]);
-}
-
+// PARAFAC2: materialise P_i Delta / dual (and optionally P_i) from the pre-image V and W_g (see pf2_fused.cu).
 template <typename T, int RM>
 __global__ void pf2_apply_kernel(T* __restrict__ pd, T* __restrict__ dual, T* __restrict__ basis,
                                  const T* __restrict__ Wmat, const T* __restrict__ Delta_new,
@@ -492,33 +344,6 @@ int b2_rowscale(const void* B, const void* A, const int32_t* group_of_row, long 
     if (blocks > b2_num_sms() * 16) blocks = b2_num_sms() * 16;
     B2_DISPATCH_DTYPE(dtype, {
         rowscale_kernel<T><<<(int)blocks, 256, 0, st>>>((const T*)B, (const T*)A, group_of_row, n, R, (T*)W, ldw);
-        B2_LAUNCH_CHECK();
-    });
-    return B2_OK;
-}
-
-int b2_pf2_polar(const void* S, const void* Delta, const void* rho, int n_groups, int R, void* Wmat, void* num_part,
-                 int dtype, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
-    if (n_groups == 0) return B2_OK;
-    const size_t smem = (size_t)(1 + 4 * kPolarWarps) * R * R * sizeof(double);
-    B2_DISPATCH_DTYPE(dtype, {
-        auto kern = pf2_polar_kernel<T>;
-        B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        kern<<<(n_groups + kPolarWarps - 1) / kPolarWarps, kPolarWarps * 32, smem, st>>>(
-            (const T*)S, (const T*)Delta, (const T*)rho, n_groups, R, (T*)Wmat, (double*)num_part);
-        B2_LAUNCH_CHECK();
-    });
-    return B2_OK;
-}
-
-int b2_pf2_delta(const void* num_part, const void* rho, int n_groups, int R, void* Delta_new, void* sums,
-                 const void* sums_in, int dtype, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
-    B2_DISPATCH_DTYPE(dtype, {
-        pf2_delta_kernel<T><<<1, 1024, 0, st>>>((const double*)num_part, (const T*)rho, n_groups, R * R, (T*)Delta_new,
-                                                (double*)sums, (const double*)sums_in);
         B2_LAUNCH_CHECK();
     });
     return B2_OK;

@@ -1,0 +1,444 @@
+// Fused PARAFAC2 B-mode ADMM path (reference decomposition.py:259-289 with penalties.py:1224-1281).
+//
+// One inner ADMM iteration = three launches:
+//   b2_pf2_rowpass : CTA per slice, one pass over the slice's rows. Per row (4 lanes per row, warp shuffles for the
+//                    R x R products):  [deferred prox of the previous iteration:  pd = V T_g, dual = V - pd]
+//                    -> x = (rho*sum(aux-dual) + Y o a) Minv_g -> V' = x + dual_pf2 (stored in the dual slot)
+//                    -> prox + dual update of the other row-local penalties -> S_g += V'^T V' with DMMA.8x8x4.
+//   b2_pf2_polar   : CTA per slice, parallel-ordering Jacobi eigen-decomposition of Delta S_g Delta^T (R/2 rotations
+//                    at once) -> W_g with P_i = V'_i W_g = polar(V'_i Delta^T), and rho_g W_g^T S_g.
+//   b2_pf2_delta   : two-level fixed-order sum over slices -> Delta_new (sums exposed for the cross-rank all-reduce).
+// The basis matrices P_i and the products P_i Delta are never materialised inside the inner loop: the next row pass
+// applies T_g = W_g Delta_new on the fly ("deferred"), and b2_pf2_apply materialises them once per outer iteration.
+#include "admm_common.cuh"
+
+namespace {
+
+constexpr int kRowsPerPass = 64;  // 256 threads, 4 lanes per row
+
+template <typename T, int CPL>
+__global__ void __launch_bounds__(256)
+pf2_rowpass_kernel(const int64_t* __restrict__ row_off, int R, const T* __restrict__ Y, const T* __restrict__ A,
+                   const T* __restrict__ rho, const T* __restrict__ Minv, PenArgs pa, int deferred,
+                   const T* __restrict__ Wmat, const T* __restrict__ Delta, T* __restrict__ x, T* __restrict__ w_out,
+                   int ldw, T* __restrict__ S_out) {
+    extern __shared__ double rp_smem[];
+    const int RR = R * R;
+    const int NB = (R + 7) / 8;
+    const int LDT = 8 * NB + 4;
+    T* Ms = (T*)rp_smem;                         // Minv_g
+    T* Ts = Ms + RR;                             // T_g = W_g Delta (deferred mode)
+    double* tile = rp_smem + ((2 * RR * sizeof(T) + 7) / 8);  // [kRowsPerPass x LDT] staged V' for the Gram MMA
+    const int g = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, l4 = lane & 3;
+    const long long r_begin = row_off[g], r_end = row_off[g + 1];
+    if (r_begin >= r_end) {
+        for (int e = tid; e < RR; e += blockDim.x) S_out[(size_t)g * RR + e] = T(0);
+        return;
+    }
+    for (int e = tid; e < RR; e += blockDim.x) Ms[e] = Minv[(size_t)g * RR + e];
+    if (deferred) {
+        const T* Wg = Wmat + (size_t)g * RR;
+        for (int e = tid; e < RR; e += blockDim.x) {
+            const int i = e / R, j = e - i * R;
+            T s = T(0);
+            for (int k = 0; k < R; ++k) s = fma(Wg[i * R + k], Delta[k * R + j], s);
+            Ts[e] = s;
+        }
+    }
+    for (int e = tid; e < kRowsPerPass * LDT; e += blockDim.x) tile[e] = 0.0;  // pad columns stay zero
+    __syncthreads();
+
+    const T rg = rho[g];
+    const int c0 = l4 * CPL;
+    T sc[CPL];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) sc[j] = (c0 + j < R) ? A[(size_t)g * R + c0 + j] : T(0);
+    // Gram accumulators: warp w owns 8x8 blocks b = w and w + 8 of the NB x NB block grid
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    const int gq = lane >> 2, tq = lane & 3;
+    const int n_pen = pa.n_pen;
+    const T* pf_aux = (const T*)pa.aux[0];
+    T* pf_dual = (T*)pa.dual[0];
+
+    for (long long row0 = r_begin; row0 < r_end; row0 += kRowsPerPass) {
+        const long long rowid = row0 + (tid >> 2);
+        const bool valid = rowid < r_end;
+        const long long row = valid ? rowid : r_end - 1;
+        const size_t base = (size_t)row * R + c0;
+        T r_[CPL], sh[CPL], dpf[CPL], xv[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) r_[j] = (c0 + j < R) ? Y[base + j] * sc[j] : T(0);
+        if (deferred) {
+            T v_[CPL], pdv[CPL];
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                v_[j] = (c0 + j < R) ? pf_dual[base + j] : T(0);
+                pdv[j] = T(0);
+            }
+#pragma unroll
+            for (int rr = 0; rr < 4 * CPL; ++rr) {
+                const T vr = __shfl_sync(0xffffffffu, v_[rr % CPL], (lane & ~3) | (rr / CPL));
+                if (rr < R) {
+#pragma unroll
+                    for (int j = 0; j < CPL; ++j)
+                        if (c0 + j < R) pdv[j] = fma(vr, Ts[rr * R + c0 + j], pdv[j]);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                dpf[j] = v_[j] - pdv[j];   // dual = V - P Delta          (decomposition.py:282-285)
+                sh[j] = pdv[j] - dpf[j];   // aux - dual = P Delta - dual (penalties.py:1280-1281)
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                const bool in = c0 + j < R;
+                const T pdv = in ? pf_aux[base + j] : T(0);
+                dpf[j] = in ? pf_dual[base + j] : T(0);
+                sh[j] = pdv - dpf[j];
+            }
+        }
+        for (int p = 1; p < n_pen; ++p) {
+            const T* ax = (const T*)pa.aux[p];
+            const T* du = (const T*)pa.dual[p];
+#pragma unroll
+            for (int j = 0; j < CPL; ++j)
+                if (c0 + j < R) sh[j] += ax[base + j] - du[base + j];
+        }
+        T s_[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            s_[j] = rg * sh[j] + r_[j];
+            xv[j] = T(0);
+        }
+#pragma unroll
+        for (int rr = 0; rr < 4 * CPL; ++rr) {
+            const T sr = __shfl_sync(0xffffffffu, s_[rr % CPL], (lane & ~3) | (rr / CPL));
+            if (rr < R) {
+#pragma unroll
+                for (int j = 0; j < CPL; ++j)
+                    if (c0 + j < R) xv[j] = fma(sr, Ms[rr * R + c0 + j], xv[j]);
+            }
+        }
+        // PARAFAC2: V' = x + dual ; stage for the Gram
+        double* trow = tile + (tid >> 2) * LDT + c0;
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            if (c0 + j < R) {
+                const T vnew = xv[j] + dpf[j];
+                if (valid) pf_dual[base + j] = vnew;
+                trow[j] = valid ? (double)vnew : 0.0;
+                if (valid && x) x[base + j] = xv[j];
+                if (valid && w_out) w_out[(size_t)row * ldw + c0 + j] = xv[j] * sc[j];
+            }
+        }
+        for (int p = 1; p < n_pen; ++p) {
+            T* ax = (T*)pa.aux[p];
+            T* du = (T*)pa.dual[p];
+            const int kind = pa.kind[p], nn = pa.nn[p];
+            const bool elementwise = kind == B2_PEN_NONNEG || kind == B2_PEN_BOX || kind == B2_PEN_L1;
+            const T p0 = (T)pa.p0[p], p1 = (T)pa.p1[p];
+#pragma unroll
+            for (int j = 0; j < CPL; ++j) {
+                if (valid && c0 + j < R) {
+                    const T v = xv[j] + du[base + j];
+                    if (elementwise) {
+                        const T z = prox_elem<T>(v, kind, nn, p0, p1, rg);
+                        ax[base + j] = z;
+                        du[base + j] = v - z;
+                    } else {
+                        du[base + j] = v;  // finished by b2_prox_l2ball / b2_prox_unimodal
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // S += tile^T tile.  MMA: M = column i (8), N = column j (8), K = rows (4 per step, r0 + h + 2t)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int b = warp + 8 * u;
+            if (b < NB * NB) {
+                const int bi = b / NB, bj = b - bi * NB;
+#pragma unroll
+                for (int r8 = 0; r8 < kRowsPerPass / 8; ++r8) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const double* rp = tile + (r8 * 8 + h + 2 * tq) * LDT + gq;
+                        dmma884(acc[u][0], acc[u][1], rp[8 * bi], rp[8 * bj]);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int b = warp + 8 * u;
+        if (b < NB * NB) {
+            const int bi = b / NB, bj = b - bi * NB;
+            const int i = 8 * bi + gq, j = 8 * bj + 2 * tq;
+            if (i < R && j < R) S_out[(size_t)g * RR + i * R + j] = (T)acc[u][0];
+            if (i < R && j + 1 < R) S_out[(size_t)g * RR + i * R + j + 1] = (T)acc[u][1];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// CTA-per-slice polar step: G = Delta S Delta^T = Q Lam Q^T by parallel-ordering (round-robin) Jacobi.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int kPolarThreads = 128;
+
+__device__ __forceinline__ void cta_matmul(const double* A, const double* B, double* C, int R, bool transA, bool transB) {
+    for (int e = threadIdx.x; e < R * R; e += blockDim.x) {
+        const int i = e / R, j = e - i * R;
+        double s = 0.0;
+        for (int k = 0; k < R; ++k) s += (transA ? A[k * R + i] : A[i * R + k]) * (transB ? B[j * R + k] : B[k * R + j]);
+        C[e] = s;
+    }
+    __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kPolarThreads)
+pf2_polar_cta_kernel(const T* __restrict__ S, const T* __restrict__ Delta, const T* __restrict__ rho, int R,
+                     T* __restrict__ Wmat, double* __restrict__ num_part) {
+    extern __shared__ double pj_smem[];
+    const int RR = R * R;
+    double* D = pj_smem;
+    double* Sg = D + RR;
+    double* G = Sg + RR;
+    double* Q = G + RR;
+    double* Tm = Q + RR;
+    double* cs = Tm + RR;            // c[16], s[16]
+    int* pq = (int*)(cs + 32);       // p[16], q[16]
+    __shared__ double red[2 * (kPolarThreads / 32)];
+    __shared__ int s_continue;
+    const int g = blockIdx.x, tid = threadIdx.x;
+    for (int e = tid; e < RR; e += blockDim.x) {
+        D[e] = (double)Delta[e];
+        Sg[e] = (double)S[(size_t)g * RR + e];
+        Q[e] = (e / R == e % R) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    cta_matmul(D, Sg, Tm, R, false, false);
+    cta_matmul(Tm, D, G, R, false, true);
+    for (int e = tid; e < RR; e += blockDim.x) {  // symmetrise round-off
+        const int i = e / R, j = e - i * R;
+        if (i < j) {
+            const double v = 0.5 * (G[i * R + j] + G[j * R + i]);
+            G[i * R + j] = v;
+            G[j * R + i] = v;
+        }
+    }
+    __syncthreads();
+    const int Re = R + (R & 1), m = Re - 1, half = Re / 2;
+    for (int sweep = 0; sweep < 40 && R > 1; ++sweep) {
+        double off = 0.0, dg = 0.0;
+        for (int e = tid; e < RR; e += blockDim.x) {
+            const double v = G[e];
+            if (e / R == e % R) dg += v * v; else off += v * v;
+        }
+        off = warp_sum(off);
+        dg = warp_sum(dg);
+        if ((tid & 31) == 0) {
+            red[2 * (tid >> 5)] = off;
+            red[2 * (tid >> 5) + 1] = dg;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            double o = 0.0, d = 0.0;
+            for (int w = 0; w < kPolarThreads / 32; ++w) {
+                o += red[2 * w];
+                d += red[2 * w + 1];
+            }
+            s_continue = (o > 1e-30 * d && o > 0.0) ? 1 : 0;
+        }
+        __syncthreads();
+        if (!s_continue) break;
+        for (int t = 0; t < m; ++t) {
+            if (tid < half) {
+                int p = (tid == 0) ? t : (t + tid) % m;
+                int q = (tid == 0) ? m : (t - tid + m) % m;
+                if (p > q) {
+                    const int tmp = p;
+                    p = q;
+                    q = tmp;
+                }
+                double c = 1.0, s = 0.0;
+                if (q < R) {
+                    const double apq = G[p * R + q], app = G[p * R + p], aqq = G[q * R + q];
+                    if (fabs(apq) > 1e-300 && fabs(apq) > 1e-20 * sqrt(fabs(app * aqq))) {
+                        const double tau = (aqq - app) / (2.0 * apq);
+                        const double tt = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                        c = 1.0 / sqrt(1.0 + tt * tt);
+                        s = tt * c;
+                    }
+                } else {
+                    q = -1;  // dummy partner of an odd rank
+                }
+                pq[tid] = p;
+                pq[16 + tid] = q;
+                cs[tid] = c;
+                cs[16 + tid] = s;
+            }
+            __syncthreads();
+            for (int e = tid; e < half * R; e += blockDim.x) {  // columns p,q of G and Q, row i
+                const int k = e / R, i = e - k * R;
+                const int p = pq[k], q = pq[16 + k];
+                if (q >= 0) {
+                    const double c = cs[k], s = cs[16 + k];
+                    const double gp = G[i * R + p], gq2 = G[i * R + q];
+                    G[i * R + p] = c * gp - s * gq2;
+                    G[i * R + q] = s * gp + c * gq2;
+                    const double qp = Q[i * R + p], qq = Q[i * R + q];
+                    Q[i * R + p] = c * qp - s * qq;
+                    Q[i * R + q] = s * qp + c * qq;
+                }
+            }
+            __syncthreads();
+            for (int e = tid; e < half * R; e += blockDim.x) {  // rows p,q of G, column j
+                const int k = e / R, j = e - k * R;
+                const int p = pq[k], q = pq[16 + k];
+                if (q >= 0) {
+                    const double c = cs[k], s = cs[16 + k];
+                    const double gp = G[p * R + j], gq2 = G[q * R + j];
+                    double np_ = c * gp - s * gq2, nq_ = s * gp + c * gq2;
+                    if (j == q) np_ = 0.0;  // the annihilated pair
+                    if (j == p) nq_ = 0.0;
+                    G[p * R + j] = np_;
+                    G[q * R + j] = nq_;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    // lam^-1/2 (directions with lam <= eps * lam_max dropped)
+    if (tid == 0) {
+        double lmax = 0.0;
+        for (int k = 0; k < R; ++k) lmax = fmax(lmax, G[k * R + k]);
+        cs[0] = lmax;
+    }
+    __syncthreads();
+    const double lmax = cs[0];
+    __syncthreads();
+    for (int e = tid; e < RR; e += blockDim.x) {
+        const int j = e % R;
+        const double lam = G[j * R + j];
+        const double isq = (lam > 1e-28 * lmax && lam > 0.0) ? 1.0 / sqrt(lam) : 0.0;
+        Tm[e] = Q[e] * isq;
+    }
+    __syncthreads();
+    cta_matmul(Tm, Q, G, R, false, true);   // G = Q lam^-1/2 Q^T
+    cta_matmul(D, G, Tm, R, true, false);   // Tm = Delta^T G = W
+    for (int e = tid; e < RR; e += blockDim.x) Wmat[(size_t)g * RR + e] = (T)Tm[e];
+    cta_matmul(Tm, Sg, G, R, true, false);  // G = W^T S
+    const double rg = (double)rho[g];
+    for (int e = tid; e < RR; e += blockDim.x) num_part[(size_t)g * RR + e] = rg * G[e];
+}
+
+// sums[e] = sum_g num_part[g][e] (e < RR) ; sums[RR] = sum_g rho[g].  One block per element, fixed order.
+template <typename T>
+__global__ void pf2_sum_kernel(const double* __restrict__ num_part, const T* __restrict__ rho, int n_groups, int RR,
+                               double* __restrict__ sums) {
+    __shared__ double scratch[32];
+    const int e = blockIdx.x;
+    double acc = 0.0;
+    if (e < RR)
+        for (int g = threadIdx.x; g < n_groups; g += blockDim.x) acc += num_part[(size_t)g * RR + e];
+    else
+        for (int g = threadIdx.x; g < n_groups; g += blockDim.x) acc += (double)rho[g];
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0) sums[e] = acc;
+}
+
+template <typename T>
+__global__ void pf2_normalise_kernel(const double* __restrict__ sums, int RR, T* __restrict__ Delta_new) {
+    for (int e = threadIdx.x; e < RR; e += blockDim.x) Delta_new[e] = (T)(sums[e] / sums[RR]);
+}
+
+template <typename T, int CPL>
+int launch_rowpass(const int64_t* row_off, int n_groups, int R, const void* Y, const void* A, const void* rho,
+                   const void* Minv, const PenArgs& pa, int deferred, const void* Wmat, const void* Delta, void* x,
+                   void* w_out, int ldw, void* S_out, cudaStream_t st) {
+    const int NB = (R + 7) / 8, LDT = 8 * NB + 4;
+    const size_t smem = ((2 * (size_t)R * R * sizeof(T) + 7) / 8) * 8 + (size_t)kRowsPerPass * LDT * sizeof(double);
+    auto kern = pf2_rowpass_kernel<T, CPL>;
+    B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<n_groups, 256, smem, st>>>(row_off, R, (const T*)Y, (const T*)A, (const T*)rho, (const T*)Minv, pa, deferred,
+                                      (const T*)Wmat, (const T*)Delta, (T*)x, (T*)w_out, ldw, (T*)S_out);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b2_pf2_rowpass(const int64_t* row_off, int n_groups, int R, const void* Y, const void* A, const void* rho,
+                   const void* Minv, const b2_penalty_desc* pens, int n_pen, int deferred, const void* Wmat,
+                   const void* Delta, void* x, void* w_out, int ldw, void* S_out, int dtype, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
+    B2_REQUIRE(n_pen >= 1 && pens[0].kind == B2_PEN_PARAFAC2, "b2_pf2_rowpass: pens[0] must be the PARAFAC2 penalty");
+    B2_REQUIRE(!deferred || (Wmat && Delta), "deferred mode needs Wmat and Delta");
+    if (n_groups == 0) return B2_OK;
+    PenArgs pa;
+    {
+        const int rc = b2_pack_penalties(pens, n_pen, &pa);
+        if (rc != B2_OK) return rc;
+    }
+    const int CPL = (R + 3) / 4;
+#define B2_CASE_CPL(C)                                                                                             \
+    case C:                                                                                                        \
+        B2_DISPATCH_DTYPE(dtype, return launch_rowpass<T, C>(row_off, n_groups, R, Y, A, rho, Minv, pa, deferred,  \
+                                                             Wmat, Delta, x, w_out, ldw, S_out, st));              \
+        break
+    switch (CPL) {
+        B2_CASE_CPL(1);
+        B2_CASE_CPL(2);
+        B2_CASE_CPL(3);
+        B2_CASE_CPL(4);
+        B2_CASE_CPL(5);
+        B2_CASE_CPL(6);
+        B2_CASE_CPL(7);
+        B2_CASE_CPL(8);
+    }
+#undef B2_CASE_CPL
+    return B2_OK;
+}
+
+int b2_pf2_polar(const void* S, const void* Delta, const void* rho, int n_groups, int R, void* Wmat, void* num_part,
+                 int dtype, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
+    if (n_groups == 0) return B2_OK;
+    const size_t smem = (size_t)(5 * R * R + 32) * sizeof(double) + 32 * sizeof(int);
+    B2_DISPATCH_DTYPE(dtype, {
+        auto kern = pf2_polar_cta_kernel<T>;
+        B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<n_groups, kPolarThreads, smem, st>>>((const T*)S, (const T*)Delta, (const T*)rho, R, (T*)Wmat,
+                                                    (double*)num_part);
+        B2_LAUNCH_CHECK();
+    });
+    return B2_OK;
+}
+
+int b2_pf2_delta(const void* num_part, const void* rho, int n_groups, int R, void* Delta_new, void* sums,
+                 const void* sums_in, int dtype, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int RR = R * R;
+    B2_REQUIRE(sums_in != nullptr || sums != nullptr, "b2_pf2_delta needs the `sums` scratch (R*R+1 doubles)");
+    B2_DISPATCH_DTYPE(dtype, {
+        if (!sums_in) {
+            pf2_sum_kernel<T><<<RR + 1, 256, 0, st>>>((const double*)num_part, (const T*)rho, n_groups, RR,
+                                                      (double*)sums);
+            B2_LAUNCH_CHECK();
+        }
+        pf2_normalise_kernel<T><<<1, 256, 0, st>>>((const double*)(sums_in ? sums_in : sums), RR, (T*)Delta_new);
+        B2_LAUNCH_CHECK();
+    });
+    return B2_OK;
+}
+
+}  // extern "C"

@@ -167,3 +167,40 @@ def test_edge_cases_and_api_errors():
         cmf_aoadmm(X, 2, init="nonsense")
     out = parafac2_aoadmm(X, 2, n_iter_max=2, non_negative=True, random_state=0, return_admm_vars=True)
     assert len(out) == 2 and isinstance(out[1].auxes[1][0], tuple)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(non_negative=True, parafac2=True, l1_penalty={2: 0.1}),
+    dict(non_negative=True, parafac2=True, unimodal={1: True}, l2_norm_bound=[0, 1, 1]),
+    dict(non_negative=True, lower_bound={2: 0.0}, upper_bound={2: 0.9}),
+])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_fused_kernels_match_stepwise_kernels(kw, dtype):
+    """The fused kernels (b2_admm_local, b2_pf2_rowpass) and the one-kernel-per-step path give the same iterates."""
+    from matcouply_b200 import _engine, cmf_aoadmm
+
+    rs = np.random.RandomState(17)
+    I, K, R = 9, 33, 5
+    Js = list(rs.randint(R, 150, size=I - 1)) + [70]
+    X = [rs.uniform(size=(J, K)).astype(dtype) for J in Js]
+    out = []
+    for fused in (True, False):
+        _engine.FUSION_DEFAULTS.update(local=fused, pf2=fused)
+        try:
+            cmf, admm = cmf_aoadmm(X, R, n_iter_max=6, tol=None, absolute_tol=None, random_state=2,
+                                   return_admm_vars=True, **kw)
+        finally:
+            _engine.FUSION_DEFAULTS.update(local=True, pf2=True)
+        out.append((cmf, admm))
+    tol = 1e-9 if dtype == np.float64 else 2e-3
+    (c1, a1), (c2, a2) = out
+    assert rel(c1[1][0], c2[1][0]) < tol and rel(c1[1][2], c2[1][2]) < tol
+    assert rel(np.concatenate(c1[1][1], 0), np.concatenate(c2[1][1], 0)) < tol
+    for m in range(3):
+        for x1, x2 in zip(a1.duals[m], a2.duals[m]):
+            assert rel(np.concatenate(x1, 0) if m == 1 else x1, np.concatenate(x2, 0) if m == 1 else x2) < 10 * tol
+        for x1, x2 in zip(a1.auxes[m], a2.auxes[m]):
+            if isinstance(x1, tuple):
+                assert rel(x1[1], x2[1]) < 10 * tol and rel(np.concatenate(x1[0], 0), np.concatenate(x2[0], 0)) < 10 * tol
+            else:
+                assert rel(np.concatenate(x1, 0) if m == 1 else x1, np.concatenate(x2, 0) if m == 1 else x2) < 10 * tol
