@@ -88,36 +88,57 @@ __device__ __forceinline__ void pava_pass(const T* __restrict__ col, long long l
             }
         }
     }
-    for (int i = 1; i < len; ++i) {
-        const double yi = (double)col[(REV ? (long long)(n - 1 - i) : (long long)i) * ld];
-        if (has_sec) stk.put(depth++, sec);
-        sec = top;
-        has_sec = true;
-        top.start = i;
-        top.sy = yi;
-        top.sy2 = __dmul_rn(yi, yi);
-        top.level = yi;
-        cum = __dadd_rn(cum, top.sy2);
-        while (has_sec && top.level <= sec.level) {  // `<=` pooling (:53)
-            top.sy = __dadd_rn(top.sy, sec.sy);
-            top.sy2 = __dadd_rn(top.sy2, sec.sy2);
-            top.start = sec.start;
-            top.level = __ddiv_rn(top.sy, (double)(i - top.start + 1));
-            if (depth > 0)
-                sec = stk.get(--depth);
-            else
-                has_sec = false;
-        }
-        const double cnt = (double)(i - top.start + 1);
-        const double levelerror = __dsub_rn(top.sy2, __ddiv_rn(__dmul_rn(top.sy, top.sy), cnt));  // (:57)
-        const double before = has_sec ? sec.err_after : 0.0;
-        top.err_after = (nn && top.level < 0.0) ? cum : __dadd_rn(levelerror, before);  // (:58-62)
-        if (MODE == 0) errR[(size_t)(i + 1) * stride] = top.err_after;
-        if (MODE == 1) {
-            const double cand = __dadd_rn(top.err_after, errR[(size_t)(n - i - 1) * stride]);
-            if (cand < best) {  // strict: first minimum wins (:88-91)
-                best = cand;
-                bidx = i + 1;
+    // The loads of y (and of errR in the forward pass) do not depend on the PAVA state: keep PF of them in flight in
+    // a register ring so that only stack pops stay on the sequential critical path.
+    constexpr int PF = 8;
+    double ybuf[PF], ebuf[PF];
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+        const int i = 1 + u;
+        ybuf[u] = (i < len) ? (double)col[(REV ? (long long)(n - 1 - i) : (long long)i) * ld] : 0.0;
+        ebuf[u] = (MODE == 1 && i < len) ? errR[(size_t)(n - i - 1) * stride] : 0.0;
+    }
+    for (int i0 = 1; i0 < len; i0 += PF) {
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const int i = i0 + u;
+            if (i >= len) break;
+            const double yi = ybuf[u];
+            const double eR = ebuf[u];
+            {
+                const int ip = i + PF;
+                ybuf[u] = (ip < len) ? (double)col[(REV ? (long long)(n - 1 - ip) : (long long)ip) * ld] : 0.0;
+                ebuf[u] = (MODE == 1 && ip < len) ? errR[(size_t)(n - ip - 1) * stride] : 0.0;
+            }
+            if (has_sec) stk.put(depth++, sec);
+            sec = top;
+            has_sec = true;
+            top.start = i;
+            top.sy = yi;
+            top.sy2 = __dmul_rn(yi, yi);
+            top.level = yi;
+            cum = __dadd_rn(cum, top.sy2);
+            while (has_sec && top.level <= sec.level) {  // `<=` pooling (:53)
+                top.sy = __dadd_rn(top.sy, sec.sy);
+                top.sy2 = __dadd_rn(top.sy2, sec.sy2);
+                top.start = sec.start;
+                top.level = __ddiv_rn(top.sy, (double)(i - top.start + 1));
+                if (depth > 0)
+                    sec = stk.get(--depth);
+                else
+                    has_sec = false;
+            }
+            const double cnt = (double)(i - top.start + 1);
+            const double levelerror = __dsub_rn(top.sy2, __ddiv_rn(__dmul_rn(top.sy, top.sy), cnt));  // (:57)
+            const double before = has_sec ? sec.err_after : 0.0;
+            top.err_after = (nn && top.level < 0.0) ? cum : __dadd_rn(levelerror, before);  // (:58-62)
+            if (MODE == 0) errR[(size_t)(i + 1) * stride] = top.err_after;
+            if (MODE == 1) {
+                const double cand = __dadd_rn(top.err_after, eR);
+                if (cand < best) {  // strict: first minimum wins (:88-91)
+                    best = cand;
+                    bidx = i + 1;
+                }
             }
         }
     }
