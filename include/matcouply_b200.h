@@ -143,10 +143,22 @@ int b2_pf2_polar(const void* S, const void* Delta, const void* rho, int n_groups
  *   deferred == 0: pens[0].aux = P Delta and pens[0].dual are read as stored.
  *   x = (rho_g * sum_p (aux_p - dual_p) + Y o a_g) Minv_g ; pens[0].dual <- V' = x + dual_pf2 ; S_out[g] = V'^T V' ;
  *   other penalties: elementwise kinds are finished (aux = prox, dual update), column-coupled kinds get dual <- x + dual.
- * x / w_out (= x o a_g, row stride ldw) are written only when non-NULL (last inner iteration). */
+ * x / w_out (= x o a_g, row stride ldw) / BtB_out[g] = x_g^T x_g are written only when non-NULL (last inner iteration). */
 int b2_pf2_rowpass(const int64_t* row_off, int n_groups, int R, const void* Y, const void* A, const void* rho,
                    const void* Minv, const b2_penalty_desc* pens_host, int n_pen, int deferred, const void* Wmat,
-                   const void* Delta, void* x, void* w_out, int ldw, void* S_out, int dtype, void* stream);
+                   const void* Delta, void* x, void* w_out, int ldw, void* S_out, void* BtB_out, int dtype,
+                   void* stream);
+
+/* ---- per-slice Gram bookkeeping shared by the C- and A-updates (decomposition.py:155, 158, 312-314) ---------------
+ * b2_slice_gram:        BtB[g] = B_g^T B_g                       (DMMA, one CTA per slice)
+ * b2_slice_coldot:      rhs[g][c] = sum_j B[j][c] * Y[j][c]      (= diag(B_g^T X_g C))
+ * b2_weighted_gram_sum: out = sum_g (a_g a_g^T) o BtB[g]         (= sum_i (B_i a_i)^T (B_i a_i)), fixed order
+ * b2_hadamard_bcast:    cross[g] = BtB[g] o CtC */
+int b2_slice_gram(const void* B, const int64_t* row_off, int n_groups, int R, void* BtB, int dtype, void* stream);
+int b2_slice_coldot(const void* B, const void* Y, const int64_t* row_off, int n_groups, int R, void* rhs, int dtype,
+                    void* stream);
+int b2_weighted_gram_sum(const void* BtB, const void* A, int n_groups, int R, void* out, int dtype, void* stream);
+int b2_hadamard_bcast(const void* BtB, const void* CtC, int n_groups, int R, void* cross, int dtype, void* stream);
 int b2_pf2_delta(const void* num_part, const void* rho, int n_groups, int R, void* Delta_new, void* sums,
                  const void* sums_in, int dtype, void* stream);
 int b2_pf2_apply(void* pd, void* dual, void* basis, const void* Wmat, const void* Delta_new,

@@ -142,6 +142,7 @@ class AOADMMEngine:
         self.CtC = z(R, R)
         self.lhsB, self.MinvB, self.rhoB = z(I, R, R), z(I, R, R), z(I)
         self.cross, self.MinvA, self.rhoA, self.rhsA = z(I, R, R), z(I, R, R), z(I), z(I, R)
+        self.BtB = z(I, R, R)  # per-slice Gram B_i^T B_i, refreshed whenever B changes
         self.MinvC, self.rhoC = z(1, R, R), z(1)
         self.rho_max = z(1)
         self.has_pf2 = any(d[0] == _lib.PEN_PARAFAC2 for d in self.modes[1].desc)
@@ -315,6 +316,7 @@ class AOADMMEngine:
             _ops.admm_local(self.N, R, self.Y, A, _lib.GROUP_INDEXED, self.gor, self.rhoB, self.MinvB, st.descs_c,
                             len(st.desc), self.n_inner, st.x, self.Wpad)
             self.w_fresh = True
+            _ops.slice_gram(st.x, self.row_off, I, R, self.BtB)
             return
         if self.fuse_pf2 and self.n_inner > 0 and st.desc and st.desc[0][0] == _lib.PEN_PARAFAC2:
             return self._step_B_pf2_fused()
@@ -322,6 +324,7 @@ class AOADMMEngine:
             _ops.admm_solve(self.N, R, self.Y, A, _lib.GROUP_INDEXED, self.gor, self.rhoB, self.MinvB, st.descs_c,
                             len(st.desc), st.x)
             self._column_coupled(st, self.row_off, I, self.max_rows, self.rhoB, self.gor, self.N)
+        _ops.slice_gram(st.x, self.row_off, I, R, self.BtB)
 
     def _step_B_pf2_fused(self):
         """PARAFAC2 B-mode inner loop with the fused row pass (csrc/pf2_fused.cu): per inner iteration one pass over
@@ -332,7 +335,8 @@ class AOADMMEngine:
         for it in range(self.n_inner):
             last = it == self.n_inner - 1
             _ops.pf2_rowpass(self.row_off, I, R, self.Y, A, self.rhoB, self.MinvB, st.descs_c, len(st.desc), it > 0,
-                             self.Wmat, self.Delta, st.x if last else None, self.Wpad if last else None, self.S)
+                             self.Wmat, self.Delta, st.x if last else None, self.Wpad if last else None, self.S,
+                             self.BtB if last else None)
             for p, (kind, nn, p0, _p1) in enumerate(st.desc):  # column-coupled companions (V is in their dual slot)
                 if kind == _lib.PEN_L2BALL:
                     _ops.prox_l2ball(st.aux[p], st.dual[p], self.row_off, I, R, p0, nn)
@@ -359,7 +363,7 @@ class AOADMMEngine:
             _ops.rowscale(self.modes[1].x, self.modes[0].x, self.gor, self.N, R, self.Wpad)
         self.w_fresh = False
         self._timed("z", lambda: _ops.xstream_z(self.p.X, self.N, K, self.Wpad, self.Z, self.ws, self.variant))
-        _ops.gram(self.Wpad, self.N, self.lhsC, self.ws)
+        _ops.weighted_gram_sum(self.BtB, self.modes[0].x, self.I, R, self.lhsC)  # sum_i (B_i a_i)^T (B_i a_i)
         self._allreduce(self.ZL)
         _ops.rho_from_trace(self.lhsC, 1, R, self.scale, self.rhoC, None)
         _ops.factor_batch(self.lhsC, 1, R, self.rhoC, None, len(st.desc), self.l2[2], self.MinvC)
@@ -378,7 +382,8 @@ class AOADMMEngine:
         C, B = self.modes[2].x, self.modes[1].x
         self._timed("y", lambda: _ops.xstream_y(self.p.X, self.N, self.K, C, self.Y, self.ws, self.variant))
         _ops.gram(C, self.K, self.CtC, self.ws)
-        _ops.slice_cross(B, self.Y, self.row_off, self.I, self.R, self.CtC, self.cross, self.rhsA)
+        _ops.hadamard_bcast(self.BtB, self.CtC, self.I, self.R, self.cross)
+        _ops.slice_coldot(B, self.Y, self.row_off, self.I, self.R, self.rhsA)
 
     def step_A(self):
         """admm_update_A (decomposition.py:120-219) after refresh_products()."""
@@ -403,6 +408,7 @@ class AOADMMEngine:
         _ops.sumsq(self.p.X, self.N, self.K, out, self.ws)
         self._allreduce(out)
         self.normX_sq = float(out.item())
+        _ops.slice_gram(self.modes[1].x, self.row_off, self.I, self.R, self.BtB)
         self.refresh_products()
 
     def outer_iteration(self):

@@ -49,9 +49,13 @@ _SIGNATURES = {
     "b2_prox_unimodal": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _sz, _vp],
     "b2_pf2_polar": [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp],
     "b2_pf2_rowpass": [_vp, _i, _i, _vp, _vp, _vp, _vp, ctypes.POINTER(PenaltyDesc), _i, _i, _vp, _vp, _vp, _vp, _i, _vp,
-                       _i, _vp],
+                       _vp, _i, _vp],
     "b2_pf2_delta": [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp],
     "b2_pf2_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp],
+    "b2_slice_gram": [_vp, _vp, _i, _i, _vp, _i, _vp],
+    "b2_slice_coldot": [_vp, _vp, _vp, _i, _i, _vp, _i, _vp],
+    "b2_weighted_gram_sum": [_vp, _vp, _i, _i, _vp, _i, _vp],
+    "b2_hadamard_bcast": [_vp, _vp, _i, _i, _vp, _i, _vp],
     "b2_reduce_stats": [_vp, _vp, _ll, _vp, _i, _vp, _sz, _vp],
     "b2_fit_terms": [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _sz, _vp],
     "b2_prox_elementwise": [_vp, _vp, _ll, _i, _i, _d, _d, _d, _i, _vp],

@@ -206,7 +206,24 @@ def admm_local(n, R, rhs, rhs_scale, group_mode, group_of_row, rho, Minv, descs,
          _stream())
 
 
-def pf2_rowpass(row_off, n_groups, R, Y, A, rho, Minv, descs, n_pen, deferred, Wmat, Delta, x, w_out, S_out):
+def pf2_rowpass(row_off, n_groups, R, Y, A, rho, Minv, descs, n_pen, deferred, Wmat, Delta, x, w_out, S_out,
+                BtB_out=None):
     call("b2_pf2_rowpass", _ptr(row_off), n_groups, R, _ptr(Y), _ptr(A), _ptr(rho), _ptr(Minv), descs, n_pen,
          int(bool(deferred)), _ptr(Wmat), _ptr(Delta), _ptr(x), _ptr(w_out), 0 if w_out is None else w_out.shape[1],
-         _ptr(S_out), dtype_code(Y.dtype), _stream())
+         _ptr(S_out), _ptr(BtB_out), dtype_code(Y.dtype), _stream())
+
+
+def slice_gram(B, row_off, n_groups, R, BtB):
+    call("b2_slice_gram", _ptr(B), _ptr(row_off), n_groups, R, _ptr(BtB), dtype_code(B.dtype), _stream())
+
+
+def slice_coldot(B, Y, row_off, n_groups, R, rhs):
+    call("b2_slice_coldot", _ptr(B), _ptr(Y), _ptr(row_off), n_groups, R, _ptr(rhs), dtype_code(B.dtype), _stream())
+
+
+def weighted_gram_sum(BtB, A, n_groups, R, out):
+    call("b2_weighted_gram_sum", _ptr(BtB), _ptr(A), n_groups, R, _ptr(out), dtype_code(BtB.dtype), _stream())
+
+
+def hadamard_bcast(BtB, CtC, n_groups, R, cross):
+    call("b2_hadamard_bcast", _ptr(BtB), _ptr(CtC), n_groups, R, _ptr(cross), dtype_code(BtB.dtype), _stream())

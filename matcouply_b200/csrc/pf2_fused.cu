@@ -16,46 +16,127 @@ namespace {
 
 constexpr int kRowsPerPass = 64;  // 256 threads, 4 lanes per row
 
+// Lane-owned column segment padded to a 16-byte multiple so that a row of the R x R operators can be fetched with
+// 128-bit shared loads at compile-time offsets (no runtime-R address arithmetic, no bounds predicates: pad = 0).
 template <typename T, int CPL>
-__global__ void __launch_bounds__(256)
+struct RowLayout {
+    static constexpr int VEC = 16 / (int)sizeof(T);
+    static constexpr int CPLP = (CPL + VEC - 1) / VEC * VEC;
+    static constexpr int LDM = 4 * CPLP;
+    static constexpr int ROWS = 4 * CPL;
+    static constexpr int ELEMS = ROWS * LDM;
+};
+
+// x[j] += sum_rr shfl(s[rr]) * M[rr][lane segment]; M in the padded RowLayout, s distributed over the 4 lanes of a row
+template <typename T, int CPL>
+__device__ __forceinline__ void lane_matvec(const T (&s_)[CPL], const T* __restrict__ mseg, int lane, T (&xv)[CPL]) {
+    using L = RowLayout<T, CPL>;
+#pragma unroll
+    for (int rr = 0; rr < 4 * CPL; ++rr) {
+        const T sr = __shfl_sync(0xffffffffu, s_[rr % CPL], (lane & ~3) | (rr / CPL));
+        T m[L::CPLP];
+#pragma unroll
+        for (int v = 0; v < L::CPLP / L::VEC; ++v) *((int4*)m + v) = *((const int4*)(mseg + rr * L::LDM) + v);
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) xv[j] = fma(sr, m[j], xv[j]);
+    }
+}
+
+// Gram of a staged [64 x LDT] fp64 tile with DMMA: warp w owns the 8x8 blocks b = w, w + 8 of the NB x NB grid.
+template <int NB>
+__device__ __forceinline__ void tile_gram(const double* tile, int warp, int gq, int tq, double (&acc)[2][2]) {
+    constexpr int LDT = 8 * NB + 4;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int b = warp + 8 * u;
+        if (b < NB * NB) {
+            const int bi = b / NB, bj = b - bi * NB;
+#pragma unroll
+            for (int r8 = 0; r8 < kRowsPerPass / 8; ++r8) {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const double* rp = tile + (r8 * 8 + h + 2 * tq) * LDT + gq;
+                    dmma884(acc[u][0], acc[u][1], rp[8 * bi], rp[8 * bj]);
+                }
+            }
+        }
+    }
+}
+
+template <typename T, int NB>
+__device__ __forceinline__ void store_gram(T* __restrict__ out, int R, int warp, int gq, int tq,
+                                           const double (&acc)[2][2]) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int b = warp + 8 * u;
+        if (b < NB * NB) {
+            const int bi = b / NB, bj = b - bi * NB;
+            const int i = 8 * bi + gq, j = 8 * bj + 2 * tq;
+            if (i < R && j < R) out[i * R + j] = (T)acc[u][0];
+            if (i < R && j + 1 < R) out[i * R + j + 1] = (T)acc[u][1];
+        }
+    }
+}
+
+template <typename T, int CPL>
+__global__ void __launch_bounds__(256, 2)
 pf2_rowpass_kernel(const int64_t* __restrict__ row_off, int R, const T* __restrict__ Y, const T* __restrict__ A,
                    const T* __restrict__ rho, const T* __restrict__ Minv, PenArgs pa, int deferred,
                    const T* __restrict__ Wmat, const T* __restrict__ Delta, T* __restrict__ x, T* __restrict__ w_out,
-                   int ldw, T* __restrict__ S_out) {
+                   int ldw, T* __restrict__ S_out, T* __restrict__ BtB_out) {
+    using L = RowLayout<T, CPL>;
     extern __shared__ double rp_smem[];
     const int RR = R * R;
-    const int NB = (R + 7) / 8;
-    const int LDT = 8 * NB + 4;
-    T* Ms = (T*)rp_smem;                         // Minv_g
-    T* Ts = Ms + RR;                             // T_g = W_g Delta (deferred mode)
-    double* tile = rp_smem + ((2 * RR * sizeof(T) + 7) / 8);  // [kRowsPerPass x LDT] staged V' for the Gram MMA
+    constexpr int NB = (CPL + 1) / 2;  // == ceil(R / 8) for every R with ceil(R / 4) == CPL
+    constexpr int LDT = 8 * NB + 4;
+    T* Ms = (T*)rp_smem;                                              // Minv_g, padded layout
+    T* Ts = Ms + L::ELEMS;                                            // T_g = W_g Delta (deferred mode), padded layout
+    double* tile = rp_smem + ((2 * L::ELEMS * sizeof(T) + 7) / 8);    // [64 x LDT] staged V' for the Gram MMA
+    double* tile2 = tile + kRowsPerPass * LDT;                        // [64 x LDT] staged x (only with BtB_out)
     const int g = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, l4 = lane & 3;
     const long long r_begin = row_off[g], r_end = row_off[g + 1];
     if (r_begin >= r_end) {
-        for (int e = tid; e < RR; e += blockDim.x) S_out[(size_t)g * RR + e] = T(0);
+        for (int e = tid; e < RR; e += blockDim.x) {
+            S_out[(size_t)g * RR + e] = T(0);
+            if (BtB_out) BtB_out[(size_t)g * RR + e] = T(0);
+        }
         return;
     }
-    for (int e = tid; e < RR; e += blockDim.x) Ms[e] = Minv[(size_t)g * RR + e];
-    if (deferred) {
-        const T* Wg = Wmat + (size_t)g * RR;
+    for (int e = tid; e < 2 * L::ELEMS; e += blockDim.x) Ms[e] = T(0);
+    if (deferred) {  // stage W_g and Delta (tile memory doubles as scratch before the row loop)
+        T* tw = (T*)tile;
+        T* td = tw + RR;
         for (int e = tid; e < RR; e += blockDim.x) {
-            const int i = e / R, j = e - i * R;
-            T s = T(0);
-            for (int k = 0; k < R; ++k) s = fma(Wg[i * R + k], Delta[k * R + j], s);
-            Ts[e] = s;
+            tw[e] = Wmat[(size_t)g * RR + e];
+            td[e] = Delta[e];
         }
     }
-    for (int e = tid; e < kRowsPerPass * LDT; e += blockDim.x) tile[e] = 0.0;  // pad columns stay zero
+    __syncthreads();
+    for (int e = tid; e < RR; e += blockDim.x) {
+        const int i = e / R, c = e - i * R;
+        const int dst = i * L::LDM + (c / CPL) * L::CPLP + (c % CPL);
+        Ms[dst] = Minv[(size_t)g * RR + e];
+        if (deferred) {
+            const T* tw = (const T*)tile;
+            const T* td = tw + RR;
+            T s = T(0);
+            for (int k = 0; k < R; ++k) s = fma(tw[i * R + k], td[k * R + c], s);
+            Ts[dst] = s;
+        }
+    }
+    __syncthreads();
+    for (int e = tid; e < 2 * kRowsPerPass * LDT; e += blockDim.x) tile[e] = 0.0;  // pad columns stay zero
     __syncthreads();
 
     const T rg = rho[g];
     const int c0 = l4 * CPL;
+    const T* mseg = Ms + l4 * L::CPLP;
+    const T* tseg = Ts + l4 * L::CPLP;
     T sc[CPL];
 #pragma unroll
     for (int j = 0; j < CPL; ++j) sc[j] = (c0 + j < R) ? A[(size_t)g * R + c0 + j] : T(0);
-    // Gram accumulators: warp w owns 8x8 blocks b = w and w + 8 of the NB x NB block grid
-    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    double accS[2][2] = {{0.0, 0.0}, {0.0, 0.0}}, accB[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
     const int gq = lane >> 2, tq = lane & 3;
     const int n_pen = pa.n_pen;
     const T* pf_aux = (const T*)pa.aux[0];
@@ -76,15 +157,7 @@ pf2_rowpass_kernel(const int64_t* __restrict__ row_off, int R, const T* __restri
                 v_[j] = (c0 + j < R) ? pf_dual[base + j] : T(0);
                 pdv[j] = T(0);
             }
-#pragma unroll
-            for (int rr = 0; rr < 4 * CPL; ++rr) {
-                const T vr = __shfl_sync(0xffffffffu, v_[rr % CPL], (lane & ~3) | (rr / CPL));
-                if (rr < R) {
-#pragma unroll
-                    for (int j = 0; j < CPL; ++j)
-                        if (c0 + j < R) pdv[j] = fma(vr, Ts[rr * R + c0 + j], pdv[j]);
-                }
-            }
+            lane_matvec<T, CPL>(v_, tseg, lane, pdv);
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
                 dpf[j] = v_[j] - pdv[j];   // dual = V - P Delta          (decomposition.py:282-285)
@@ -112,16 +185,8 @@ pf2_rowpass_kernel(const int64_t* __restrict__ row_off, int R, const T* __restri
             s_[j] = rg * sh[j] + r_[j];
             xv[j] = T(0);
         }
-#pragma unroll
-        for (int rr = 0; rr < 4 * CPL; ++rr) {
-            const T sr = __shfl_sync(0xffffffffu, s_[rr % CPL], (lane & ~3) | (rr / CPL));
-            if (rr < R) {
-#pragma unroll
-                for (int j = 0; j < CPL; ++j)
-                    if (c0 + j < R) xv[j] = fma(sr, Ms[rr * R + c0 + j], xv[j]);
-            }
-        }
-        // PARAFAC2: V' = x + dual ; stage for the Gram
+        lane_matvec<T, CPL>(s_, mseg, lane, xv);
+        // PARAFAC2: V' = x + dual ; stage for the Gram(s)
         double* trow = tile + (tid >> 2) * LDT + c0;
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
@@ -129,6 +194,7 @@ pf2_rowpass_kernel(const int64_t* __restrict__ row_off, int R, const T* __restri
                 const T vnew = xv[j] + dpf[j];
                 if (valid) pf_dual[base + j] = vnew;
                 trow[j] = valid ? (double)vnew : 0.0;
+                if (BtB_out) trow[kRowsPerPass * LDT + j] = valid ? (double)xv[j] : 0.0;
                 if (valid && x) x[base + j] = xv[j];
                 if (valid && w_out) w_out[(size_t)row * ldw + c0 + j] = xv[j] * sc[j];
             }
@@ -154,34 +220,90 @@ pf2_rowpass_kernel(const int64_t* __restrict__ row_off, int R, const T* __restri
             }
         }
         __syncthreads();
-        // S += tile^T tile.  MMA: M = column i (8), N = column j (8), K = rows (4 per step, r0 + h + 2t)
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int b = warp + 8 * u;
-            if (b < NB * NB) {
-                const int bi = b / NB, bj = b - bi * NB;
-#pragma unroll
-                for (int r8 = 0; r8 < kRowsPerPass / 8; ++r8) {
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const double* rp = tile + (r8 * 8 + h + 2 * tq) * LDT + gq;
-                        dmma884(acc[u][0], acc[u][1], rp[8 * bi], rp[8 * bj]);
-                    }
-                }
-            }
-        }
+        // S += V'^T V' (and B^T B += x^T x).  MMA: M = column i (8), N = column j (8), K = rows (r0 + h + 2t)
+        tile_gram<NB>(tile, warp, gq, tq, accS);
+        if (BtB_out) tile_gram<NB>(tile2, warp, gq, tq, accB);
         __syncthreads();
     }
+    store_gram<T, NB>(S_out + (size_t)g * RR, R, warp, gq, tq, accS);
+    if (BtB_out) store_gram<T, NB>(BtB_out + (size_t)g * RR, R, warp, gq, tq, accB);
+}
+
+// Per-slice Gram B_g^T B_g with the same staged-tile DMMA scheme (used after the non-PARAFAC2 B-updates and at start-up)
+template <typename T, int CPL>
+__global__ void __launch_bounds__(256)
+slice_gram_kernel(const T* __restrict__ B, const int64_t* __restrict__ row_off, int R, T* __restrict__ BtB) {
+    extern __shared__ double rp_smem[];
+    const int RR = R * R;
+    constexpr int NB = (CPL + 1) / 2;
+    constexpr int LDT = 8 * NB + 4;
+    double* tile = rp_smem;
+    const int g = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, l4 = lane & 3;
+    const long long r_begin = row_off[g], r_end = row_off[g + 1];
+    for (int e = tid; e < kRowsPerPass * LDT; e += blockDim.x) tile[e] = 0.0;
+    __syncthreads();
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    const int gq = lane >> 2, tq = lane & 3, c0 = l4 * CPL;
+    for (long long row0 = r_begin; row0 < r_end; row0 += kRowsPerPass) {
+        const long long row = row0 + (tid >> 2);
+        const bool valid = row < r_end;
+        double* trow = tile + (tid >> 2) * LDT + c0;
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const int b = warp + 8 * u;
-        if (b < NB * NB) {
-            const int bi = b / NB, bj = b - bi * NB;
-            const int i = 8 * bi + gq, j = 8 * bj + 2 * tq;
-            if (i < R && j < R) S_out[(size_t)g * RR + i * R + j] = (T)acc[u][0];
-            if (i < R && j + 1 < R) S_out[(size_t)g * RR + i * R + j + 1] = (T)acc[u][1];
-        }
+        for (int j = 0; j < CPL; ++j)
+            if (c0 + j < R) trow[j] = valid ? (double)B[(size_t)row * R + c0 + j] : 0.0;
+        __syncthreads();
+        tile_gram<NB>(tile, warp, gq, tq, acc);
+        __syncthreads();
     }
+    store_gram<T, NB>(BtB + (size_t)g * RR, R, warp, gq, tq, acc);
+}
+
+// rhs[g][c] = sum_j B[j][c] * Y[j][c] over the rows of slice g (= diag(B_g^T X_g C), decomposition.py:158); fixed order
+template <typename T>
+__global__ void __launch_bounds__(256)
+slice_coldot_kernel(const T* __restrict__ B, const T* __restrict__ Y, const int64_t* __restrict__ row_off, int R,
+                    T* __restrict__ rhs) {
+    __shared__ double part[256];
+    const int g = blockIdx.x, tid = threadIdx.x;
+    const long long r_begin = row_off[g], r_end = row_off[g + 1];
+    const long long cnt = (r_end - r_begin) * R;
+    const int tpr = (int)blockDim.x / R * R;  // active threads: multiple of R so a thread always sees one column
+    double acc = 0.0;
+    if (tid < tpr) {
+        const T* Bg = B + r_begin * R;
+        const T* Yg = Y + r_begin * R;
+        for (long long e = tid; e < cnt; e += tpr) acc += (double)Bg[e] * (double)Yg[e];
+    }
+    part[tid] = tid < tpr ? acc : 0.0;
+    __syncthreads();
+    if (tid < R) {
+        double s = 0.0;
+        for (int t = tid; t < tpr; t += R) s += part[t];
+        rhs[(size_t)g * R + tid] = (T)s;
+    }
+}
+
+// lhs (R x R) = sum_g (a_g a_g^T) o BtB_g  (= sum_i (B_i a_i)^T (B_i a_i), decomposition.py:312-314); one block per
+// output element, fixed summation order over slices.
+template <typename T>
+__global__ void weighted_gram_sum_kernel(const T* __restrict__ BtB, const T* __restrict__ A, int n_groups, int R,
+                                         T* __restrict__ out) {
+    __shared__ double scratch[32];
+    const int e = blockIdx.x, i = e / R, j = e - i * R;
+    double acc = 0.0;
+    for (int g = threadIdx.x; g < n_groups; g += blockDim.x)
+        acc += (double)BtB[(size_t)g * R * R + e] * (double)A[(size_t)g * R + i] * (double)A[(size_t)g * R + j];
+    acc = block_sum(acc, scratch);
+    if (threadIdx.x == 0) out[e] = (T)acc;
+}
+
+// cross[g] = BtB[g] o CtC  (decomposition.py:155)
+template <typename T>
+__global__ void hadamard_bcast_kernel(const T* __restrict__ BtB, const T* __restrict__ CtC, long long total, int RR,
+                                      T* __restrict__ cross) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
+        cross[i] = BtB[i] * CtC[i % RR];
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -252,7 +374,7 @@ pf2_polar_cta_kernel(const T* __restrict__ S, const T* __restrict__ Delta, const
                 o += red[2 * w];
                 d += red[2 * w + 1];
             }
-            s_continue = (o > 1e-30 * d && o > 0.0) ? 1 : 0;
+            s_continue = (o > 1e-26 * d && o > 0.0) ? 1 : 0;  // off/diag <= 1e-13: eigenvectors at round-off
         }
         __syncthreads();
         if (!s_continue) break;
@@ -360,13 +482,23 @@ __global__ void pf2_normalise_kernel(const double* __restrict__ sums, int RR, T*
 template <typename T, int CPL>
 int launch_rowpass(const int64_t* row_off, int n_groups, int R, const void* Y, const void* A, const void* rho,
                    const void* Minv, const PenArgs& pa, int deferred, const void* Wmat, const void* Delta, void* x,
-                   void* w_out, int ldw, void* S_out, cudaStream_t st) {
+                   void* w_out, int ldw, void* S_out, void* BtB_out, cudaStream_t st) {
+    using L = RowLayout<T, CPL>;
     const int NB = (R + 7) / 8, LDT = 8 * NB + 4;
-    const size_t smem = ((2 * (size_t)R * R * sizeof(T) + 7) / 8) * 8 + (size_t)kRowsPerPass * LDT * sizeof(double);
+    const size_t smem = ((2 * (size_t)L::ELEMS * sizeof(T) + 7) / 8) * 8 + 2 * (size_t)kRowsPerPass * LDT * sizeof(double);
     auto kern = pf2_rowpass_kernel<T, CPL>;
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<n_groups, 256, smem, st>>>(row_off, R, (const T*)Y, (const T*)A, (const T*)rho, (const T*)Minv, pa, deferred,
-                                      (const T*)Wmat, (const T*)Delta, (T*)x, (T*)w_out, ldw, (T*)S_out);
+                                      (const T*)Wmat, (const T*)Delta, (T*)x, (T*)w_out, ldw, (T*)S_out, (T*)BtB_out);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+
+template <typename T, int CPL>
+int launch_slice_gram(const void* B, const int64_t* row_off, int n_groups, int R, void* BtB, cudaStream_t st) {
+    const int NB = (R + 7) / 8, LDT = 8 * NB + 4;
+    const size_t smem = (size_t)kRowsPerPass * LDT * sizeof(double);
+    slice_gram_kernel<T, CPL><<<n_groups, 256, smem, st>>>((const T*)B, row_off, R, (T*)BtB);
     B2_LAUNCH_CHECK();
     return B2_OK;
 }
@@ -377,7 +509,8 @@ extern "C" {
 
 int b2_pf2_rowpass(const int64_t* row_off, int n_groups, int R, const void* Y, const void* A, const void* rho,
                    const void* Minv, const b2_penalty_desc* pens, int n_pen, int deferred, const void* Wmat,
-                   const void* Delta, void* x, void* w_out, int ldw, void* S_out, int dtype, void* stream) {
+                   const void* Delta, void* x, void* w_out, int ldw, void* S_out, void* BtB_out, int dtype,
+                   void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
     B2_REQUIRE(n_pen >= 1 && pens[0].kind == B2_PEN_PARAFAC2, "b2_pf2_rowpass: pens[0] must be the PARAFAC2 penalty");
@@ -392,7 +525,7 @@ int b2_pf2_rowpass(const int64_t* row_off, int n_groups, int R, const void* Y, c
 #define B2_CASE_CPL(C)                                                                                             \
     case C:                                                                                                        \
         B2_DISPATCH_DTYPE(dtype, return launch_rowpass<T, C>(row_off, n_groups, R, Y, A, rho, Minv, pa, deferred,  \
-                                                             Wmat, Delta, x, w_out, ldw, S_out, st));              \
+                                                             Wmat, Delta, x, w_out, ldw, S_out, BtB_out, st));     \
         break
     switch (CPL) {
         B2_CASE_CPL(1);
@@ -436,6 +569,63 @@ int b2_pf2_delta(const void* num_part, const void* rho, int n_groups, int R, voi
             B2_LAUNCH_CHECK();
         }
         pf2_normalise_kernel<T><<<1, 256, 0, st>>>((const double*)(sums_in ? sums_in : sums), RR, (T*)Delta_new);
+        B2_LAUNCH_CHECK();
+    });
+    return B2_OK;
+}
+
+int b2_slice_gram(const void* B, const int64_t* row_off, int n_groups, int R, void* BtB, int dtype, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
+    if (n_groups == 0) return B2_OK;
+    const int CPL = (R + 3) / 4;
+#define B2_CASE_CPL(C)                                                                                    \
+    case C:                                                                                               \
+        B2_DISPATCH_DTYPE(dtype, return launch_slice_gram<T, C>(B, row_off, n_groups, R, BtB, st));       \
+        break
+    switch (CPL) {
+        B2_CASE_CPL(1);
+        B2_CASE_CPL(2);
+        B2_CASE_CPL(3);
+        B2_CASE_CPL(4);
+        B2_CASE_CPL(5);
+        B2_CASE_CPL(6);
+        B2_CASE_CPL(7);
+        B2_CASE_CPL(8);
+    }
+#undef B2_CASE_CPL
+    return B2_OK;
+}
+
+int b2_slice_coldot(const void* B, const void* Y, const int64_t* row_off, int n_groups, int R, void* rhs, int dtype,
+                    void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
+    if (n_groups == 0) return B2_OK;
+    B2_DISPATCH_DTYPE(dtype, {
+        slice_coldot_kernel<T><<<n_groups, 256, 0, st>>>((const T*)B, (const T*)Y, row_off, R, (T*)rhs);
+        B2_LAUNCH_CHECK();
+    });
+    return B2_OK;
+}
+
+int b2_weighted_gram_sum(const void* BtB, const void* A, int n_groups, int R, void* out, int dtype, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    B2_DISPATCH_DTYPE(dtype, {
+        weighted_gram_sum_kernel<T><<<R * R, 256, 0, st>>>((const T*)BtB, (const T*)A, n_groups, R, (T*)out);
+        B2_LAUNCH_CHECK();
+    });
+    return B2_OK;
+}
+
+int b2_hadamard_bcast(const void* BtB, const void* CtC, int n_groups, int R, void* cross, int dtype, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_groups == 0) return B2_OK;
+    const long long total = (long long)n_groups * R * R;
+    long long blocks = (total + 255) / 256;
+    if (blocks > b2_num_sms() * 8) blocks = b2_num_sms() * 8;
+    B2_DISPATCH_DTYPE(dtype, {
+        hadamard_bcast_kernel<T><<<(int)blocks, 256, 0, st>>>((const T*)BtB, (const T*)CtC, total, R * R, (T*)cross);
         B2_LAUNCH_CHECK();
     });
     return B2_OK;

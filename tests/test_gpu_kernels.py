@@ -426,3 +426,42 @@ def test_errors_are_reported_not_swallowed():
         _ops.xstream_y(X, 4, 4, C, Y, ws)
     with pytest.raises(RuntimeError, match="CUDA tensors"):
         _ops.xstream_y(X.cpu(), 4, 4, C, Y, ws)
+
+
+@pytest.mark.parametrize("R", [1, 3, 8, 12, 16, 20, 27, 32])
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_slice_gram_family(R, dtype):
+    """b2_slice_gram (DMMA), b2_slice_coldot, b2_weighted_gram_sum, b2_hadamard_bcast vs NumPy."""
+    _lib, _ops, _ = _imports()
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    rs = np.random.RandomState(R)
+    G = 11
+    sizes, off, B = ragged(rs, G, 1, 200, R)
+    sizes[3] = 0  # an empty slice
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    B = B[: off[-1]]
+    Y = rs.standard_normal(size=B.shape)
+    A = rs.uniform(size=(G, R))
+    CtC = rs.standard_normal(size=(R, R))
+    Bd, Yd, offd = dev(B, tdt), dev(Y, tdt), dev(off, torch.int64)
+    Bh, Yh = Bd.double().cpu().numpy(), Yd.double().cpu().numpy()
+    BtB = torch.full((G, R, R), float("nan"), dtype=tdt, device="cuda")
+    _ops.slice_gram(Bd, offd, G, R, BtB)
+    ref = np.stack([Bh[off[g]:off[g + 1]].T @ Bh[off[g]:off[g + 1]] for g in range(G)])
+    tol = 1e-12 if dtype == "f64" else 2e-5
+    np.testing.assert_allclose(BtB.double().cpu().numpy(), ref, rtol=tol, atol=tol * 200)
+    rhs = torch.full((G, R), float("nan"), dtype=tdt, device="cuda")
+    _ops.slice_coldot(Bd, Yd, offd, G, R, rhs)
+    ref_rhs = np.stack([np.sum(Bh[off[g]:off[g + 1]] * Yh[off[g]:off[g + 1]], axis=0) for g in range(G)])
+    np.testing.assert_allclose(rhs.double().cpu().numpy(), ref_rhs, rtol=tol, atol=tol * 200)
+    Ad = dev(A, tdt)
+    Ah = Ad.double().cpu().numpy()
+    lhs = torch.empty((R, R), dtype=tdt, device="cuda")
+    _ops.weighted_gram_sum(BtB, Ad, G, R, lhs)
+    BtBh = BtB.double().cpu().numpy()
+    np.testing.assert_allclose(lhs.double().cpu().numpy(), sum(np.outer(a, a) * M for a, M in zip(Ah, BtBh)),
+                               rtol=tol * 10, atol=tol * 200)
+    cross = torch.empty((G, R, R), dtype=tdt, device="cuda")
+    Cd = dev(CtC, tdt)
+    _ops.hadamard_bcast(BtB, Cd, G, R, cross)
+    np.testing.assert_allclose(cross.double().cpu().numpy(), BtBh * Cd.double().cpu().numpy(), rtol=tol)
