@@ -110,10 +110,13 @@ int b2_admm_solve(long long n, int R, const void* rhs, const void* rhs_scale, in
 /* Whole inner ADMM loop in one pass for modes whose penalties are all row-local (NONNEG, BOX, L1; n_pen <= 2):
  * `n_inner` iterations of the update above with the row state held in registers (decomposition.py:259-289, 325-342,
  * 176-217).  If w_out != NULL also writes w_out[row][0:R] = x[row] o rhs_scale[g] (row stride ldw) — the scaled
- * factor B_i * a_i consumed by b2_xstream_z. */
+ * factor B_i * a_i consumed by b2_xstream_z.  With group_mode INDEXED and row_off != NULL (or group_mode SINGLE) the
+ * kernel runs one CTA per group with Minv_g staged in shared memory; BtB_out (optional, INDEXED + row_off only)
+ * receives B_g^T B_g of the new x. */
 int b2_admm_local(long long n, int R, const void* rhs, const void* rhs_scale, int group_mode,
-                  const int32_t* group_of_row, const void* rho, const void* Minv, const b2_penalty_desc* pens_host,
-                  int n_pen, int n_inner, void* x, void* w_out, int ldw, int dtype, void* stream);
+                  const int32_t* group_of_row, const int64_t* row_off, int n_groups, const void* rho, const void* Minv,
+                  const b2_penalty_desc* pens_host, int n_pen, int n_inner, void* x, void* w_out, int ldw,
+                  void* BtB_out, int dtype, void* stream);
 
 /* ---- column-coupled proximal operators (V arrives in `dual`, see b2_admm_solve) --------------------------------*/
 /* L2Ball (penalties.py:920-925): per group and column  aux = clip(V)*bound/max(||clip(V)_col||, bound); dual = V - aux. */

@@ -314,9 +314,9 @@ class AOADMMEngine:
         if self._row_local(st):  # whole inner loop in one fused pass, W = B o a emitted for the Z pass
             # W = B o a stays valid for the C-step: A only changes after the C-step (decomposition.py:948-988)
             _ops.admm_local(self.N, R, self.Y, A, _lib.GROUP_INDEXED, self.gor, self.rhoB, self.MinvB, st.descs_c,
-                            len(st.desc), self.n_inner, st.x, self.Wpad)
+                            len(st.desc), self.n_inner, st.x, self.Wpad, row_off=self.row_off, n_groups=I,
+                            BtB_out=self.BtB)
             self.w_fresh = True
-            _ops.slice_gram(st.x, self.row_off, I, R, self.BtB)
             return
         if self.fuse_pf2 and self.n_inner > 0 and st.desc and st.desc[0][0] == _lib.PEN_PARAFAC2:
             return self._step_B_pf2_fused()

@@ -200,10 +200,11 @@ def to_device(a, dtype, device):
     return torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).to(device)
 
 
-def admm_local(n, R, rhs, rhs_scale, group_mode, group_of_row, rho, Minv, descs, n_pen, n_inner, x, w_out=None):
-    call("b2_admm_local", n, R, _ptr(rhs), _ptr(rhs_scale), group_mode, _ptr(group_of_row), _ptr(rho), _ptr(Minv),
-         descs, n_pen, n_inner, _ptr(x), _ptr(w_out), 0 if w_out is None else w_out.shape[1], dtype_code(x.dtype),
-         _stream())
+def admm_local(n, R, rhs, rhs_scale, group_mode, group_of_row, rho, Minv, descs, n_pen, n_inner, x, w_out=None,
+               row_off=None, n_groups=0, BtB_out=None):
+    call("b2_admm_local", n, R, _ptr(rhs), _ptr(rhs_scale), group_mode, _ptr(group_of_row), _ptr(row_off), n_groups,
+         _ptr(rho), _ptr(Minv), descs, n_pen, n_inner, _ptr(x), _ptr(w_out),
+         0 if w_out is None else w_out.shape[1], _ptr(BtB_out), dtype_code(x.dtype), _stream())
 
 
 def pf2_rowpass(row_off, n_groups, R, Y, A, rho, Minv, descs, n_pen, deferred, Wmat, Delta, x, w_out, S_out,

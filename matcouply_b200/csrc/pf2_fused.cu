@@ -14,70 +14,6 @@
 
 namespace {
 
-constexpr int kRowsPerPass = 64;  // 256 threads, 4 lanes per row
-
-// Lane-owned column segment padded to a 16-byte multiple so that a row of the R x R operators can be fetched with
-// 128-bit shared loads at compile-time offsets (no runtime-R address arithmetic, no bounds predicates: pad = 0).
-template <typename T, int CPL>
-struct RowLayout {
-    static constexpr int VEC = 16 / (int)sizeof(T);
-    static constexpr int CPLP = (CPL + VEC - 1) / VEC * VEC;
-    static constexpr int LDM = 4 * CPLP;
-    static constexpr int ROWS = 4 * CPL;
-    static constexpr int ELEMS = ROWS * LDM;
-};
-
-// x[j] += sum_rr shfl(s[rr]) * M[rr][lane segment]; M in the padded RowLayout, s distributed over the 4 lanes of a row
-template <typename T, int CPL>
-__device__ __forceinline__ void lane_matvec(const T (&s_)[CPL], const T* __restrict__ mseg, int lane, T (&xv)[CPL]) {
-    using L = RowLayout<T, CPL>;
-#pragma unroll
-    for (int rr = 0; rr < 4 * CPL; ++rr) {
-        const T sr = __shfl_sync(0xffffffffu, s_[rr % CPL], (lane & ~3) | (rr / CPL));
-        T m[L::CPLP];
-#pragma unroll
-        for (int v = 0; v < L::CPLP / L::VEC; ++v) *((int4*)m + v) = *((const int4*)(mseg + rr * L::LDM) + v);
-#pragma unroll
-        for (int j = 0; j < CPL; ++j) xv[j] = fma(sr, m[j], xv[j]);
-    }
-}
-
-// Gram of a staged [64 x LDT] fp64 tile with DMMA: warp w owns the 8x8 blocks b = w, w + 8 of the NB x NB grid.
-template <int NB>
-__device__ __forceinline__ void tile_gram(const double* tile, int warp, int gq, int tq, double (&acc)[2][2]) {
-    constexpr int LDT = 8 * NB + 4;
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const int b = warp + 8 * u;
-        if (b < NB * NB) {
-            const int bi = b / NB, bj = b - bi * NB;
-#pragma unroll
-            for (int r8 = 0; r8 < kRowsPerPass / 8; ++r8) {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    const double* rp = tile + (r8 * 8 + h + 2 * tq) * LDT + gq;
-                    dmma884(acc[u][0], acc[u][1], rp[8 * bi], rp[8 * bj]);
-                }
-            }
-        }
-    }
-}
-
-template <typename T, int NB>
-__device__ __forceinline__ void store_gram(T* __restrict__ out, int R, int warp, int gq, int tq,
-                                           const double (&acc)[2][2]) {
-#pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const int b = warp + 8 * u;
-        if (b < NB * NB) {
-            const int bi = b / NB, bj = b - bi * NB;
-            const int i = 8 * bi + gq, j = 8 * bj + 2 * tq;
-            if (i < R && j < R) out[i * R + j] = (T)acc[u][0];
-            if (i < R && j + 1 < R) out[i * R + j + 1] = (T)acc[u][1];
-        }
-    }
-}
-
 template <typename T, int CPL>
 __global__ void __launch_bounds__(256, 2)
 pf2_rowpass_kernel(const int64_t* __restrict__ row_off, int R, const T* __restrict__ Y, const T* __restrict__ A,

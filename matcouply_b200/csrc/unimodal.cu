@@ -10,7 +10,7 @@
 //   3. re-run PAVA on the two winning prefixes (y[:t*] forward, y[t*:] reversed) and expand their block stacks.
 // Re-running PAVA on a prefix reproduces exactly the blocks the reference reads back through index_range, because
 // the block stack of a prefix is never modified by later elements.
-// PAVA keeps the two top blocks in registers; deeper blocks live in a per-thread stack in global memory that is
+// PAVA keeps the two top blocks in registers (lazily spilled); deeper blocks live in a per-thread stack in global memory that is
 // interleaved across threads (element j of slot t at [j * nslots + t]) so that warps access it coalesced.
 #include "common.cuh"
 
@@ -110,28 +110,40 @@ __device__ __forceinline__ void pava_pass(const T* __restrict__ col, long long l
                 ybuf[u] = (ip < len) ? (double)col[(REV ? (long long)(n - 1 - ip) : (long long)ip) * ld] : 0.0;
                 ebuf[u] = (MODE == 1 && ip < len) ? errR[(size_t)(n - ip - 1) * stride] : 0.0;
             }
-            if (has_sec) stk.put(depth++, sec);
-            sec = top;
-            has_sec = true;
-            top.start = i;
-            top.sy = yi;
-            top.sy2 = __dmul_rn(yi, yi);
-            top.level = yi;
-            cum = __dadd_rn(cum, top.sy2);
-            while (has_sec && top.level <= sec.level) {  // `<=` pooling (:53)
-                top.sy = __dadd_rn(top.sy, sec.sy);
-                top.sy2 = __dadd_rn(top.sy2, sec.sy2);
-                top.start = sec.start;
-                top.level = __ddiv_rn(top.sy, (double)(i - top.start + 1));
-                if (depth > 0)
-                    sec = stk.get(--depth);
-                else
+            // new single-element block; it absorbs the blocks below while its level is <= theirs (`<=` pooling, :53).
+            // Lazy stack: `top`/`sec` live in registers, memory is touched only when a third live block must be
+            // spilled (rising runs) or when a cascade drains both registers (falling runs).
+            Block cur;
+            cur.start = i;
+            cur.sy = yi;
+            cur.sy2 = __dmul_rn(yi, yi);
+            cur.level = yi;
+            cum = __dadd_rn(cum, cur.sy2);
+            bool has_top = true;
+            while (has_top && cur.level <= top.level) {
+                cur.sy = __dadd_rn(cur.sy, top.sy);
+                cur.sy2 = __dadd_rn(cur.sy2, top.sy2);
+                cur.start = top.start;
+                cur.level = __ddiv_rn(cur.sy, (double)(i - cur.start + 1));
+                if (has_sec) {
+                    top = sec;
                     has_sec = false;
+                } else if (depth > 0) {
+                    top = stk.get(--depth);
+                } else {
+                    has_top = false;
+                }
             }
-            const double cnt = (double)(i - top.start + 1);
-            const double levelerror = __dsub_rn(top.sy2, __ddiv_rn(__dmul_rn(top.sy, top.sy), cnt));  // (:57)
-            const double before = has_sec ? sec.err_after : 0.0;
-            top.err_after = (nn && top.level < 0.0) ? cum : __dadd_rn(levelerror, before);  // (:58-62)
+            const double cnt = (double)(i - cur.start + 1);
+            const double levelerror = __dsub_rn(cur.sy2, __ddiv_rn(__dmul_rn(cur.sy, cur.sy), cnt));  // (:57)
+            const double before = has_top ? top.err_after : 0.0;
+            cur.err_after = (nn && cur.level < 0.0) ? cum : __dadd_rn(levelerror, before);  // (:58-62)
+            if (has_top) {
+                if (has_sec) stk.put(depth++, sec);
+                sec = top;
+                has_sec = true;
+            }
+            top = cur;
             if (MODE == 0) errR[(size_t)(i + 1) * stride] = top.err_after;
             if (MODE == 1) {
                 const double cand = __dadd_rn(top.err_after, eR);

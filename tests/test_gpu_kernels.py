@@ -246,7 +246,8 @@ def test_admm_solve_elementwise(mode, R):
 @pytest.mark.parametrize("R", [1, 3, 8, 16, 20, 32])
 @pytest.mark.parametrize("n_pen", [0, 1, 2])
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
-def test_admm_local_equals_iterated_admm_solve(R, n_pen, dtype):
+@pytest.mark.parametrize("grouped", [False, True])
+def test_admm_local_equals_iterated_admm_solve(R, n_pen, dtype, grouped):
     """The fused whole-inner-loop kernel must reproduce 5 launches of the one-iteration kernel (and W = x o a)."""
     _lib, _ops, O = _imports()
     tdt = torch.float64 if dtype == "f64" else torch.float32
@@ -268,7 +269,15 @@ def test_admm_local_equals_iterated_admm_solve(R, n_pen, dtype):
         descs = _ops.make_descs([(c[0], c[1], c[2], c[3], a, d) for c, a, d in zip(cases, aux, dual)])
         x = torch.zeros((n, R), dtype=tdt, device="cuda")
         W = torch.zeros((n, R + 4), dtype=tdt, device="cuda")
-        if fused:
+        BtB = torch.zeros((G, R, R), dtype=tdt, device="cuda")
+        if fused and grouped:  # CTA-per-slice path: Minv staged in shared memory, B^T B fused
+            _ops.admm_local(n, R, dev(rhs, tdt), scale, _lib.GROUP_INDEXED, gor, rho, Minv, descs, n_pen, 5, x, W,
+                            row_off=dev(off, torch.int64), n_groups=G, BtB_out=BtB)
+            xh = x.double().cpu().numpy()
+            ref = np.stack([xh[off[g]:off[g + 1]].T @ xh[off[g]:off[g + 1]] for g in range(G)])
+            np.testing.assert_allclose(BtB.double().cpu().numpy(), ref, rtol=1e-11 if dtype == "f64" else 1e-4,
+                                       atol=1e-11 if dtype == "f64" else 1e-3)
+        elif fused:
             _ops.admm_local(n, R, dev(rhs, tdt), scale, _lib.GROUP_INDEXED, gor, rho, Minv, descs, n_pen, 5, x, W)
         else:
             for _ in range(5):
