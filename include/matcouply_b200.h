@@ -49,6 +49,14 @@ typedef struct {
     void* dual;             /* n x R scaled dual variable */
 } b2_penalty_desc;
 
+/* kernel-selection switches (process-wide; default 1 = on).  They only choose between equivalent kernels — tests flip
+ * them to cross-check the tensor-core formulations against the scalar ones. */
+enum { B2_OPT_PF2_ROWPASS_MMA = 0 /* DMMA row pass of b2_pf2_rowpass */,
+       B2_OPT_POLAR_WARP = 1 /* warp-per-slice Jacobi in b2_pf2_polar */,
+       B2_OPT_COUNT = 2 };
+int b2_set_option(int option, int value);
+int b2_get_option(int option);
+
 const char* b2_last_error(void);
 int b2_version(void);
 int b2_device_sm_count(void);
@@ -180,7 +188,7 @@ int b2_prox_elementwise(const void* v, void* out, long long n, int kind, int non
                         double rho, int dtype, void* stream);
 
 /* ---- measurement helpers (bench.py / DESIGN.md roofline denominators) -------------------------------------------
- * kind 0: fp64 FMA pipe, 1: DMMA.8x8x4, 2: fp32 FMA. Runs `iters` dependent-chain-free iterations on every SM and
+ * kind 0: fp64 FMA pipe, 1: DMMA.8x8x4, 2: fp32 FMA, 3: DMMA + DFMA interleaved (pipe overlap probe). Runs `iters` dependent-chain-free iterations on every SM and
  * writes the number of floating-point operations issued to flops_host. Time it with CUDA events around the call. */
 int b2_microbench_flops(int kind, int iters, double* flops_host, void* sink, void* stream);
 

@@ -7,12 +7,13 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmatcouply_b200.so")
+LIB_PATH = os.environ.get("B2_LIB_PATH_DEBUG") or os.path.join(_HERE, "libmatcouply_b200.so")
 
 F32, F64 = 0, 1
 VARIANT_AUTO, VARIANT_FMA, VARIANT_DMMA = 0, 1, 2
 PEN_NONNEG, PEN_BOX, PEN_L1, PEN_L2BALL, PEN_UNIMODAL, PEN_PARAFAC2 = range(6)
 GROUP_SINGLE, GROUP_INDEXED, GROUP_IDENTITY = 0, 1, 2
+OPT_PF2_ROWPASS_MMA, OPT_POLAR_WARP = 0, 1
 MAX_RANK = 32
 MAX_PENALTIES_PER_MODE = 4
 
@@ -61,12 +62,14 @@ _SIGNATURES = {
     "b2_fit_terms": [_vp, _vp, _vp, _i, _i, _vp, _i, _vp, _sz, _vp],
     "b2_prox_elementwise": [_vp, _vp, _ll, _i, _i, _d, _d, _d, _i, _vp],
     "b2_microbench_flops": [_i, _i, ctypes.POINTER(_d), _vp, _vp],
+    "b2_set_option": [_i, _i],
 }
 _OTHER = {
     "b2_last_error": ([], ctypes.c_char_p),
     "b2_version": ([], _i),
     "b2_device_sm_count": ([], _i),
     "b2_launch_count": ([], ctypes.c_ulonglong),
+    "b2_get_option": ([_i], _i),
     "b2_xstream_workspace_bytes": ([_i, _i, _i], _sz),
     "b2_xstream_z_ldw": ([_i, _i, _i], _i),
     "b2_unimodal_workspace_bytes": ([_i, _i, _i], _sz),

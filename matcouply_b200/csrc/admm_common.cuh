@@ -65,7 +65,7 @@ __device__ __forceinline__ void lane_matvec(const T (&s_)[CPL], const T* __restr
 // Gram of a staged [64 x LDT] fp64 tile with DMMA: warp w owns the 8x8 blocks b = w, w + 8 of the NB x NB grid.
 template <int NB>
 __device__ __forceinline__ void tile_gram(const double* tile, int warp, int gq, int tq, double (&acc)[2][2]) {
-    constexpr int LDT = 8 * NB + 4;
+    constexpr int LDT = 8 * NB + 2;  // 2*LDT == 4 (mod 16): conflict-free fragment reads
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
         const int b = warp + 8 * u;
@@ -97,6 +97,11 @@ __device__ __forceinline__ void store_gram(T* __restrict__ out, int R, int warp,
         }
     }
 }
+
+// tensor-core row pass (pf2_mma.cu); returns -1 when it does not apply to the given shapes
+int b2_pf2_rowpass_mma_try(const int64_t* row_off, int n_groups, int R, const void* Y, const void* A, const void* rho,
+                           const void* Minv, const PenArgs& pa, int deferred, const void* Wmat, const void* Delta,
+                           void* x, void* w_out, int ldw, void* S_out, void* BtB_out, int dtype, cudaStream_t st);
 
 // host: validate and pack the caller's descriptors
 inline int b2_pack_penalties(const b2_penalty_desc* pens, int n_pen, PenArgs* pa) {

@@ -98,7 +98,7 @@ admm_local_grouped_kernel(const int64_t* __restrict__ row_off, long long n, int 
                           T* __restrict__ BtB_out) {
     using L = RowLayout<T, CPL>;
     constexpr int NB = (CPL + 1) / 2;
-    constexpr int LDT = 8 * NB + 4;
+    constexpr int LDT = 8 * NB + 2;  // 2*LDT == 4 (mod 16): conflict-free fragment reads
     extern __shared__ double al_smem[];
     T* Ms = (T*)al_smem;
     double* tile = al_smem + ((L::ELEMS * sizeof(T) + 7) / 8);
@@ -227,7 +227,7 @@ int launch_local_grouped(int n_pen, const int64_t* row_off, int n_groups, long l
                          const void* rhs_scale, const void* rho, const void* Minv, const PenArgs& pa, int n_inner,
                          void* x, void* w_out, int ldw, void* BtB_out, cudaStream_t st) {
     using L = RowLayout<T, CPL>;
-    constexpr int NB = (CPL + 1) / 2, LDT = 8 * NB + 4;
+    constexpr int NB = (CPL + 1) / 2, LDT = 8 * NB + 2;
     const size_t smem = ((L::ELEMS * sizeof(T) + 7) / 8) * 8 + (size_t)kRowsPerPass * LDT * sizeof(double);
     const int grid = row_off ? n_groups : (int)((n + kRowsPerPass - 1) / kRowsPerPass);
 #define B2_LAUNCH_GROUPED(NP)                                                                                      \

@@ -39,6 +39,7 @@ extern unsigned long long g_b2_launches;  // kernels launched through this libra
     } while (0)
 
 int b2_num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
+int b2_option_value(int option);  // kernel-selection switches, see b2_set_option
 
 // dtype dispatch: calls `fn<float>(args...)` or `fn<double>(args...)`
 #define B2_DISPATCH_DTYPE(dtype, ...)                                                                   \
@@ -143,6 +144,52 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// ---- explicit shared-space loads (LDS).  `volatile` keeps them ordered against the mbarrier wait / arrive asm ----
+__device__ __forceinline__ double lds_f64(uint32_t saddr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ float lds_f32(uint32_t saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ int2 lds_b64(uint32_t saddr) {
+    int2 v;
+    asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ int4 lds_b128(uint32_t saddr) {
+    int4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(saddr));
+    return v;
+}
+template <typename T>
+__device__ __forceinline__ T lds_elem(uint32_t saddr);
+template <>
+__device__ __forceinline__ double lds_elem<double>(uint32_t saddr) { return lds_f64(saddr); }
+template <>
+__device__ __forceinline__ float lds_elem<float>(uint32_t saddr) { return lds_f32(saddr); }
+
+// ---- consumer-side release of a TMA ring stage ----------------------------------------------------------------
+// The producer may overwrite the stage as soon as the `empty` barrier completes, so every lane's shared-memory reads of
+// the stage must have RETURNED before the elected lane arrives.  __syncwarp() alone does not give that (ptxas hoists
+// WARPSYNC above the loads and the arrive above the math that consumes them — observed as sporadically stale operand
+// rows).  `dep_bits` must be computed from the results of the instructions that consumed every value loaded from the
+// stage: the warp vote cannot execute before those results exist in all lanes, and its (always false) outcome feeds
+// the barrier address, which pins the arrive behind it.  Combine the per-value bits with max(): the signed maximum of
+// the high words equals the sentinel only if one of the values IS that NaN (an xor could hit it by chance).
+__device__ __forceinline__ int dep_bits_of(double v) { return __double2hiint(v); }
+__device__ __forceinline__ int dep_bits_of(float v) { return __float_as_int(v); }
+__device__ __forceinline__ void stage_release(uint64_t* empty_bar, int lane, int dep_bits) {
+    // 0x7ff7a5a5 / 0x7fb7a5a5: hi word of a NaN with a payload no arithmetic instruction produces
+    const unsigned never = __any_sync(0xffffffffu, dep_bits == 0x7ff7a5a5) ? 1u : 0u;
+    if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(empty_bar) + never) : "memory");
+    }
 }
 
 // Byte offset of element (row, 16-byte chunk `c16`) inside a SWIZZLE_128B box whose rows are 128 bytes

@@ -24,7 +24,7 @@ pf2_rowpass_kernel(const int64_t* __restrict__ row_off, int R, const T* __restri
     extern __shared__ double rp_smem[];
     const int RR = R * R;
     constexpr int NB = (CPL + 1) / 2;  // == ceil(R / 8) for every R with ceil(R / 4) == CPL
-    constexpr int LDT = 8 * NB + 4;
+    constexpr int LDT = 8 * NB + 2;  // 2*LDT == 4 (mod 16): conflict-free fragment reads
     T* Ms = (T*)rp_smem;                                              // Minv_g, padded layout
     T* Ts = Ms + L::ELEMS;                                            // T_g = W_g Delta (deferred mode), padded layout
     double* tile = rp_smem + ((2 * L::ELEMS * sizeof(T) + 7) / 8);    // [64 x LDT] staged V' for the Gram MMA
@@ -172,7 +172,7 @@ slice_gram_kernel(const T* __restrict__ B, const int64_t* __restrict__ row_off, 
     extern __shared__ double rp_smem[];
     const int RR = R * R;
     constexpr int NB = (CPL + 1) / 2;
-    constexpr int LDT = 8 * NB + 4;
+    constexpr int LDT = 8 * NB + 2;  // 2*LDT == 4 (mod 16): conflict-free fragment reads
     double* tile = rp_smem;
     const int g = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, l4 = lane & 3;
@@ -420,7 +420,7 @@ int launch_rowpass(const int64_t* row_off, int n_groups, int R, const void* Y, c
                    const void* Minv, const PenArgs& pa, int deferred, const void* Wmat, const void* Delta, void* x,
                    void* w_out, int ldw, void* S_out, void* BtB_out, cudaStream_t st) {
     using L = RowLayout<T, CPL>;
-    const int NB = (R + 7) / 8, LDT = 8 * NB + 4;
+    const int NB = (R + 7) / 8, LDT = 8 * NB + 2;
     const size_t smem = ((2 * (size_t)L::ELEMS * sizeof(T) + 7) / 8) * 8 + 2 * (size_t)kRowsPerPass * LDT * sizeof(double);
     auto kern = pf2_rowpass_kernel<T, CPL>;
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -432,7 +432,7 @@ int launch_rowpass(const int64_t* row_off, int n_groups, int R, const void* Y, c
 
 template <typename T, int CPL>
 int launch_slice_gram(const void* B, const int64_t* row_off, int n_groups, int R, void* BtB, cudaStream_t st) {
-    const int NB = (R + 7) / 8, LDT = 8 * NB + 4;
+    const int NB = (R + 7) / 8, LDT = 8 * NB + 2;
     const size_t smem = (size_t)kRowsPerPass * LDT * sizeof(double);
     slice_gram_kernel<T, CPL><<<n_groups, 256, smem, st>>>((const T*)B, row_off, R, (T*)BtB);
     B2_LAUNCH_CHECK();
@@ -456,6 +456,11 @@ int b2_pf2_rowpass(const int64_t* row_off, int n_groups, int R, const void* Y, c
     {
         const int rc = b2_pack_penalties(pens, n_pen, &pa);
         if (rc != B2_OK) return rc;
+    }
+    if (b2_option_value(B2_OPT_PF2_ROWPASS_MMA)) {  // tensor-core formulation (pf2_mma.cu) when it applies
+        const int rc = b2_pf2_rowpass_mma_try(row_off, n_groups, R, Y, A, rho, Minv, pa, deferred, Wmat, Delta, x, w_out,
+                                              ldw, S_out, BtB_out, dtype, st);
+        if (rc >= 0) return rc;
     }
     const int CPL = (R + 3) / 4;
 #define B2_CASE_CPL(C)                                                                                             \

@@ -20,34 +20,50 @@ constexpr int kThreads = kConsumerThreads + 32;  // + producer warp
 // Y = X * C
 // ---------------------------------------------------------------------------------------------------------
 // Stage layout (1024-byte aligned): NBOX swizzled boxes [TM rows x 128 B] of X, then the C chunk [KC x LDC].
-template <typename T>
+// FMA path: 128-row tiles, 2 boxes per stage.  DMMA path: 256-row tiles (4 m-blocks = 12..16 independent accumulator
+// chains per warp: the DMMA pipe needs that much ILP with only 8 consumer warps per SM), 1 box per stage.
+template <typename T, bool DMMA>
 struct YCfg {
-    static constexpr int TM = 128;                    // rows per tile
+    static constexpr int TM = DMMA ? 256 : 128;       // rows per tile
+    static constexpr int MB = TM / 64;                // 8-row m-blocks per consumer warp (DMMA path)
     static constexpr int EPB = 128 / (int)sizeof(T);  // elements per 128-byte box row
-    static constexpr int NBOX = 2;
-    static constexpr int KC = NBOX * EPB;  // K-chunk per stage (32 fp64 / 64 fp32)
+    static constexpr int NBOX = DMMA ? 1 : 2;
+    static constexpr int KC = NBOX * EPB;  // K-chunk per stage
     static constexpr int BOX_BYTES = TM * 128;
     static constexpr int X_BYTES = NBOX * BOX_BYTES;
 };
 
-// pad/copy C (K x R, ld R) into Cp (Kp x LDC), zero filled, so that a K-chunk is one contiguous 16B-aligned bulk copy
+// pad/copy C (K x R, ld R) into Cp (Kp x LDC), zero filled, so that a K-chunk is one contiguous 16B-aligned bulk copy.
+// mma_order: rows are permuted inside every group of 16 into the order the DMMA path consumes them — staged row
+// 4*k4 + t holds source row 8*(t>>1) + 2*k4 + (t&1) (see the A-fragment mapping in xstream_y_kernel).
 template <typename T>
-__global__ void pad_c_kernel(const T* __restrict__ C, T* __restrict__ Cp, int K, int R, int Kp, int LDC) {
+__global__ void pad_c_kernel(const T* __restrict__ C, T* __restrict__ Cp, int K, int R, int Kp, int LDC, int mma_order) {
     const int n = Kp * LDC;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int k = i / LDC, c = i - k * LDC;
+        int k = i / LDC;
+        const int c = i - k * LDC;
+        if (mma_order) {
+            const int j = k & 15, k4 = j >> 2, t = j & 3;
+            k = (k & ~15) + 8 * (t >> 1) + 2 * k4 + (t & 1);
+        }
         Cp[i] = (k < K && c < R) ? C[(size_t)k * R + c] : T(0);
     }
 }
 
 // CT = columns per thread in the FMA path (thread tile 2 rows x CT cols, 4 column groups) ; LDC = 4*CT.
-// DMMA path (fp64): warp w owns rows [16w,16w+16) = 2 m-blocks, NBLK = LDC_used/8 n-blocks; LDC = 8 (mod 16).
+// DMMA path (fp64): warp w owns rows [16w,16w+16) = 2 m-blocks, NBLK n-blocks of 8 columns; LDC = 8*NBLK + 4.
+// Shared-memory operand reads are 64-bit, i.e. served per half-warp (g = 0..3, t = 0..3) in 128-byte wavefronts:
+//   A: MMA k-index t of k-step k4 is mapped to box column 8*(t>>1) + 2*k4 + (t&1), so that under SWIZZLE_128B the 16
+//      lanes hit 16 distinct 8-byte bank pairs (the natural 4*k4 + t mapping is 2-way conflicted: rows g and g^1 land
+//      in the same 32-byte window);
+//   B: the staged C rows are stored in that same MMA order (pad_c_kernel) with LDC = 4 or 12 (mod 16), so lane (g,t)
+//      reads word (4*k4 + t)*LDC + g: 16 distinct words mod 16.
 template <typename T, int CT, bool DMMA, int NBLK>
 __global__ void __launch_bounds__(kThreads, 1)
 xstream_y_kernel(const __grid_constant__ CUtensorMap tmap_x, const T* __restrict__ Cp, T* __restrict__ Y, long long N,
                  int R, int Kp, int LDC, int num_tiles, int stages) {
-    using Cfg = YCfg<T>;
-    constexpr int TM = Cfg::TM, EPB = Cfg::EPB, NBOX = Cfg::NBOX, KC = Cfg::KC;
+    using Cfg = YCfg<T, DMMA>;
+    constexpr int TM = Cfg::TM, EPB = Cfg::EPB, NBOX = Cfg::NBOX, KC = Cfg::KC, MB = Cfg::MB;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // carve: [stages x (X boxes | C chunk)] | full[stages] | empty[stages]
     const uint32_t c_bytes = (uint32_t)(KC * LDC * sizeof(T));
@@ -55,6 +71,7 @@ xstream_y_kernel(const __grid_constant__ CUtensorMap tmap_x, const T* __restrict
     unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* full = (uint64_t*)(base + (size_t)stages * stage_bytes);
     uint64_t* empty = full + stages;
+    const uint32_t base_s = smem_u32(base);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -105,31 +122,29 @@ xstream_y_kernel(const __grid_constant__ CUtensorMap tmap_x, const T* __restrict
             for (int c = 0; c < CT; ++c) acc0[c] = acc1[c] = T(0);
             for (int kc = 0; kc < kchunks; ++kc) {
                 mbar_wait(&full[s], ph);
-                const unsigned char* st = base + (size_t)s * stage_bytes;
-                const T* Cs = (const T*)(st + Cfg::X_BYTES) + tc * CT;
+                const uint32_t st = base_s + (uint32_t)s * stage_bytes;
+                const uint32_t Cs = st + Cfg::X_BYTES + (uint32_t)(tc * CT * sizeof(T));
 #pragma unroll
                 for (int b = 0; b < NBOX; ++b) {
-                    const unsigned char* box = st + b * Cfg::BOX_BYTES;
+                    const uint32_t box = st + b * Cfg::BOX_BYTES;
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         T x0[EPC], x1[EPC];
-                        *(int4*)x0 = *(const int4*)(box + swz128(tr, q));
-                        *(int4*)x1 = *(const int4*)(box + swz128(tr + 64, q));
+                        *(int4*)x0 = lds_b128(box + swz128(tr, q));
+                        *(int4*)x1 = lds_b128(box + swz128(tr + 64, q));
 #pragma unroll
                         for (int e = 0; e < EPC; ++e) {
-                            const T* crow = Cs + (size_t)(b * EPB + q * EPC + e) * LDC;
+                            const uint32_t crow = Cs + (uint32_t)((b * EPB + q * EPC + e) * LDC * sizeof(T));
                             T cv[CT];
                             if constexpr ((CT * sizeof(T)) % 16 == 0) {
 #pragma unroll
-                                for (int v = 0; v < (int)(CT * sizeof(T) / 16); ++v)
-                                    *((int4*)cv + v) = *((const int4*)crow + v);
+                                for (int v = 0; v < (int)(CT * sizeof(T) / 16); ++v) *((int4*)cv + v) = lds_b128(crow + 16 * v);
                             } else if constexpr ((CT * sizeof(T)) % 8 == 0) {
 #pragma unroll
-                                for (int v = 0; v < (int)(CT * sizeof(T) / 8); ++v)
-                                    *((int2*)cv + v) = *((const int2*)crow + v);
+                                for (int v = 0; v < (int)(CT * sizeof(T) / 8); ++v) *((int2*)cv + v) = lds_b64(crow + 8 * v);
                             } else {
 #pragma unroll
-                                for (int c = 0; c < CT; ++c) cv[c] = crow[c];
+                                for (int c = 0; c < CT; ++c) cv[c] = lds_elem<T>(crow + c * (uint32_t)sizeof(T));
                             }
 #pragma unroll
                             for (int c = 0; c < CT; ++c) {
@@ -139,8 +154,10 @@ xstream_y_kernel(const __grid_constant__ CUtensorMap tmap_x, const T* __restrict
                         }
                     }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[s]);
+                int dep = 0;
+#pragma unroll
+                for (int c = 0; c < CT; ++c) dep = max(dep, max(dep_bits_of(acc0[c]), dep_bits_of(acc1[c])));
+                stage_release(&empty[s], lane, dep);
                 if (++s == stages) {
                     s = 0;
                     ph ^= 1;
@@ -157,49 +174,53 @@ xstream_y_kernel(const __grid_constant__ CUtensorMap tmap_x, const T* __restrict
             }
         }
     } else {
-        // fp64 tensor-core path. lane = 4g + t. A frag: X[16w + 8m + g][k0 + t]; B frag: C[k0 + t][8n + g].
+        // fp64 tensor-core path. lane = 4g + t. A frag: X[16w + 8m + g][col(k4, t)]; B frag: C[col(k4, t)][8n + g].
         const int g = lane >> 2, t = lane & 3;
+        const uint32_t a_chunk0 = 4u * (t >> 1), a_half = (t & 1) * 8u;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            double acc[2][NBLK][2];
+            double acc[MB][NBLK][2];
 #pragma unroll
-            for (int m = 0; m < 2; ++m)
+            for (int m = 0; m < MB; ++m)
 #pragma unroll
                 for (int n = 0; n < NBLK; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
             for (int kc = 0; kc < kchunks; ++kc) {
                 mbar_wait(&full[s], ph);
-                const unsigned char* st = base + (size_t)s * stage_bytes;
-                const double* Cs = (const double*)(st + Cfg::X_BYTES);
+                const uint32_t st = base_s + (uint32_t)s * stage_bytes;
+                const uint32_t Cs = st + Cfg::X_BYTES + (uint32_t)(g * sizeof(double));
 #pragma unroll
                 for (int b = 0; b < NBOX; ++b) {
-                    const unsigned char* box = st + b * Cfg::BOX_BYTES;
+                    const uint32_t box = st + b * Cfg::BOX_BYTES;
 #pragma unroll
                     for (int k4 = 0; k4 < EPB / 4; ++k4) {
-                        const int kk = k4 * 4 + t;  // column inside the box (0..15)
-                        double a[2], bf[NBLK];
+                        double a[MB], bf[NBLK];
 #pragma unroll
-                        for (int m = 0; m < 2; ++m) {
-                            const uint32_t row = warp * 16 + m * 8 + g;
-                            a[m] = *(const double*)(box + swz128(row, kk >> 1) + (kk & 1) * 8);
+                        for (int m = 0; m < MB; ++m) {
+                            const uint32_t row = warp * (8 * MB) + m * 8 + g;
+                            a[m] = lds_f64(box + swz128(row, a_chunk0 + k4) + a_half);
                         }
-                        const double* crow = Cs + (size_t)(b * EPB + kk) * LDC + g;
+                        const uint32_t crow = Cs + (uint32_t)((b * EPB + k4 * 4 + t) * LDC * sizeof(double));
 #pragma unroll
-                        for (int n = 0; n < NBLK; ++n) bf[n] = crow[n * 8];
+                        for (int n = 0; n < NBLK; ++n) bf[n] = lds_f64(crow + n * 64);
 #pragma unroll
-                        for (int m = 0; m < 2; ++m)
+                        for (int m = 0; m < MB; ++m)
 #pragma unroll
                             for (int n = 0; n < NBLK; ++n) dmma884(acc[m][n][0], acc[m][n][1], a[m], bf[n]);
                     }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty[s]);
+                int dep = 0;
+#pragma unroll
+                for (int m = 0; m < MB; ++m)
+#pragma unroll
+                    for (int n = 0; n < NBLK; ++n) dep = max(dep, dep_bits_of(acc[m][n][0]));
+                stage_release(&empty[s], lane, dep);
                 if (++s == stages) {
                     s = 0;
                     ph ^= 1;
                 }
             }
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {
-                const long long row = (long long)tile * TM + warp * 16 + m * 8 + g;
+            for (int m = 0; m < MB; ++m) {
+                const long long row = (long long)tile * TM + warp * (8 * MB) + m * 8 + g;
                 if (row < N) {
 #pragma unroll
                     for (int n = 0; n < NBLK; ++n) {
@@ -239,6 +260,7 @@ xstream_z_kernel(const __grid_constant__ CUtensorMap tmap_x, const T* __restrict
     unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* full = (uint64_t*)(base + (size_t)stages * stage_bytes);
     uint64_t* empty = full + stages;
+    const uint32_t base_s = smem_u32(base);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n_cons_warps = (blockDim.x >> 5) - 1;
@@ -286,23 +308,27 @@ xstream_z_kernel(const __grid_constant__ CUtensorMap tmap_x, const T* __restrict
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&full[s], ph);
-        const unsigned char* st = base + (size_t)s * stage_bytes;
-        const unsigned char* box = st + (size_t)box_id * Cfg::BOX_BYTES;
-        const T* Ws = (const T*)(st + x_bytes);
+        const uint32_t st = base_s + (uint32_t)s * stage_bytes;
+        const uint32_t box = st + (uint32_t)box_id * Cfg::BOX_BYTES;
+        const uint32_t Ws = st + x_bytes;
 #pragma unroll 4
         for (int r = 0; r < (active ? TMZ : 0); ++r) {
             T x[EPC];
-            *(int4*)x = *(const int4*)(box + swz128(r, chunk));
-            const T* wr = Ws + r * ldw;
+            *(int4*)x = lds_b128(box + swz128(r, chunk));
+            const uint32_t wr = Ws + (uint32_t)(r * ldw * sizeof(T));
 #pragma unroll
             for (int c = 0; c < RP; ++c) {
-                const T w = (c < R) ? wr[c] : T(0);
+                const T w = (c < R) ? lds_elem<T>(wr + c * (uint32_t)sizeof(T)) : T(0);
 #pragma unroll
                 for (int e = 0; e < EPC; ++e) acc[e][c] = fma(x[e], w, acc[e][c]);
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
+        int dep = 0;
+#pragma unroll
+        for (int e = 0; e < EPC; ++e)
+#pragma unroll
+            for (int c = 0; c < RP; ++c) dep = max(dep, dep_bits_of(acc[e][c]));
+        stage_release(&empty[s], lane, dep);
         if (++s == stages) {
             s = 0;
             ph ^= 1;
@@ -325,7 +351,8 @@ xstream_z_kernel(const __grid_constant__ CUtensorMap tmap_x, const T* __restrict
 // Z = X^T * W, fp64 tensor-core path.  CTA = (row group, k-block of 128 columns); stage = 8 swizzled boxes
 // [32 rows x 16 doubles] of X plus the W tile [32 x ldw].  Warp w owns the 16 k's of box w (2 m-blocks).
 // MMA roles: M = k index (8), N = factor column (8), K = data rows (4, taken as r0+h+2t so that the swizzled
-// A-fragment reads and the ldw = 4 (mod 8) strided B-fragment reads are bank-conflict free).
+// A-fragment reads are bank-conflict free; the B-fragment reads word (r0+h+2t)*ldw + g, conflict free per half-warp
+// for ldw = 8*NBLK + 2, i.e. 2*ldw = 4 (mod 16)).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kZdTM = 32;
 constexpr int kZdKZ = 128;
@@ -342,6 +369,7 @@ xstream_z_dmma_kernel(const __grid_constant__ CUtensorMap tmap_x, const double* 
     unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* full = (uint64_t*)(base + (size_t)stages * stage_bytes);
     uint64_t* empty = full + stages;
+    const uint32_t base_s = smem_u32(base);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -375,18 +403,22 @@ xstream_z_dmma_kernel(const __grid_constant__ CUtensorMap tmap_x, const double* 
         return;
     }
     const int g = lane >> 2, t = lane & 3;
-    double acc[2][NBLK][2];
+    // Two independent accumulator sets (rows r0+h+2t, h = 0 / 1, summed at the end): 4*NBLK dependent DMMA
+    // chains per warp instead of 2*NBLK — with 8 consumer warps per SM the DMMA pipe needs that much ILP.
+    double acc[2][2][NBLK][2];
 #pragma unroll
-    for (int m = 0; m < 2; ++m)
+    for (int u = 0; u < 2; ++u)
 #pragma unroll
-        for (int n = 0; n < NBLK; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int n = 0; n < NBLK; ++n) acc[u][m][n][0] = acc[u][m][n][1] = 0.0;
     int s = 0;
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&full[s], ph);
-        const unsigned char* st = base + (size_t)s * stage_bytes;
-        const unsigned char* box = st + (size_t)warp * kZdBoxBytes;
-        const double* Ws = (const double*)(st + kZdXBytes);
+        const uint32_t st = base_s + (uint32_t)s * stage_bytes;
+        const uint32_t box = st + (uint32_t)warp * kZdBoxBytes;
+        const uint32_t Ws = st + kZdXBytes + (uint32_t)(g * sizeof(double));
 #pragma unroll
         for (int rg = 0; rg < kZdTM / 8; ++rg) {
 #pragma unroll
@@ -396,19 +428,25 @@ xstream_z_dmma_kernel(const __grid_constant__ CUtensorMap tmap_x, const double* 
 #pragma unroll
                 for (int m = 0; m < 2; ++m) {
                     const uint32_t kk = 8 * m + g;
-                    a[m] = *(const double*)(box + swz128(row, kk >> 1) + (kk & 1) * 8);
+                    a[m] = lds_f64(box + swz128(row, kk >> 1) + (kk & 1) * 8);
                 }
-                const double* wrow = Ws + row * ldw + g;
+                const uint32_t wrow = Ws + (uint32_t)(row * ldw * sizeof(double));
 #pragma unroll
-                for (int n = 0; n < NBLK; ++n) bf[n] = wrow[n * 8];
+                for (int n = 0; n < NBLK; ++n) bf[n] = lds_f64(wrow + n * 64);
 #pragma unroll
                 for (int m = 0; m < 2; ++m)
 #pragma unroll
-                    for (int n = 0; n < NBLK; ++n) dmma884(acc[m][n][0], acc[m][n][1], a[m], bf[n]);
+                    for (int n = 0; n < NBLK; ++n) dmma884(acc[h][m][n][0], acc[h][m][n][1], a[m], bf[n]);
             }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
+        int dep = 0;
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int n = 0; n < NBLK; ++n) dep = max(dep, dep_bits_of(acc[u][m][n][0]));
+        stage_release(&empty[s], lane, dep);
         if (++s == stages) {
             s = 0;
             ph ^= 1;
@@ -422,8 +460,8 @@ xstream_z_dmma_kernel(const __grid_constant__ CUtensorMap tmap_x, const double* 
 #pragma unroll
             for (int n = 0; n < NBLK; ++n) {
                 const int col = n * 8 + 2 * t;
-                if (col < R) out[(size_t)k * R + col] = acc[m][n][0];
-                if (col + 1 < R) out[(size_t)k * R + col + 1] = acc[m][n][1];
+                if (col < R) out[(size_t)k * R + col] = acc[0][m][n][0] + acc[1][m][n][0];
+                if (col + 1 < R) out[(size_t)k * R + col + 1] = acc[0][m][n][1] + acc[1][m][n][1];
             }
         }
     }
@@ -524,22 +562,21 @@ int launch_y_dmma(const CUtensorMap& map, const double* Cp, double* Y, long long
     return B2_OK;
 }
 
-template <typename T>
+template <typename T, bool DMMA>
 int xstream_y_impl(const void* X, long long N, int K, int ldx, const void* C, int R, void* Y, void* ws, size_t ws_bytes,
-                   int variant, int max_ctas, cudaStream_t st) {
-    using Cfg = YCfg<T>;
+                   int max_ctas, cudaStream_t st) {
+    using Cfg = YCfg<T, DMMA>;
     const int dtype = sizeof(T) == 8 ? B2_F64 : B2_F32;
-    const bool dmma = (variant == B2_VARIANT_DMMA);
-    B2_REQUIRE(!dmma || dtype == B2_F64, "the DMMA variant exists for fp64 only");
+    constexpr bool dmma = DMMA;
     B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
     if (N == 0) return B2_OK;
     const int Kp = ((K + Cfg::KC - 1) / Cfg::KC) * Cfg::KC;
     int CT = (R + 3) / 4, LDC = 4 * CT, NBLK = (R + 7) / 8;
-    if (dmma) LDC = (NBLK <= 1) ? 8 : (NBLK <= 3 ? 24 : 40);  // == 8 (mod 16): conflict-free B-fragment reads
+    if (dmma) LDC = 8 * NBLK + 4;  // == 4 or 12 (mod 16): conflict-free B-fragment reads
     const size_t cp_bytes = (size_t)Kp * LDC * sizeof(T);
     B2_REQUIRE(ws_bytes >= cp_bytes, "xstream_y workspace too small: need %zu bytes, got %zu", cp_bytes, ws_bytes);
     B2_REQUIRE(((uintptr_t)ws) % 16 == 0, "workspace must be 16-byte aligned");
-    pad_c_kernel<T><<<(Kp * LDC + 255) / 256, 256, 0, st>>>((const T*)C, (T*)ws, K, R, Kp, LDC);
+    pad_c_kernel<T><<<(Kp * LDC + 255) / 256, 256, 0, st>>>((const T*)C, (T*)ws, K, R, Kp, LDC, dmma ? 1 : 0);
     B2_LAUNCH_CHECK();
 
     alignas(64) CUtensorMap map;
@@ -556,7 +593,7 @@ int xstream_y_impl(const void* X, long long N, int K, int ldx, const void* C, in
     if (max_ctas > 0 && max_ctas < grid) grid = max_ctas;
     if (grid > num_tiles) grid = num_tiles;
 
-    if (dmma) {
+    if constexpr (dmma) {
         const double* Cp = (const double*)ws;
         double* Yd = (double*)Y;
         switch (NBLK) {
@@ -603,7 +640,7 @@ int launch_z_dmma(const CUtensorMap& map, const double* W, int ldw, double* part
 int z_ldw_for(int R, int dtype, int variant) {
     if (variant == B2_VARIANT_DMMA && dtype == B2_F64) {
         const int nblk = (R + 7) / 8;
-        return 8 * nblk + 4;  // == 4 (mod 8): B-fragment rows r0+2t land in alternating 64-byte bank halves
+        return 8 * nblk + 2;  // 2*ldw == 4 (mod 16): B-fragment rows r0+h+2t, t = 0..3, start 4 words apart
     }
     return R;
 }
@@ -714,8 +751,12 @@ extern "C" {
 
 int b2_xstream_y(const void* X, long long n_rows, int K, int ldx, const void* C, int R, void* Y, int dtype, void* ws,
                  size_t ws_bytes, int variant, int max_ctas, void* stream) {
-    B2_DISPATCH_DTYPE(dtype, return xstream_y_impl<T>(X, n_rows, K, ldx, C, R, Y, ws, ws_bytes, variant, max_ctas,
-                                                      (cudaStream_t)stream));
+    if (variant == B2_VARIANT_DMMA) {
+        B2_REQUIRE(dtype == B2_F64, "the DMMA variant exists for fp64 only");
+        return xstream_y_impl<double, true>(X, n_rows, K, ldx, C, R, Y, ws, ws_bytes, max_ctas, (cudaStream_t)stream);
+    }
+    B2_DISPATCH_DTYPE(dtype, return xstream_y_impl<T, false>(X, n_rows, K, ldx, C, R, Y, ws, ws_bytes, max_ctas,
+                                                             (cudaStream_t)stream));
 }
 
 int b2_xstream_z(const void* X, long long n_rows, int K, int ldx, const void* W, int ldw, int R, void* Z, int dtype,

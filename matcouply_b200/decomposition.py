@@ -260,14 +260,19 @@ def cmf_aoadmm(
     verbose=False,
     device=None,
     process_group=None,
+    shard=None,
+    gather_factors=True,
 ):
     """Fit a regularized coupled matrix factorization with AO-ADMM on a B200 (same signature and semantics as the
     reference ``matcouply.decomposition.cmf_aoadmm``, decomposition.py:662-1100).
 
     ``matrices`` is a list of ``J_i x K`` arrays (NumPy, or torch tensors), a 3-D array iterated along axis 0, or a
     device-resident :class:`matcouply_b200.PackedMatrices`.  float32 inputs run the fp32 kernels, everything else fp64.
-    Extra keywords: ``device`` (CUDA device, default current) and ``process_group`` (slices of ``matrices`` are then
-    this rank's shard; see ``matcouply_b200.distributed``).
+    Extra keywords: ``device`` (CUDA device, default current); ``process_group`` + ``shard``
+    (:class:`matcouply_b200.distributed.ShardSpec`): ``matrices`` then holds only this rank's slices ``[lo, hi)`` of
+    the global problem, the initial state is drawn for the GLOBAL problem from ``random_state`` (so the run equals the
+    unsharded one) and cut to the shard, and a few small all-reduces per outer iteration couple the ranks;
+    ``gather_factors`` returns the complete ``A`` / ``B_is`` on every rank instead of the local share.
     """
     import torch
 
@@ -288,6 +293,13 @@ def cmf_aoadmm(
         all_f32 = all(str(getattr(m, "dtype", "")).endswith("float32") for m in matrices)
         packed = PackedMatrices.from_list(matrices, torch.float32 if all_f32 else torch.float64, device)
         shape_view = matrices
+    if shard is not None:
+        if process_group is None:
+            raise ValueError("`shard` needs a `process_group`")
+        if packed.n_slices != shard.hi - shard.lo or any(
+                int(s[0]) != int(j) for s, j in zip(packed.shapes, shard.row_counts[shard.lo:shard.hi])):
+            raise ValueError("`matrices` must hold exactly the slices [shard.lo, shard.hi) of the global problem")
+        shape_view = [_ShapeOnly((j, packed.K)) for j in shard.row_counts]  # the GLOBAL problem
     cmf = initialize_cmf(shape_view, rank, init, random_state=random_state)
 
     l2_penalty = [l2 if l2 is not None else 0 for l2 in _listify(l2_penalty, "l2_penalty")]
@@ -321,6 +333,10 @@ def cmf_aoadmm(
                           constant_B=constant_B, inner_n_iter_max=inner_n_iter_max,
                           update=(update_A, update_B_is, update_C), group=process_group)
     _, (A0, B0, C0) = cmf
+    if shard is not None:
+        from .distributed import shard_state
+
+        A0, B0, auxes, duals = shard_state(A0, B0, auxes, duals, regs, shard)
     engine.load_state(np.asarray(A0), [np.asarray(b) for b in B0], np.asarray(C0), auxes, duals)
     engine.prepare()
     norm_X_sq = engine.normX_sq
@@ -401,9 +417,14 @@ def cmf_aoadmm(
         feasibility_criterion = None
 
     A, B_is, C = engine.factors()
+    if shard is not None and gather_factors:
+        from .distributed import allgather_rows
+
+        A = allgather_rows(A, shard, process_group)
+        B_is = allgather_rows(B_is, shard, process_group)
     out = [CoupledMatrixFactorization((None, [A, B_is, C]))]
     if return_admm_vars:
-        aux_out, dual_out = engine.admm_vars()
+        aux_out, dual_out = engine.admm_vars()  # rank-local share for modes 0 and 1 when sharded
         out.append(ADMMVars(auxes=tuple(aux_out), duals=tuple(dual_out)))
     if return_errors:
         if not satisfied_stopping_condition and not (tol or absolute_tol):

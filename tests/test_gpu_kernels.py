@@ -474,3 +474,76 @@ def test_slice_gram_family(R, dtype):
     Cd = dev(CtC, tdt)
     _ops.hadamard_bcast(BtB, Cd, G, R, cross)
     np.testing.assert_allclose(cross.double().cpu().numpy(), BtBh * Cd.double().cpu().numpy(), rtol=tol)
+
+
+@pytest.mark.parametrize("R", [2, 4, 6, 8, 12, 16, 20, 22, 28, 32, 5])
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("mma", [1, 0])
+def test_pf2_rowpass_both_formulations(R, dtype, mma):
+    """b2_pf2_rowpass (DMMA tile kernel / shuffle kernel) vs a NumPy restatement of one fused inner iteration
+    (decomposition.py:259-289, penalties.py:1256-1281): deferred and stored PARAFAC2 aux, an elementwise and a
+    column-coupled companion penalty, ragged slices with an empty one, x / W / B^T B emission."""
+    _lib, _ops, _ = _imports()
+    lib = _lib.load()
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    if dtype == "f32" and R % 4 != 0 and mma:
+        pytest.skip("row size not a multiple of 16 bytes: the tensor-core kernel is not selected")
+    rs = np.random.RandomState(100 + R)
+    G = 7
+    sizes, off, _ = ragged(rs, G, 1, 300, R)
+    sizes[2] = 0
+    sizes[5] = 64
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    N = int(off[-1])
+    f = lambda *s: rs.standard_normal(size=s)  # noqa: E731
+    Y, A, rho = f(N, R), rs.uniform(0.5, 1.5, size=(G, R)), rs.uniform(0.5, 2.0, size=G)
+    Minv = np.stack([np.linalg.inv(m @ m.T + R * np.eye(R)) for m in f(G, R, R)])
+    Wm, Delta = f(G, R, R) / np.sqrt(R), f(R, R)
+    pf_aux, pf_dual, nn_aux, nn_dual, l2_aux, l2_dual = (f(N, R) for _ in range(6))
+    tol = 1e-11 if dtype == "f64" else 3e-4
+    lib.b2_set_option(_lib.OPT_PF2_ROWPASS_MMA, mma)
+    try:
+        for deferred in (0, 1):
+            for last in (0, 1):
+                d = {k: dev(v, tdt) for k, v in dict(Y=Y, A=A, rho=rho, Minv=Minv, Wm=Wm, Delta=Delta, pf_aux=pf_aux,
+                                                     pf_dual=pf_dual, nn_aux=nn_aux, nn_dual=nn_dual, l2_aux=l2_aux,
+                                                     l2_dual=l2_dual).items()}
+                h = {k: v.double().cpu().numpy() for k, v in d.items()}  # the inputs as the kernel sees them
+                descs = _ops.make_descs([(_lib.PEN_PARAFAC2, 0, 0, 0, d["pf_aux"], d["pf_dual"]),
+                                         (_lib.PEN_NONNEG, 0, 0, 0, d["nn_aux"], d["nn_dual"]),
+                                         (_lib.PEN_L2BALL, 1, 1.0, 0, d["l2_aux"], d["l2_dual"])])
+                x = torch.full((N, R), float("nan"), dtype=tdt, device="cuda")
+                Wp = _ops.alloc_w(N, R, tdt, "cuda")
+                S = torch.full((G, R, R), float("nan"), dtype=tdt, device="cuda")
+                BtB = torch.full((G, R, R), float("nan"), dtype=tdt, device="cuda")
+                _ops.pf2_rowpass(dev(off, torch.int64), G, R, d["Y"], d["A"], d["rho"], d["Minv"], descs, 3, deferred,
+                                 d["Wm"], d["Delta"], x if last else None, Wp if last else None, S,
+                                 BtB if last else None)
+                torch.cuda.synchronize()
+                gor = np.repeat(np.arange(G), sizes)
+                if deferred:
+                    T = np.einsum("gik,kj->gij", h["Wm"], h["Delta"])
+                    pd = np.einsum("nk,nkj->nj", h["pf_dual"], T[gor])
+                    dpf = h["pf_dual"] - pd
+                else:
+                    pd, dpf = h["pf_aux"], h["pf_dual"]
+                sh = (pd - dpf) + (h["nn_aux"] - h["nn_dual"]) + (h["l2_aux"] - h["l2_dual"])
+                s = h["rho"][gor][:, None] * sh + h["Y"] * h["A"][gor]
+                xr = np.einsum("nk,nkj->nj", s, h["Minv"][gor])
+                vn = xr + dpf
+                np.testing.assert_allclose(d["pf_dual"].double().cpu().numpy(), vn, rtol=tol, atol=tol * 10)
+                v_nn = xr + h["nn_dual"]
+                np.testing.assert_allclose(d["nn_aux"].double().cpu().numpy(), np.maximum(v_nn, 0), rtol=tol, atol=tol * 10)
+                np.testing.assert_allclose(d["nn_dual"].double().cpu().numpy(), np.minimum(v_nn, 0), rtol=tol, atol=tol * 10)
+                np.testing.assert_allclose(d["l2_dual"].double().cpu().numpy(), xr + h["l2_dual"], rtol=tol, atol=tol * 10)
+                np.testing.assert_array_equal(d["l2_aux"].double().cpu().numpy(), h["l2_aux"])  # untouched here
+                Sref = np.stack([vn[off[g]:off[g + 1]].T @ vn[off[g]:off[g + 1]] for g in range(G)])
+                np.testing.assert_allclose(S.double().cpu().numpy(), Sref, rtol=tol * 10, atol=tol * 1e3)
+                if last:
+                    np.testing.assert_allclose(x.double().cpu().numpy(), xr, rtol=tol, atol=tol * 10)
+                    np.testing.assert_allclose(Wp[:N, :R].double().cpu().numpy(), xr * h["A"][gor], rtol=tol, atol=tol * 10)
+                    assert float(Wp[:N, R:].abs().max() if Wp.shape[1] > R else 0.0) == 0.0
+                    Bref = np.stack([xr[off[g]:off[g + 1]].T @ xr[off[g]:off[g + 1]] for g in range(G)])
+                    np.testing.assert_allclose(BtB.double().cpu().numpy(), Bref, rtol=tol * 10, atol=tol * 1e3)
+    finally:
+        lib.b2_set_option(_lib.OPT_PF2_ROWPASS_MMA, 1)
