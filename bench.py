@@ -181,6 +181,32 @@ def oracle_iter_seconds(mats, R, kw):
     return max(((t2 - t1) - (t1 - t0)) / 2.0, 1e-9)
 
 
+E2E_ITERS = 50  # outer iterations of the timed end-to-end call (the parity horizon of BASELINE.json's north_star)
+
+
+def e2e_sample_size(cfg, es, budget_bytes=8 << 30):
+    """Slices of the e2e leg: about `budget_bytes` of X in page-locked host memory."""
+    mean_j = sum(cfg["J"]) / 2
+    return int(max(8, min(cfg["I"], budget_bytes // (mean_j * cfg["K"] * es))))
+
+
+def gen_pinned_sample(cfg, sizes, n_slices, dtype, device):
+    """First n_slices of the workload (same generator as the HBM-resident data) as NumPy views of ONE page-locked
+    host buffer: the input of the e2e leg."""
+    import torch
+
+    packed = gen_device_data(cfg, sizes, 0, n_slices, dtype, device)
+    K = cfg["K"]
+    host = torch.empty((packed.N, K), dtype=dtype, pin_memory=True)
+    host.copy_(packed.X[:, :K])
+    torch.cuda.synchronize()
+    off = packed.row_offsets
+    del packed
+    torch.cuda.empty_cache()
+    arr = host.numpy()
+    return [arr[a:b] for a, b in zip(off[:-1], off[1:])], int(off[-1])
+
+
 def cpu_sample_size(cfg):
     # ~13 ms per (1152 x 1024, R=20) slice-iteration on 8 cores (BASELINE.md §3) -> a few seconds per iteration
     rows_budget = 300_000 if cfg["kw"].get("unimodal") is None else 40_000
@@ -328,9 +354,12 @@ def main():
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, copy kernel)" if "hbm_gbs" in peaks else "fallback 6650"
     dom, t_dom = ("xstream_z", t_z) if t_z >= t_y else ("xstream_y", t_y)
     achieved = x_bytes_local / t_dom / 1e6  # GB/s: algorithmic bytes = the X shard read once per launch
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+    traffic, traffic_src = None, None
+    try:  # DRAM bytes per algorithmic byte from the committed `ncu --set full` capture, scaled to this launch
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj[dom]["ratio"] * x_bytes_local
+        traffic_src = (f"(dram__bytes_read.sum + dram__bytes_write.sum) / algorithmic bytes = {tj[dom]['ratio']:.4f} in "
+                       f"the {tj['source']}, times this launch's algorithmic bytes")
     except Exception:
         pass
     line = {
@@ -343,7 +372,7 @@ def main():
                    "x_bytes_rank0": int(x_bytes_local), "x_passes_per_iteration": 2,
                    "l2_flush": "not needed: X shard >> 126 MB L2", "parallelism": f"slices sharded over {world} GPU(s)"},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                     "frac": achieved / hbm_peak, "traffic": traffic, "peak_source": peak_src,
+                     "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "xstream_y_ms": t_y, "xstream_z_ms": t_z,
                      "xstream_y_gbs": x_bytes_local / t_y / 1e6, "xstream_z_gbs": x_bytes_local / t_z / 1e6,
                      "iteration_stream_gbs": 2 * x_bytes_local / ms_step / 1e6},
@@ -363,27 +392,37 @@ def main():
                 "value": 1.0 / (t_s * total_rows / rows), "unit": "iter/s", "cores": os.cpu_count(), "kind": "port",
                 "sample": f"first {S} of {cfg['I']} slices ({rows} of {total_rows} rows): {t_s:.3f} s per outer "
                           f"iteration, scaled linearly in rows (every reference loop is per slice)"}
-        # ---- e2e: public API with HOST buffers on the same sample (pack + H2D + K iterations + D2H timed) ----
+        # ---- e2e: public API with HOST buffers (pinned), whole call timed: pack + H2D + k iterations + D2H ----
         from matcouply_b200 import cmf_aoadmm
 
         kw = dict(cfg["kw"], random_state=0, tol=None, absolute_tol=None)
-        cmf_aoadmm(mats[:4], cfg["R"], n_iter_max=1, **kw)  # warm-up of the call path
+        S2 = e2e_sample_size(cfg, es)
+        views, rows2 = gen_pinned_sample(cfg, sizes, S2, dtype, device)
+        cmf_aoadmm(views, cfg["R"], n_iter_max=1, **kw)  # warm-up of the call path (allocator, staging buffers)
         torch.cuda.synchronize()
-        k_e2e = max(args.steps, 5)
-        t0 = time.perf_counter()
-        cmf = cmf_aoadmm(mats, cfg["R"], n_iter_max=k_e2e, return_errors=True, **kw)
-        torch.cuda.synchronize()
-        t_call = time.perf_counter() - t0
-        h2d = rows * cfg["K"] * es + 7 * rows * cfg["R"] * 8
-        d2h = rows * cfg["R"] * 8 + k_e2e * 64 * 8
+        times = {}
+        for k in (5, E2E_ITERS):
+            t0 = time.perf_counter()
+            cmf = cmf_aoadmm(views, cfg["R"], n_iter_max=k, return_errors=True, **kw)
+            torch.cuda.synchronize()
+            times[k] = time.perf_counter() - t0
+            del cmf
+        k_e2e, t_call = E2E_ITERS, times[E2E_ITERS]
+        n_state = 1 + sum(1 if r.__class__.__name__ == "Parafac2" else 2 for r in regs[1])  # B + aux/dual uploads
+        h2d = rows2 * cfg["K"] * es + n_state * rows2 * cfg["R"] * 8
+        d2h = rows2 * cfg["R"] * 8 + (k_e2e + 1) * 64 * 8
+        t_iter = (times[E2E_ITERS] - times[5]) / (E2E_ITERS - 5)
         line["e2e"] = {
-            "value": 1.0 / (t_call / k_e2e * total_rows / rows), "unit": "iter/s",
+            "value": 1.0 / (t_call / k_e2e * total_rows / rows2), "unit": "iter/s",
             "h2d_bytes_per_step": int(h2d / k_e2e), "d2h_bytes_per_step": int(d2h / k_e2e),
-            "note": f"cmf_aoadmm(list of host arrays) on the first {S} slices ({rows} rows), {k_e2e} outer iterations, "
-                    f"whole call timed ({t_call:.3f} s incl. packing, H2D of X and state, D2H of factors) and scaled "
-                    f"linearly in rows to the full workload; the 155 GB data set cannot be staged from host memory "
-                    f"inside a few-minute run"}
-        del cmf
+            "note": f"cmf_aoadmm(list of page-locked host arrays, n_iter_max={k_e2e}, return_errors=True) on the first "
+                    f"{S2} slices ({rows2} rows, {rows2 * cfg['K'] * es / 1e9:.1f} GB of X): whole call timed "
+                    f"({t_call:.3f} s: host RNG init of the state, H2D of X and state, {k_e2e} outer iterations with the "
+                    f"per-iteration diagnostics D2H, D2H of the factors), iterations/s = {k_e2e} / t_call, scaled "
+                    f"linearly in rows to the full workload (155 GB of host data cannot be staged inside a few-minute "
+                    f"run). The same call with n_iter_max=5 takes {times[5]:.3f} s, i.e. {1000 * t_iter:.2f} ms per "
+                    f"iteration + {times[5] - 5 * t_iter:.3f} s of fixed cost (upload + init + download)"}
+        del views
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

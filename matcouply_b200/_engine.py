@@ -51,20 +51,84 @@ class PackedMatrices:
                 raise ValueError("All matrices must be two-dimensional with the same number of columns")
         N = int(sum(sizes))
         ld = _ops.padded_ld(K, dtype)
-        X = torch.zeros((N, ld), dtype=dtype, device=device)
+        X = torch.empty((N, ld), dtype=dtype, device=device)
+        if ld != K:
+            X[:, K:] = 0
         if all(isinstance(m, np.ndarray) for m in matrices):
-            host = torch.empty((N, K), dtype=dtype, pin_memory=torch.cuda.is_available())
-            r = 0
-            for m in matrices:
-                host[r:r + m.shape[0]] = torch.from_numpy(np.ascontiguousarray(m))
-                r += m.shape[0]
-            X[:, :K].copy_(host, non_blocking=True)
+            cls._upload_host_slices(X, matrices, sizes, K, dtype)
         else:
             r = 0
             for m in matrices:
                 X[r:r + m.shape[0], :K] = torch.as_tensor(m).to(device=device, dtype=dtype)
                 r += m.shape[0]
         return cls(X, np.concatenate([[0], np.cumsum(sizes)]), K)
+
+    STAGE_BYTES = 128 << 20  # size of each of the two pinned staging buffers used for pageable inputs
+
+    @classmethod
+    def _upload_host_slices(cls, X, matrices, sizes, K, dtype):
+        """Host -> HBM upload of the slice list, asynchronous on the current stream.
+
+        Runs of slices that sit back to back in host memory are copied with one cudaMemcpyAsync each.  Page-locked
+        inputs go straight from the caller's memory; pageable ones are staged through two alternating pinned buffers
+        so the CPU-side gather of chunk n+1 overlaps the DMA of chunk n (no N x K pinned shadow copy)."""
+        es = X.element_size()
+        mats = [m if m.flags.c_contiguous else np.ascontiguousarray(m) for m in matrices]
+
+        def root(a):
+            while isinstance(getattr(a, "base", None), np.ndarray):
+                a = a.base
+            return a
+
+        # merge slices that are views of ONE host allocation and adjacent in it (e.g. X[i] of a stacked array)
+        runs, r = [], 0  # [first row, n rows, first slice index, n slices]
+        for i, (m, J) in enumerate(zip(mats, sizes)):
+            p = mats[i - 1] if i else None
+            if runs and m.dtype == p.dtype and root(m) is root(p) and root(m) is not m and \
+                    m.ctypes.data == p.ctypes.data + p.nbytes:
+                runs[-1][1] += J
+                runs[-1][3] += 1
+            else:
+                runs.append([r, J, i, 1])
+            r += J
+
+        def run_tensor(i0, cnt, nrows):
+            m = mats[i0]
+            if cnt > 1:
+                m = np.lib.stride_tricks.as_strided(m, shape=(nrows, K), strides=(K * m.itemsize, m.itemsize),
+                                                    writeable=False)
+            return torch.from_numpy(m)
+
+        stage, events, turn = [None, None], [None, None], 0
+        for r0, nrows, i0, cnt in runs:
+            if nrows == 0:
+                continue
+            import warnings
+
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")  # read-only NumPy views: we only read
+                src = run_tensor(i0, cnt, nrows)
+            if src.is_pinned():
+                X[r0:r0 + nrows, :K].copy_(src, non_blocking=True)
+                continue
+            # pageable: chunks of <= STAGE_BYTES through the pinned ring
+            rows_per_chunk = max(1, cls.STAGE_BYTES // max(1, K * es))
+            for c0 in range(0, nrows, rows_per_chunk):
+                c1 = min(nrows, c0 + rows_per_chunk)
+                if stage[turn] is None:
+                    stage[turn] = torch.empty(rows_per_chunk * K, dtype=dtype, pin_memory=True)
+                if events[turn] is not None:
+                    events[turn].synchronize()  # the DMA that last read this buffer has finished
+                buf = stage[turn][: (c1 - c0) * K].view(c1 - c0, K)
+                buf.copy_(src[c0:c1])  # CPU gather (+ dtype conversion)
+                X[r0 + c0:r0 + c1, :K].copy_(buf, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                events[turn] = ev
+                turn ^= 1
+        for ev in events:
+            if ev is not None:
+                ev.synchronize()  # staging buffers may be recycled by the allocator after return
 
 
 class _ModeState:
