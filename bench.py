@@ -190,12 +190,12 @@ def e2e_sample_size(cfg, es, budget_bytes=8 << 30):
     return int(max(8, min(cfg["I"], budget_bytes // (mean_j * cfg["K"] * es))))
 
 
-def gen_pinned_sample(cfg, sizes, n_slices, dtype, device):
-    """First n_slices of the workload (same generator as the HBM-resident data) as NumPy views of ONE page-locked
+def gen_pinned_sample(cfg, sizes, lo, hi, dtype, device):
+    """Slices lo..hi of the workload (same generator as the HBM-resident data) as NumPy views of ONE page-locked
     host buffer: the input of the e2e leg."""
     import torch
 
-    packed = gen_device_data(cfg, sizes, 0, n_slices, dtype, device)
+    packed = gen_device_data(cfg, sizes, lo, hi, dtype, device)
     K = cfg["K"]
     host = torch.empty((packed.N, K), dtype=dtype, pin_memory=True)
     host.copy_(packed.X[:, :K])
@@ -205,6 +205,63 @@ def gen_pinned_sample(cfg, sizes, n_slices, dtype, device):
     torch.cuda.empty_cache()
     arr = host.numpy()
     return [arr[a:b] for a, b in zip(off[:-1], off[1:])], int(off[-1])
+
+
+def run_e2e(cfg, sizes, dtype, es, device, world, rank, group, regs):
+    """e2e leg: the public `cmf_aoadmm` call on page-locked HOST arrays, whole call timed (host RNG init of the state,
+    H2D of X and state, E2E_ITERS outer iterations with the per-iteration diagnostics D2H, D2H of the factors).  With
+    N ranks every rank uploads and fits its row-balanced shard of an N-times larger sample (NCCL all-reduces inside
+    the call); the time is the max over ranks."""
+    import torch
+
+    from matcouply_b200 import cmf_aoadmm
+    from matcouply_b200.distributed import make_shard
+
+    kw = dict(cfg["kw"], random_state=0, tol=None, absolute_tol=None)
+    S2 = min(cfg["I"], e2e_sample_size(cfg, es) * world)
+    sub = dict(cfg, I=S2)
+    sizes2 = sizes[:S2]
+    if world > 1:
+        import torch.distributed as dist
+
+        sh = make_shard([int(j) for j in sizes2], rank, world)
+        kw.update(process_group=group, shard=sh, gather_factors=False)
+        lo, hi = sh.lo, sh.hi
+    else:
+        lo, hi = 0, S2
+    views, _rows_local = gen_pinned_sample(sub, sizes2, lo, hi, dtype, device)
+    rows2 = int(sizes2.sum())
+    cmf_aoadmm(views, cfg["R"], n_iter_max=1, **kw)  # warm-up of the call path (allocator, staging buffers)
+    times = {}
+    for k in (5, E2E_ITERS):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        out = cmf_aoadmm(views, cfg["R"], n_iter_max=k, return_errors=True, **kw)
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        times[k] = float(t.item())
+        del out
+    del views
+    k_e2e, t_call = E2E_ITERS, times[E2E_ITERS]
+    total_rows = int(sizes.sum())
+    n_state = 1 + sum(1 if r.__class__.__name__ == "Parafac2" else 2 for r in regs[1])  # B + aux/dual uploads
+    h2d = rows2 * cfg["K"] * es + n_state * rows2 * cfg["R"] * 8
+    d2h = rows2 * cfg["R"] * 8 + (k_e2e + 1) * 64 * 8
+    t_iter = (times[E2E_ITERS] - times[5]) / (E2E_ITERS - 5)
+    return {
+        "value": 1.0 / (t_call / k_e2e * total_rows / rows2), "unit": "iter/s",
+        "h2d_bytes_per_step": int(h2d / k_e2e), "d2h_bytes_per_step": int(d2h / k_e2e),
+        "note": f"cmf_aoadmm(list of page-locked host arrays, n_iter_max={k_e2e}, return_errors=True) on the first "
+                f"{S2} slices ({rows2} rows, {rows2 * cfg['K'] * es / 1e9:.1f} GB of X) sharded over {world} GPU(s): whole "
+                f"call timed, max over ranks ({t_call:.3f} s: host RNG init of the state, H2D of X and state, {k_e2e} "
+                f"outer iterations with the per-iteration diagnostics D2H, D2H of the factors), iterations/s = {k_e2e} / "
+                f"t_call, scaled linearly in rows to the full workload (155 GB of host data cannot be staged inside a "
+                f"few-minute run). The same call with n_iter_max=5 takes {times[5]:.3f} s, i.e. {1000 * t_iter:.2f} ms "
+                f"per iteration + {times[5] - 5 * t_iter:.3f} s of fixed cost (upload + init + download)"}
 
 
 def cpu_sample_size(cfg):
@@ -340,6 +397,12 @@ def main():
     ms_total, t_y, t_z = (float(v) for v in tmax.cpu())
     ms_step = ms_total / args.steps
 
+    rows_rank0 = int(packed.N)
+    del eng, packed
+    torch.cuda.empty_cache()
+    e2e = None
+    if not args.no_cpu:
+        e2e = run_e2e(cfg, sizes, dtype, es, device, world, rank, group, regs)  # collective: every rank takes part
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -368,7 +431,7 @@ def main():
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": cfg["dtype"],
         "data": "synthetic",
         "config": {"workload": cfg["desc"] + (" [REDUCED: shard did not fit HBM]" if reduced else ""),
-                   "slices_total": int(cfg["I"]) if not reduced else int(hi - lo), "rows_rank0": int(packed.N),
+                   "slices_total": int(cfg["I"]) if not reduced else int(hi - lo), "rows_rank0": rows_rank0,
                    "x_bytes_rank0": int(x_bytes_local), "x_passes_per_iteration": 2,
                    "l2_flush": "not needed: X shard >> 126 MB L2", "parallelism": f"slices sharded over {world} GPU(s)"},
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
@@ -378,8 +441,6 @@ def main():
                      "iteration_stream_gbs": 2 * x_bytes_local / ms_step / 1e6},
         "gpu_launches": launches, "clocks": clocks,
     }
-    del eng, packed
-    torch.cuda.empty_cache()
     if not args.no_cpu:
         # ---- cpu_baseline: oracle port on a bounded sample of the same workload (rank 0, N=1 only) ----
         S = cpu_sample_size(cfg)
@@ -392,37 +453,8 @@ def main():
                 "value": 1.0 / (t_s * total_rows / rows), "unit": "iter/s", "cores": os.cpu_count(), "kind": "port",
                 "sample": f"first {S} of {cfg['I']} slices ({rows} of {total_rows} rows): {t_s:.3f} s per outer "
                           f"iteration, scaled linearly in rows (every reference loop is per slice)"}
-        # ---- e2e: public API with HOST buffers (pinned), whole call timed: pack + H2D + k iterations + D2H ----
-        from matcouply_b200 import cmf_aoadmm
-
-        kw = dict(cfg["kw"], random_state=0, tol=None, absolute_tol=None)
-        S2 = e2e_sample_size(cfg, es)
-        views, rows2 = gen_pinned_sample(cfg, sizes, S2, dtype, device)
-        cmf_aoadmm(views, cfg["R"], n_iter_max=1, **kw)  # warm-up of the call path (allocator, staging buffers)
-        torch.cuda.synchronize()
-        times = {}
-        for k in (5, E2E_ITERS):
-            t0 = time.perf_counter()
-            cmf = cmf_aoadmm(views, cfg["R"], n_iter_max=k, return_errors=True, **kw)
-            torch.cuda.synchronize()
-            times[k] = time.perf_counter() - t0
-            del cmf
-        k_e2e, t_call = E2E_ITERS, times[E2E_ITERS]
-        n_state = 1 + sum(1 if r.__class__.__name__ == "Parafac2" else 2 for r in regs[1])  # B + aux/dual uploads
-        h2d = rows2 * cfg["K"] * es + n_state * rows2 * cfg["R"] * 8
-        d2h = rows2 * cfg["R"] * 8 + (k_e2e + 1) * 64 * 8
-        t_iter = (times[E2E_ITERS] - times[5]) / (E2E_ITERS - 5)
-        line["e2e"] = {
-            "value": 1.0 / (t_call / k_e2e * total_rows / rows2), "unit": "iter/s",
-            "h2d_bytes_per_step": int(h2d / k_e2e), "d2h_bytes_per_step": int(d2h / k_e2e),
-            "note": f"cmf_aoadmm(list of page-locked host arrays, n_iter_max={k_e2e}, return_errors=True) on the first "
-                    f"{S2} slices ({rows2} rows, {rows2 * cfg['K'] * es / 1e9:.1f} GB of X): whole call timed "
-                    f"({t_call:.3f} s: host RNG init of the state, H2D of X and state, {k_e2e} outer iterations with the "
-                    f"per-iteration diagnostics D2H, D2H of the factors), iterations/s = {k_e2e} / t_call, scaled "
-                    f"linearly in rows to the full workload (155 GB of host data cannot be staged inside a few-minute "
-                    f"run). The same call with n_iter_max=5 takes {times[5]:.3f} s, i.e. {1000 * t_iter:.2f} ms per "
-                    f"iteration + {times[5] - 5 * t_iter:.3f} s of fixed cost (upload + init + download)"}
-        del views
+    if e2e is not None:
+        line["e2e"] = e2e
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -141,13 +141,15 @@ size_t b2_unimodal_workspace_bytes(int n_groups, int R, int max_rows);
  *   b2_pf2_polar:  W_i such that P_i = V_i W_i = polar(V_i Delta^T)   (R x R Jacobi eigen-decomposition of
  *                  Delta S_i Delta^T instead of the J_i x R SVD of :1234-1235), and
  *                  num_part[g] = rho_i W_i^T S_i = rho_i P_i^T V_i (summand of :1244).
+ *                  Qstore (optional, n_groups x R x R doubles) receives the eigenvectors; with warm != 0 the Jacobi
+ *                  sweeps start from the eigenvectors stored by the previous call (same result, fewer sweeps).
  *   b2_pf2_delta:  Delta_new = sum_g num_part[g] / sum_g rho[g]  in fixed order (:1240-1245); also writes the
  *                  un-normalised sums to `sums` (R*R + 1 values: numerator, then sum rho) for a cross-rank all-reduce;
  *                  with `sums_in` != NULL it only normalises those (already reduced) sums.
  *   b2_pf2_apply:  pd[row] = V[row] W_g Delta_new (= P_i Delta) ; dual[row] = V[row] - pd[row] (:282-285);
  *                  optionally basis[row] = V[row] W_g (= P_i). */
 int b2_pf2_polar(const void* S, const void* Delta, const void* rho, int n_groups, int R, void* Wmat, void* num_part,
-                 int dtype, void* stream);
+                 void* Qstore, int warm, int dtype, void* stream);
 /* Fused row pass of one B-mode inner iteration when pens[0] is PARAFAC2 (one CTA per slice):
  *   deferred != 0: pens[0].dual holds the pre-image V of the previous prox; P Delta = V (W_g Delta) and
  *                  dual = V - P Delta are formed on the fly (pens[0].aux is not read);
@@ -174,6 +176,11 @@ int b2_pf2_delta(const void* num_part, const void* rho, int n_groups, int R, voi
                  const void* sums_in, int dtype, void* stream);
 int b2_pf2_apply(void* pd, void* dual, void* basis, const void* Wmat, const void* Delta_new,
                  const int32_t* group_of_row, long long n, int R, int dtype, void* stream);
+/* Feasibility-gap terms of the PARAFAC2 penalty from the deferred state, nothing materialised
+ * (decomposition.py:406-415 with penalties.py:1287-1304):  out[0] = sum_i ||V_i W_i Delta - x_i||^2 (= ||P_i Delta - B_i||^2),
+ * out[1] = sum ||x||^2, out[2] = sum |x|.  ws >= 3 * n_groups doubles. */
+int b2_pf2_gap(const void* V, const void* x, const int64_t* row_off, int n_groups, int R, const void* Wmat,
+               const void* Delta, double* out, int dtype, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- fused reductions for feasibility gaps / loss (decomposition.py:351-452, 617-627; penalties.py:589-592) ------
  * out[0] = sum((x-y)^2), out[1] = sum(x^2), out[2] = sum(|x|) over n elements (y may be NULL -> out[0] = 0). double. */

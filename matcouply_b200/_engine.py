@@ -217,6 +217,11 @@ class AOADMMEngine:
             self.pf2_sums = torch.zeros(R * R + 1, dtype=torch.float64, device=dev)
             self.pf2_basis0 = None   # initial basis matrices (host) until the first B-update replaces them
             self.pf2_fresh = False
+            # deferred state: the PARAFAC2 dual slot holds the pre-image V of the last prox and (aux, dual) =
+            # (V W_g Delta, V - V W_g Delta) exist only implicitly; _materialize_pf2() writes them out on demand
+            self.pf2_deferred = False
+            self.pf2_gap_part = torch.zeros(3 * max(I, 1), dtype=torch.float64, device=dev)
+            self.pf2_Q = torch.zeros(I, R, R, dtype=torch.float64, device=dev)  # Jacobi eigenvectors (warm start)
         self.scal = torch.zeros(64, dtype=torch.float64, device=dev)
         self.normX_sq = None
         uni = None
@@ -246,6 +251,7 @@ class AOADMMEngine:
                     basis, delta = aux
                     self.pf2_basis0 = [np.asarray(b, dtype=np.float64) for b in basis]
                     self.pf2_fresh = False
+                    self.pf2_deferred = False
                     self.Delta.copy_(self._up(delta))
                     pd = np.concatenate([np.asarray(b) @ np.asarray(delta) for b in basis], 0)
                     st[m].aux.append(self._up(pd))
@@ -281,7 +287,7 @@ class AOADMMEngine:
                         ok = (self.row_off[1:] - starts) > j
                         pd[(starts + j)[ok]] = self.Delta[j]
                     st[m].aux.append(pd)
-                    self.pf2_basis0, self.pf2_fresh = None, False
+                    self.pf2_basis0, self.pf2_fresh, self.pf2_deferred = None, False, False
                 else:
                     st[m].aux.append(rnd(n, R))
                 st[m].dual.append(rnd(n, R))
@@ -307,6 +313,7 @@ class AOADMMEngine:
                 if kind == _lib.PEN_PARAFAC2:
                     if self.pf2_fresh:
                         # P_i = V_i W_i with V = dual + P Delta (the pre-image of the last prox call)
+                        self._materialize_pf2()
                         V = (st.dual[p] + st.aux[p]).contiguous()
                         basis, tmp = torch.empty_like(V), torch.empty_like(V)
                         _ops.pf2_apply(tmp, V, basis, self.Wmat, self.Delta, self.gor, self.N, self.R)
@@ -353,6 +360,14 @@ class AOADMMEngine:
                 _ops.pf2_apply(st.aux[p], st.dual[p], None, self.Wmat, self.Delta, gor, n_rows, R)
                 self.pf2_fresh = True
 
+    def _materialize_pf2(self):
+        """Write out P Delta (aux slot) and dual = V - P Delta of the PARAFAC2 penalty if they are deferred."""
+        if self.has_pf2 and self.pf2_deferred:
+            st = self.modes[1]
+            p = [d[0] for d in st.desc].index(_lib.PEN_PARAFAC2)
+            _ops.pf2_apply(st.aux[p], st.dual[p], None, self.Wmat, self.Delta, self.gor, self.N, self.R)
+            self.pf2_deferred = False
+
     def _timed(self, key, fn):
         self.n_xstream_launches += 1
         if self.xstream_events is None:
@@ -384,6 +399,7 @@ class AOADMMEngine:
             return
         if self.fuse_pf2 and self.n_inner > 0 and st.desc and st.desc[0][0] == _lib.PEN_PARAFAC2:
             return self._step_B_pf2_fused()
+        self._materialize_pf2()
         for _ in range(self.n_inner):
             _ops.admm_solve(self.N, R, self.Y, A, _lib.GROUP_INDEXED, self.gor, self.rhoB, self.MinvB, st.descs_c,
                             len(st.desc), st.x)
@@ -398,20 +414,24 @@ class AOADMMEngine:
         A = self.modes[0].x
         for it in range(self.n_inner):
             last = it == self.n_inner - 1
-            _ops.pf2_rowpass(self.row_off, I, R, self.Y, A, self.rhoB, self.MinvB, st.descs_c, len(st.desc), it > 0,
-                             self.Wmat, self.Delta, st.x if last else None, self.Wpad if last else None, self.S,
-                             self.BtB if last else None)
+            # deferred from the start when the previous outer iteration left (V, W_g, Delta) behind
+            _ops.pf2_rowpass(self.row_off, I, R, self.Y, A, self.rhoB, self.MinvB, st.descs_c, len(st.desc),
+                             it > 0 or self.pf2_deferred, self.Wmat, self.Delta, st.x if last else None,
+                             self.Wpad if last else None, self.S, self.BtB if last else None)
             for p, (kind, nn, p0, _p1) in enumerate(st.desc):  # column-coupled companions (V is in their dual slot)
                 if kind == _lib.PEN_L2BALL:
                     _ops.prox_l2ball(st.aux[p], st.dual[p], self.row_off, I, R, p0, nn)
                 elif kind == _lib.PEN_UNIMODAL:
                     _ops.prox_unimodal(st.aux[p], st.dual[p], self.row_off, I, R, self.max_rows, nn, self.ws)
-            _ops.pf2_polar(self.S, self.Delta, self.rhoB, I, R, self.Wmat, self.num_part)
+            # cold Jacobi start on the first inner iteration (bounds the round-off drift of the accumulated
+            # rotations), warm start from the previous inner iteration's eigenvectors afterwards
+            _ops.pf2_polar(self.S, self.Delta, self.rhoB, I, R, self.Wmat, self.num_part, self.pf2_Q, warm=it > 0)
             _ops.pf2_delta(self.num_part, self.rhoB, I, R, self.Delta, self.pf2_sums)
             if self.world > 1:
                 self._allreduce(self.pf2_sums)
                 _ops.pf2_delta(self.num_part, self.rhoB, I, R, self.Delta, None, self.pf2_sums)
-        _ops.pf2_apply(st.aux[0], st.dual[0], None, self.Wmat, self.Delta, self.gor, self.N, R)
+        # P Delta and dual = V - P Delta stay implicit: the next row pass and the gap reduction apply W_g Delta on the fly
+        self.pf2_deferred = True
         self.pf2_fresh = True
         self.w_fresh = True
 
@@ -509,7 +529,11 @@ class AOADMMEngine:
                 layout.append((m, -1, slot))
                 slot += 3
             for p in range(len(st.desc)):
-                _ops.reduce_stats(st.x, st.aux[p], sizes[m], scal[slot:slot + 3], self.ws)
+                if m == 1 and st.desc[p][0] == _lib.PEN_PARAFAC2 and self.pf2_deferred:
+                    _ops.pf2_gap(st.dual[p], st.x, self.row_off, self.I, self.R, self.Wmat, self.Delta,
+                                 scal[slot:slot + 3], self.pf2_gap_part)
+                else:
+                    _ops.reduce_stats(st.x, st.aux[p], sizes[m], scal[slot:slot + 3], self.ws)
                 layout.append((m, p, slot))
                 slot += 3
         if self.world > 1:

@@ -49,11 +49,12 @@ _SIGNATURES = {
                       _vp, _i, _vp],
     "b2_prox_l2ball": [_vp, _vp, _vp, _i, _i, _d, _i, _i, _vp],
     "b2_prox_unimodal": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _sz, _vp],
-    "b2_pf2_polar": [_vp, _vp, _vp, _i, _i, _vp, _vp, _i, _vp],
+    "b2_pf2_polar": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
     "b2_pf2_rowpass": [_vp, _i, _i, _vp, _vp, _vp, _vp, ctypes.POINTER(PenaltyDesc), _i, _i, _vp, _vp, _vp, _vp, _i, _vp,
                        _vp, _i, _vp],
     "b2_pf2_delta": [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp],
     "b2_pf2_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp],
+    "b2_pf2_gap": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _sz, _vp],
     "b2_slice_gram": [_vp, _vp, _i, _i, _vp, _i, _vp],
     "b2_slice_coldot": [_vp, _vp, _vp, _i, _i, _vp, _i, _vp],
     "b2_weighted_gram_sum": [_vp, _vp, _i, _i, _vp, _i, _vp],

@@ -153,9 +153,9 @@ def prox_unimodal(aux, dual, row_off, n_groups, R, max_rows, nn, ws, peaks=None)
          dtype_code(aux.dtype), _ptr(ws.uni), ws.uni_bytes, _stream())
 
 
-def pf2_polar(S, Delta, rho, n_groups, R, Wmat, num_part):
-    call("b2_pf2_polar", _ptr(S), _ptr(Delta), _ptr(rho), n_groups, R, _ptr(Wmat), _ptr(num_part),
-         dtype_code(S.dtype), _stream())
+def pf2_polar(S, Delta, rho, n_groups, R, Wmat, num_part, Qstore=None, warm=False):
+    call("b2_pf2_polar", _ptr(S), _ptr(Delta), _ptr(rho), n_groups, R, _ptr(Wmat), _ptr(num_part), _ptr(Qstore),
+         int(bool(warm)), dtype_code(S.dtype), _stream())
 
 
 def pf2_delta(num_part, rho, n_groups, R, Delta_new, sums, sums_in=None):
@@ -212,6 +212,12 @@ def pf2_rowpass(row_off, n_groups, R, Y, A, rho, Minv, descs, n_pen, deferred, W
     call("b2_pf2_rowpass", _ptr(row_off), n_groups, R, _ptr(Y), _ptr(A), _ptr(rho), _ptr(Minv), descs, n_pen,
          int(bool(deferred)), _ptr(Wmat), _ptr(Delta), _ptr(x), _ptr(w_out), 0 if w_out is None else w_out.shape[1],
          _ptr(S_out), _ptr(BtB_out), dtype_code(Y.dtype), _stream())
+
+
+def pf2_gap(V, x, row_off, n_groups, R, Wmat, Delta, out, part):
+    """out[0:3] = (sum ||V W Delta - x||^2, sum x^2, sum |x|); part: scratch of >= 3 * n_groups doubles."""
+    call("b2_pf2_gap", _ptr(V), _ptr(x), _ptr(row_off), n_groups, R, _ptr(Wmat), _ptr(Delta), _ptr(out),
+         dtype_code(V.dtype), _ptr(part), part.numel() * part.element_size(), _stream())
 
 
 def slice_gram(B, row_off, n_groups, R, BtB):

@@ -86,15 +86,22 @@ struct GramAcc {
 #pragma unroll
         for (int q = 0; q < NPAIR; ++q) acc[q][0] = acc[q][1] = 0.0;
     }
-    // v: the warp's rows in D layout (padding positions MUST be zero); tile: 8 * LDT doubles owned by this warp
-    __device__ __forceinline__ void add(const double (&v)[PL::NB][2], double* __restrict__ tile, int g, int t) {
-        // WAR guard: the fragment loads of the previous call must have returned in every lane before the tile is
-        // overwritten.  ptxas may sink loads below a WARPSYNC, so order the stores behind a warp vote on the
-        // accumulators those loads fed (same device as stage_release in common.cuh).
-        int dep = 0;
+    // high words of the accumulators: a value that cannot exist before every fragment load feeding them has returned
+    __device__ __forceinline__ int dep() const {
+        int d = 0;
 #pragma unroll
-        for (int q = 0; q < NPAIR; ++q) dep = max(dep, __double2hiint(acc[q][0]));
-        const unsigned never = __any_sync(0xffffffffu, dep == 0x7ff7a5a5) ? 1u : 0u;
+        for (int q = 0; q < NPAIR; ++q) d = max(d, __double2hiint(acc[q][0]));
+        return d;
+    }
+    // v: the warp's rows in D layout (padding positions MUST be zero); tile: 8 * LDT doubles owned by this warp.
+    // extra_dep: dep() of another GramAcc that shares `tile` (0 if none).
+    __device__ __forceinline__ void add(const double (&v)[PL::NB][2], double* __restrict__ tile, int g, int t,
+                                        int extra_dep = 0) {
+        // WAR guard: the fragment loads of the previous call(s) on this tile must have returned in every lane before
+        // the tile is overwritten.  ptxas may sink loads below a WARPSYNC, so order the stores behind a warp vote on
+        // the accumulators those loads fed (same device as stage_release in common.cuh).
+        const int d = max(dep(), extra_dep);
+        const unsigned never = __any_sync(0xffffffffu, d == 0x7ff7a5a5) ? 1u : 0u;
         double* tl = tile + never;
 #pragma unroll
         for (int b = 0; b < PL::NB; ++b) *(double2*)(tl + g * LDT + 8 * b + 2 * t) = make_double2(v[b][0], v[b][1]);

@@ -260,7 +260,7 @@ __device__ __forceinline__ void cta_matmul(const double* A, const double* B, dou
 template <typename T>
 __global__ void __launch_bounds__(kPolarThreads)
 pf2_polar_cta_kernel(const T* __restrict__ S, const T* __restrict__ Delta, const T* __restrict__ rho, int R,
-                     T* __restrict__ Wmat, double* __restrict__ num_part) {
+                     T* __restrict__ Wmat, double* __restrict__ num_part, double* __restrict__ Qstore, int warm) {
     extern __shared__ double pj_smem[];
     const int RR = R * R;
     double* D = pj_smem;
@@ -281,6 +281,15 @@ pf2_polar_cta_kernel(const T* __restrict__ S, const T* __restrict__ Delta, const
     __syncthreads();
     cta_matmul(D, Sg, Tm, R, false, false);
     cta_matmul(Tm, D, G, R, false, true);
+    if (warm) {
+        // Warm start: rotate into the eigenbasis of the previous inner iteration (G changes little between inner
+        // iterations, so Q0^T G Q0 is nearly diagonal and Jacobi needs 1-3 sweeps instead of 6-8).  The accumulated
+        // rotations start from Q0, so Q stays the eigenvector matrix of G itself.
+        for (int e = tid; e < RR; e += blockDim.x) Q[e] = Qstore[(size_t)g * RR + e];
+        __syncthreads();
+        cta_matmul(G, Q, Tm, R, false, false);
+        cta_matmul(Q, Tm, G, R, true, false);
+    }
     for (int e = tid; e < RR; e += blockDim.x) {  // symmetrise round-off
         const int i = e / R, j = e - i * R;
         if (i < j) {
@@ -380,6 +389,8 @@ pf2_polar_cta_kernel(const T* __restrict__ S, const T* __restrict__ Delta, const
     __syncthreads();
     const double lmax = cs[0];
     __syncthreads();
+    if (Qstore)
+        for (int e = tid; e < RR; e += blockDim.x) Qstore[(size_t)g * RR + e] = Q[e];
     for (int e = tid; e < RR; e += blockDim.x) {
         const int j = e % R;
         const double lam = G[j * R + j];
@@ -426,6 +437,95 @@ int launch_rowpass(const int64_t* row_off, int n_groups, int R, const void* Y, c
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<n_groups, 256, smem, st>>>(row_off, R, (const T*)Y, (const T*)A, (const T*)rho, (const T*)Minv, pa, deferred,
                                       (const T*)Wmat, (const T*)Delta, (T*)x, (T*)w_out, ldw, (T*)S_out, (T*)BtB_out);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+
+
+// Feasibility-gap terms of the PARAFAC2 penalty straight from the deferred state (decomposition.py:406-415 with
+// penalties.py:1287-1304): per slice  d2 = ||V_g T_g - x_g||^2 (T_g = W_g Delta, V_g T_g = P_g Delta),  x2 = ||x_g||^2,
+// ab = sum |x_g|.  Nothing is materialised.  part[g*3 + {0,1,2}]; fixed summation order.
+template <typename T, int CPL>
+__global__ void __launch_bounds__(256)
+pf2_gap_kernel(const int64_t* __restrict__ row_off, int R, const T* __restrict__ V, const T* __restrict__ x,
+               const T* __restrict__ Wmat, const T* __restrict__ Delta, double* __restrict__ part) {
+    using L = RowLayout<T, CPL>;
+    extern __shared__ double rp_smem[];
+    __shared__ double scratch[32];
+    const int RR = R * R;
+    T* Ts = (T*)rp_smem;
+    T* tw = Ts + L::ELEMS;
+    T* td = tw + RR;
+    const int g = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, l4 = lane & 3;
+    const long long r_begin = row_off[g], r_end = row_off[g + 1];
+    for (int e = tid; e < L::ELEMS; e += blockDim.x) Ts[e] = T(0);
+    for (int e = tid; e < RR; e += blockDim.x) {
+        tw[e] = Wmat[(size_t)g * RR + e];
+        td[e] = Delta[e];
+    }
+    __syncthreads();
+    for (int e = tid; e < RR; e += blockDim.x) {
+        const int i = e / R, c = e - i * R;
+        T s = T(0);
+        for (int k = 0; k < R; ++k) s = fma(tw[i * R + k], td[k * R + c], s);
+        Ts[i * L::LDM + (c / CPL) * L::CPLP + (c % CPL)] = s;
+    }
+    __syncthreads();
+    const int c0 = l4 * CPL;
+    const T* tseg = Ts + l4 * L::CPLP;
+    double d2 = 0.0, x2 = 0.0, ab = 0.0;
+    for (long long row0 = r_begin; row0 < r_end; row0 += kRowsPerPass) {
+        const long long rowid = row0 + (tid >> 2);
+        const bool valid = rowid < r_end;
+        const size_t base = (size_t)(valid ? rowid : r_end - 1) * R + c0;
+        T v_[CPL], pdv[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            v_[j] = (c0 + j < R) ? V[base + j] : T(0);
+            pdv[j] = T(0);
+        }
+        lane_matvec<T, CPL>(v_, tseg, lane, pdv);
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            if (valid && c0 + j < R) {
+                const double xv = (double)x[base + j];
+                const double d = xv - (double)pdv[j];
+                d2 += d * d;
+                x2 += xv * xv;
+                ab += fabs(xv);
+            }
+        }
+    }
+    d2 = block_sum(d2, scratch);
+    x2 = block_sum(x2, scratch);
+    ab = block_sum(ab, scratch);
+    if (tid == 0) {
+        part[(size_t)g * 3 + 0] = d2;
+        part[(size_t)g * 3 + 1] = x2;
+        part[(size_t)g * 3 + 2] = ab;
+    }
+}
+
+__global__ void pf2_gap_final_kernel(const double* __restrict__ part, int n_groups, double* __restrict__ out) {
+    __shared__ double scratch[32];
+    for (int k = 0; k < 3; ++k) {
+        double acc = 0.0;
+        for (int g = threadIdx.x; g < n_groups; g += blockDim.x) acc += part[(size_t)g * 3 + k];
+        acc = block_sum(acc, scratch);
+        if (threadIdx.x == 0) out[k] = acc;
+        __syncthreads();
+    }
+}
+
+template <typename T, int CPL>
+int launch_gap(const int64_t* row_off, int n_groups, int R, const void* V, const void* x, const void* Wmat,
+               const void* Delta, double* part, cudaStream_t st) {
+    using L = RowLayout<T, CPL>;
+    const size_t smem = (((size_t)L::ELEMS + 2 * (size_t)R * R) * sizeof(T) + 7) / 8 * 8;
+    auto kern = pf2_gap_kernel<T, CPL>;
+    B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<n_groups, 256, smem, st>>>(row_off, R, (const T*)V, (const T*)x, (const T*)Wmat, (const T*)Delta, part);
     B2_LAUNCH_CHECK();
     return B2_OK;
 }
@@ -483,16 +583,17 @@ int b2_pf2_rowpass(const int64_t* row_off, int n_groups, int R, const void* Y, c
 }
 
 int b2_pf2_polar(const void* S, const void* Delta, const void* rho, int n_groups, int R, void* Wmat, void* num_part,
-                 int dtype, void* stream) {
+                 void* Qstore, int warm, int dtype, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
+    B2_REQUIRE(!warm || Qstore, "b2_pf2_polar: a warm start needs the eigenvector store");
     if (n_groups == 0) return B2_OK;
     const size_t smem = (size_t)(5 * R * R + 32) * sizeof(double) + 32 * sizeof(int);
     B2_DISPATCH_DTYPE(dtype, {
         auto kern = pf2_polar_cta_kernel<T>;
         B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<n_groups, kPolarThreads, smem, st>>>((const T*)S, (const T*)Delta, (const T*)rho, R, (T*)Wmat,
-                                                    (double*)num_part);
+                                                    (double*)num_part, (double*)Qstore, warm);
         B2_LAUNCH_CHECK();
     });
     return B2_OK;
@@ -512,6 +613,38 @@ int b2_pf2_delta(const void* num_part, const void* rho, int n_groups, int R, voi
         pf2_normalise_kernel<T><<<1, 256, 0, st>>>((const double*)(sums_in ? sums_in : sums), RR, (T*)Delta_new);
         B2_LAUNCH_CHECK();
     });
+    return B2_OK;
+}
+
+int b2_pf2_gap(const void* V, const void* x, const int64_t* row_off, int n_groups, int R, const void* Wmat,
+               const void* Delta, double* out, int dtype, void* ws, size_t ws_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
+    B2_REQUIRE(ws_bytes >= (size_t)3 * (n_groups > 0 ? n_groups : 1) * sizeof(double), "b2_pf2_gap workspace too small");
+    if (n_groups == 0) {
+        B2_CHECK_CUDA(cudaMemsetAsync(out, 0, 3 * sizeof(double), st));
+        return B2_OK;
+    }
+    const int CPL = (R + 3) / 4;
+    int rc = B2_OK;
+#define B2_CASE_CPL(C)                                                                                           \
+    case C:                                                                                                      \
+        B2_DISPATCH_DTYPE(dtype, rc = launch_gap<T, C>(row_off, n_groups, R, V, x, Wmat, Delta, (double*)ws, st)); \
+        break
+    switch (CPL) {
+        B2_CASE_CPL(1);
+        B2_CASE_CPL(2);
+        B2_CASE_CPL(3);
+        B2_CASE_CPL(4);
+        B2_CASE_CPL(5);
+        B2_CASE_CPL(6);
+        B2_CASE_CPL(7);
+        B2_CASE_CPL(8);
+    }
+#undef B2_CASE_CPL
+    if (rc != B2_OK) return rc;
+    pf2_gap_final_kernel<<<1, 256, 0, st>>>((const double*)ws, n_groups, out);
+    B2_LAUNCH_CHECK();
     return B2_OK;
 }
 

@@ -10,6 +10,7 @@
 //     x       = (rho_g * sum_p(aux_p - dual_p) + Y o a_g) Minv_g
 //     S_g    += V'^T V',  V' = x + dual_pf2        (and B_g^T B_g += x^T x on the last inner iteration)
 // Results go straight from registers to HBM; no block-wide barrier inside the row loop.
+#pragma once
 #include "admm_common.cuh"
 #include "mma_tiles.cuh"
 
@@ -57,8 +58,11 @@ __device__ __forceinline__ void store_row(T* __restrict__ grow, int t, int R, co
     }
 }
 
-template <typename T, int NBF, int HALF>
-__global__ void __launch_bounds__((kConsWarps + 1) * 32)
+// NEXTRA: number of penalties besides PARAFAC2 (compile time: their duals stay in registers).  LAST: the last inner
+// iteration also emits x, W = x o a and B^T B.  The launch bound of two CTAs per SM (<= 112 registers) matters: the
+// row loop is latency bound, and a second resident CTA doubles the warps that hide it.
+template <typename T, int NBF, int HALF, int NEXTRA, bool LAST>
+__global__ void __launch_bounds__((kConsWarps + 1) * 32) __maxnreg__((NBF + HALF) <= 3 ? 112 : 168)
 pf2_rowpass_mma_kernel(const int64_t* __restrict__ row_off, int R, RowpassInputs in, const T* __restrict__ A,
                        const T* __restrict__ rho, const T* __restrict__ Minv, PenArgs pa, int deferred,
                        const T* __restrict__ Wmat, const T* __restrict__ Delta, T* __restrict__ x_out,
@@ -67,11 +71,11 @@ pf2_rowpass_mma_kernel(const int64_t* __restrict__ row_off, int R, RowpassInputs
     using GA = GramAcc<PL>;
     constexpr int NB = PL::NB;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    // carve: Ms | Ts | gram tiles (2 per consumer warp) | scale a_g | ring: stages x n_in x [64 x R] | barriers
+    // carve: Ms | Ts | gram tiles (1 per consumer warp) | scale a_g | ring: stages x n_in x [64 x R] | barriers
     double* Ms = (double*)smem_raw;
     double* Ts = Ms + PL::NPOS * PL::LDM;
     double* gtiles = Ts + PL::NPOS * PL::LDM;
-    double* a_s = gtiles + 2 * kConsWarps * 8 * GA::LDT;
+    double* a_s = gtiles + kConsWarps * 8 * GA::LDT;
     unsigned char* ring = (unsigned char*)(((uintptr_t)(a_s + PL::NPOS) + 127) & ~(uintptr_t)127);
     const uint32_t arr_bytes = (uint32_t)(kTileRows * R * sizeof(T));  // multiple of 16 (R*sizeof(T) % 16 == 0)
     const uint32_t stage_bytes = (uint32_t)in.n * arr_bytes;
@@ -86,7 +90,7 @@ pf2_rowpass_mma_kernel(const int64_t* __restrict__ row_off, int R, RowpassInputs
     if (r_begin >= r_end) {
         for (int e = tid; e < RR; e += blockDim.x) {
             S_out[(size_t)g_slice * RR + e] = T(0);
-            if (BtB_out) BtB_out[(size_t)g_slice * RR + e] = T(0);
+            if (LAST) BtB_out[(size_t)g_slice * RR + e] = T(0);
         }
         return;
     }
@@ -154,12 +158,10 @@ pf2_rowpass_mma_kernel(const int64_t* __restrict__ row_off, int R, RowpassInputs
         sc[b][0] = a_s[8 * b + 2 * t];
         sc[b][1] = a_s[8 * b + 2 * t + 1];
     }
-    const int n_extra = pa.n_pen - 1;
     GA accS, accB;
     accS.clear();
-    accB.clear();
-    double* tileS = gtiles + (size_t)warp * 8 * GA::LDT;
-    double* tileB = gtiles + (size_t)(kConsWarps + warp) * 8 * GA::LDT;
+    if (LAST) accB.clear();
+    double* tileG = gtiles + (size_t)warp * 8 * GA::LDT;  // shared by the S and B^T B accumulations
     T* pf_dual = (T*)pa.dual[0];
 
     int s = 0;
@@ -169,7 +171,7 @@ pf2_rowpass_mma_kernel(const int64_t* __restrict__ row_off, int R, RowpassInputs
         const bool valid = row < r_end;
         mbar_wait(&full[s], ph);
         const uint32_t st = ring_s + (uint32_t)s * stage_bytes + (uint32_t)((warp * 8 + g) * R * sizeof(T));
-        double y[NB][2], v[NB][2], dpf[NB][2], sh[NB][2], du[kMaxExtra][NB][2];
+        double y[NB][2], v[NB][2], dpf[NB][2], sh[NB][2], du[NEXTRA > 0 ? NEXTRA : 1][NB][2];
         load_row<PL, T>(st, t, R, valid, y);
         load_row<PL, T>(st + arr_bytes, t, R, valid, v);
         int a_idx = 2;
@@ -196,8 +198,8 @@ pf2_rowpass_mma_kernel(const int64_t* __restrict__ row_off, int R, RowpassInputs
                 }
         }
 #pragma unroll
-        for (int p = 0; p < kMaxExtra; ++p) {
-            if (p < n_extra) {
+        for (int p = 0; p < NEXTRA; ++p) {
+            {
                 double ax[NB][2];
                 load_row<PL, T>(st + (uint32_t)(a_idx + 2 * p) * arr_bytes, t, R, valid, ax);
                 load_row<PL, T>(st + (uint32_t)(a_idx + 2 * p + 1) * arr_bytes, t, R, valid, du[p]);
@@ -231,8 +233,8 @@ pf2_rowpass_mma_kernel(const int64_t* __restrict__ row_off, int R, RowpassInputs
         const size_t goff = (size_t)row * R;
         if (valid) {
             store_row<PL, T>(pf_dual + goff, t, R, vn);
-            if (x_out) store_row<PL, T>(x_out + goff, t, R, xv);
-            if (w_out) {
+            if (LAST) store_row<PL, T>(x_out + goff, t, R, xv);
+            if (LAST) {
                 double wv[NB][2];
 #pragma unroll
                 for (int b = 0; b < NB; ++b)
@@ -241,8 +243,8 @@ pf2_rowpass_mma_kernel(const int64_t* __restrict__ row_off, int R, RowpassInputs
                 store_row<PL, T>(w_out + (size_t)row * ldw, t, R, wv);
             }
 #pragma unroll
-            for (int p = 0; p < kMaxExtra; ++p) {
-                if (p < n_extra) {
+            for (int p = 0; p < NEXTRA; ++p) {
+                {
                     const int kind = pa.kind[p + 1], nn = pa.nn[p + 1];
                     const bool elementwise = kind == B2_PEN_NONNEG || kind == B2_PEN_BOX || kind == B2_PEN_L1;
                     const T p0 = (T)pa.p0[p + 1], p1 = (T)pa.p1[p + 1];
@@ -262,14 +264,14 @@ pf2_rowpass_mma_kernel(const int64_t* __restrict__ row_off, int R, RowpassInputs
                 }
             }
         }
-        accS.add(vn, tileS, g, t);
-        if (BtB_out) {
+        accS.add(vn, tileG, g, t, LAST ? accB.dep() : 0);
+        if (LAST) {
             double xz[NB][2];
 #pragma unroll
             for (int b = 0; b < NB; ++b)
 #pragma unroll
                 for (int e = 0; e < 2; ++e) xz[b][e] = valid ? xv[b][e] : 0.0;
-            accB.add(xz, tileB, g, t);
+            accB.add(xz, tileG, g, t, accS.dep());
         }
     }
     // cross-warp reduction of the Gram partials; the ring is free now (all tiles consumed by every warp after the barrier)
@@ -277,31 +279,32 @@ pf2_rowpass_mma_kernel(const int64_t* __restrict__ row_off, int R, RowpassInputs
     double* red = (double*)ring;
     gram_reduce_store<PL, T>(accS, red, warp, lane, kConsWarps, ctid, cthreads, R, S_out + (size_t)g_slice * RR,
                              consumer_barrier);
-    if (BtB_out) {
+    if (LAST) {
         consumer_barrier();
         gram_reduce_store<PL, T>(accB, red, warp, lane, kConsWarps, ctid, cthreads, R, BtB_out + (size_t)g_slice * RR,
                                  consumer_barrier);
     }
 }
 
-template <typename T, int NBF, int HALF>
-int launch_mma(const int64_t* row_off, int n_groups, int R, const RowpassInputs& in, const void* A, const void* rho,
-               const void* Minv, const PenArgs& pa, int deferred, const void* Wmat, const void* Delta, void* x,
-               void* w_out, int ldw, void* S_out, void* BtB_out, cudaStream_t st) {
+template <typename T, int NBF, int HALF, int NEXTRA, bool LAST>
+int launch_mma_k(const int64_t* row_off, int n_groups, int R, const RowpassInputs& in, const void* A, const void* rho,
+                 const void* Minv, const PenArgs& pa, int deferred, const void* Wmat, const void* Delta, void* x,
+                 void* w_out, int ldw, void* S_out, void* BtB_out, cudaStream_t st) {
     using PL = PosLayout<NBF, HALF>;
     using GA = GramAcc<PL>;
-    const size_t fixed = (size_t)(2 * PL::NPOS * PL::LDM + 2 * kConsWarps * 8 * GA::LDT + PL::NPOS) * sizeof(double) + 128;
+    const size_t fixed = (size_t)(2 * PL::NPOS * PL::LDM + kConsWarps * 8 * GA::LDT + PL::NPOS) * sizeof(double) + 128;
     const size_t stage_bytes = (size_t)in.n * kTileRows * R * sizeof(T);
     const size_t red_bytes = (size_t)kConsWarps * GA::NPAIR * 64 * sizeof(double);
-    // two CTAs per SM when possible: budget ~110 KB each
-    int stages = (int)((110 * 1024 - fixed - 64) / stage_bytes);
+    // two CTAs per SM: (228 KB - 2 x 1 KB reserved) / 2 = 113 KB each
+    const size_t budget = 113 * 1024;
+    int stages = (int)((budget - fixed - 64 - 128) / stage_bytes);
     if (stages > 4) stages = 4;
     if (stages < 2) stages = 2;
     size_t ring_bytes = (size_t)stages * stage_bytes;
     if (ring_bytes < red_bytes) ring_bytes = red_bytes;
     const size_t smem = fixed + ring_bytes + 2 * (size_t)stages * sizeof(uint64_t) + 64;
     if (smem > 227 * 1024) return -1;  // too many / too wide input arrays for two stages: use the shuffle kernel
-    auto kern = pf2_rowpass_mma_kernel<T, NBF, HALF>;
+    auto kern = pf2_rowpass_mma_kernel<T, NBF, HALF, NEXTRA, LAST>;
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<n_groups, (kConsWarps + 1) * 32, smem, st>>>(row_off, R, in, (const T*)A, (const T*)rho, (const T*)Minv, pa,
                                                         deferred, (const T*)Wmat, (const T*)Delta, (T*)x, (T*)w_out, ldw,
@@ -310,38 +313,35 @@ int launch_mma(const int64_t* row_off, int n_groups, int R, const RowpassInputs&
     return B2_OK;
 }
 
-}  // namespace
+template <typename T, int NBF, int HALF>
+int launch_mma(const int64_t* row_off, int n_groups, int R, const RowpassInputs& in, const void* A, const void* rho,
+               const void* Minv, const PenArgs& pa, int deferred, const void* Wmat, const void* Delta, void* x,
+               void* w_out, int ldw, void* S_out, void* BtB_out, cudaStream_t st) {
+    const int n_extra = pa.n_pen - 1;
+    const bool last = x != nullptr;
+    if (last && !(w_out && BtB_out)) return -1;   // the fused engine always asks for all three on the last iteration
+    if (!last && (w_out || BtB_out)) return -1;
+#define B2_MMA_K(NE, LA)                                                                                              \
+    if (n_extra == NE && last == LA)                                                                                  \
+        return launch_mma_k<T, NBF, HALF, NE, LA>(row_off, n_groups, R, in, A, rho, Minv, pa, deferred, Wmat, Delta, x, \
+                                                  w_out, ldw, S_out, BtB_out, st);
+    B2_MMA_K(0, false) B2_MMA_K(0, true) B2_MMA_K(1, false) B2_MMA_K(1, true) B2_MMA_K(2, false) B2_MMA_K(2, true)
+#undef B2_MMA_K
+    return -1;
+}
 
-// Returns B2_OK after launching, a positive error code on failure, or -1 when this formulation does not apply
-// (the caller then uses the shuffle-based kernel of pf2_fused.cu).
-int b2_pf2_rowpass_mma_try(const int64_t* row_off, int n_groups, int R, const void* Y, const void* A, const void* rho,
-                           const void* Minv, const PenArgs& pa, int deferred, const void* Wmat, const void* Delta,
-                           void* x, void* w_out, int ldw, void* S_out, void* BtB_out, int dtype, cudaStream_t st) {
-    const size_t es = dtype == B2_F64 ? 8 : 4;
-    if (((size_t)R * es) % 16 != 0) return -1;
-    if (pa.n_pen - 1 > kMaxExtra) return -1;
-    if (w_out && (((size_t)ldw * es) % (2 * es) != 0)) return -1;
-    RowpassInputs in;
-    in.n = 0;
-    in.ptr[in.n++] = Y;
-    in.ptr[in.n++] = pa.dual[0];
-    if (!deferred) in.ptr[in.n++] = pa.aux[0];
-    for (int p = 1; p < pa.n_pen; ++p) {
-        in.ptr[in.n++] = pa.aux[p];
-        in.ptr[in.n++] = pa.dual[p];
-    }
-    for (int a = 0; a < in.n; ++a)
-        if (((uintptr_t)in.ptr[a]) % 16 != 0) return -1;
+// dtype-specific dispatch over the position layouts; defined in pf2_mma_f64.cu / pf2_mma_f32.cu
+template <typename T>
+int pf2_rowpass_mma_dispatch(const int64_t* row_off, int n_groups, int R, const RowpassInputs& in, const void* A,
+                             const void* rho, const void* Minv, const PenArgs& pa, int deferred, const void* Wmat,
+                             const void* Delta, void* x, void* w_out, int ldw, void* S_out, void* BtB_out,
+                             cudaStream_t st) {
     const int nbf = R / 8, rem = R % 8;
     const int NBF = rem >= 5 ? nbf + 1 : nbf, HALF = (rem >= 1 && rem <= 4) ? 1 : 0;
-#define B2_MMA_CASE(F, H)                                                                                          \
-    if (NBF == F && HALF == H) {                                                                                   \
-        if (dtype == B2_F64)                                                                                       \
-            return launch_mma<double, F, H>(row_off, n_groups, R, in, A, rho, Minv, pa, deferred, Wmat, Delta, x,   \
-                                            w_out, ldw, S_out, BtB_out, st);                                       \
-        return launch_mma<float, F, H>(row_off, n_groups, R, in, A, rho, Minv, pa, deferred, Wmat, Delta, x, w_out, \
-                                       ldw, S_out, BtB_out, st);                                                   \
-    }
+#define B2_MMA_CASE(F, H)                                                                                           \
+    if (NBF == F && HALF == H)                                                                                      \
+        return launch_mma<T, F, H>(row_off, n_groups, R, in, A, rho, Minv, pa, deferred, Wmat, Delta, x, w_out, ldw, \
+                                   S_out, BtB_out, st);
     B2_MMA_CASE(0, 1)
     B2_MMA_CASE(1, 0)
     B2_MMA_CASE(1, 1)
@@ -353,3 +353,5 @@ int b2_pf2_rowpass_mma_try(const int64_t* row_off, int n_groups, int R, const vo
 #undef B2_MMA_CASE
     return -1;
 }
+
+}  // namespace

@@ -547,3 +547,108 @@ def test_pf2_rowpass_both_formulations(R, dtype, mma):
                     np.testing.assert_allclose(BtB.double().cpu().numpy(), Bref, rtol=tol * 10, atol=tol * 1e3)
     finally:
         lib.b2_set_option(_lib.OPT_PF2_ROWPASS_MMA, 1)
+
+
+@pytest.mark.parametrize("R", [4, 8, 20, 32])
+@pytest.mark.parametrize("n_extra", [0, 1])
+def test_pf2_rowpass_mma_penalty_counts(R, n_extra):
+    """The tensor-core row pass is compiled per number of companion penalties (0, 1, 2): cover 0 and 1 as well
+    (2 is covered by test_pf2_rowpass_both_formulations), deferred and last-iteration variants."""
+    _lib, _ops, _ = _imports()
+    rs = np.random.RandomState(7 + R + n_extra)
+    G = 5
+    sizes, off, _ = ragged(rs, G, 1, 200, R)
+    N = int(off[-1])
+    f = lambda *s: rs.standard_normal(size=s)  # noqa: E731
+    Y, A, rho = f(N, R), rs.uniform(0.5, 1.5, size=(G, R)), rs.uniform(0.5, 2.0, size=G)
+    Minv = np.stack([np.linalg.inv(m @ m.T + R * np.eye(R)) for m in f(G, R, R)])
+    Wm, Delta = f(G, R, R) / np.sqrt(R), f(R, R)
+    gor = np.repeat(np.arange(G), sizes)
+    for deferred in (0, 1):
+        for last in (0, 1):
+            h = dict(pf_aux=f(N, R), pf_dual=f(N, R), l1_aux=f(N, R), l1_dual=f(N, R))
+            d = {k: dev(v) for k, v in h.items()}
+            pens = [(_lib.PEN_PARAFAC2, 0, 0, 0, d["pf_aux"], d["pf_dual"])]
+            if n_extra:
+                pens.append((_lib.PEN_L1, 0, 0.3, 0, d["l1_aux"], d["l1_dual"]))
+            descs = _ops.make_descs(pens)
+            x = torch.full((N, R), float("nan"), dtype=torch.float64, device="cuda")
+            Wp = _ops.alloc_w(N, R, torch.float64, "cuda")
+            S = torch.full((G, R, R), float("nan"), dtype=torch.float64, device="cuda")
+            BtB = torch.full((G, R, R), float("nan"), dtype=torch.float64, device="cuda")
+            _ops.pf2_rowpass(dev(off, torch.int64), G, R, dev(Y), dev(A), dev(rho), dev(Minv), descs, len(pens), deferred,
+                             dev(Wm), dev(Delta), x if last else None, Wp if last else None, S, BtB if last else None)
+            torch.cuda.synchronize()
+            if deferred:
+                T = np.einsum("gik,kj->gij", Wm, Delta)
+                pd = np.einsum("nk,nkj->nj", h["pf_dual"], T[gor])
+                dpf = h["pf_dual"] - pd
+            else:
+                pd, dpf = h["pf_aux"], h["pf_dual"]
+            sh = pd - dpf
+            if n_extra:
+                sh = sh + h["l1_aux"] - h["l1_dual"]
+            xr = np.einsum("nk,nkj->nj", rho[gor][:, None] * sh + Y * A[gor], Minv[gor])
+            vn = xr + dpf
+            np.testing.assert_allclose(d["pf_dual"].cpu().numpy(), vn, rtol=1e-11, atol=1e-10)
+            if n_extra:
+                v1 = xr + h["l1_dual"]
+                z = np.sign(v1) * np.maximum(np.abs(v1) - 0.3 / rho[gor][:, None], 0)
+                np.testing.assert_allclose(d["l1_aux"].cpu().numpy(), z, rtol=1e-11, atol=1e-10)
+                np.testing.assert_allclose(d["l1_dual"].cpu().numpy(), v1 - z, rtol=1e-11, atol=1e-10)
+            Sref = np.stack([vn[off[g]:off[g + 1]].T @ vn[off[g]:off[g + 1]] for g in range(G)])
+            np.testing.assert_allclose(S.cpu().numpy(), Sref, rtol=1e-10, atol=1e-8)
+            if last:
+                np.testing.assert_allclose(x.cpu().numpy(), xr, rtol=1e-11, atol=1e-10)
+                np.testing.assert_allclose(Wp[:N, :R].cpu().numpy(), xr * A[gor], rtol=1e-11, atol=1e-10)
+                Bref = np.stack([xr[off[g]:off[g + 1]].T @ xr[off[g]:off[g + 1]] for g in range(G)])
+                np.testing.assert_allclose(BtB.cpu().numpy(), Bref, rtol=1e-10, atol=1e-8)
+
+
+@pytest.mark.parametrize("R", [1, 3, 8, 20, 27, 32])
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_pf2_gap_from_deferred_state(R, dtype):
+    """b2_pf2_gap: ||V W Delta - x||^2, ||x||^2, sum|x| from the deferred PARAFAC2 state (decomposition.py:406-415)."""
+    _lib, _ops, _ = _imports()
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    rs = np.random.RandomState(31 + R)
+    G = 9
+    sizes, off, _ = ragged(rs, G, 1, 150, R)
+    sizes[3] = 0
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    N = int(off[-1])
+    V, x = rs.standard_normal(size=(N, R)), rs.standard_normal(size=(N, R))
+    Wm, Delta = rs.standard_normal(size=(G, R, R)) / np.sqrt(R), rs.standard_normal(size=(R, R))
+    d = {k: dev(v, tdt) for k, v in dict(V=V, x=x, Wm=Wm, Delta=Delta).items()}
+    h = {k: v.double().cpu().numpy() for k, v in d.items()}
+    out = torch.zeros(3, dtype=torch.float64, device="cuda")
+    part = torch.zeros(3 * G, dtype=torch.float64, device="cuda")
+    _ops.pf2_gap(d["V"], d["x"], dev(off, torch.int64), G, R, d["Wm"], d["Delta"], out, part)
+    gor = np.repeat(np.arange(G), sizes)
+    pd = np.einsum("nk,nkj->nj", h["V"], np.einsum("gik,kj->gij", h["Wm"], h["Delta"])[gor])
+    ref = np.array([((pd - h["x"]) ** 2).sum(), (h["x"] ** 2).sum(), np.abs(h["x"]).sum()])
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-11 if dtype == "f64" else 2e-5)
+
+
+@pytest.mark.parametrize("R", [2, 5, 20, 32])
+def test_parafac2_polar_warm_start_equals_cold(R):
+    """A Jacobi warm start from the previous call's eigenvectors must give the same W and numerator as a cold start."""
+    _lib, _ops, _ = _imports()
+    rs = np.random.RandomState(77 + R)
+    G = 6
+    V1 = [rs.standard_normal(size=(R + 10, R)) for _ in range(G)]
+    V2 = [v + 1e-2 * rs.standard_normal(size=v.shape) for v in V1]
+    Delta = rs.standard_normal(size=(R, R))
+    rho = rs.uniform(0.5, 2.0, size=G)
+    S1 = dev(np.stack([v.T @ v for v in V1]))
+    S2 = dev(np.stack([v.T @ v for v in V2]))
+    z = lambda: torch.zeros(G, R, R, dtype=torch.float64, device="cuda")  # noqa: E731
+    Wc, nc, Ww, nw, Q = z(), z(), z(), z(), z()
+    _ops.pf2_polar(S2, dev(Delta), dev(rho), G, R, Wc, nc)                       # cold reference on S2
+    _ops.pf2_polar(S1, dev(Delta), dev(rho), G, R, Ww, nw, Q, warm=False)         # fills Q from S1
+    _ops.pf2_polar(S2, dev(Delta), dev(rho), G, R, Ww, nw, Q, warm=True)          # warm on S2
+    np.testing.assert_allclose(Ww.cpu().numpy(), Wc.cpu().numpy(), rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(nw.cpu().numpy(), nc.cpu().numpy(), rtol=1e-9, atol=1e-11)
+    for g in range(G):  # and it is the polar factor: P = V W has orthonormal columns
+        P = V2[g] @ Ww[g].cpu().numpy()
+        np.testing.assert_allclose(P.T @ P, np.eye(R), atol=1e-9)
