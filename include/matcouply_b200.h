@@ -52,8 +52,9 @@ typedef struct {
 /* kernel-selection switches (process-wide; default 1 = on).  They only choose between equivalent kernels — tests flip
  * them to cross-check the tensor-core formulations against the scalar ones. */
 enum { B2_OPT_PF2_ROWPASS_MMA = 0 /* DMMA row pass of b2_pf2_rowpass */,
-       B2_OPT_POLAR_WARP = 1 /* warp-per-slice Jacobi in b2_pf2_polar */,
-       B2_OPT_COUNT = 2 };
+       B2_OPT_POLAR_WARP = 1 /* reserved */,
+       B2_OPT_ADMM_LOCAL_MMA = 2 /* DMMA formulation of b2_admm_local (CTA-per-slice path) */,
+       B2_OPT_COUNT = 3 };
 int b2_set_option(int option, int value);
 int b2_get_option(int option);
 

@@ -103,6 +103,11 @@ int b2_pf2_rowpass_mma_try(const int64_t* row_off, int n_groups, int R, const vo
                            const void* Minv, const PenArgs& pa, int deferred, const void* Wmat, const void* Delta,
                            void* x, void* w_out, int ldw, void* S_out, void* BtB_out, int dtype, cudaStream_t st);
 
+// tensor-core fused row-local ADMM loop (admm_mma.cu); returns -1 when it does not apply
+int b2_admm_local_mma_try(const int64_t* row_off, int n_groups, int R, const void* rhs, const void* rhs_scale,
+                          const void* rho, const void* Minv, const PenArgs& pa, int n_inner, void* x, void* w_out,
+                          int ldw, void* BtB_out, int dtype, cudaStream_t st);
+
 // host: validate and pack the caller's descriptors
 inline int b2_pack_penalties(const b2_penalty_desc* pens, int n_pen, PenArgs* pa) {
     B2_REQUIRE(n_pen >= 0 && n_pen <= kMaxPen, "at most %d penalties per mode are supported (got %d)", kMaxPen, n_pen);

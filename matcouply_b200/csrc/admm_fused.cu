@@ -269,6 +269,12 @@ int b2_admm_local(long long n, int R, const void* rhs, const void* rhs_scale, in
     for (int p = 0; p < n_pen; ++p)
         B2_REQUIRE(pa.kind[p] == B2_PEN_NONNEG || pa.kind[p] == B2_PEN_BOX || pa.kind[p] == B2_PEN_L1,
                    "b2_admm_local handles row-local penalties only (penalty %d has kind %d)", p, pa.kind[p]);
+    if (group_mode == B2_GROUP_INDEXED && row_off != nullptr && n_inner > 0 && b2_option_value(B2_OPT_ADMM_LOCAL_MMA)) {
+        // tensor-core formulation (admm_mma.cu) when it applies
+        const int rc = b2_admm_local_mma_try(row_off, n_groups, R, rhs, rhs_scale, rho, Minv, pa, n_inner, x, w_out, ldw,
+                                             BtB_out, dtype, st);
+        if (rc >= 0) return rc;
+    }
     const int CPL = (R + 3) / 4;
     // CTA-per-group path (operator staged in shared memory): slices via row_off, or a single group in 64-row blocks
     const bool grouped = (group_mode == B2_GROUP_INDEXED && row_off != nullptr) || group_mode == B2_GROUP_SINGLE;

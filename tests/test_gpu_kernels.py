@@ -246,10 +246,12 @@ def test_admm_solve_elementwise(mode, R):
 @pytest.mark.parametrize("R", [1, 3, 8, 16, 20, 32])
 @pytest.mark.parametrize("n_pen", [0, 1, 2])
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
-@pytest.mark.parametrize("grouped", [False, True])
+@pytest.mark.parametrize("grouped", [False, True, "mma"])
 def test_admm_local_equals_iterated_admm_solve(R, n_pen, dtype, grouped):
-    """The fused whole-inner-loop kernel must reproduce 5 launches of the one-iteration kernel (and W = x o a)."""
+    """The fused whole-inner-loop kernel must reproduce 5 launches of the one-iteration kernel (and W = x o a).
+    grouped=True: CTA-per-slice shuffle kernel, "mma": its tensor-core (DMMA) formulation."""
     _lib, _ops, O = _imports()
+    _lib.load().b2_set_option(_lib.OPT_ADMM_LOCAL_MMA, 1 if grouped == "mma" else 0)
     tdt = torch.float64 if dtype == "f64" else torch.float32
     rs = np.random.RandomState(R * 10 + n_pen)
     G = 7
@@ -284,6 +286,7 @@ def test_admm_local_equals_iterated_admm_solve(R, n_pen, dtype, grouped):
                 _ops.admm_solve(n, R, dev(rhs, tdt), scale, _lib.GROUP_INDEXED, gor, rho, Minv, descs, n_pen, x)
             _ops.rowscale(x, scale, gor, n, R, W)
         results.append([t.double().cpu().numpy() for t in [x, W] + aux + dual])
+    _lib.load().b2_set_option(_lib.OPT_ADMM_LOCAL_MMA, 1)
     tol = 1e-11 if dtype == "f64" else 2e-4
     for a, b in zip(*results):
         np.testing.assert_allclose(a, b, rtol=tol, atol=tol)
