@@ -128,9 +128,11 @@ int b2_admm_local(long long n, int R, const void* rhs, const void* rhs_scale, in
                   void* BtB_out, int dtype, void* stream);
 
 /* ---- column-coupled proximal operators (V arrives in `dual`, see b2_admm_solve) --------------------------------*/
-/* L2Ball (penalties.py:920-925): per group and column  aux = clip(V)*bound/max(||clip(V)_col||, bound); dual = V - aux. */
+/* L2Ball (penalties.py:920-925): per group and column  aux = clip(V)*bound/max(||clip(V)_col||, bound); dual = V - aux.
+ * phase 0: everything.  Row-sharded groups (mode 0 over several ranks): phase 1 only writes the local column sums of
+ * squares to colsq_io (n_groups x R doubles), the caller all-reduces them, phase 2 scales with the reduced sums. */
 int b2_prox_l2ball(void* aux, void* dual, const int64_t* row_off, int n_groups, int R, double bound, int non_negativity,
-                   int dtype, void* stream);
+                   double* colsq_io, int phase, int dtype, void* stream);
 /* Unimodality (penalties.py:1014-1015 -> _unimodal_regression.py:24-141): per group and column aux = unimodal
  * regression of V (PAVA prefix/suffix isotonic fits, `<=` pooling, first strict minimum peak); dual = V - aux.
  * peaks (may be NULL): n_groups x R int32 peak indices t*.  ws >= b2_unimodal_workspace_bytes(). fp64 arithmetic. */

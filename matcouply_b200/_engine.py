@@ -146,7 +146,7 @@ class _ModeState:
 class AOADMMEngine:
     def __init__(self, packed, rank, regs, l2_penalty=(0, 0, 0), feasibility_penalty_scale=1.0, constant_A=False,
                  constant_B=False, inner_n_iter_max=5, update=(True, True, True), group=None, xstream_variant=None,
-                 fuse_local=None, fuse_pf2=None):
+                 fuse_local=None, fuse_pf2=None, shard_rows=None):
         _lib.load()
         self.p = packed
         self.dev = packed.X.device
@@ -162,6 +162,8 @@ class AOADMMEngine:
         self.update_A, self.update_B, self.update_C = update
         self.group = group
         self.world = 1 if group is None else torch.distributed.get_world_size(group)
+        # (first global slice index of this rank, global number of slices): needed by the matrix-wise mode-0 penalties
+        self.shard_rows = (0, packed.n_slices) if shard_rows is None else (int(shard_rows[0]), int(shard_rows[1]))
         self.variant = _lib.VARIANT_AUTO if xstream_variant is None else xstream_variant
         self.fuse_local = FUSION_DEFAULTS["local"] if fuse_local is None else bool(fuse_local)
         self.fuse_pf2 = FUSION_DEFAULTS["pf2"] if fuse_pf2 is None else bool(fuse_pf2)
@@ -189,8 +191,8 @@ class AOADMMEngine:
                         "Matrix-wise penalties (L2Ball, Unimodality) on mode 0 have no row update: "
                         "use constant_feasibility_penalty=True (or 'A'), as with the reference"
                     )
-                if self.world > 1:
-                    raise NotImplementedError("column-coupled penalties on mode 0 are not sharded yet")
+                if self.world > 1 and shard_rows is None:
+                    raise ValueError("matrix-wise penalties on a row-sharded mode 0 need `shard_rows`")
             if kind == _lib.PEN_PARAFAC2:
                 raise ValueError("PARAFAC2 constraint can only be imposed with mode=1")
         for kind, *_ in self.modes[2].desc:
@@ -484,7 +486,35 @@ class AOADMMEngine:
         for _ in range(self.n_inner):
             _ops.admm_solve(I, R, self.rhsA, None, _lib.GROUP_IDENTITY, None, self.rhoA, self.MinvA, st.descs_c,
                             len(st.desc), st.x)
-            self._column_coupled(st, self.off_single_I, 1, I, self.rhoA, None, I)
+            if self.world > 1:
+                self._column_coupled_A_sharded(st)
+            else:
+                self._column_coupled(st, self.off_single_I, 1, I, self.rhoA, None, I)
+
+    def _column_coupled_A_sharded(self, st):
+        """Matrix-wise penalties on mode 0 when the rows of A are sharded over ranks (last row):
+        L2Ball needs the column norms over ALL I rows -> all-reduce of R partial sums of squares (penalties.py:923);
+        Unimodality needs whole columns -> the I x R pre-image is gathered (sum of disjoint row blocks), the prox runs
+        replicated and every rank keeps its rows (penalties.py:1015)."""
+        R, I = self.R, self.I
+        lo, I_glob = self.shard_rows
+        for p, (kind, nn, p0, _p1) in enumerate(st.desc):
+            if kind == _lib.PEN_L2BALL:
+                colsq = torch.zeros(R, dtype=torch.float64, device=self.dev)
+                if I > 0:
+                    _ops.prox_l2ball(st.aux[p], st.dual[p], self.off_single_I, 1, R, p0, nn, colsq, phase=1)
+                self._allreduce(colsq)
+                if I > 0:
+                    _ops.prox_l2ball(st.aux[p], st.dual[p], self.off_single_I, 1, R, p0, nn, colsq, phase=2)
+            elif kind == _lib.PEN_UNIMODAL:
+                full = torch.zeros((I_glob, R), dtype=self.dtype, device=self.dev)
+                full[lo:lo + I] = st.dual[p]
+                self._allreduce(full)
+                aux_full = torch.empty_like(full)
+                off = torch.tensor([0, I_glob], dtype=torch.int64, device=self.dev)
+                _ops.prox_unimodal(aux_full, full, off, 1, R, I_glob, nn, self.ws)
+                st.aux[p].copy_(aux_full[lo:lo + I])
+                st.dual[p].copy_(full[lo:lo + I])
 
     def prepare(self):
         """Before the first iteration: ||X||^2 and the products for the initial fit (decomposition.py:906-913)."""

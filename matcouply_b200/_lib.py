@@ -47,7 +47,7 @@ _SIGNATURES = {
     "b2_admm_solve": [_ll, _i, _vp, _vp, _i, _vp, _vp, _vp, ctypes.POINTER(PenaltyDesc), _i, _vp, _i, _vp],
     "b2_admm_local": [_ll, _i, _vp, _vp, _i, _vp, _vp, _i, _vp, _vp, ctypes.POINTER(PenaltyDesc), _i, _i, _vp, _vp, _i,
                       _vp, _i, _vp],
-    "b2_prox_l2ball": [_vp, _vp, _vp, _i, _i, _d, _i, _i, _vp],
+    "b2_prox_l2ball": [_vp, _vp, _vp, _i, _i, _d, _i, _vp, _i, _i, _vp],
     "b2_prox_unimodal": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _sz, _vp],
     "b2_pf2_polar": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
     "b2_pf2_rowpass": [_vp, _i, _i, _vp, _vp, _vp, _vp, ctypes.POINTER(PenaltyDesc), _i, _i, _vp, _vp, _vp, _vp, _i, _vp,

@@ -142,9 +142,10 @@ def admm_solve(n, R, rhs, rhs_scale, group_mode, group_of_row, rho, Minv, descs,
          descs, n_pen, _ptr(x), dtype_code(x.dtype), _stream())
 
 
-def prox_l2ball(aux, dual, row_off, n_groups, R, bound, nn):
-    call("b2_prox_l2ball", _ptr(aux), _ptr(dual), _ptr(row_off), n_groups, R, float(bound), int(bool(nn)),
-         dtype_code(aux.dtype), _stream())
+def prox_l2ball(aux, dual, row_off, n_groups, R, bound, nn, colsq=None, phase=0):
+    """phase 0: whole prox; phase 1 / 2: local column sums of squares -> colsq / scale with the (all-reduced) colsq."""
+    call("b2_prox_l2ball", _ptr(aux), _ptr(dual), _ptr(row_off), n_groups, R, float(bound), int(bool(nn)), _ptr(colsq),
+         int(phase), dtype_code(aux.dtype), _stream())
 
 
 def prox_unimodal(aux, dual, row_off, n_groups, R, max_rows, nn, ws, peaks=None):

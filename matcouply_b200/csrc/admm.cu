@@ -86,7 +86,7 @@ __global__ void prox_elementwise_kernel(const T* __restrict__ v, T* __restrict__
 // L2 ball: CTA per group; pass 1 column sums of squares of clip(V), pass 2 scale + dual update.
 template <typename T>
 __global__ void prox_l2ball_kernel(T* __restrict__ aux, T* __restrict__ dual, const int64_t* __restrict__ row_off, int R,
-                                   T bound, int nn) {
+                                   T bound, int nn, double* __restrict__ colsq_io, int phase) {
     __shared__ double colsq[B2_MAX_RANK];
     __shared__ double part[8][B2_MAX_RANK];
     const int g = blockIdx.x;
@@ -97,7 +97,7 @@ __global__ void prox_l2ball_kernel(T* __restrict__ aux, T* __restrict__ dual, co
     // accumulate per-thread per-column requires fixed column per thread => stride must be a multiple of R.
     const int tpr = blockDim.x / R * R;  // active threads: multiple of R so a thread always sees the same column
     double acc = 0.0;
-    if ((int)threadIdx.x < tpr) {
+    if ((int)threadIdx.x < tpr && phase != 2) {
         for (long long e = threadIdx.x; e < cnt; e += tpr) {
             T v = V[e];
             if (nn && v < T(0)) v = T(0);
@@ -111,11 +111,17 @@ __global__ void prox_l2ball_kernel(T* __restrict__ aux, T* __restrict__ dual, co
     __syncthreads();
     if ((int)threadIdx.x < R) {
         double s = 0.0;
-        for (int t = threadIdx.x; t < tpr; t += R) s += l2_scratch[t];
+        if (phase == 2) {
+            s = colsq_io[(size_t)g * R + threadIdx.x];  // sums of squares reduced over all ranks by the caller
+        } else {
+            for (int t = threadIdx.x; t < tpr; t += R) s += l2_scratch[t];
+            if (phase == 1) colsq_io[(size_t)g * R + threadIdx.x] = s;
+        }
         colsq[threadIdx.x] = s;
     }
     __syncthreads();
     (void)part;
+    if (phase == 1) return;
     if ((int)threadIdx.x < tpr) {
         const int c = threadIdx.x % R;
         T nrm = (T)sqrt(colsq[c]);
@@ -235,14 +241,16 @@ int b2_prox_elementwise(const void* v, void* out, long long n, int kind, int non
 }
 
 int b2_prox_l2ball(void* aux, void* dual, const int64_t* row_off, int n_groups, int R, double bound, int non_negativity,
-                   int dtype, void* stream) {
+                   double* colsq_io, int phase, int dtype, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
+    B2_REQUIRE(phase >= 0 && phase <= 2 && (phase == 0 || colsq_io), "b2_prox_l2ball: phase 1/2 need colsq_io");
     if (n_groups == 0) return B2_OK;
     const int threads = 256;
     B2_DISPATCH_DTYPE(dtype, {
         prox_l2ball_kernel<T><<<n_groups, threads, threads * sizeof(double), st>>>((T*)aux, (T*)dual, row_off, R,
-                                                                                   (T)bound, non_negativity);
+                                                                                   (T)bound, non_negativity, colsq_io,
+                                                                                   phase);
         B2_LAUNCH_CHECK();
     });
     return B2_OK;

@@ -350,31 +350,37 @@ pf2_polar_cta_kernel(const T* __restrict__ S, const T* __restrict__ Delta, const
                 cs[16 + tid] = s;
             }
             __syncthreads();
-            for (int e = tid; e < half * R; e += blockDim.x) {  // columns p,q of G and Q, row i
-                const int k = e / R, i = e - k * R;
-                const int p = pq[k], q = pq[16 + k];
-                if (q >= 0) {
-                    const double c = cs[k], s = cs[16 + k];
-                    const double gp = G[i * R + p], gq2 = G[i * R + q];
-                    G[i * R + p] = c * gp - s * gq2;
-                    G[i * R + q] = s * gp + c * gq2;
-                    const double qp = Q[i * R + p], qq = Q[i * R + q];
-                    Q[i * R + p] = c * qp - s * qq;
-                    Q[i * R + q] = s * qp + c * qq;
-                }
+            // Two-sided update G <- J^T G J as independent 2x2 blocks: thread (k, k') owns rows {p,q} of pair k and
+            // columns {p',q'} of pair k' (column rotation first, then row rotation: the same operation order as a
+            // column pass followed by a row pass, without the barrier in between).
+            for (int id = tid; id < half * half; id += blockDim.x) {
+                const int k = id / half, k2 = id - k * half;
+                const int p = pq[k], q = pq[16 + k], p2 = pq[k2], q2 = pq[16 + k2];
+                const double c = cs[k], sn = cs[16 + k], c2 = cs[k2], sn2 = cs[16 + k2];
+                const bool hq = q >= 0, hq2 = q2 >= 0;
+                const double b00 = G[p * R + p2], b01 = hq2 ? G[p * R + q2] : 0.0;
+                const double b10 = hq ? G[q * R + p2] : 0.0, b11 = (hq && hq2) ? G[q * R + q2] : 0.0;
+                // columns (dummy partner: c2 = 1, sn2 = 0)
+                const double d00 = c2 * b00 - sn2 * b01, d01 = sn2 * b00 + c2 * b01;
+                const double d10 = c2 * b10 - sn2 * b11, d11 = sn2 * b10 + c2 * b11;
+                // rows
+                double e00 = c * d00 - sn * d10, e01 = c * d01 - sn * d11;
+                double e10 = sn * d00 + c * d10, e11 = sn * d01 + c * d11;
+                if (k == k2) e01 = e10 = 0.0;  // the annihilated pair
+                G[p * R + p2] = e00;
+                if (hq2) G[p * R + q2] = e01;
+                if (hq) G[q * R + p2] = e10;
+                if (hq && hq2) G[q * R + q2] = e11;
             }
-            __syncthreads();
-            for (int e = tid; e < half * R; e += blockDim.x) {  // rows p,q of G, column j
-                const int k = e / R, j = e - k * R;
+            // eigenvectors: Q <- Q J (lane = row i, warps stride over the pairs)
+            for (int k = tid >> 5; k < half; k += kPolarThreads / 32) {
+                const int i = tid & 31;
                 const int p = pq[k], q = pq[16 + k];
-                if (q >= 0) {
-                    const double c = cs[k], s = cs[16 + k];
-                    const double gp = G[p * R + j], gq2 = G[q * R + j];
-                    double np_ = c * gp - s * gq2, nq_ = s * gp + c * gq2;
-                    if (j == q) np_ = 0.0;  // the annihilated pair
-                    if (j == p) nq_ = 0.0;
-                    G[p * R + j] = np_;
-                    G[q * R + j] = nq_;
+                if (i < R && q >= 0) {
+                    const double c = cs[k], sn = cs[16 + k];
+                    const double qp = Q[i * R + p], qq = Q[i * R + q];
+                    Q[i * R + p] = c * qp - sn * qq;
+                    Q[i * R + q] = sn * qp + c * qq;
                 }
             }
             __syncthreads();

@@ -331,7 +331,8 @@ def cmf_aoadmm(
     engine = AOADMMEngine(packed, rank, regs, l2_penalty=l2_penalty,
                           feasibility_penalty_scale=feasibility_penalty_scale, constant_A=constant_A,
                           constant_B=constant_B, inner_n_iter_max=inner_n_iter_max,
-                          update=(update_A, update_B_is, update_C), group=process_group)
+                          update=(update_A, update_B_is, update_C), group=process_group,
+                          shard_rows=None if shard is None else (shard.lo, shard.n_global))
     _, (A0, B0, C0) = cmf
     if shard is not None:
         from .distributed import shard_state

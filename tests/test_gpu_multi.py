@@ -63,7 +63,7 @@ def _rel(a, b):
     return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
 
 
-@pytest.mark.parametrize("name", ["c2_nn_pf2_l1_ragged", "c1_nn_cmf", "c3_unimodal_l2ball_pf2"])
+@pytest.mark.parametrize("name", ["c2_nn_pf2_l1_ragged", "c1_nn_cmf", "c3_unimodal_l2ball_pf2", "c0_readme"])
 def test_two_rank_run_matches_reference_trajectory(name, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -80,3 +80,60 @@ def test_two_rank_run_matches_reference_trajectory(name, tmp_path):
     errs = (_rel(r0["A"], g["A_traj"][k - 1]), _rel(r0["B"], g["B_traj"][k - 1]), _rel(r0["C"], g["C_traj"][k - 1]))
     assert max(errs) < 1e-8, errs
     np.testing.assert_allclose(r0["loss"], g["regularized_loss"][: k + 1], rtol=1e-8)
+
+
+def _mode0_case():
+    rs = np.random.RandomState(5)
+    I, K, R = 23, 12, 3
+    Js = rs.randint(6, 30, size=I)
+    A = np.exp(-0.5 * ((np.arange(I)[:, None] - np.array([5.0, 11.0, 17.0])[None, :]) / 3.0) ** 2) + 0.05  # unimodal columns
+    C = rs.uniform(size=(K, R))
+    X = [(rs.uniform(size=(J, R)) * A[i]) @ C.T + 0.05 * rs.standard_normal(size=(J, K)) for i, J in enumerate(Js)]
+    kw = dict(unimodal={0: True}, l2_norm_bound={0: 2.0}, non_negative=True, constant_feasibility_penalty=True,
+              random_state=3)
+    return X, R, kw
+
+
+def _worker_mode0(rank, world, port, k_iter, out_dir):
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    from matcouply_b200 import cmf_aoadmm
+    from matcouply_b200.distributed import make_shard
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        X, R, kw = _mode0_case()
+        sh = make_shard([x.shape[0] for x in X], rank, world)
+        cmf, diag = cmf_aoadmm(X[sh.lo:sh.hi], R, n_iter_max=k_iter, tol=None, absolute_tol=None, return_errors=True,
+                               process_group=dist.group.WORLD, shard=sh, **kw)
+        _, (A, B_is, C) = cmf
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), A=A, B=np.concatenate(B_is, 0), C=C,
+                 loss=np.asarray(diag.regularized_loss))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_matrix_penalties_on_sharded_mode0(tmp_path):
+    """Unimodality + L2Ball on mode 0 (whole columns of A, whose rows are sharded): all-reduced column norms and the
+    gathered unimodal prox must reproduce the single-process reference algorithm (oracle)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+
+    from oracle import aoadmm_oracle as O
+
+    k = 15
+    X, R, kw = _mode0_case()
+    o = O.ao_admm(X, R, n_iter_max=k, tol=None, absolute_tol=None, **kw)
+    mp.spawn(_worker_mode0, args=(2, _free_port(), k, str(tmp_path)), nprocs=2, join=True)
+    r0 = np.load(os.path.join(str(tmp_path), "rank0.npz"))
+    r1 = np.load(os.path.join(str(tmp_path), "rank1.npz"))
+    for key in ("A", "B", "C", "loss"):
+        np.testing.assert_array_equal(r0[key], r1[key])
+    errs = (_rel(r0["A"], o["A"]), _rel(r0["B"], np.concatenate(o["B_is"], 0)), _rel(r0["C"], o["C"]))
+    assert max(errs) < 1e-8, errs
+    np.testing.assert_allclose(r0["loss"], o["regularized_loss"][: k + 1], rtol=1e-8)
