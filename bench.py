@@ -298,10 +298,31 @@ def run_reference(args, cfg, sizes):
                                    f"{t_iter_sample:.3f} s per outer iteration on the sample, scaled linearly in rows"},
         "e2e": {"value": value, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_JSON_OUT = None
+
+
+def _claim_stdout():
+    """The contract is ONE JSON line on stdout.  Native libraries (NCCL prints its version banner) write to fd 1 too,
+    so fd 1 is pointed at stderr for the whole run and the JSON line goes to a private duplicate of the real stdout."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+    return _JSON_OUT
+
+
+def emit(line):
+    out = _claim_stdout()
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -455,7 +476,7 @@ def main():
                           f"iteration, scaled linearly in rows (every reference loop is per slice)"}
     if e2e is not None:
         line["e2e"] = e2e
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

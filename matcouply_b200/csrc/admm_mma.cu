@@ -56,7 +56,7 @@ __device__ __forceinline__ void store_row(T* __restrict__ grow, int t, int R, co
 }
 
 template <typename T, int NBF, int HALF, int NP>
-__global__ void __launch_bounds__((kConsWarps + 1) * 32) __maxnreg__((NBF + HALF) <= 3 ? 112 : 168)
+__global__ void __launch_bounds__((kConsWarps + 1) * 32) __maxnreg__((NBF + HALF) <= 3 ? 96 : 168)
 admm_local_mma_kernel(const int64_t* __restrict__ row_off, int R, LocalInputs in, const T* __restrict__ A,
                       const T* __restrict__ rho, const T* __restrict__ Minv, PenArgs pa, int n_inner,
                       T* __restrict__ x_out, T* __restrict__ w_out, int ldw, T* __restrict__ BtB_out, int stages) {
@@ -248,6 +248,8 @@ int launch_k(const int64_t* row_off, int n_groups, int R, const LocalInputs& in,
     if (smem > 227 * 1024) return -1;
     auto kern = admm_local_mma_kernel<T, NBF, HALF, NP>;
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // ask for the largest shared-memory carve-out: otherwise the driver sizes it for ONE resident CTA
+    B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     kern<<<n_groups, (kConsWarps + 1) * 32, smem, st>>>(row_off, R, in, (const T*)A, (const T*)rho, (const T*)Minv, pa,
                                                         n_inner, (T*)x, (T*)w_out, ldw, (T*)BtB_out, stages);
     B2_LAUNCH_CHECK();

@@ -59,10 +59,10 @@ __device__ __forceinline__ void store_row(T* __restrict__ grow, int t, int R, co
 }
 
 // NEXTRA: number of penalties besides PARAFAC2 (compile time: their duals stay in registers).  LAST: the last inner
-// iteration also emits x, W = x o a and B^T B.  The launch bound of two CTAs per SM (<= 112 registers) matters: the
+// iteration also emits x, W = x o a and B^T B.  Two CTAs per SM (9 warps each: 5 warps on one SM sub-partition x 96 registers fit its 16K-register file) matter: the
 // row loop is latency bound, and a second resident CTA doubles the warps that hide it.
 template <typename T, int NBF, int HALF, int NEXTRA, bool LAST>
-__global__ void __launch_bounds__((kConsWarps + 1) * 32) __maxnreg__((NBF + HALF) <= 3 ? 112 : 168)
+__global__ void __launch_bounds__((kConsWarps + 1) * 32) __maxnreg__((NBF + HALF) <= 3 ? 96 : 168)
 pf2_rowpass_mma_kernel(const int64_t* __restrict__ row_off, int R, RowpassInputs in, const T* __restrict__ A,
                        const T* __restrict__ rho, const T* __restrict__ Minv, PenArgs pa, int deferred,
                        const T* __restrict__ Wmat, const T* __restrict__ Delta, T* __restrict__ x_out,
@@ -306,6 +306,8 @@ int launch_mma_k(const int64_t* row_off, int n_groups, int R, const RowpassInput
     if (smem > 227 * 1024) return -1;  // too many / too wide input arrays for two stages: use the shuffle kernel
     auto kern = pf2_rowpass_mma_kernel<T, NBF, HALF, NEXTRA, LAST>;
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // ask for the largest shared-memory carve-out: otherwise the driver sizes it for ONE resident CTA
+    B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     kern<<<n_groups, (kConsWarps + 1) * 32, smem, st>>>(row_off, R, in, (const T*)A, (const T*)rho, (const T*)Minv, pa,
                                                         deferred, (const T*)Wmat, (const T*)Delta, (T*)x, (T*)w_out, ldw,
                                                         (T*)S_out, (T*)BtB_out, stages);

@@ -37,7 +37,7 @@ struct __align__(16) Rec {
 
 constexpr int kThreads = 128;
 constexpr int kYRing = 8;   // elements of the column in flight ahead of the PAVA front (cp.async into shared memory)
-constexpr int kStack = 8;   // most recent stack blocks (below the register-resident top) cached in shared memory
+constexpr int kStack = 4;   // most recent stack blocks (below the register-resident top) cached in shared memory
 
 // shared memory, all arrays [depth][thread] so that a warp access is conflict free
 struct SharedState {
@@ -185,12 +185,13 @@ __device__ __forceinline__ void fill_prefix(T* __restrict__ aux, T* __restrict__
     ++e;
     int next_s = e < e_end ? e->start : len;
     T next_v = e < e_end ? (T)e->err_after : T(0);
-    for (int j0 = 0; j0 < len; j0 += 4) {
-        T vv[4];
+    constexpr int U = 8;  // independent loads in flight per trip
+    for (int j0 = 0; j0 < len; j0 += U) {
+        T vv[U];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) vv[u] = (j0 + u < len) ? dual[o0 + (long long)(j0 + u) * step] : T(0);
+        for (int u = 0; u < U; ++u) vv[u] = (j0 + u < len) ? dual[o0 + (long long)(j0 + u) * step] : T(0);
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             const int j = j0 + u;
             if (j < len) {
                 if (j == next_s) {
@@ -253,11 +254,16 @@ unimodal_kernel(T* __restrict__ aux, T* __restrict__ dual, const int64_t* __rest
             };
             best = cand_at(lo);
             bidx = lo;
-            for (int i = lo + 1; i < hi; ++i) {
-                const double cand = cand_at(i);
-                if (cand < best) {
-                    best = cand;
-                    bidx = i;
+            for (int i0 = lo + 1; i0 < hi; i0 += 8) {
+                double cand[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) cand[u] = (i0 + u < hi) ? cand_at(i0 + u) : 0.0;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    if (i0 + u < hi && cand[u] < best) {
+                        best = cand[u];
+                        bidx = i0 + u;
+                    }
                 }
             }
         }
