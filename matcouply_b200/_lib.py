@@ -13,7 +13,7 @@ F32, F64 = 0, 1
 VARIANT_AUTO, VARIANT_FMA, VARIANT_DMMA = 0, 1, 2
 PEN_NONNEG, PEN_BOX, PEN_L1, PEN_L2BALL, PEN_UNIMODAL, PEN_PARAFAC2 = range(6)
 GROUP_SINGLE, GROUP_INDEXED, GROUP_IDENTITY = 0, 1, 2
-OPT_PF2_ROWPASS_MMA, OPT_POLAR_WARP, OPT_ADMM_LOCAL_MMA = 0, 1, 2
+OPT_PF2_ROWPASS_MMA, OPT_POLAR_WARP, OPT_ADMM_LOCAL_MMA, OPT_XSTREAM_HYBRID = 0, 1, 2, 3
 MAX_RANK = 32
 MAX_PENALTIES_PER_MODE = 4
 

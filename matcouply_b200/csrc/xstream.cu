@@ -58,7 +58,12 @@ __global__ void pad_c_kernel(const T* __restrict__ C, T* __restrict__ Cp, int K,
 //      in the same 32-byte window);
 //   B: the staged C rows are stored in that same MMA order (pad_c_kernel) with LDC = 4 or 12 (mod 16), so lane (g,t)
 //      reads word (4*k4 + t)*LDC + g: 16 distinct words mod 16.
-template <typename T, int CT, bool DMMA, int NBLK>
+// EX (DMMA path): columns 8*NBLK .. 8*NBLK+EX-1 (R = 8*NBLK + 1..4) are NOT padded to a third tensor-core block:
+// they are contracted with DFMAs on the A fragments the lane already holds (lane (g,t) has X[row g][k(t)] and needs
+// C[k(t)][8*NBLK + e], which sits in the 4 pad words of the staged C row) and summed over the 4 t-lanes at the end
+// of the tile.  DMMA and DFMA share the fp64 units (b2_microbench_flops kind 3), so what this buys is the saved
+// padding: R = 20 costs 20 columns of pipe time instead of 24.
+template <typename T, int CT, bool DMMA, int NBLK, int EX>
 __global__ void __launch_bounds__(kThreads, 1)
 xstream_y_kernel(const __grid_constant__ CUtensorMap tmap_x, const T* __restrict__ Cp, T* __restrict__ Y, long long N,
                  int R, int Kp, int LDC, int num_tiles, int stages) {
@@ -179,10 +184,14 @@ xstream_y_kernel(const __grid_constant__ CUtensorMap tmap_x, const T* __restrict
         const uint32_t a_chunk0 = 4u * (t >> 1), a_half = (t & 1) * 8u;
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             double acc[MB][NBLK][2];
+            double accx[MB][EX > 0 ? EX : 1];
 #pragma unroll
-            for (int m = 0; m < MB; ++m)
+            for (int m = 0; m < MB; ++m) {
 #pragma unroll
                 for (int n = 0; n < NBLK; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
+#pragma unroll
+                for (int e = 0; e < (EX > 0 ? EX : 1); ++e) accx[m][e] = 0.0;
+            }
             for (int kc = 0; kc < kchunks; ++kc) {
                 mbar_wait(&full[s], ph);
                 const uint32_t st = base_s + (uint32_t)s * stage_bytes;
@@ -201,6 +210,17 @@ xstream_y_kernel(const __grid_constant__ CUtensorMap tmap_x, const T* __restrict
                         const uint32_t crow = Cs + (uint32_t)((b * EPB + k4 * 4 + t) * LDC * sizeof(double));
 #pragma unroll
                         for (int n = 0; n < NBLK; ++n) bf[n] = lds_f64(crow + n * 64);
+                        if constexpr (EX > 0) {
+                            // extra columns: C[k(t)][8*NBLK + e] (same address for all g: broadcast)
+                            double ce[EX];
+                            const uint32_t cex = crow - (uint32_t)(g * sizeof(double)) + NBLK * 64;
+#pragma unroll
+                            for (int v = 0; v < EX / 2; ++v) *((int4*)ce + v) = lds_b128(cex + 16 * v);
+#pragma unroll
+                            for (int m = 0; m < MB; ++m)
+#pragma unroll
+                                for (int e = 0; e < EX; ++e) accx[m][e] = fma(a[m], ce[e], accx[m][e]);
+                        }
 #pragma unroll
                         for (int m = 0; m < MB; ++m)
 #pragma unroll
@@ -209,14 +229,28 @@ xstream_y_kernel(const __grid_constant__ CUtensorMap tmap_x, const T* __restrict
                 }
                 int dep = 0;
 #pragma unroll
-                for (int m = 0; m < MB; ++m)
+                for (int m = 0; m < MB; ++m) {
 #pragma unroll
                     for (int n = 0; n < NBLK; ++n) dep = max(dep, dep_bits_of(acc[m][n][0]));
+                    if constexpr (EX > 0) {
+#pragma unroll
+                        for (int e = 0; e < EX; ++e) dep = max(dep, dep_bits_of(accx[m][e]));
+                    }
+                }
                 stage_release(&empty[s], lane, dep);
                 if (++s == stages) {
                     s = 0;
                     ph ^= 1;
                 }
+            }
+            if constexpr (EX > 0) {  // sum the DFMA partials over the 4 lanes (t) that share a row
+#pragma unroll
+                for (int m = 0; m < MB; ++m)
+#pragma unroll
+                    for (int e = 0; e < EX; ++e) {
+                        accx[m][e] += __shfl_xor_sync(0xffffffffu, accx[m][e], 1);
+                        accx[m][e] += __shfl_xor_sync(0xffffffffu, accx[m][e], 2);
+                    }
             }
 #pragma unroll
             for (int m = 0; m < MB; ++m) {
@@ -227,6 +261,11 @@ xstream_y_kernel(const __grid_constant__ CUtensorMap tmap_x, const T* __restrict
                         const int col = n * 8 + 2 * t;
                         if (col < R) Y[row * R + col] = (T)acc[m][n][0];
                         if (col + 1 < R) Y[row * R + col + 1] = (T)acc[m][n][1];
+                    }
+                    if constexpr (EX > 0) {  // lane t writes extra column t
+#pragma unroll
+                        for (int e = 0; e < EX; ++e)
+                            if (e == t && 8 * NBLK + e < R) Y[row * R + 8 * NBLK + e] = (T)accx[m][e];
                     }
                 }
             }
@@ -359,7 +398,10 @@ constexpr int kZdKZ = 128;
 constexpr int kZdBoxBytes = kZdTM * 128;
 constexpr int kZdXBytes = (kZdKZ / 16) * kZdBoxBytes;
 
-template <int NBLK>
+// EX: as in xstream_y_kernel — the remainder columns 8*NBLK .. 8*NBLK+EX-1 of W are contracted with DFMAs on the A
+// fragments (lane (g,t) holds X[row(t)][k(g)] and needs W[row(t)][8*NBLK + e]: a broadcast over g) and summed over
+// the 4 t-lanes once, after the last tile.
+template <int NBLK, int EX>
 __global__ void __launch_bounds__(kThreads, 1)
 xstream_z_dmma_kernel(const __grid_constant__ CUtensorMap tmap_x, const double* __restrict__ W, int ldw,
                       double* __restrict__ part, int K, int R, int num_tiles, int stages) {
@@ -406,12 +448,17 @@ xstream_z_dmma_kernel(const __grid_constant__ CUtensorMap tmap_x, const double* 
     // Two independent accumulator sets (rows r0+h+2t, h = 0 / 1, summed at the end): 4*NBLK dependent DMMA
     // chains per warp instead of 2*NBLK — with 8 consumer warps per SM the DMMA pipe needs that much ILP.
     double acc[2][2][NBLK][2];
+    double accx[2][EX > 0 ? EX : 1];  // [m][extra column], summed over this lane's rows
 #pragma unroll
     for (int u = 0; u < 2; ++u)
 #pragma unroll
         for (int m = 0; m < 2; ++m)
 #pragma unroll
             for (int n = 0; n < NBLK; ++n) acc[u][m][n][0] = acc[u][m][n][1] = 0.0;
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int e = 0; e < (EX > 0 ? EX : 1); ++e) accx[m][e] = 0.0;
     int s = 0;
     uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -433,6 +480,16 @@ xstream_z_dmma_kernel(const __grid_constant__ CUtensorMap tmap_x, const double* 
                 const uint32_t wrow = Ws + (uint32_t)(row * ldw * sizeof(double));
 #pragma unroll
                 for (int n = 0; n < NBLK; ++n) bf[n] = lds_f64(wrow + n * 64);
+                if constexpr (EX > 0) {
+                    double we[EX];
+                    const uint32_t wex = wrow - (uint32_t)(g * sizeof(double)) + NBLK * 64;
+#pragma unroll
+                    for (int v = 0; v < EX / 2; ++v) *((int4*)we + v) = lds_b128(wex + 16 * v);
+#pragma unroll
+                    for (int m = 0; m < 2; ++m)
+#pragma unroll
+                        for (int e = 0; e < EX; ++e) accx[m][e] = fma(a[m], we[e], accx[m][e]);
+                }
 #pragma unroll
                 for (int m = 0; m < 2; ++m)
 #pragma unroll
@@ -446,6 +503,12 @@ xstream_z_dmma_kernel(const __grid_constant__ CUtensorMap tmap_x, const double* 
             for (int m = 0; m < 2; ++m)
 #pragma unroll
                 for (int n = 0; n < NBLK; ++n) dep = max(dep, dep_bits_of(acc[u][m][n][0]));
+        if constexpr (EX > 0) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m)
+#pragma unroll
+                for (int e = 0; e < EX; ++e) dep = max(dep, dep_bits_of(accx[m][e]));
+        }
         stage_release(&empty[s], lane, dep);
         if (++s == stages) {
             s = 0;
@@ -453,6 +516,15 @@ xstream_z_dmma_kernel(const __grid_constant__ CUtensorMap tmap_x, const double* 
         }
     }
     double* out = part + (size_t)blockIdx.x * K * R;
+    if constexpr (EX > 0) {  // sum the DFMA partials over the 4 lanes (t) that share a k
+#pragma unroll
+        for (int m = 0; m < 2; ++m)
+#pragma unroll
+            for (int e = 0; e < EX; ++e) {
+                accx[m][e] += __shfl_xor_sync(0xffffffffu, accx[m][e], 1);
+                accx[m][e] += __shfl_xor_sync(0xffffffffu, accx[m][e], 2);
+            }
+    }
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
         const int k = k_base + warp * 16 + m * 8 + g;
@@ -462,6 +534,11 @@ xstream_z_dmma_kernel(const __grid_constant__ CUtensorMap tmap_x, const double* 
                 const int col = n * 8 + 2 * t;
                 if (col < R) out[(size_t)k * R + col] = acc[0][m][n][0] + acc[1][m][n][0];
                 if (col + 1 < R) out[(size_t)k * R + col + 1] = acc[0][m][n][1] + acc[1][m][n][1];
+            }
+            if constexpr (EX > 0) {  // lane t writes extra column t
+#pragma unroll
+                for (int e = 0; e < EX; ++e)
+                    if (e == t && 8 * NBLK + e < R) out[(size_t)k * R + 8 * NBLK + e] = accx[m][e];
             }
         }
     }
@@ -543,19 +620,32 @@ int encode_x_map(CUtensorMap* map, const void* X, long long N, int K, int ldx, i
     return B2_OK;
 }
 
+// R = 8*NBLK + (1..4) with NBLK >= 1: the remainder goes to the DFMA path (EX = 2 or 4 columns incl. padding);
+// otherwise R is padded up to whole tensor-core blocks.
+void y_dmma_split(int R, int* NBLK, int* EX) {
+    const int nb = R / 8, rem = R % 8;
+    if (nb >= 1 && rem >= 1 && rem <= 4 && b2_option_value(B2_OPT_XSTREAM_HYBRID)) {
+        *NBLK = nb;
+        *EX = rem <= 2 ? 2 : 4;
+    } else {
+        *NBLK = (R + 7) / 8;
+        *EX = 0;
+    }
+}
+
 template <typename T, int CT>
 int launch_y_fma(const CUtensorMap& map, const T* Cp, T* Y, long long N, int R, int Kp, int num_tiles, int grid,
                  int stages, size_t smem, cudaStream_t st) {
-    auto kern = xstream_y_kernel<T, CT, false, 1>;
+    auto kern = xstream_y_kernel<T, CT, false, 1, 0>;
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreads, smem, st>>>(map, Cp, Y, N, R, Kp, 4 * CT, num_tiles, stages);
     B2_LAUNCH_CHECK();
     return B2_OK;
 }
-template <int NBLK>
+template <int NBLK, int EX>
 int launch_y_dmma(const CUtensorMap& map, const double* Cp, double* Y, long long N, int R, int Kp, int LDC, int num_tiles,
                   int grid, int stages, size_t smem, cudaStream_t st) {
-    auto kern = xstream_y_kernel<double, 1, true, NBLK>;
+    auto kern = xstream_y_kernel<double, 1, true, NBLK, EX>;
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreads, smem, st>>>(map, Cp, Y, N, R, Kp, LDC, num_tiles, stages);
     B2_LAUNCH_CHECK();
@@ -571,8 +661,11 @@ int xstream_y_impl(const void* X, long long N, int K, int ldx, const void* C, in
     B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
     if (N == 0) return B2_OK;
     const int Kp = ((K + Cfg::KC - 1) / Cfg::KC) * Cfg::KC;
-    int CT = (R + 3) / 4, LDC = 4 * CT, NBLK = (R + 7) / 8;
-    if (dmma) LDC = 8 * NBLK + 4;  // == 4 or 12 (mod 16): conflict-free B-fragment reads
+    int CT = (R + 3) / 4, LDC = 4 * CT, NBLK = (R + 7) / 8, EX = 0;
+    if (dmma) {
+        y_dmma_split(R, &NBLK, &EX);
+        LDC = 8 * NBLK + 4;  // == 4 or 12 (mod 16): conflict-free B-fragment reads; the 4 pad words hold the EX columns
+    }
     const size_t cp_bytes = (size_t)Kp * LDC * sizeof(T);
     B2_REQUIRE(ws_bytes >= cp_bytes, "xstream_y workspace too small: need %zu bytes, got %zu", cp_bytes, ws_bytes);
     B2_REQUIRE(((uintptr_t)ws) % 16 == 0, "workspace must be 16-byte aligned");
@@ -596,12 +689,12 @@ int xstream_y_impl(const void* X, long long N, int K, int ldx, const void* C, in
     if constexpr (dmma) {
         const double* Cp = (const double*)ws;
         double* Yd = (double*)Y;
-        switch (NBLK) {
-            case 1: return launch_y_dmma<1>(map, Cp, Yd, N, R, Kp, LDC, num_tiles, grid, stages, smem, st);
-            case 2: return launch_y_dmma<2>(map, Cp, Yd, N, R, Kp, LDC, num_tiles, grid, stages, smem, st);
-            case 3: return launch_y_dmma<3>(map, Cp, Yd, N, R, Kp, LDC, num_tiles, grid, stages, smem, st);
-            default: return launch_y_dmma<4>(map, Cp, Yd, N, R, Kp, LDC, num_tiles, grid, stages, smem, st);
-        }
+#define B2_Y_CASE(NB, E) \
+    if (NBLK == NB && EX == E) return launch_y_dmma<NB, E>(map, Cp, Yd, N, R, Kp, LDC, num_tiles, grid, stages, smem, st);
+        B2_Y_CASE(1, 0) B2_Y_CASE(2, 0) B2_Y_CASE(3, 0) B2_Y_CASE(4, 0)
+        B2_Y_CASE(1, 2) B2_Y_CASE(1, 4) B2_Y_CASE(2, 2) B2_Y_CASE(2, 4) B2_Y_CASE(3, 2) B2_Y_CASE(3, 4)
+#undef B2_Y_CASE
+        B2_REQUIRE(false, "xstream_y: no kernel for NBLK=%d EX=%d", NBLK, EX);
     }
     const T* Cp = (const T*)ws;
     T* Yt = (T*)Y;
@@ -627,10 +720,10 @@ int launch_z(const CUtensorMap& map, const T* W, int ldw, T* part, int K, int R,
     return B2_OK;
 }
 
-template <int NBLK>
+template <int NBLK, int EX>
 int launch_z_dmma(const CUtensorMap& map, const double* W, int ldw, double* part, int K, int R, int num_tiles, dim3 grid,
                   int stages, size_t smem, cudaStream_t st) {
-    auto kern = xstream_z_dmma_kernel<NBLK>;
+    auto kern = xstream_z_dmma_kernel<NBLK, EX>;
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, kThreads, smem, st>>>(map, W, ldw, part, K, R, num_tiles, stages);
     B2_LAUNCH_CHECK();
@@ -647,7 +740,8 @@ int z_ldw_for(int R, int dtype, int variant) {
 
 int xstream_z_dmma_impl(const void* X, long long N, int K, int ldx, const void* W, int ldw, int R, void* Z, void* ws,
                         size_t ws_bytes, int max_ctas, cudaStream_t st) {
-    const int NBLK = (R + 7) / 8;
+    int NBLK, EX;
+    y_dmma_split(R, &NBLK, &EX);  // ldw keeps the padded-block formula, so the EX columns are simply W[:, 8*NBLK ...]
     B2_REQUIRE(ldw == z_ldw_for(R, B2_F64, B2_VARIANT_DMMA), "xstream_z (DMMA): W row stride must be %d, got %d",
                z_ldw_for(R, B2_F64, B2_VARIANT_DMMA), ldw);
     const int kblocks = (K + kZdKZ - 1) / kZdKZ;
@@ -669,12 +763,12 @@ int xstream_z_dmma_impl(const void* X, long long N, int K, int ldx, const void* 
     dim3 grid(groups, kblocks);
     const double* Wd = (const double*)W;
     double* part = (double*)ws;
-    switch (NBLK) {
-        case 1: rc = launch_z_dmma<1>(map, Wd, ldw, part, K, R, num_tiles, grid, stages, smem, st); break;
-        case 2: rc = launch_z_dmma<2>(map, Wd, ldw, part, K, R, num_tiles, grid, stages, smem, st); break;
-        case 3: rc = launch_z_dmma<3>(map, Wd, ldw, part, K, R, num_tiles, grid, stages, smem, st); break;
-        default: rc = launch_z_dmma<4>(map, Wd, ldw, part, K, R, num_tiles, grid, stages, smem, st); break;
-    }
+    rc = B2_ERR_INVALID;
+#define B2_Z_CASE(NB, E) \
+    if (NBLK == NB && EX == E) rc = launch_z_dmma<NB, E>(map, Wd, ldw, part, K, R, num_tiles, grid, stages, smem, st);
+    B2_Z_CASE(1, 0) B2_Z_CASE(2, 0) B2_Z_CASE(3, 0) B2_Z_CASE(4, 0)
+    B2_Z_CASE(1, 2) B2_Z_CASE(1, 4) B2_Z_CASE(2, 2) B2_Z_CASE(2, 4) B2_Z_CASE(3, 2) B2_Z_CASE(3, 4)
+#undef B2_Z_CASE
     if (rc != B2_OK) return rc;
     const int n = K * R;
     reduce_partials_kernel<double><<<(n + 255) / 256, 256, 0, st>>>(part, (double*)Z, n, groups);

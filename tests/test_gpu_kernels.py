@@ -31,7 +31,9 @@ def packed_x(N, K, dtype, rs):
 
 
 XSTREAM_SHAPES = [(1, 1, 1), (37, 15, 3), (128, 32, 4), (300, 33, 5), (1000, 512, 16), (2500, 100, 20), (777, 70, 32),
-                  (513, 1030, 8), (5000, 256, 12)]
+                  (513, 1030, 8), (5000, 256, 12),
+                  # R = 8 b + 1..4: tensor-core blocks + DFMA remainder columns (EX = 2 / 4)
+                  (400, 64, 9), (401, 64, 10), (333, 40, 18), (500, 96, 26), (450, 72, 28), (300, 48, 11), (299, 80, 17)]
 
 
 @pytest.mark.parametrize("N,K,R", XSTREAM_SHAPES)
@@ -655,3 +657,27 @@ def test_parafac2_polar_warm_start_equals_cold(R):
     for g in range(G):  # and it is the polar factor: P = V W has orthonormal columns
         P = V2[g] @ Ww[g].cpu().numpy()
         np.testing.assert_allclose(P.T @ P, np.eye(R), atol=1e-9)
+
+
+@pytest.mark.parametrize("N,K,R", [(400, 64, 9), (401, 64, 10), (333, 40, 18), (2500, 100, 20), (500, 96, 26), (450, 72, 28)])
+def test_xstream_hybrid_remainder_columns(N, K, R):
+    """B2_OPT_XSTREAM_HYBRID (off by default): tensor-core blocks + DFMA remainder columns must give the same Y and Z."""
+    _lib, _ops, _ = _imports()
+    lib = _lib.load()
+    rs = np.random.RandomState(N + R)
+    Xh, X = packed_x(N, K, torch.float64, rs)
+    C, Wh = rs.standard_normal(size=(K, R)), rs.standard_normal(size=(N, R))
+    ws = _ops.Workspace(torch.device("cuda"), K, R, torch.float64)
+    lib.b2_set_option(_lib.OPT_XSTREAM_HYBRID, 1)
+    try:
+        Y = torch.zeros((N, R), dtype=torch.float64, device="cuda")
+        _ops.xstream_y(X, N, K, dev(C), Y, ws, _lib.VARIANT_DMMA)
+        W = _ops.alloc_w(N, R, torch.float64, "cuda", _lib.VARIANT_DMMA)
+        W[:N, :R] = dev(Wh)
+        Z = torch.zeros((K, R), dtype=torch.float64, device="cuda")
+        _ops.xstream_z(X, N, K, W, Z, ws, _lib.VARIANT_DMMA)
+        torch.cuda.synchronize()
+    finally:
+        lib.b2_set_option(_lib.OPT_XSTREAM_HYBRID, 0)
+    np.testing.assert_allclose(Y.cpu().numpy(), Xh @ C, rtol=1e-12, atol=1e-11)
+    np.testing.assert_allclose(Z.cpu().numpy(), Xh.T @ Wh, rtol=1e-12, atol=1e-10)
