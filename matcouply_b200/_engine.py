@@ -543,6 +543,10 @@ class AOADMMEngine:
         """Returns dict(gaps=(A_gaps, B_gaps, C_gaps), sse_terms=(inner, quad), sq=[|A|^2,|B|^2,|C|^2],
         l1=[[...],[...],[...]] sums of |x| per penalty) — everything the host loss/stopping logic needs
         (decomposition.py:351-417, 420-452, 617-627, 1016-1023)."""
+        return self._read_diagnostics(self._launch_diagnostics())
+
+    def _launch_diagnostics(self):
+        """Launch the fused reductions into the scalar pack `self.scal`; returns (layout, n_slots). No host sync."""
         scal = self.scal
         scal.zero_()
         slot = 2  # [0:2] fit terms
@@ -568,7 +572,12 @@ class AOADMMEngine:
                 slot += 3
         if self.world > 1:
             self._allreduce(scal[:shard_end])
-        host = scal[:slot].cpu().numpy()
+        return layout, slot
+
+    def _read_diagnostics(self, launched):
+        """The ONE device->host copy (and sync) of an outer iteration."""
+        layout, slot = launched
+        host = self.scal[:slot].cpu().numpy()
         gaps, sq, l1 = ([], [], []), [0.0, 0.0, 0.0], ([], [], [])
         for m, p, s in layout:
             d2, x2, ab = host[s:s + 3]
@@ -577,3 +586,37 @@ class AOADMMEngine:
                 gaps[m].append(np.sqrt(d2) / np.sqrt(x2))
                 l1[m].append(ab)
         return dict(gaps=gaps, fit=(host[0], host[1]), sq=sq, l1=l1)
+
+    # ------------------------------------------------------------------------------------------------------
+    # CUDA-graph replay of the steady-state outer iteration (launch-bound problem sizes)
+    # ------------------------------------------------------------------------------------------------------
+    GRAPH_MAX_X_BYTES = 1 << 30  # below this an outer iteration is dominated by launch latency, not by HBM time
+
+    def graph_eligible(self):
+        """Small single-GPU problems: ~50-100 kernel launches per outer iteration cost more than the kernels.  The
+        launch sequence of a steady-state iteration is fixed (same kernels, same buffers), so it is captured once
+        into a CUDA graph and replayed; the host only reads the scalar pack.  Sharded runs stay eager (NCCL calls)."""
+        return (self.world == 1 and self.xstream_events is None
+                and self.N * self.K * self.p.X.element_size() <= self.GRAPH_MAX_X_BYTES)
+
+    def graph_iteration(self, with_diagnostics):
+        """One outer iteration (+ the diagnostics reductions) as a graph replay; captured on first use.  Must only be
+        called once the host-side state flags are steady (after >= 2 eager iterations).  Returns what
+        _launch_diagnostics() returns, or None."""
+        key = bool(with_diagnostics)
+        if not hasattr(self, "_graphs"):
+            self._graphs = {}
+        entry = self._graphs.get(key)
+        if entry is None:
+            flags = (self.w_fresh, getattr(self, "pf2_deferred", None), getattr(self, "pf2_fresh", None))
+            g = torch.cuda.CUDAGraph()
+            torch.cuda.synchronize()
+            with torch.cuda.graph(g):
+                self.outer_iteration()
+                launched = self._launch_diagnostics() if with_diagnostics else None
+            after = (self.w_fresh, getattr(self, "pf2_deferred", None), getattr(self, "pf2_fresh", None))
+            if flags != after:
+                raise RuntimeError("graph capture outside the steady state of the engine")
+            entry = self._graphs[key] = (g, launched)
+        entry[0].replay()
+        return entry[1]

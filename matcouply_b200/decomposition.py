@@ -262,6 +262,7 @@ def cmf_aoadmm(
     process_group=None,
     shard=None,
     gather_factors=True,
+    use_cuda_graph=None,
 ):
     """Fit a regularized coupled matrix factorization with AO-ADMM on a B200 (same signature and semantics as the
     reference ``matcouply.decomposition.cmf_aoadmm``, decomposition.py:662-1100).
@@ -273,6 +274,9 @@ def cmf_aoadmm(
     the global problem, the initial state is drawn for the GLOBAL problem from ``random_state`` (so the run equals the
     unsharded one) and cut to the shard, and a few small all-reduces per outer iteration couple the ranks;
     ``gather_factors`` returns the complete ``A`` / ``B_is`` on every rank instead of the local share.
+    ``use_cuda_graph=True``: replay the steady-state outer iteration as one CUDA graph (single GPU, small problems).
+    Off by default: measured on the README configuration the iteration is bound by the ~90 DEPENDENT tiny kernels
+    (0.76 ms per iteration eager and replayed alike), not by host launch overhead, and the capture costs ~0.15 s.
     """
     import torch
 
@@ -354,11 +358,17 @@ def cmf_aoadmm(
     feasibility_criterion = None
     message = "MAXIMUM NUMBER OF ITERATIONS REACHED"
     it = -1
+    want_diag = bool(tol or absolute_tol or return_errors)
+    use_graph = bool(use_cuda_graph) and engine.graph_eligible()
     for it in range(n_iter_max):
-        engine.outer_iteration()
+        launched = None
+        if use_graph and it >= 2:  # steady state: replay the captured launch sequence (see AOADMMEngine.graph_iteration)
+            launched = engine.graph_iteration(want_diag)
+        else:
+            engine.outer_iteration()
 
-        if tol or absolute_tol or return_errors:
-            diag = engine.diagnostics()
+        if want_diag:
+            diag = engine._read_diagnostics(launched) if launched is not None else engine.diagnostics()
             curr_gaps = diag["gaps"]
             feasibility_gaps.append(curr_gaps)
             if tol or absolute_tol:

@@ -204,3 +204,28 @@ def test_fused_kernels_match_stepwise_kernels(kw, dtype):
                 assert rel(x1[1], x2[1]) < 10 * tol and rel(np.concatenate(x1[0], 0), np.concatenate(x2[0], 0)) < 10 * tol
             else:
                 assert rel(np.concatenate(x1, 0) if m == 1 else x1, np.concatenate(x2, 0) if m == 1 else x2) < 10 * tol
+
+
+@pytest.mark.parametrize("name", ["c0_readme", "c1_nn_cmf", "c2_nn_pf2_l1_ragged", "c3_unimodal_l2ball_pf2"])
+def test_cuda_graph_replay_equals_eager_launches(name):
+    """The steady-state outer iteration replayed as a CUDA graph launches the same kernels on the same buffers as the
+    eager loop: factors, ADMM variables and diagnostics must be bit-identical."""
+    from matcouply_b200 import cmf_aoadmm
+
+    g, X, rank, kw = load_case(name)
+    kw = dict(kw)
+    kw.pop("n_iter_max", None)
+    outs = []
+    for graph in (False, True):
+        cmf, admm, diag = cmf_aoadmm(X, rank, n_iter_max=12, return_errors=True, return_admm_vars=True,
+                                     use_cuda_graph=graph, **dict(kw, tol=None, absolute_tol=None))
+        outs.append((cmf, admm, diag))
+    (c0, a0, d0), (c1, a1, d1) = outs
+    np.testing.assert_array_equal(c0[1][0], c1[1][0])
+    np.testing.assert_array_equal(np.concatenate(c0[1][1], 0), np.concatenate(c1[1][1], 0))
+    np.testing.assert_array_equal(c0[1][2], c1[1][2])
+    np.testing.assert_array_equal(d0.regularized_loss, d1.regularized_loss)
+    np.testing.assert_array_equal(d0.rec_errors, d1.rec_errors)
+    for m in (0, 2):
+        for x, y in zip(a0.duals[m], a1.duals[m]):
+            np.testing.assert_array_equal(x, y)
