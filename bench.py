@@ -208,8 +208,9 @@ def gen_pinned_sample(cfg, sizes, lo, hi, dtype, device):
 
 
 def run_e2e(cfg, sizes, dtype, es, device, world, rank, group, regs):
-    """e2e leg: the public `cmf_aoadmm` call on page-locked HOST arrays, whole call timed (host RNG init of the state,
-    H2D of X and state, E2E_ITERS outer iterations with the per-iteration diagnostics D2H, D2H of the factors).  With
+    """e2e leg: the public `cmf_aoadmm` call on page-locked HOST arrays, whole call timed (initial state drawn from
+    the RandomState stream, H2D of X, E2E_ITERS outer iterations with the per-iteration diagnostics D2H, D2H of the
+    factors).  With
     N ranks every rank uploads and fits its row-balanced shard of an N-times larger sample (NCCL all-reduces inside
     the call); the time is the max over ranks."""
     import torch
@@ -257,7 +258,7 @@ def run_e2e(cfg, sizes, dtype, es, device, world, rank, group, regs):
         "h2d_bytes_per_step": int(h2d / k_e2e), "d2h_bytes_per_step": int(d2h / k_e2e),
         "note": f"cmf_aoadmm(list of page-locked host arrays, n_iter_max={k_e2e}, return_errors=True) on the first "
                 f"{S2} slices ({rows2} rows, {rows2 * cfg['K'] * es / 1e9:.1f} GB of X) sharded over {world} GPU(s): whole "
-                f"call timed, max over ranks ({t_call:.3f} s: host RNG init of the state, H2D of X and state, {k_e2e} "
+                f"call timed, max over ranks ({t_call:.3f} s: initial state drawn from the RandomState stream, H2D of X, {k_e2e} "
                 f"outer iterations with the per-iteration diagnostics D2H, D2H of the factors), iterations/s = {k_e2e} / "
                 f"t_call, scaled linearly in rows to the full workload (155 GB of host data cannot be staged inside a "
                 f"few-minute run). The same call with n_iter_max=5 takes {times[5]:.3f} s, i.e. {1000 * t_iter:.2f} ms "

@@ -199,6 +199,13 @@ int b2_fit_terms(const void* rhs, const void* cross, const void* A, int n_groups
 int b2_prox_elementwise(const void* v, void* out, long long n, int kind, int non_negativity, double p0, double p1,
                         double rho, int dtype, void* stream);
 
+/* ---- initial state: device-side continuation of a NumPy RandomState (MT19937) stream ----------------------------
+ * out[0:n] = the next n doubles `np.random.RandomState.random_sample` / `uniform(0, 1)` would return for the generator
+ * whose state is state_io (device, 625 uint32: the 624 key words and the position, as in RandomState.get_state());
+ * state_io is advanced so the host generator can continue the stream (decomposition.py:31-39, 78-89;
+ * penalties.py:125-147, 239-261 draw everything from one RandomState). */
+int b2_mt19937_uniform(void* state_io, double* out, long long n, void* stream);
+
 /* ---- measurement helpers (bench.py / DESIGN.md roofline denominators) -------------------------------------------
  * kind 0: fp64 FMA pipe, 1: DMMA.8x8x4, 2: fp32 FMA, 3: DMMA + DFMA interleaved (pipe overlap probe). Runs `iters` dependent-chain-free iterations on every SM and
  * writes the number of floating-point operations issued to flops_host. Time it with CUDA events around the call. */

@@ -27,6 +27,19 @@ from . import _lib, _ops
 FUSION_DEFAULTS = {"local": True, "pf2": True}
 
 
+def _stack_rows(mats):
+    """np.concatenate(mats, 0) without the copy when the matrices already are adjacent views of one array."""
+    mats = [np.asarray(m) for m in mats]
+    if len(mats) > 1 and all(m.flags.c_contiguous for m in mats):
+        base = mats[0].base
+        if isinstance(base, np.ndarray) and base.ndim == 2 and base.flags.c_contiguous and \
+                all(m.base is base for m in mats) and mats[0].ctypes.data == base.ctypes.data and \
+                all(b.ctypes.data == a.ctypes.data + a.nbytes for a, b in zip(mats[:-1], mats[1:])) and \
+                sum(m.shape[0] for m in mats) == base.shape[0] and mats[0].shape[1] == base.shape[1]:
+            return base
+    return np.concatenate(mats, 0)
+
+
 class PackedMatrices:
     """Ragged list of J_i x K matrices packed along rows (``np.concatenate(matrices, 0)``) on the device."""
 
@@ -129,6 +142,37 @@ class PackedMatrices:
         for ev in events:
             if ev is not None:
                 ev.synchronize()  # staging buffers may be recycled by the allocator after return
+
+
+class DeviceRows:
+    """A list of per-slice ``J_i x R`` matrices held as ONE packed ``N x R`` CUDA tensor (what ``np.concatenate(list,
+    0)`` would be).  Used for the B-mode variables that are drawn on the device (`_ops.mt19937_uniform`): they never
+    exist on the host unless somebody indexes / iterates this object, which materialises NumPy arrays lazily."""
+
+    def __init__(self, tensor, row_offsets):
+        self.tensor = tensor
+        self.row_offsets = np.asarray(row_offsets, dtype=np.int64)
+        self._host = None
+
+    def __len__(self):
+        return len(self.row_offsets) - 1
+
+    def _materialise(self):
+        if self._host is None:
+            flat = self.tensor.detach().to(torch.float64).cpu().numpy()
+            self._host = [flat[a:b] for a, b in zip(self.row_offsets[:-1], self.row_offsets[1:])]
+        return self._host
+
+    def __getitem__(self, i):
+        return self._materialise()[i]
+
+    def __iter__(self):
+        return iter(self._materialise())
+
+    def cut(self, lo, hi):
+        """Slices [lo, hi) as a DeviceRows (a view of the same device memory)."""
+        off = self.row_offsets
+        return DeviceRows(self.tensor[int(off[lo]):int(off[hi])], off[lo:hi + 1] - off[lo])
 
 
 class _ModeState:
@@ -239,11 +283,26 @@ class AOADMMEngine:
     def _up(self, a):
         return _ops.to_device(np.asarray(a), self.dtype, self.dev)
 
+    def _up_rows(self, rows):
+        """A mode-1 variable (list of J_i x R arrays, packed N x R array, or DeviceRows) as a packed device tensor."""
+        if isinstance(rows, DeviceRows):
+            src = rows.tensor
+            t = src.to(device=self.dev, dtype=self.dtype)
+            if t.data_ptr() != src.data_ptr():
+                return t.contiguous()
+            # same memory: adopt a freshly drawn block as the engine's state, but copy a shard cut out of the
+            # (much larger) globally drawn block so that the latter can be freed
+            whole = src.is_contiguous() and src.untyped_storage().nbytes() == src.numel() * src.element_size()
+            return src if whole else src.clone()
+        if isinstance(rows, np.ndarray):
+            return self._up(rows)
+        return self._up(_stack_rows(rows))
+
     def load_state(self, A, B_is, C, auxes, duals):
         """A: I x R, B_is: list of J_i x R (or packed N x R), C: K x R; auxes/duals: 3 lists as in ADMMVars."""
         st = self.modes
         st[0].x = self._up(A)
-        st[1].x = self._up(B_is if isinstance(B_is, np.ndarray) else np.concatenate(B_is, 0))
+        st[1].x = self._up_rows(B_is)
         st[2].x = self._up(C)
         for m in range(3):
             st[m].aux, st[m].dual = [], []
@@ -251,18 +310,28 @@ class AOADMMEngine:
                 aux, dual = auxes[m][p], duals[m][p]
                 if kind == _lib.PEN_PARAFAC2:
                     basis, delta = aux
-                    self.pf2_basis0 = [np.asarray(b, dtype=np.float64) for b in basis]
                     self.pf2_fresh = False
                     self.pf2_deferred = False
                     self.Delta.copy_(self._up(delta))
-                    pd = np.concatenate([np.asarray(b) @ np.asarray(delta) for b in basis], 0)
-                    st[m].aux.append(self._up(pd))
+                    if basis.__class__.__name__ == "_EyeBases":
+                        # P_i = eye(J_i, R): row j < R of slice i of P_i Delta is Delta[j]; built on the device
+                        self.pf2_basis0 = basis
+                        pd = torch.zeros((self.N, self.R), dtype=self.dtype, device=self.dev)
+                        starts, ends = self.row_off[:-1], self.row_off[1:]
+                        for j in range(self.R):
+                            ok = (ends - starts) > j
+                            pd[(starts + j)[ok]] = self.Delta[j]
+                        st[m].aux.append(pd)
+                    else:
+                        self.pf2_basis0 = [np.asarray(b, dtype=np.float64) for b in basis]
+                        pd = np.concatenate([np.asarray(b) @ np.asarray(delta) for b in basis], 0)
+                        st[m].aux.append(self._up(pd))
                 elif m == 1:
-                    st[m].aux.append(self._up(np.concatenate(aux, 0) if not isinstance(aux, np.ndarray) else aux))
+                    st[m].aux.append(self._up_rows(aux))
                 else:
                     st[m].aux.append(self._up(aux))
                 if m == 1:
-                    st[m].dual.append(self._up(np.concatenate(dual, 0) if not isinstance(dual, np.ndarray) else dual))
+                    st[m].dual.append(self._up_rows(dual))
                 else:
                     st[m].dual.append(self._up(dual))
             st[m].descs_c = _ops.make_descs(
@@ -297,8 +366,12 @@ class AOADMMEngine:
                 [(d[0], d[1], d[2], d[3], a, u) for d, a, u in zip(st[m].desc, st[m].aux, st[m].dual)])
 
     def _split(self, t):
-        host = t.detach().to(torch.float64).cpu().numpy()
-        return [host[a:b].copy() for a, b in zip(self.p.row_offsets[:-1], self.p.row_offsets[1:])]
+        """Packed device rows -> list of per-slice NumPy arrays (views of ONE host array: no per-slice copies)."""
+        t = t.detach().to(torch.float64)
+        host_t = torch.empty(t.shape, dtype=torch.float64, pin_memory=True)  # DMA straight into page-locked memory
+        host_t.copy_(t)
+        host = host_t.numpy()
+        return [host[a:b] for a, b in zip(self.p.row_offsets[:-1], self.p.row_offsets[1:])]
 
     def factors(self):
         st = self.modes
@@ -321,7 +394,7 @@ class AOADMMEngine:
                         _ops.pf2_apply(tmp, V, basis, self.Wmat, self.Delta, self.gor, self.N, self.R)
                         bases = self._split(basis)
                     else:
-                        bases = self.pf2_basis0
+                        bases = list(self.pf2_basis0)
                     auxes[m].append((bases, f64(self.Delta)))
                 elif m == 1:
                     auxes[m].append(self._split(st.aux[p]))

@@ -235,3 +235,37 @@ def weighted_gram_sum(BtB, A, n_groups, R, out):
 
 def hadamard_bcast(BtB, CtC, n_groups, R, cross):
     call("b2_hadamard_bcast", _ptr(BtB), _ptr(CtC), n_groups, R, _ptr(cross), dtype_code(BtB.dtype), _stream())
+
+
+def mt19937_uniform(random_state, n, device):
+    """The next ``n`` doubles of ``random_state.uniform(size=n)`` (== ``random_sample``), generated ON THE DEVICE with
+    identical bits; ``random_state`` (a legacy ``np.random.RandomState``) is advanced exactly as if it had drawn them."""
+    name, key, pos, has_gauss, cached = random_state.get_state(legacy=True)
+    if name != "MT19937":
+        raise TypeError("device draws need a MT19937 RandomState")
+    st = np.empty(625, dtype=np.uint32)
+    st[:624] = key
+    st[624] = pos
+    # a side stream: the generator kernel (one CTA) overlaps whatever the caller's stream is doing (cmf_aoadmm: the
+    # H2D copy of the data), and reading back the advanced state only waits for the generator
+    main = torch.cuda.current_stream(device)
+    side = _side_stream(device)
+    with torch.cuda.stream(side):
+        dstate = torch.from_numpy(st.view(np.int32)).to(device)
+        out = torch.empty(int(n), dtype=torch.float64, device=device)
+        call("b2_mt19937_uniform", _ptr(dstate), _ptr(out), int(n), _stream())
+        new = dstate.cpu().numpy().view(np.uint32)
+    main.wait_stream(side)
+    out.record_stream(main)
+    random_state.set_state(("MT19937", new[:624].copy(), int(new[624]), has_gauss, cached))
+    return out
+
+
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device):
+    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+    return _SIDE_STREAMS[key]

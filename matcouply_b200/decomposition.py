@@ -10,6 +10,8 @@ kernels on the B200.  There is no CPU path: without the compiled library / a CUD
 from copy import copy
 from typing import NamedTuple, Optional
 
+import os
+
 import numpy as np
 
 from . import penalties
@@ -148,10 +150,16 @@ class _ShapeOnly:
         self.shape = tuple(shape)
 
 
-def initialize_cmf(matrices, rank, init, random_state=None):
+def initialize_cmf(matrices, rank, init, random_state=None, _device=None):
     """decomposition.py:18-75: a given factorization is used as is, "random" draws A, C, B_0..B_{I-1} (in this
-    order) uniformly from one RandomState."""
+    order) uniformly from one RandomState.  ``_device`` (internal, used by cmf_aoadmm): draw the B_i block on that
+    CUDA device from the same stream and return ``(A, DeviceRows, C)`` instead of a CoupledMatrixFactorization."""
     random_state = penalties._check_random_state(random_state)
+    if _device is not None and init == "random":
+        n_slices, n_cols = len(matrices), matrices[0].shape[1]
+        A = random_state.uniform(size=(n_slices, rank))
+        C = random_state.uniform(size=(n_cols, rank))
+        return A, penalties._device_rows_uniform(random_state, matrices, rank, _device), C
     if isinstance(init, (tuple, list, CoupledMatrixFactorization)):
         weights, (A, B_is, C) = init
         if weights is not None:
@@ -304,7 +312,13 @@ def cmf_aoadmm(
                 int(s[0]) != int(j) for s, j in zip(packed.shapes, shard.row_counts[shard.lo:shard.hi])):
             raise ValueError("`matrices` must hold exactly the slices [shard.lo, shard.hi) of the global problem")
         shape_view = [_ShapeOnly((j, packed.K)) for j in shard.row_counts]  # the GLOBAL problem
-    cmf = initialize_cmf(shape_view, rank, init, random_state=random_state)
+    # default path: the big B-mode blocks (B_i, aux, dual) are drawn on the device from random_state's own MT19937
+    # stream (bit-identical to host draws, see csrc/rng.cu); B2_HOST_RNG=1 forces the host draws
+    dev_draw = None if os.environ.get("B2_HOST_RNG") else device
+    if init == "random" and dev_draw is not None:
+        A0, B0, C0 = initialize_cmf(shape_view, rank, init, random_state=random_state, _device=dev_draw)
+    else:
+        _, (A0, B0, C0) = initialize_cmf(shape_view, rank, init, random_state=random_state)
 
     l2_penalty = [l2 if l2 is not None else 0 for l2 in _listify(l2_penalty, "l2_penalty")]
     regs = _parse_all_penalties(
@@ -321,8 +335,12 @@ def cmf_aoadmm(
         regs[2] = []
 
     # aux first, then dual, each in mode order from the same RandomState (decomposition.py:78-89)
-    auxes = [[reg.init_aux(shape_view, rank, m, random_state=random_state) for reg in regs[m]] for m in range(3)]
-    duals = [[reg.init_dual(shape_view, rank, m, random_state=random_state) for reg in regs[m]] for m in range(3)]
+    penalties._DEVICE_DRAW["device"] = dev_draw
+    try:
+        auxes = [[reg.init_aux(shape_view, rank, m, random_state=random_state) for reg in regs[m]] for m in range(3)]
+        duals = [[reg.init_dual(shape_view, rank, m, random_state=random_state) for reg in regs[m]] for m in range(3)]
+    finally:
+        penalties._DEVICE_DRAW["device"] = None
 
     if isinstance(constant_feasibility_penalty, str) and constant_feasibility_penalty not in {"A", "B"}:
         raise ValueError(
@@ -337,12 +355,11 @@ def cmf_aoadmm(
                           constant_B=constant_B, inner_n_iter_max=inner_n_iter_max,
                           update=(update_A, update_B_is, update_C), group=process_group,
                           shard_rows=None if shard is None else (shard.lo, shard.n_global))
-    _, (A0, B0, C0) = cmf
     if shard is not None:
         from .distributed import shard_state
 
         A0, B0, auxes, duals = shard_state(A0, B0, auxes, duals, regs, shard)
-    engine.load_state(np.asarray(A0), [np.asarray(b) for b in B0], np.asarray(C0), auxes, duals)
+    engine.load_state(np.asarray(A0), B0, np.asarray(C0), auxes, duals)
     engine.prepare()
     norm_X_sq = engine.normX_sq
 

@@ -68,17 +68,20 @@ def shard_state(A, B_is, auxes, duals, regs, shard: ShardSpec):
     tuple ``(basis list, Delta)``: the bases are sliced, Delta is replicated), mode 2 variables are replicated."""
     lo, hi = shard.lo, shard.hi
 
+    def rows(v):
+        return v.cut(lo, hi) if hasattr(v, "cut") else list(v[lo:hi])  # DeviceRows stay on the device
+
     def cut(mode, v):
         if mode == 0:
             return np.asarray(v)[lo:hi]
         if mode == 1:
             if isinstance(v, tuple):  # PARAFAC2: (bases, coordinate matrix)
-                return (list(v[0][lo:hi]), v[1])
-            return list(v[lo:hi])
+                return (rows(v[0]), v[1])
+            return rows(v)
         return v
 
     A_loc = np.asarray(A)[lo:hi]
-    B_loc = list(B_is[lo:hi])
+    B_loc = rows(B_is)
     aux_loc = [[cut(m, v) for v in auxes[m]] for m in range(3)]
     dual_loc = [[cut(m, v) for v in duals[m]] for m in range(3)]
     return A_loc, B_loc, aux_loc, dual_loc

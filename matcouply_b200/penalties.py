@@ -40,6 +40,42 @@ def _check_random_state(seed):
     raise ValueError("Seed should be None, int or np.random.RandomState")
 
 
+# set by cmf_aoadmm around its own init_aux / init_dual calls (see _init_variable); None = draw on the host
+_DEVICE_DRAW = {"device": None}
+
+
+def _device_rows_uniform(random_state, matrices, rank, device):
+    """``[random_state.uniform(size=(J_i, rank)) for each matrix]`` as a DeviceRows (one packed CUDA tensor)."""
+    from . import _ops
+    from ._engine import DeviceRows
+
+    off = np.concatenate([[0], np.cumsum([int(m.shape[0]) for m in matrices])]).astype(np.int64)
+    flat = _ops.mt19937_uniform(random_state, int(off[-1]) * rank, device)
+    return DeviceRows(flat.view(int(off[-1]), rank), off)
+
+
+class _EyeBases:
+    """The default PARAFAC2 basis matrices ``[np.eye(J_i, rank) for i]`` (penalties.py:1175) without materialising
+    them: list-like, builds the NumPy matrices only when indexed / iterated."""
+
+    def __init__(self, row_counts, rank):
+        self.row_counts, self.rank = list(row_counts), int(rank)
+
+    def __len__(self):
+        return len(self.row_counts)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return _EyeBases(self.row_counts[i], self.rank)
+        return np.eye(self.row_counts[i], self.rank)
+
+    def __iter__(self):
+        return (np.eye(j, self.rank) for j in self.row_counts)
+
+    def cut(self, lo, hi):
+        return _EyeBases(self.row_counts[lo:hi], self.rank)
+
+
 def _is_tensor(x):
     if isinstance(x, np.ndarray):
         return True
@@ -141,6 +177,10 @@ class ADMMPenalty(ABC):
                 "Cannot use a tensor (matrix) to initialize auxiliary matrices for mode 1. Must be a list instead."
             )
 
+        if init == "random_uniform" and mode == 1 and _DEVICE_DRAW["device"] is not None:
+            # fast path of cmf_aoadmm: the sum_i J_i x R block is drawn ON THE DEVICE from the same MT19937 stream
+            # (identical bits, random_state advanced accordingly) and never touches host memory
+            return _device_rows_uniform(random_state, matrices, rank, _DEVICE_DRAW["device"])
         if init == "random_uniform":
             draw = lambda shape: random_state.uniform(size=shape)  # noqa: E731
         elif init == "random_standard_normal":
@@ -439,6 +479,8 @@ class Parafac2(MatricesPenalty):
             coordinate_matrix = np.zeros((rank, rank))
         else:
             raise ValueError(f"Unknown aux init: {self.aux_init}")
+        if _DEVICE_DRAW["device"] is not None:  # cmf_aoadmm fast path: P_i = eye(J_i, rank) is never built on the host
+            return _EyeBases([int(M.shape[0]) for M in matrices], rank), coordinate_matrix
         return [np.eye(M.shape[0], rank) for M in matrices], coordinate_matrix
 
     def factor_matrices_update(self, factor_matrices, feasibility_penalties, auxes):  # penalties.py:1224-1250

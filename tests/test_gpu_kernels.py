@@ -681,3 +681,20 @@ def test_xstream_hybrid_remainder_columns(N, K, R):
         lib.b2_set_option(_lib.OPT_XSTREAM_HYBRID, 0)
     np.testing.assert_allclose(Y.cpu().numpy(), Xh @ C, rtol=1e-12, atol=1e-11)
     np.testing.assert_allclose(Z.cpu().numpy(), Xh.T @ Wh, rtol=1e-12, atol=1e-10)
+
+
+@pytest.mark.parametrize("seed,skip,n", [(0, 0, 1), (1, 0, 311), (2, 3, 312), (3, 623, 5000), (4, 624, 1250), (5, 1, 100001)])
+def test_device_mt19937_continues_numpy_randomstate(seed, skip, n):
+    """b2_mt19937_uniform: same doubles as RandomState.uniform / random_sample, and the host generator continues the
+    stream afterwards (decomposition.py:31-39 draws A, C, B_i, aux, dual from ONE RandomState)."""
+    _lib, _ops, _ = _imports()
+    ref = np.random.RandomState(seed)
+    rs = np.random.RandomState(seed)
+    if skip:
+        ref.randint(0, 2 ** 31, size=skip)  # odd / block-boundary positions in the 624-word state
+        rs.randint(0, 2 ** 31, size=skip)
+    want = ref.uniform(size=n)
+    got = _ops.mt19937_uniform(rs, n, torch.device("cuda"))
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    np.testing.assert_array_equal(rs.uniform(size=7), ref.uniform(size=7))          # host continues the stream
+    np.testing.assert_array_equal(rs.standard_normal(size=3), ref.standard_normal(size=3))
