@@ -190,7 +190,7 @@ class _ModeState:
 class AOADMMEngine:
     def __init__(self, packed, rank, regs, l2_penalty=(0, 0, 0), feasibility_penalty_scale=1.0, constant_A=False,
                  constant_B=False, inner_n_iter_max=5, update=(True, True, True), group=None, xstream_variant=None,
-                 fuse_local=None, fuse_pf2=None, shard_rows=None):
+                 fuse_local=None, fuse_pf2=None, shard_rows=None, inner_tol=None):
         _lib.load()
         self.p = packed
         self.dev = packed.X.device
@@ -211,6 +211,11 @@ class AOADMMEngine:
         self.variant = _lib.VARIANT_AUTO if xstream_variant is None else xstream_variant
         self.fuse_local = FUSION_DEFAULTS["local"] if fuse_local is None else bool(fuse_local)
         self.fuse_pf2 = FUSION_DEFAULTS["pf2"] if fuse_pf2 is None else bool(fuse_pf2)
+        # inner-loop convergence checks (decomposition.py:92-116) need a host decision after every inner iteration:
+        # the one-kernel-per-step path is used and the fused whole-loop kernels are bypassed
+        self.inner_tol = float(inner_tol) if inner_tol and inner_tol > 0 else None
+        if self.inner_tol is not None:
+            self.fuse_local = self.fuse_pf2 = False
         self.w_fresh = False
         R, I, K, N, dt, dev = self.R, self.I, self.K, self.N, self.dtype, self.dev
 
@@ -476,9 +481,12 @@ class AOADMMEngine:
             return self._step_B_pf2_fused()
         self._materialize_pf2()
         for _ in range(self.n_inner):
+            x_old = st.x.clone() if self.inner_tol is not None else None
             _ops.admm_solve(self.N, R, self.Y, A, _lib.GROUP_INDEXED, self.gor, self.rhoB, self.MinvB, st.descs_c,
                             len(st.desc), st.x)
             self._column_coupled(st, self.row_off, I, self.max_rows, self.rhoB, self.gor, self.N)
+            if self._inner_converged(1, x_old):
+                break
         _ops.slice_gram(st.x, self.row_off, I, R, self.BtB)
 
     def _step_B_pf2_fused(self):
@@ -531,9 +539,12 @@ class AOADMMEngine:
                             len(st.desc), self.n_inner, st.x)
             return
         for _ in range(self.n_inner):
+            x_old = st.x.clone() if self.inner_tol is not None else None
             _ops.admm_solve(K, R, self.Z, None, _lib.GROUP_SINGLE, None, self.rhoC, self.MinvC, st.descs_c,
                             len(st.desc), st.x)
             self._column_coupled(st, self.off_single_K, 1, K, self.rhoC, None, K)
+            if self._inner_converged(2, x_old):
+                break
 
     def refresh_products(self):
         """Y = X C (one X pass), CtC, cross_i = (B_i^T B_i) o CtC, rhsA_i = colsum(B_i o Y_i)
@@ -557,12 +568,40 @@ class AOADMMEngine:
                             len(st.desc), self.n_inner, st.x)
             return
         for _ in range(self.n_inner):
+            x_old = st.x.clone() if self.inner_tol is not None else None
             _ops.admm_solve(I, R, self.rhsA, None, _lib.GROUP_IDENTITY, None, self.rhoA, self.MinvA, st.descs_c,
                             len(st.desc), st.x)
             if self.world > 1:
                 self._column_coupled_A_sharded(st)
             else:
                 self._column_coupled(st, self.off_single_I, 1, I, self.rhoA, None, I)
+            if self._inner_converged(0, x_old):
+                break
+
+    def _inner_converged(self, mode, x_old):
+        """_check_inner_convergence (decomposition.py:92-116): relative change of the factor <= inner_tol and, with
+        penalties, every feasibility gap of this mode < inner_tol.  One fused reduction + one D2H per inner iteration;
+        sharded modes (0, 1) all-reduce the sums so that every rank takes the same decision."""
+        if self.inner_tol is None:
+            return False
+        st = self.modes[mode]
+        n = (self.I, self.N, self.K)[mode] * self.R
+        scal = self.scal
+        scal.zero_()
+        _ops.reduce_stats(st.x, x_old, n, scal[0:3], self.ws)
+        for p in range(len(st.desc)):
+            _ops.reduce_stats(st.x, st.aux[p], n, scal[3 + 3 * p:6 + 3 * p], self.ws)
+        used = 3 + 3 * len(st.desc)
+        if self.world > 1 and mode != 2:
+            self._allreduce(scal[:used])
+        host = scal[:used].cpu().numpy()
+        change, norm = np.sqrt(host[0]), np.sqrt(host[1])
+        if change > self.inner_tol * norm:
+            return False
+        if len(st.desc) == 0:
+            return True
+        gaps = [np.sqrt(host[3 + 3 * p]) / np.sqrt(host[4 + 3 * p]) for p in range(len(st.desc))]
+        return max(gaps) < self.inner_tol
 
     def _column_coupled_A_sharded(self, st):
         """Matrix-wise penalties on mode 0 when the rows of A are sharded over ranks (last row):

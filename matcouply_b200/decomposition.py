@@ -292,8 +292,6 @@ def cmf_aoadmm(
 
     if not torch.cuda.is_available():
         raise RuntimeError("matcouply_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
-    if inner_tol:
-        raise NotImplementedError("inner_tol (inner-loop convergence checks) is not on the fused path yet")
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
 
     random_state = penalties._check_random_state(random_state)
@@ -354,7 +352,7 @@ def cmf_aoadmm(
                           feasibility_penalty_scale=feasibility_penalty_scale, constant_A=constant_A,
                           constant_B=constant_B, inner_n_iter_max=inner_n_iter_max,
                           update=(update_A, update_B_is, update_C), group=process_group,
-                          shard_rows=None if shard is None else (shard.lo, shard.n_global))
+                          shard_rows=None if shard is None else (shard.lo, shard.n_global), inner_tol=inner_tol)
     if shard is not None:
         from .distributed import shard_state
 

@@ -357,7 +357,26 @@ def _svd(M):
     return np.linalg.svd(M, full_matrices=False)
 
 
-def solve_mode_B(matrices, regs, A, Bs, C, auxes, duals, l2, n_inner, scale, constant_rho):
+def _inner_converged(new, old, regs, auxes, mode, inner_tol):
+    """_check_inner_convergence (decomposition.py:92-116)."""
+    if not inner_tol or inner_tol < 0:
+        return False
+    if mode == 1:
+        norm = _rss(new)
+        change = _rss([b - pb for b, pb in zip(new, old)])
+        gaps = [_rss(reg.shifted_list(aux, new)) / norm for reg, aux in zip(regs, auxes)] if regs else []
+    else:
+        norm = _fro(new)
+        change = _fro(new - old)
+        gaps = [_fro(reg.shifted(aux, new)) / norm for reg, aux in zip(regs, auxes)] if regs else []
+    if change > inner_tol * norm:
+        return False
+    if len(regs) == 0:
+        return True
+    return max(gaps) < inner_tol
+
+
+def solve_mode_B(matrices, regs, A, Bs, C, auxes, duals, l2, n_inner, scale, constant_rho, inner_tol=None):
     """decomposition.py:222-292."""
     R = A.shape[1]
     CtC = np.dot(C.T, C)
@@ -373,6 +392,7 @@ def solve_mode_B(matrices, regs, A, Bs, C, auxes, duals, l2, n_inner, scale, con
     svds = [_svd(L) for L in lhs]
     Bs = list(Bs)
     for _ in range(n_inner):
+        old_Bs = list(Bs)
         shifted = [reg.shifted_list(aux, dual) for reg, aux, dual in zip(regs, auxes, duals)]
         for i in range(len(matrices)):
             U, s, Uh = svds[i]
@@ -385,10 +405,12 @@ def solve_mode_B(matrices, regs, A, Bs, C, auxes, duals, l2, n_inner, scale, con
             auxes[n] = reg.prox_list(moved, rhos, auxes[n])
             sh = reg.shifted_list(auxes[n], duals[n])
             duals[n] = [B - s_ for B, s_ in zip(Bs, sh)]
+        if _inner_converged(Bs, old_Bs, regs, auxes, 1, inner_tol):
+            break
     return Bs, auxes, duals
 
 
-def solve_mode_C(matrices, regs, A, Bs, C, auxes, duals, l2, n_inner, scale):
+def solve_mode_C(matrices, regs, A, Bs, C, auxes, duals, l2, n_inner, scale, inner_tol=None):
     """decomposition.py:295-344."""
     R = C.shape[1]
     lhs, rhs = 0, 0
@@ -400,6 +422,7 @@ def solve_mode_C(matrices, regs, A, Bs, C, auxes, duals, l2, n_inner, scale):
     lhs = lhs + np.eye(R) * (rho * len(regs) + l2)
     U, s, Uh = _svd(lhs)
     for _ in range(n_inner):
+        old_C = C
         acc = 0
         for reg, aux, dual in zip(regs, auxes, duals):
             acc += reg.shifted(aux, dual)
@@ -407,10 +430,12 @@ def solve_mode_C(matrices, regs, A, Bs, C, auxes, duals, l2, n_inner, scale):
         for n, reg in enumerate(regs):
             auxes[n] = reg.prox(C + duals[n], rho, auxes[n])
             duals[n] = C - reg.shifted(auxes[n], duals[n])
+        if _inner_converged(C, old_C, regs, auxes, 2, inner_tol):
+            break
     return C, auxes, duals
 
 
-def solve_mode_A(matrices, regs, A, Bs, C, auxes, duals, l2, n_inner, scale, constant_rho):
+def solve_mode_A(matrices, regs, A, Bs, C, auxes, duals, l2, n_inner, scale, constant_rho, inner_tol=None):
     """decomposition.py:120-219. Returns also (rhses, cross_products) for the fit term."""
     R = A.shape[1]
     K = C.shape[0]
@@ -430,6 +455,7 @@ def solve_mode_A(matrices, regs, A, Bs, C, auxes, duals, l2, n_inner, scale, con
     svds = [_svd(L + np.eye(R) * (rho * len(regs) + l2)) for L, rho in zip(cross, rhos)]
     A = A.copy()
     for _ in range(n_inner):
+        old_A = A.copy()
         shifted = [reg.shifted(aux, dual) for reg, aux, dual in zip(regs, auxes, duals)]
         for i in range(len(matrices)):
             U, s, Uh = svds[i]
@@ -447,6 +473,8 @@ def solve_mode_A(matrices, regs, A, Bs, C, auxes, duals, l2, n_inner, scale, con
                     new_aux[i, :] = reg.prox_row(moved[i], rho, auxes[n][i])
                 auxes[n] = new_aux
             duals[n] = A - reg.shifted(auxes[n], duals[n])
+        if _inner_converged(A, old_A, regs, auxes, 0, inner_tol):
+            break
     return A, auxes, duals, (rhs, cross)
 
 
@@ -521,7 +549,7 @@ def ao_admm(matrices, rank, n_iter_max=1000, l2_penalty=None, l1_penalty=None, n
             feasibility_penalty_scale=1, constant_feasibility_penalty=False, aux_init="random_uniform",
             dual_init="random_uniform", random_state=None, tol=1e-8, absolute_tol=1e-10, feasibility_tol=1e-4,
             inner_n_iter_max=5, update_A=True, update_B_is=True, update_C=True, return_errors=True, init=None,
-            trajectory=None):
+            trajectory=None, inner_tol=None):
     """Returns a dict with factors, auxes, duals and the diagnostics lists of ``return_errors=True``.
 
     ``trajectory``: optional list; after every outer iteration a dict of deep copies
@@ -571,13 +599,13 @@ def ao_admm(matrices, rank, n_iter_max=1000, l2_penalty=None, l1_penalty=None, n
         inter = None
         if update_B_is:
             Bs, aux[1], dual[1] = solve_mode_B(matrices, regs[1], A, Bs, C, aux[1], dual[1], l2[1], inner_n_iter_max,
-                                           feasibility_penalty_scale, const_B)
+                                           feasibility_penalty_scale, const_B, inner_tol)
         if update_C:
             C, aux[2], dual[2] = solve_mode_C(matrices, regs[2], A, Bs, C, aux[2], dual[2], l2[2], inner_n_iter_max,
-                                          feasibility_penalty_scale)
+                                          feasibility_penalty_scale, inner_tol)
         if update_A:
             A, aux[0], dual[0], inter = solve_mode_A(matrices, regs[0], A, Bs, C, aux[0], dual[0], l2[0],
-                                                 inner_n_iter_max, feasibility_penalty_scale, const_A)
+                                                 inner_n_iter_max, feasibility_penalty_scale, const_A, inner_tol)
         if trajectory is not None:
             trajectory.append(snapshot(A, Bs, C, aux, dual))
         if not (tol or absolute_tol or return_errors):  # decomposition.py:990, 1055

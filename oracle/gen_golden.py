@@ -192,7 +192,16 @@ def operator_goldens():
 
 def main():
     os.makedirs(OUT, exist_ok=True)
-    operator_goldens()
+    only = sys.argv[1:]  # optional: names of the cases to (re)generate
+    if only:
+        global make_case
+        _make = make_case
+
+        def make_case(name, *a, **k):  # noqa: F811
+            if name in only:
+                _make(name, *a, **k)
+    else:
+        operator_goldens()
 
     X0, _ = get_simple_simulated_data(noise_level=0.2, random_state=1)
     readme = dict(non_negative=True, l1_penalty={2: 0.1}, l2_norm_bound=[1, 1, 0], parafac2=True,
@@ -227,6 +236,12 @@ def main():
               dict(non_negative=True, update_C=False, random_state=2, n_iter_max=30))
     make_case("nn_l2ball_mode1_only", synth(9, 8, 12, 9, 20, 4), 4,
               dict(non_negative={1: True}, l2_norm_bound={1: 0.8}, random_state=4, n_iter_max=60))
+
+
+    # inner-loop convergence checks (decomposition.py:92-116): up to 20 inner iterations, stop early at inner_tol
+    make_case("inner_tol_nn_pf2", synth(10, 8, 14, 6, 18, 3, kind="parafac2"), 3,
+              dict(non_negative=True, parafac2=True, l2_norm_bound={2: 1.5}, inner_tol=1e-3, inner_n_iter_max=20,
+                   random_state=6, n_iter_max=60))
 
 
 if __name__ == "__main__":
