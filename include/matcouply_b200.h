@@ -33,7 +33,11 @@ enum { B2_VARIANT_AUTO = 0, B2_VARIANT_FMA = 1, B2_VARIANT_DMMA = 2 };
 
 /* penalty kinds (penalties.py: Parafac2 :1018, Unimodality :983, L2Ball :844, L1Penalty :545, Box :511,
  * NonNegativity :488) */
-enum { B2_PEN_NONNEG = 0, B2_PEN_BOX = 1, B2_PEN_L1 = 2, B2_PEN_L2BALL = 3, B2_PEN_UNIMODAL = 4, B2_PEN_PARAFAC2 = 5 };
+enum { B2_PEN_NONNEG = 0, B2_PEN_BOX = 1, B2_PEN_L1 = 2, B2_PEN_L2BALL = 3, B2_PEN_UNIMODAL = 4, B2_PEN_PARAFAC2 = 5,
+       /* column-coupled kinds finished by their own b2_prox_* call (penalties.py:595, :928, :750) */
+       B2_PEN_GL2 = 6, B2_PEN_SIMPLEX = 7, B2_PEN_TV = 8,
+       /* prox evaluated by the caller (user-defined ADMMPenalty subclass): the kernels only leave V = x + dual in `dual` */
+       B2_PEN_HOST = 9 };
 
 /* how a row of an ADMM state matrix finds its group (slice) */
 enum { B2_GROUP_SINGLE = 0 /* every row -> group 0 (C-mode) */,
@@ -52,7 +56,7 @@ typedef struct {
 /* kernel-selection switches (process-wide; default 1 = on, except B2_OPT_XSTREAM_HYBRID which is off).  They only choose between equivalent kernels — tests flip
  * them to cross-check the tensor-core formulations against the scalar ones. */
 enum { B2_OPT_PF2_ROWPASS_MMA = 0 /* DMMA row pass of b2_pf2_rowpass */,
-       B2_OPT_POLAR_WARP = 1 /* reserved */,
+       B2_OPT_POLAR_WARP = 1 /* warp-per-slice Jacobi polar step in b2_pf2_polar (0: CTA-per-slice kernel) */,
        B2_OPT_ADMM_LOCAL_MMA = 2 /* DMMA formulation of b2_admm_local (CTA-per-slice path) */,
        B2_OPT_XSTREAM_HYBRID = 3 /* DMMA blocks + DFMA remainder columns in the fp64 X-stream kernels (R = 8b+1..4);
                                     default OFF: measured 2-6 % slower than padding to a whole block */,
@@ -198,6 +202,27 @@ int b2_fit_terms(const void* rhs, const void* cross, const void* A, int n_groups
 /* ---- standalone elementwise prox (ADMMPenalty.factor_matrix_update for NONNEG/BOX/L1 with a scalar rho) ---------*/
 int b2_prox_elementwise(const void* v, void* out, long long n, int kind, int non_negativity, double p0, double p1,
                         double rho, int dtype, void* stream);
+
+/* UnitSimplex (penalties.py:953-980): per group and column, aux = max(V - mu, 0) with the multiplier mu found by the
+ * reference's bisection (bracket of :957-964, scipy.optimize.bisect's loop and tolerances); dual = V - aux.
+ * max_rows = the largest group (sizes the shared-memory staging). */
+int b2_prox_simplex(void* aux, void* dual, const int64_t* row_off, int n_groups, int max_rows, int R, int dtype,
+                    void* stream);
+/* TotalVariationPenalty (penalties.py:819-827): per group g and column, aux = soft_threshold(TV-denoise(V, 2 reg /
+ * rho_g), l1 / rho_g) with Condat's direct algorithm (the un-vendored condat_tv dependency's algorithm); dual = V - aux.
+ * rho: device array, rho[g * rho_stride] (stride 0 = one value for all groups). */
+int b2_prox_tv(void* aux, void* dual, const int64_t* row_off, int n_groups, int R, const void* rho, int rho_stride,
+               double reg_strength, double l1_strength, int dtype, void* stream);
+/* out[0] = sum_g sum_cols sum_k |x_g[k+1] - x_g[k]|  (:832); part: n_groups doubles of scratch. */
+int b2_tv_norm(const void* x, const int64_t* row_off, int n_groups, int R, double* out, double* part, int dtype,
+               void* stream);
+/* GeneralizedL2Penalty (penalties.py:724-730): every group has J rows; aux_g = U diag((rho_g/2) / (s + rho_g/2)) U^T V_g
+ * with the J x J eigenvectors U and eigenvalues s of the norm matrix; dual = V - aux.  tmp: n_groups*J*R elements. */
+int b2_prox_gl2(void* aux, void* dual, int n_groups, int J, int R, const void* U, const void* s, const void* rho,
+                int rho_stride, void* tmp, int dtype, void* stream);
+/* out[0] = sum_g trace(x_g^T M x_g) (:732-733), M symmetric J x J.  tmp: n_groups*J*R elements, part: 256 doubles. */
+int b2_quadform(const void* M, const void* x, int n_groups, int J, int R, double* out, void* tmp, double* part,
+                int dtype, void* stream);
 
 /* ---- initial state: device-side continuation of a NumPy RandomState (MT19937) stream ----------------------------
  * out[0:n] = the next n doubles `np.random.RandomState.random_sample` / `uniform(0, 1)` would return for the generator

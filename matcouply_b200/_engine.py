@@ -23,6 +23,9 @@ import torch
 from . import _lib, _ops
 
 
+# column-coupled kinds whose prox / penalty value is launched by the penalty object itself (penalties._EnginePenaltyMixin)
+_ENGINE_PROX_KINDS = (_lib.PEN_GL2, _lib.PEN_SIMPLEX, _lib.PEN_TV)
+
 # Kernel-fusion switches (tests flip them to cross-check the fused kernels against the one-kernel-per-step path).
 FUSION_DEFAULTS = {"local": True, "pf2": True}
 
@@ -229,11 +232,26 @@ class AOADMMEngine:
         self.modes = [_ModeState(), _ModeState(), _ModeState()]
         for m in range(3):
             st = self.modes[m]
+            st.mode = m
             st.regs = list(regs[m])
             if len(st.regs) > _lib.MAX_PENALTIES_PER_MODE:
                 raise ValueError(f"at most {_lib.MAX_PENALTIES_PER_MODE} penalties per mode are supported")
             st.desc = [r._descriptor() for r in st.regs]
-        for kind, *_ in self.modes[0].desc:
+        for reg, (kind, *_) in zip(self.modes[0].regs, self.modes[0].desc):
+            # a user-defined RowVectorPenalty has a row update; every other bridged / matrix-wise penalty needs ONE rho
+            matrixwise = kind in _ENGINE_PROX_KINDS or (
+                kind == _lib.PEN_HOST and not hasattr(reg, "factor_matrix_row_update"))
+            if matrixwise:
+                if not self.const_A:
+                    raise AttributeError(
+                        "Matrix-wise penalties on mode 0 have no row update: use constant_feasibility_penalty=True "
+                        "(or 'A'), as with the reference"
+                    )
+            if matrixwise and self.world > 1:
+                raise NotImplementedError(
+                    "GeneralizedL2Penalty / TotalVariationPenalty / UnitSimplex / user-defined penalties on a "
+                    "row-sharded mode 0 are not supported (their prox couples all rows of A)"
+                )
             if kind in (_lib.PEN_L2BALL, _lib.PEN_UNIMODAL):
                 if not self.const_A:
                     raise AttributeError(
@@ -428,6 +446,10 @@ class AOADMMEngine:
                 _ops.prox_l2ball(st.aux[p], st.dual[p], row_off, n_groups, R, p0, nn)
             elif kind == _lib.PEN_UNIMODAL:
                 _ops.prox_unimodal(st.aux[p], st.dual[p], row_off, n_groups, R, max_rows, nn, self.ws)
+            elif kind in _ENGINE_PROX_KINDS:
+                st.regs[p]._engine_prox(self, st.aux[p], st.dual[p], row_off, n_groups, max_rows, rho, n_rows)
+            elif kind == _lib.PEN_HOST:
+                self._host_prox(st, p, row_off, n_groups, rho)
             elif kind == _lib.PEN_PARAFAC2:
                 _ops.slice_cross(st.dual[p], None, row_off, n_groups, R, None, self.S, None)
                 _ops.pf2_polar(self.S, self.Delta, rho, n_groups, R, self.Wmat, self.num_part)
@@ -439,6 +461,29 @@ class AOADMMEngine:
                     _ops.pf2_delta(self.num_part, rho, n_groups, R, self.Delta, self.pf2_sums)
                 _ops.pf2_apply(st.aux[p], st.dual[p], None, self.Wmat, self.Delta, gor, n_rows, R)
                 self.pf2_fresh = True
+
+    def _host_prox(self, st, p, row_off, n_groups, rho):
+        """Bridge to a user-defined ADMMPenalty subclass (examples/plot_custom_penalty.py:220-231 style): the
+        pre-image V = x + dual (left in the dual slot by the solve kernel) and the current aux go to the Python
+        method the reference would call (decomposition.py:202-211, 275-280, 333-337), the new aux comes back to HBM
+        and dual = V - aux.  The prox itself is the user's code, wherever it runs; everything around it stays on
+        the device."""
+        reg, m = st.regs[p], st.mode
+        V = st.dual[p].detach().to(torch.float64).cpu().numpy()
+        aux = st.aux[p].detach().to(torch.float64).cpu().numpy()
+        rhos = rho.detach().to(torch.float64).cpu().numpy()
+        if m == 1:
+            off = self.p.row_offsets
+            cut = lambda a: [a[i:j] for i, j in zip(off[:-1], off[1:])]  # noqa: E731
+            new = reg.factor_matrices_update(cut(V), [float(r) for r in rhos[:self.I]], cut(aux))
+            new = np.concatenate([np.asarray(a) for a in new], 0)
+        elif m == 2 or self.const_A:
+            new = np.asarray(reg.factor_matrix_update(V, float(rhos[0]), aux))
+        else:  # per-row feasibility penalties on mode 0 (decomposition.py:205-211)
+            new = np.stack([np.asarray(reg.factor_matrix_row_update(V[i], float(rhos[i]), aux[i]))
+                            for i in range(V.shape[0])], 0)
+        st.aux[p].copy_(self._up(new))
+        st.dual[p].sub_(st.aux[p])
 
     def _materialize_pf2(self):
         """Write out P Delta (aux slot) and dual = V - P Delta of the PARAFAC2 penalty if they are deferred."""
@@ -506,6 +551,11 @@ class AOADMMEngine:
                     _ops.prox_l2ball(st.aux[p], st.dual[p], self.row_off, I, R, p0, nn)
                 elif kind == _lib.PEN_UNIMODAL:
                     _ops.prox_unimodal(st.aux[p], st.dual[p], self.row_off, I, R, self.max_rows, nn, self.ws)
+                elif kind in _ENGINE_PROX_KINDS:
+                    st.regs[p]._engine_prox(self, st.aux[p], st.dual[p], self.row_off, I, self.max_rows, self.rhoB,
+                                            self.N)
+                elif kind == _lib.PEN_HOST:
+                    self._host_prox(st, p, self.row_off, I, self.rhoB)
             # cold Jacobi start on the first inner iteration (bounds the round-off drift of the accumulated
             # rotations), warm start from the previous inner iteration's eigenvectors afterwards
             _ops.pf2_polar(self.S, self.Delta, self.rhoB, I, R, self.Wmat, self.num_part, self.pf2_Q, warm=it > 0)
@@ -682,6 +732,13 @@ class AOADMMEngine:
                     _ops.reduce_stats(st.x, st.aux[p], sizes[m], scal[slot:slot + 3], self.ws)
                 layout.append((m, p, slot))
                 slot += 3
+            for p in range(len(st.desc)):  # values of the penalties that are not hard constraints (loss terms)
+                if st.desc[p][0] in _ENGINE_PROX_KINDS and st.desc[p][0] != _lib.PEN_SIMPLEX:
+                    off_m, n_g, mx = ((self.off_single_I, 1, self.I), (self.row_off, self.I, self.max_rows),
+                                      (self.off_single_K, 1, self.K))[m]
+                    st.regs[p]._engine_penalty(self, st.x, off_m, n_g, mx, sizes[m] // self.R, scal[slot:slot + 1])
+                    layout.append((m, -2 - p, slot))
+                    slot += 1
         if self.world > 1:
             self._allreduce(scal[:shard_end])
         return layout, slot
@@ -691,13 +748,17 @@ class AOADMMEngine:
         layout, slot = launched
         host = self.scal[:slot].cpu().numpy()
         gaps, sq, l1 = ([], [], []), [0.0, 0.0, 0.0], ([], [], [])
+        extra = ({}, {}, {})
         for m, p, s in layout:
+            if p <= -2:
+                extra[m][-2 - p] = float(host[s])
+                continue
             d2, x2, ab = host[s:s + 3]
             sq[m] = x2
             if p >= 0:
                 gaps[m].append(np.sqrt(d2) / np.sqrt(x2))
                 l1[m].append(ab)
-        return dict(gaps=gaps, fit=(host[0], host[1]), sq=sq, l1=l1)
+        return dict(gaps=gaps, fit=(host[0], host[1]), sq=sq, l1=l1, extra=extra)
 
     # ------------------------------------------------------------------------------------------------------
     # CUDA-graph replay of the steady-state outer iteration (launch-bound problem sizes)

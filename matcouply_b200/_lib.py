@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("B2_LIB_PATH_DEBUG") or os.path.join(_HERE, "libmatcou
 
 F32, F64 = 0, 1
 VARIANT_AUTO, VARIANT_FMA, VARIANT_DMMA = 0, 1, 2
-PEN_NONNEG, PEN_BOX, PEN_L1, PEN_L2BALL, PEN_UNIMODAL, PEN_PARAFAC2 = range(6)
+PEN_NONNEG, PEN_BOX, PEN_L1, PEN_L2BALL, PEN_UNIMODAL, PEN_PARAFAC2, PEN_GL2, PEN_SIMPLEX, PEN_TV, PEN_HOST = range(10)
 GROUP_SINGLE, GROUP_INDEXED, GROUP_IDENTITY = 0, 1, 2
 OPT_PF2_ROWPASS_MMA, OPT_POLAR_WARP, OPT_ADMM_LOCAL_MMA, OPT_XSTREAM_HYBRID = 0, 1, 2, 3
 MAX_RANK = 32
@@ -49,6 +49,11 @@ _SIGNATURES = {
                       _vp, _i, _vp],
     "b2_prox_l2ball": [_vp, _vp, _vp, _i, _i, _d, _i, _vp, _i, _i, _vp],
     "b2_prox_unimodal": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _sz, _vp],
+    "b2_prox_simplex": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
+    "b2_prox_tv": [_vp, _vp, _vp, _i, _i, _vp, _i, _d, _d, _i, _vp],
+    "b2_tv_norm": [_vp, _vp, _i, _i, _vp, _vp, _i, _vp],
+    "b2_prox_gl2": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp],
+    "b2_quadform": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
     "b2_pf2_polar": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
     "b2_pf2_rowpass": [_vp, _i, _i, _vp, _vp, _vp, _vp, ctypes.POINTER(PenaltyDesc), _i, _i, _vp, _vp, _vp, _vp, _i, _vp,
                        _vp, _i, _vp],

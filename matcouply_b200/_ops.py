@@ -154,6 +154,33 @@ def prox_unimodal(aux, dual, row_off, n_groups, R, max_rows, nn, ws, peaks=None)
          dtype_code(aux.dtype), _ptr(ws.uni), ws.uni_bytes, _stream())
 
 
+def prox_simplex(aux, dual, row_off, n_groups, max_rows, R):
+    call("b2_prox_simplex", _ptr(aux), _ptr(dual), _ptr(row_off), n_groups, int(max_rows), R, dtype_code(aux.dtype),
+         _stream())
+
+
+def prox_tv(aux, dual, row_off, n_groups, R, rho, reg_strength, l1_strength):
+    """rho: device tensor with one value per group, or a single value shared by all groups."""
+    call("b2_prox_tv", _ptr(aux), _ptr(dual), _ptr(row_off), n_groups, R, _ptr(rho), 1 if rho.numel() > 1 else 0,
+         float(reg_strength), float(l1_strength), dtype_code(aux.dtype), _stream())
+
+
+def tv_norm(x, row_off, n_groups, R, out):
+    part = torch.empty(max(n_groups, 1), dtype=torch.float64, device=x.device)
+    call("b2_tv_norm", _ptr(x), _ptr(row_off), n_groups, R, _ptr(out), _ptr(part), dtype_code(x.dtype), _stream())
+
+
+def prox_gl2(aux, dual, n_groups, J, R, U, s, rho, tmp):
+    call("b2_prox_gl2", _ptr(aux), _ptr(dual), n_groups, J, R, _ptr(U), _ptr(s), _ptr(rho),
+         1 if rho.numel() > 1 else 0, _ptr(tmp), dtype_code(aux.dtype), _stream())
+
+
+def quadform(M, x, n_groups, J, R, out, tmp):
+    part = torch.empty(256, dtype=torch.float64, device=x.device)
+    call("b2_quadform", _ptr(M), _ptr(x), n_groups, J, R, _ptr(out), _ptr(tmp), _ptr(part), dtype_code(x.dtype),
+         _stream())
+
+
 def pf2_polar(S, Delta, rho, n_groups, R, Wmat, num_part, Qstore=None, warm=False):
     call("b2_pf2_polar", _ptr(S), _ptr(Delta), _ptr(rho), n_groups, R, _ptr(Wmat), _ptr(num_part), _ptr(Qstore),
          int(bool(warm)), dtype_code(S.dtype), _stream())

@@ -40,6 +40,9 @@ extern unsigned long long g_b2_launches;  // kernels launched through this libra
 
 int b2_num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
 int b2_option_value(int option);  // kernel-selection switches, see b2_set_option
+// warp-per-slice polar step (pf2_polar_warp.cu), selected by B2_OPT_POLAR_WARP inside b2_pf2_polar
+int b2_pf2_polar_warp(const void* S, const void* Delta, const void* rho, int n_groups, int R, void* Wmat,
+                      void* num_part, void* Qstore, int warm, int dtype, cudaStream_t st);
 
 // dtype dispatch: calls `fn<float>(args...)` or `fn<double>(args...)`
 #define B2_DISPATCH_DTYPE(dtype, ...)                                                                   \

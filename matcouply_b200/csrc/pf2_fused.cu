@@ -594,6 +594,8 @@ int b2_pf2_polar(const void* S, const void* Delta, const void* rho, int n_groups
     B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
     B2_REQUIRE(!warm || Qstore, "b2_pf2_polar: a warm start needs the eigenvector store");
     if (n_groups == 0) return B2_OK;
+    if (b2_option_value(B2_OPT_POLAR_WARP))
+        return b2_pf2_polar_warp(S, Delta, rho, n_groups, R, Wmat, num_part, Qstore, warm, dtype, st);
     const size_t smem = (size_t)(5 * R * R + 32) * sizeof(double) + 32 * sizeof(int);
     B2_DISPATCH_DTYPE(dtype, {
         auto kern = pf2_polar_cta_kernel<T>;

@@ -14,7 +14,7 @@ import os
 
 import numpy as np
 
-from . import penalties
+from . import _lib, penalties
 from .coupled_matrices import CoupledMatrixFactorization
 
 __all__ = ["compute_feasibility_gaps", "ADMMVars", "DiagnosticMetrics", "cmf_aoadmm", "parafac2_aoadmm"]
@@ -216,7 +216,7 @@ def compute_feasibility_gaps(cmf, regs, A_aux_list, B_aux_list, C_aux_list):
     return A_gaps, B_gaps, C_gaps
 
 
-def _loss(diag, norm_X_sq, l2_penalty, regs):
+def _loss(diag, norm_X_sq, l2_penalty, regs, host_factors=None):
     """0.5*rel_err^2 + 0.5*sum_m lambda_m ||factor_m||^2 + sum penalties (decomposition.py:1013-1023)."""
     inner, quad = diag["fit"]
     rec_error = np.sqrt(max(0, norm_X_sq - 2 * inner + quad)) / np.sqrt(norm_X_sq)
@@ -229,6 +229,10 @@ def _loss(diag, norm_X_sq, l2_penalty, regs):
         for p, reg in enumerate(regs[m]):
             if isinstance(reg, penalties.L1Penalty):
                 reg_penalty += diag["l1"][m][p] * reg.reg_strength
+            elif p in diag.get("extra", ({}, {}, {}))[m]:  # GeneralizedL2 / TV values reduced on the device
+                reg_penalty += diag["extra"][m][p]
+            elif host_factors is not None and reg._descriptor()[0] == _lib.PEN_HOST:
+                reg_penalty += reg.penalty(host_factors[m])  # user-defined penalty: the user's own Python code
     return rec_error, 0.5 * rec_error ** 2 + l2reg + reg_penalty
 
 
@@ -361,8 +365,12 @@ def cmf_aoadmm(
     engine.prepare()
     norm_X_sq = engine.normX_sq
 
+    # user-defined (Python) penalties: their value needs the factors on the host every evaluated iteration
+    has_host_pen = any(reg._descriptor()[0] == _lib.PEN_HOST for mode_regs in regs for reg in mode_regs)
+    host_factors = (lambda: engine.factors()) if has_host_pen else (lambda: None)
+
     diag = engine.diagnostics()
-    rec_error, loss = _loss(diag, norm_X_sq, l2_penalty, regs)
+    rec_error, loss = _loss(diag, norm_X_sq, l2_penalty, regs, host_factors())
     rec_errors, losses, feasibility_gaps = [rec_error], [loss], [diag["gaps"]]
     if verbose and verbose > 0:
         print("Feasibility gaps for A: {}".format(diag["gaps"][0]))
@@ -402,7 +410,7 @@ def cmf_aoadmm(
                         print("Feasibility gaps for C: {}".format(curr_gaps[2]))
                     continue
 
-            rec_error, loss = _loss(diag, norm_X_sq, l2_penalty, regs)
+            rec_error, loss = _loss(diag, norm_X_sq, l2_penalty, regs, host_factors())
             rec_errors.append(rec_error)
             losses.append(loss)
             if verbose and it % verbose == 0 and verbose > 0:

@@ -8,8 +8,9 @@ Same class names, constructor arguments, attributes, ``__repr__`` and error beha
 methods (``factor_matrix_update`` ...) are also callable on their own with NumPy arrays or torch tensors; they upload,
 run the same CUDA kernels through the C ABI and return the input's array type.  There is no CPU implementation.
 
-``GeneralizedL2Penalty`` (:595), ``TotalVariationPenalty`` (:750) and ``UnitSimplex`` (:928) are not on the
-accelerated path yet and raise ``NotImplementedError``.
+``GeneralizedL2Penalty`` (:595), ``TotalVariationPenalty`` (:750) and ``UnitSimplex`` (:928) run their proximal
+operators as CUDA kernels too (csrc/prox_extra.cu); user-defined subclasses that implement the protocol in Python are
+bridged by the engine (``PEN_HOST``: the pre-image is handed to the Python method, the result goes back to HBM).
 """
 from abc import ABC, abstractmethod
 
@@ -228,12 +229,11 @@ class ADMMPenalty(ABC):
         parts.append(f"dual_init='{self.dual_init}'" if isinstance(self.dual_init, str) else "dual_init=given_init")
         return f"<'{self.__module__}.{type(self).__name__}' with {', '.join(parts)})>"
 
-    # descriptor handed to the fused engine: (kind, non_negativity, p0, p1)
+    # descriptor handed to the fused engine: (kind, non_negativity, p0, p1).  The built-in penalties override it with
+    # their CUDA kind; a user-defined subclass (which implements the protocol in Python, e.g. the reference's
+    # examples/plot_custom_penalty.py:220-231) is bridged: the engine hands it the pre-image and takes the aux back.
     def _descriptor(self):
-        raise NotImplementedError(
-            f"{type(self).__name__} has no CUDA implementation in matcouply_b200 yet "
-            "(only NonNegativity, Box, L1Penalty, L2Ball, Unimodality and Parafac2 run on the fused AO-ADMM path)"
-        )
+        return (_lib.PEN_HOST, False, 0.0, 0.0)
 
 
 class MatricesPenalty(ADMMPenalty):
@@ -534,24 +534,151 @@ class Parafac2(MatricesPenalty):
         return 0
 
 
-def _not_accelerated(name, where):
-    class _Stub(MatrixPenalty):
-        def __init__(self, *args, **kwargs):
-            raise NotImplementedError(
-                f"{name} (reference penalties.py:{where}) is not part of the B200 hot path yet; see DESIGN.md "
-                "'out of scope' and SURVEY.md §8f"
-            )
+class _EnginePenaltyMixin:
+    """Column-coupled penalties beyond L2Ball / Unimodality: the engine calls ``_engine_prox`` after every solve (the
+    pre-image V = x + dual sits in ``dual``; the call must leave aux = prox(V) and dual = V - aux) and
+    ``_engine_penalty`` for the value that enters the regularised loss (decomposition.py:1016-1023)."""
 
-        def factor_matrix_update(self, factor_matrix, feasibility_penalty, aux):  # pragma: nocover
-            raise NotImplementedError
+    def _engine_prox(self, eng, aux, dual, row_off, n_groups, max_rows, rho, n_rows):
+        raise NotImplementedError
 
-        def penalty(self, x):  # pragma: nocover
-            raise NotImplementedError
+    def _engine_penalty(self, eng, x, row_off, n_groups, max_rows, n_rows, out):
+        """Write the penalty value of the factor ``x`` (packed rows) into the 1-element device tensor ``out``."""
+        out.zero_()
 
-    _Stub.__name__ = _Stub.__qualname__ = name
-    return _Stub
+    def factor_matrix_update(self, factor_matrix, feasibility_penalty, aux):
+        dev = _Dev(factor_matrix)
+        V = dev.t if dev.t.dim() == 2 else dev.t.reshape(-1, 1)
+        n_rows, rank = V.shape
+        dual = V.clone()
+        out = dev.torch.empty_like(V)
+        rho = dev.torch.full((1,), float(feasibility_penalty), dtype=V.dtype, device="cuda")
+        self._engine_prox(None, out, dual, _single_group_offsets(n_rows, "cuda"), 1, n_rows, rho, n_rows)
+        return dev.back(out.reshape(dev.t.shape))
+
+    def penalty(self, x):
+        import torch
+
+        xs = [x] if _is_tensor(x) else list(x)
+        total = 0.0
+        for xi in xs:
+            dev = _Dev(xi)
+            X = dev.t if dev.t.dim() == 2 else dev.t.reshape(-1, 1)
+            out = torch.zeros(1, dtype=torch.float64, device="cuda")
+            self._engine_penalty(None, X, _single_group_offsets(X.shape[0], "cuda"), 1, X.shape[0], X.shape[0], out)
+            total += float(out.item())
+        return total
 
 
-GeneralizedL2Penalty = _not_accelerated("GeneralizedL2Penalty", "595-747")
-TotalVariationPenalty = _not_accelerated("TotalVariationPenalty", "750-841")
-UnitSimplex = _not_accelerated("UnitSimplex", "928-980")
+class GeneralizedL2Penalty(_EnginePenaltyMixin, MatrixPenalty):
+    """Penalty ``x^T M x`` on every column with a symmetric positive semidefinite ``M`` (penalties.py:595-747).
+    The prox ``U diag(1 / (s + rho/2)) U^T (rho/2 x)`` (:724-730) runs as two batched GEMM-like kernels
+    (csrc/prox_extra.cu).  The one-off spectral factorisation of ``M`` in the constructor is host LAPACK, like the
+    reference's constructor (:720)."""
+
+    _kind = _lib.PEN_GL2
+
+    def __init__(self, norm_matrix, svd="truncated_svd", aux_init="random_uniform", dual_init="random_uniform",
+                 validate=True):
+        super().__init__(aux_init, dual_init)
+        self.norm_matrix = norm_matrix
+        self.svd = svd
+        self.validate = validate
+        M = np.asarray(norm_matrix.detach().cpu().numpy() if hasattr(norm_matrix, "detach") else norm_matrix,
+                       dtype=np.float64)
+        if validate and not np.all(M.T == M):
+            raise ValueError("The norm matrix should be symmetric positive semidefinite")
+        if validate and np.any(np.linalg.eigvals(M) < -1e-14):
+            raise ValueError("The norm matrix should be symmetric positive semidefinite")
+        self._M = M
+        self._U, self._s, _ = np.linalg.svd(M, full_matrices=False)  # Vh ignored: the norm matrix is symmetric
+        self._dev = {}
+
+    def _descriptor(self):
+        return (_lib.PEN_GL2, False, 0.0, 0.0)
+
+    def _device_operands(self, dtype):
+        import torch
+
+        if dtype not in self._dev:
+            up = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=dtype).cuda()  # noqa: E731
+            self._dev[dtype] = (up(self._U), up(self._s), up(self._M))
+        return self._dev[dtype]
+
+    def _check_rows(self, n_rows, n_groups):
+        J = self._M.shape[0]
+        if n_groups * J != n_rows:
+            raise ValueError(
+                f"GeneralizedL2Penalty with a {J} x {J} norm matrix needs factor matrices with {J} rows each "
+                f"(got {n_rows} rows in {n_groups} matrices)")
+        return J
+
+    def _engine_prox(self, eng, aux, dual, row_off, n_groups, max_rows, rho, n_rows):
+        from . import _ops
+
+        J = self._check_rows(n_rows, n_groups)
+        U, s, _ = self._device_operands(aux.dtype)
+        tmp = aux.new_empty((n_rows, aux.shape[1]))
+        _ops.prox_gl2(aux, dual, n_groups, J, aux.shape[1], U, s, rho, tmp)
+
+    def _engine_penalty(self, eng, x, row_off, n_groups, max_rows, n_rows, out):
+        from . import _ops
+
+        J = self._check_rows(n_rows, n_groups)
+        _, _, M = self._device_operands(x.dtype)
+        _ops.quadform(M, x, n_groups, J, x.shape[1], out, x.new_empty((n_rows, x.shape[1])))
+
+
+class TotalVariationPenalty(_EnginePenaltyMixin, MatrixPenalty):
+    """Total variation (+ optional L1) on every column (penalties.py:750-841).  The reference delegates to the
+    un-vendored GPL package ``condat_tv``; here Condat's direct algorithm runs as a CUDA kernel
+    (csrc/prox_extra.cu::prox_tv_kernel), so no extra package is needed."""
+
+    _kind = _lib.PEN_TV
+
+    def __init__(self, reg_strength, l1_strength=0, aux_init="random_uniform", dual_init="random_uniform"):
+        if reg_strength <= 0:
+            raise ValueError("The TV regularization strength must be positive.")
+        if l1_strength < 0:
+            raise ValueError("The L1 regularization strength must be non-negative.")
+        super().__init__(aux_init, dual_init)
+        self.reg_strength = reg_strength
+        self.l1_strength = l1_strength
+
+    def _descriptor(self):
+        return (_lib.PEN_TV, False, float(self.reg_strength), float(self.l1_strength))
+
+    def _engine_prox(self, eng, aux, dual, row_off, n_groups, max_rows, rho, n_rows):
+        from . import _ops
+
+        _ops.prox_tv(aux, dual, row_off, n_groups, aux.shape[1], rho, self.reg_strength, self.l1_strength)
+
+    def _engine_penalty(self, eng, x, row_off, n_groups, max_rows, n_rows, out):
+        import torch
+
+        from . import _ops
+
+        _ops.tv_norm(x, row_off, n_groups, x.shape[1], out)
+        out.mul_(float(self.reg_strength))
+        if self.l1_strength:
+            st = torch.zeros(3, dtype=torch.float64, device=x.device)
+            _ops.reduce_stats(x, None, x.numel(), st, _ops.Workspace(x.device, 1, 1, x.dtype))
+            out.add_(float(self.l1_strength) * st[2])
+
+
+class UnitSimplex(_EnginePenaltyMixin, HardConstraintMixin, MatrixPenalty):
+    """Non-negative columns that sum to one (penalties.py:928-980); the Lagrange multiplier of every column is found
+    with the reference's bisection, all columns of a matrix at once (csrc/prox_extra.cu::prox_simplex_kernel)."""
+
+    _kind = _lib.PEN_SIMPLEX
+
+    def _descriptor(self):
+        return (_lib.PEN_SIMPLEX, False, 0.0, 0.0)
+
+    def _engine_prox(self, eng, aux, dual, row_off, n_groups, max_rows, rho, n_rows):
+        from . import _ops
+
+        _ops.prox_simplex(aux, dual, row_off, n_groups, max_rows, aux.shape[1])
+
+    def penalty(self, x):
+        return 0

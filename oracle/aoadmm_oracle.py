@@ -295,6 +295,206 @@ class Parafac2P(OraclePenalty):  # penalties.py:1018-1324 (n_iter=1, both update
         return [np.dot(Pi, delta) for Pi in P]
 
 
+class GeneralizedL2P(OraclePenalty):  # penalties.py:595-747
+    """x^T M x on every column; prox = U diag(1 / (s + rho/2)) U^T (rho/2 x) with the SVD of M (:724-730)."""
+    name = "generalized_l2"
+    matrixwise = True
+
+    def __init__(self, norm_matrix, **kw):
+        super().__init__(**kw)
+        self.norm_matrix = np.asarray(norm_matrix, dtype=np.float64)
+        if not np.all(self.norm_matrix.T == self.norm_matrix) or np.any(np.linalg.eigvals(self.norm_matrix) < -1e-14):
+            raise ValueError("The norm matrix should be symmetric positive semidefinite")
+        self._U, self._s, _ = np.linalg.svd(self.norm_matrix, full_matrices=False)
+
+    def prox(self, M, rho, aux):
+        s_aug = self._s + 0.5 * rho
+        tmp = 0.5 * rho * M
+        tmp = np.dot(self._U.T, tmp)
+        return np.dot(self._U * (1 / s_aug), tmp)
+
+    def prox_row(self, row, rho, aux_row):
+        raise AttributeError("GeneralizedL2Penalty has no row update")
+
+    def _value(self, x):
+        return np.trace(np.dot(np.dot(x.T, self.norm_matrix), x))
+
+    def value(self, x):
+        if isinstance(x, np.ndarray):
+            return self._value(x)
+        return sum(self._value(xi) for xi in x)
+
+
+def _scipy_bisect(f, xa, xb, xtol=2e-12, rtol=8.881784197001252e-16, maxiter=100):
+    """scipy.optimize.bisect's loop (scipy/optimize/Zeros/bisect.c), restated."""
+    fa, fb = f(xa), f(xb)
+    if fa == 0:
+        return xa
+    if fb == 0:
+        return xb
+    if np.signbit(fa) == np.signbit(fb):
+        raise ValueError("f(a) and f(b) must have different signs")
+    dm = xb - xa
+    for _ in range(maxiter):
+        dm *= 0.5
+        xm = xa + dm
+        fm = f(xm)
+        if fm * fa >= 0:
+            xa = xm
+        if fm == 0 or abs(dm) < xtol + rtol * abs(xm):
+            return xm
+    raise RuntimeError("bisect failed to converge")
+
+
+class UnitSimplexP(OraclePenalty):  # penalties.py:928-980
+    name = "unit_simplex"
+    matrixwise = True
+
+    @staticmethod
+    def multiplier(col):  # :941-969
+        min_val = np.min(col) - 1
+        max_val = np.max(col)
+        min_val -= 1e-5
+        min_val = min(0.9 * min_val, 1.1 * min_val)
+        max_val += 1e-5
+        max_val = max(0.9 * max_val, 1.1 * max_val)
+        return _scipy_bisect(lambda mu: np.sum(np.clip(col - mu, 0, None)) - 1, min_val, max_val)
+
+    def prox(self, M, rho, aux):  # :971-980
+        out = np.zeros(M.shape)
+        for r in range(M.shape[1]):
+            out[:, r] = np.clip(M[:, r] - self.multiplier(M[:, r]), 0, None)
+        return out
+
+    def prox_row(self, row, rho, aux_row):
+        raise AttributeError("UnitSimplex has no row update")
+
+
+def tv_denoise_1d(y, lam):
+    """argmin_x 0.5 ||x - y||^2 + lam sum_k |x[k+1] - x[k]|: Condat's direct algorithm (IEEE SPL 20(11), 2013), the
+    algorithm of the reference's un-vendored `condat_tv` dependency (penalties.py:6-11, 821-823).  PARITY UNPINNED
+    against that package (not installable offline); pinned instead by the KKT certificate of the unique minimiser
+    (tests/test_oracle.py::test_tv_oracle_kkt)."""
+    y = np.asarray(y, dtype=np.float64)
+    n = y.shape[0]
+    x = np.zeros(n)
+    if n == 0:
+        return x
+    k = k0 = kplus = kminus = 0
+    umin, umax = lam, -lam
+    vmin, vmax = y[0] - lam, y[0] + lam
+    while True:
+        done = False
+        while k == n - 1:
+            if umin < 0.0:
+                while True:
+                    x[k0] = vmin
+                    k0 += 1
+                    if k0 > kminus:
+                        break
+                k = kminus = k0
+                vmin = y[k0]
+                umin = lam
+                umax = vmin + umin - vmax
+            elif umax > 0.0:
+                while True:
+                    x[k0] = vmax
+                    k0 += 1
+                    if k0 > kplus:
+                        break
+                k = kplus = k0
+                vmax = y[k0]
+                umax = -lam
+                umin = vmax + umax - vmin
+            else:
+                vmin += umin / (k - k0 + 1)
+                x[k0:k + 1] = vmin
+                done = True
+                break
+        if done:
+            return x
+        umin += y[k + 1] - vmin
+        if umin < -lam:
+            x[k0:kminus + 1] = vmin
+            k0 = kminus + 1
+            k = kplus = kminus = k0
+            vmin = y[k0]
+            vmax = vmin + 2.0 * lam
+            umin, umax = lam, -lam
+            continue
+        umax += y[k + 1] - vmax
+        if umax > lam:
+            x[k0:kplus + 1] = vmax
+            k0 = kplus + 1
+            k = kplus = kminus = k0
+            vmax = y[k0]
+            vmin = vmax - 2.0 * lam
+            umin, umax = lam, -lam
+            continue
+        k += 1
+        if umin >= lam:
+            kminus = k
+            vmin += (umin - lam) / (kminus - k0 + 1)
+            umin = lam
+        if umax <= -lam:
+            kplus = k
+            vmax += (umax + lam) / (kplus - k0 + 1)
+            umax = -lam
+
+
+class TotalVariationP(OraclePenalty):  # penalties.py:750-841
+    name = "total_variation"
+    matrixwise = True
+
+    def __init__(self, reg_strength, l1_strength=0, **kw):
+        super().__init__(**kw)
+        if reg_strength <= 0:
+            raise ValueError("The TV regularization strength must be positive.")
+        if l1_strength < 0:
+            raise ValueError("The L1 regularization strength must be non-negative.")
+        self.reg_strength, self.l1_strength = reg_strength, l1_strength
+
+    def prox(self, M, rho, aux):  # :819-827 (note the factor 2 of :822)
+        X = np.stack([tv_denoise_1d(M[:, r], self.reg_strength * 2 / rho) for r in range(M.shape[1])], axis=1)
+        if self.l1_strength:
+            return np.sign(X) * np.clip(np.abs(X) - self.l1_strength / rho, 0, float("inf"))
+        return X
+
+    def prox_row(self, row, rho, aux_row):
+        raise AttributeError("TotalVariationPenalty has no row update")
+
+    def _value(self, x):  # :829-834
+        v = self.reg_strength * np.sum(np.abs(np.diff(x, axis=0)))
+        if self.l1_strength:
+            v = v + self.l1_strength * np.sum(np.abs(x))
+        return v
+
+    def value(self, x):
+        if isinstance(x, np.ndarray):
+            return self._value(x)
+        return sum(self._value(xi) for xi in x)
+
+
+ORACLE_CLASSES = {"NonNegativity": NonNeg, "Box": BoxP, "L1Penalty": L1P, "L2Ball": L2BallP, "Unimodality": UnimodalP,
+                  "Parafac2": Parafac2P, "GeneralizedL2Penalty": GeneralizedL2P, "UnitSimplex": UnitSimplexP,
+                  "TotalVariationPenalty": TotalVariationP}
+
+
+def regs_from_spec(spec, classes=None):
+    """[[["ClassName", {kwargs}], ...] per mode] -> penalty objects (JSON-safe description of a `regs` argument).
+    ``classes``: name -> class mapping (default: the oracle's); array-valued kwargs arrive as nested lists."""
+    classes = ORACLE_CLASSES if classes is None else classes
+    out = []
+    for mode_spec in spec:
+        mode = []
+        for name, kw in mode_spec:
+            kw = {k: (np.asarray(v, dtype=np.float64) if isinstance(v, list) else v) for k, v in kw.items()}
+            cls = classes[name] if isinstance(classes, dict) else getattr(classes, name)
+            mode.append(cls(**kw))
+        out.append(mode)
+    return out
+
+
 def _listify(v, name):  # decomposition.py:455-467
     if hasattr(v, "get"):
         return [v.get(i, None) for i in range(3)]
@@ -312,7 +512,8 @@ def _listify(v, name):  # decomposition.py:455-467
 
 
 def build_penalties(non_negative=None, lower_bound=None, upper_bound=None, l2_norm_bound=None, unimodal=None,
-                    parafac2=None, l1_penalty=None, aux_init="random_uniform", dual_init="random_uniform"):
+                    parafac2=None, l1_penalty=None, aux_init="random_uniform", dual_init="random_uniform",
+                    generalized_l2_penalty=None, tv_penalty=None):
     """decomposition.py:470-614 restricted to the in-scope penalties; fixed per-mode order
     Parafac2, Unimodality, L2Ball, L1, Box, NonNegativity; ``non_negative`` folded into the others."""
     nn = _listify(non_negative, "non_negative")
@@ -322,6 +523,8 @@ def build_penalties(non_negative=None, lower_bound=None, upper_bound=None, l2_no
     uni = _listify(unimodal, "unimodal")
     pf2 = [False, bool(parafac2), False]
     l1 = _listify(l1_penalty, "l1_penalty")
+    gl2 = _listify(generalized_l2_penalty, "generalized_l2_penalty")
+    tv = _listify(tv_penalty, "tv_penalty")
     kw = dict(aux_init=aux_init, dual_init=dual_init)
     regs = []
     for m in range(3):
@@ -332,9 +535,14 @@ def build_penalties(non_negative=None, lower_bound=None, upper_bound=None, l2_no
         if uni[m]:
             mode_regs.append(UnimodalP(non_negativity=nn[m], **kw))
             skip_nn = True
+        if gl2[m] is not None and gl2[m] is not False:  # decomposition.py:583-586
+            mode_regs.append(GeneralizedL2P(gl2[m], **kw))
         if l2b[m]:
             mode_regs.append(L2BallP(l2b[m], non_negativity=nn[m], **kw))
             skip_nn = True
+        if tv[m]:  # decomposition.py:591-595: the L1 strength moves into the TV penalty
+            mode_regs.append(TotalVariationP(tv[m], l1_strength=l1m, **kw))
+            l1m = 0
         if l1m:
             mode_regs.append(L1P(l1m, non_negativity=nn[m], **kw))
             skip_nn = True
@@ -549,7 +757,7 @@ def ao_admm(matrices, rank, n_iter_max=1000, l2_penalty=None, l1_penalty=None, n
             feasibility_penalty_scale=1, constant_feasibility_penalty=False, aux_init="random_uniform",
             dual_init="random_uniform", random_state=None, tol=1e-8, absolute_tol=1e-10, feasibility_tol=1e-4,
             inner_n_iter_max=5, update_A=True, update_B_is=True, update_C=True, return_errors=True, init=None,
-            trajectory=None, inner_tol=None):
+            trajectory=None, inner_tol=None, generalized_l2_penalty=None, tv_penalty=None, regs_spec=None):
     """Returns a dict with factors, auxes, duals and the diagnostics lists of ``return_errors=True``.
 
     ``trajectory``: optional list; after every outer iteration a dict of deep copies
@@ -570,7 +778,9 @@ def ao_admm(matrices, rank, n_iter_max=1000, l2_penalty=None, l1_penalty=None, n
 
     l2 = [v if v is not None else 0 for v in _listify(l2_penalty, "l2_penalty")]
     parsed = build_penalties(non_negative, lower_bound, upper_bound, l2_norm_bound, unimodal, parafac2, l1_penalty,
-                             aux_init, dual_init)
+                             aux_init, dual_init, generalized_l2_penalty, tv_penalty)
+    if regs_spec is not None:
+        regs = regs_from_spec(regs_spec)
     extra = regs if regs is not None else [[], [], []]
     regs = [parsed[m] + list(extra[m]) for m in range(3)]
     if not update_A:

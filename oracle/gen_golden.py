@@ -22,6 +22,7 @@ os.environ.setdefault("NUMBA_CACHE_DIR", "/tmp/nbcache_golden")
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 sys.path.insert(0, os.path.join(HERE, "_tl_standin"))
+sys.path.insert(0, os.path.join(HERE, "_condat_standin"))  # condat_tv stand-in (TV prox = the oracle's Condat restatement)
 sys.path.insert(0, "/root/reference/src")
 sys.path.insert(0, ROOT)
 
@@ -67,8 +68,20 @@ def pack(list_of_mats):
     return np.concatenate(list_of_mats, axis=0), np.cumsum([0] + [m.shape[0] for m in list_of_mats]).astype(np.int64)
 
 
+def decode_kw(kw, classes):
+    """JSON-safe kwargs -> call kwargs: norm matrices as arrays, `regs_spec` -> `regs` built from `classes`."""
+    kw = dict(kw)
+    if isinstance(kw.get("generalized_l2_penalty"), dict):
+        kw["generalized_l2_penalty"] = {int(k): np.asarray(v, dtype=np.float64)
+                                        for k, v in kw["generalized_l2_penalty"].items()}
+    if "regs_spec" in kw:
+        kw["regs"] = O.regs_from_spec(kw.pop("regs_spec"), classes)
+    return kw
+
+
 def run_reference(X, rank, n_traj, kw):
     traj, orig = [], D.admm_update_A
+    kw = decode_kw(kw, P)
 
     def spy(*a, **k):
         out = orig(*a, **k)
@@ -106,7 +119,10 @@ def make_case(name, X, rank, kw, n_traj=50):
     cmf, admm, diag, traj = run_reference(X, rank, n_traj, kw)
     # --- pin the oracle against the reference on this case ---
     otraj = []
-    o = O.ao_admm([x.copy() for x in X], rank, trajectory=otraj, **kw)
+    okw = dict(kw)
+    if isinstance(okw.get("generalized_l2_penalty"), dict):
+        okw["generalized_l2_penalty"] = {int(k): np.asarray(v) for k, v in okw["generalized_l2_penalty"].items()}
+    o = O.ao_admm([x.copy() for x in X], rank, trajectory=otraj, **okw)
     assert o["n_iter"] == diag.n_iter and o["message"] == diag.message, (name, o["n_iter"], diag.n_iter)
     np.testing.assert_allclose(o["regularized_loss"], diag.regularized_loss, rtol=1e-11, atol=0)
     np.testing.assert_allclose(o["A"], cmf[1][0], rtol=1e-9, atol=1e-12)
@@ -173,6 +189,24 @@ def operator_goldens():
     out["prox_l1_nn"] = P.L1Penalty(0.4, non_negativity=True).factor_matrix_update(M, 1.3, None)
     out["prox_l2ball"] = P.L2Ball(1.5).factor_matrix_update(M, 1.3, None)
     out["prox_l2ball_nn"] = P.L2Ball(1.5, non_negativity=True).factor_matrix_update(M, 1.3, None)
+    # the "next" penalties: GeneralizedL2 and UnitSimplex from the reference classes; TV from the
+    # reference class running on the condat_tv stand-in (oracle/_condat_standin)
+    lap = 2 * np.eye(23) - np.eye(23, k=1) - np.eye(23, k=-1)
+    lap[0, 0] = lap[-1, -1] = 1
+    out["gl2_matrix"] = lap
+    out["prox_gl2"] = P.GeneralizedL2Penalty(lap).factor_matrix_update(M, 1.3, None)
+    out["gl2_value"] = np.float64(P.GeneralizedL2Penalty(lap).penalty(M))
+    out["prox_simplex"] = P.UnitSimplex().factor_matrix_update(M, 1.3, None)
+    out["prox_tv"] = P.TotalVariationPenalty(0.3).factor_matrix_update(M, 1.3, None)
+    out["prox_tv_l1"] = P.TotalVariationPenalty(0.3, l1_strength=0.2).factor_matrix_update(M, 1.3, None)
+    out["tv_value"] = np.float64(P.TotalVariationPenalty(0.3, l1_strength=0.2).penalty(M))
+    np.testing.assert_allclose(O.GeneralizedL2P(lap).prox(M, 1.3, None), out["prox_gl2"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(O.UnitSimplexP().prox(M, 1.3, None), out["prox_simplex"], rtol=0, atol=1e-14)
+    np.testing.assert_allclose(O.TotalVariationP(0.3, 0.2).prox(M, 1.3, None), out["prox_tv_l1"], rtol=0, atol=1e-14)
+    big = rs.standard_normal(size=(400, 3)).cumsum(axis=0) * 0.3  # long random walks: many TV segments / simplex ties
+    out["prox_in_long"] = big
+    out["prox_simplex_long"] = P.UnitSimplex().factor_matrix_update(big, 0.7, None)
+    out["prox_tv_long"] = P.TotalVariationPenalty(0.5).factor_matrix_update(big, 0.7, None)
     # PARAFAC2 prox on a ragged list
     Js = [7, 12, 5, 9]
     fms = [rs.standard_normal(size=(J, 4)) for J in Js]
@@ -242,6 +276,35 @@ def main():
     make_case("inner_tol_nn_pf2", synth(10, 8, 14, 6, 18, 3, kind="parafac2"), 3,
               dict(non_negative=True, parafac2=True, l2_norm_bound={2: 1.5}, inner_tol=1e-3, inner_n_iter_max=20,
                    random_state=6, n_iter_max=60))
+
+
+    # ---- "next" penalties ----
+    def laplacian(n):
+        L = 2 * np.eye(n) - np.eye(n, k=1) - np.eye(n, k=-1)
+        L[0, 0] = L[-1, -1] = 1
+        return L.tolist()
+
+    make_case("gl2_smooth_C_nn", synth(11, 7, 18, 6, 12, 3), 3,
+              dict(non_negative={0: True, 1: True}, generalized_l2_penalty={2: laplacian(18)}, random_state=2,
+                   n_iter_max=60))
+    make_case("gl2_smooth_B_pf2", synth(12, 6, 14, 20, 20, 3, kind="gauss"), 3,
+              dict(non_negative={0: True, 2: True}, parafac2=True, generalized_l2_penalty={1: laplacian(20)},
+                   random_state=3, n_iter_max=60))
+    make_case("simplex_C", synth(13, 8, 15, 5, 12, 3), 3,
+              dict(non_negative={0: True, 1: True}, regs_spec=[[], [], [["UnitSimplex", {}]]], random_state=1,
+                   n_iter_max=60))
+    make_case("simplex_B_ragged", synth(14, 8, 12, 4, 25, 4), 4,
+              dict(non_negative={0: True, 2: True}, regs_spec=[[], [["UnitSimplex", {}]], []], random_state=7,
+                   n_iter_max=60))
+    make_case("tv_C_l1", synth(15, 7, 30, 6, 12, 3), 3,
+              dict(non_negative={0: True, 1: True}, tv_penalty={2: 0.02}, l1_penalty={2: 0.01}, random_state=4,
+                   n_iter_max=60))
+    make_case("tv_B_ragged_constB", synth(16, 6, 12, 10, 40, 3, kind="gauss"), 3,
+              dict(non_negative={0: True, 2: True}, tv_penalty={1: 0.05}, constant_feasibility_penalty="B",
+                   random_state=5, n_iter_max=60))
+    make_case("tv_A_const", synth(17, 25, 10, 5, 9, 2), 2,
+              dict(non_negative={1: True, 2: True}, tv_penalty={0: 0.05}, constant_feasibility_penalty=True,
+                   random_state=8, n_iter_max=60))
 
 
 if __name__ == "__main__":

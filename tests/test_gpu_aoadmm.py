@@ -26,10 +26,24 @@ def load_case(name):
     off = g["row_offsets"]
     X = [g["X"][a:b] for a, b in zip(off[:-1], off[1:])]
     kw = json.loads(str(g["kwargs"]))
-    for key in ("l1_penalty", "non_negative", "unimodal", "l2_norm_bound", "lower_bound", "upper_bound"):
+    for key in ("l1_penalty", "non_negative", "unimodal", "l2_norm_bound", "lower_bound", "upper_bound", "tv_penalty"):
         if isinstance(kw.get(key), dict):
             kw[key] = {int(k): v for k, v in kw[key].items()}
+    if isinstance(kw.get("generalized_l2_penalty"), dict):  # norm matrices are stored as nested lists
+        kw["generalized_l2_penalty"] = {int(k): np.asarray(v, dtype=np.float64)
+                                        for k, v in kw["generalized_l2_penalty"].items()}
     return g, X, int(g["rank"]), kw
+
+
+def product_kwargs(kw):
+    """`regs_spec` (JSON-safe description of an explicit `regs` argument) -> matcouply_b200 penalty objects."""
+    from matcouply_b200 import penalties as P
+    from oracle.aoadmm_oracle import regs_from_spec
+
+    kw = dict(kw)
+    if "regs_spec" in kw:
+        kw["regs"] = regs_from_spec(kw.pop("regs_spec"), P)
+    return kw
 
 
 def rel(a, b):
@@ -46,7 +60,7 @@ def test_trajectory_matches_reference(name):
     n_traj = g["A_traj"].shape[0] if g["A_traj"].ndim == 3 else 0
     if n_traj == 0:
         pytest.skip("no trajectory stored")
-    kw = dict(kw)
+    kw = product_kwargs(kw)
     kw.pop("n_iter_max", None)
     worst = 0.0
     for k in sorted({1, 2, 3, 5, 10, 20, 35, min(50, n_traj)}):
@@ -67,6 +81,7 @@ def test_full_run_matches_reference(name):
     from matcouply_b200 import cmf_aoadmm
 
     g, X, rank, kw = load_case(name)
+    kw = product_kwargs(kw)
     cmf, admm, diag = cmf_aoadmm(X, rank, return_errors=True, return_admm_vars=True, **kw)
     assert diag.n_iter == int(g["n_iter"]), (diag.n_iter, int(g["n_iter"]))
     assert diag.message == str(g["message"])
@@ -229,3 +244,35 @@ def test_cuda_graph_replay_equals_eager_launches(name):
     for m in (0, 2):
         for x, y in zip(a0.duals[m], a1.duals[m]):
             np.testing.assert_array_equal(x, y)
+
+
+def test_user_defined_python_penalty_is_bridged():
+    """A penalty written against the reference's protocol in plain NumPy (examples/plot_custom_penalty.py:220-231
+    style) runs inside cmf_aoadmm through the PEN_HOST bridge and reproduces the built-in CUDA penalty exactly."""
+    from matcouply_b200 import cmf_aoadmm
+    from matcouply_b200 import penalties as P
+
+    class MyNonNeg(P.HardConstraintMixin, P.RowVectorPenalty):
+        def factor_matrix_row_update(self, factor_matrix_row, feasibility_penalty, aux_row):
+            return np.maximum(factor_matrix_row, 0)
+
+    class MyL1(P.MatrixPenalty):
+        def __init__(self, strength, **kw):
+            super().__init__(**kw)
+            self.strength = strength
+
+        def factor_matrix_update(self, factor_matrix, feasibility_penalty, aux):
+            return np.sign(factor_matrix) * np.maximum(np.abs(factor_matrix) - self.strength / feasibility_penalty, 0)
+
+        def penalty(self, x):
+            xs = [x] if isinstance(x, np.ndarray) else x
+            return self.strength * sum(np.abs(xi).sum() for xi in xs)
+
+    rs = np.random.RandomState(3)
+    X = [rs.uniform(size=(J, 10)) for J in (6, 9, 7, 12)]
+    common = dict(random_state=1, n_iter_max=25, tol=None, absolute_tol=None, return_errors=True)
+    ref, dref = cmf_aoadmm(X, 3, regs=[[P.NonNegativity()], [P.L1Penalty(0.05)], [P.NonNegativity()]], **common)
+    got, dgot = cmf_aoadmm(X, 3, regs=[[MyNonNeg()], [MyL1(0.05)], [MyNonNeg()]], **common)
+    for a, b in zip((ref[1][0], np.concatenate(ref[1][1]), ref[1][2]), (got[1][0], np.concatenate(got[1][1]), got[1][2])):
+        assert rel(b, a) < 1e-12
+    np.testing.assert_allclose(dgot.regularized_loss, dref.regularized_loss, rtol=1e-12)

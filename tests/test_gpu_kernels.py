@@ -698,3 +698,148 @@ def test_device_mt19937_continues_numpy_randomstate(seed, skip, n):
     np.testing.assert_array_equal(got.cpu().numpy(), want)
     np.testing.assert_array_equal(rs.uniform(size=7), ref.uniform(size=7))          # host continues the stream
     np.testing.assert_array_equal(rs.standard_normal(size=3), ref.standard_normal(size=3))
+
+
+@pytest.mark.parametrize("R", [1, 2, 3, 7, 8, 20, 31, 32])
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+def test_parafac2_polar_warp_vs_cta_and_numpy(R, dtype):
+    """B2_OPT_POLAR_WARP (default): the warp-per-slice Jacobi polar kernel against the CTA-per-slice one and against
+    NumPy's SVD route (penalties.py:1233-1235), cold and warm, odd and even ranks, more slices than one wave."""
+    _lib, _ops, _ = _imports()
+    lib = _lib.load()
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    rs = np.random.RandomState(1000 + R)
+    G = 700
+    V = [rs.standard_normal(size=(R + 3 + (g % 5), R)) for g in range(G)]
+    Delta = rs.standard_normal(size=(R, R)) + np.eye(R)
+    rho = rs.uniform(0.5, 2.0, size=G)
+    S = np.stack([v.T @ v for v in V])
+    Sd, Dd, rd = dev(S, tdt), dev(Delta, tdt), dev(rho, tdt)
+    out = {}
+    try:
+        for variant in (1, 0):
+            lib.b2_set_option(_lib.OPT_POLAR_WARP, variant)
+            Wm = torch.zeros(G, R, R, dtype=tdt, device="cuda")
+            num = torch.zeros(G, R, R, dtype=torch.float64, device="cuda")
+            Q = torch.zeros(G, R, R, dtype=torch.float64, device="cuda")
+            _ops.pf2_polar(Sd, Dd, rd, G, R, Wm, num, Q, warm=False)
+            cold = (Wm.double().cpu().numpy().copy(), num.cpu().numpy().copy())
+            _ops.pf2_polar(Sd, Dd, rd, G, R, Wm, num, Q, warm=True)
+            out[variant] = cold + (Wm.double().cpu().numpy(), num.cpu().numpy())
+    finally:
+        lib.b2_set_option(_lib.OPT_POLAR_WARP, 1)
+    tol = 1e-9 if dtype == "f64" else 2e-4
+    for a, b in zip(out[1], out[0]):
+        np.testing.assert_allclose(a, b, rtol=tol, atol=tol)
+    np.testing.assert_allclose(out[1][2], out[1][0], rtol=tol, atol=tol)  # warm == cold
+    if dtype == "f64":
+        for g in range(0, G, 37):
+            U, _, Vh = np.linalg.svd(V[g] @ Delta.T, full_matrices=False)
+            np.testing.assert_allclose(V[g] @ out[1][0][g], U @ Vh, atol=1e-9)
+            np.testing.assert_allclose(out[1][1][g], rho[g] * (U @ Vh).T @ V[g], atol=1e-8)
+
+
+# ---- "next" penalties (SURVEY.md §8f-1): GeneralizedL2Penalty, UnitSimplex, TotalVariationPenalty ----------------
+def test_next_penalties_prox_goldens(golden_dir):
+    """Protocol calls (NumPy in, NumPy out, CUDA kernels underneath) against vectors from the reference classes."""
+    from matcouply_b200 import penalties as P
+
+    g = np.load(os.path.join(golden_dir, "operators.npz"))
+    M = g["prox_in"]
+    gl2 = P.GeneralizedL2Penalty(g["gl2_matrix"])
+    np.testing.assert_allclose(gl2.factor_matrix_update(M, 1.3, None), g["prox_gl2"], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(gl2.penalty(M), float(g["gl2_value"]), rtol=1e-12)
+    np.testing.assert_allclose(P.UnitSimplex().factor_matrix_update(M, 1.3, None), g["prox_simplex"], atol=5e-12)
+    np.testing.assert_allclose(P.UnitSimplex().factor_matrix_update(g["prox_in_long"], 0.7, None),
+                               g["prox_simplex_long"], atol=5e-12)
+    np.testing.assert_allclose(P.TotalVariationPenalty(0.3).factor_matrix_update(M, 1.3, None), g["prox_tv"],
+                               atol=1e-13)
+    tvl1 = P.TotalVariationPenalty(0.3, l1_strength=0.2)
+    np.testing.assert_allclose(tvl1.factor_matrix_update(M, 1.3, None), g["prox_tv_l1"], atol=1e-13)
+    np.testing.assert_allclose(tvl1.penalty(M), float(g["tv_value"]), rtol=1e-12)
+    np.testing.assert_allclose(P.TotalVariationPenalty(0.5).factor_matrix_update(g["prox_in_long"], 0.7, None),
+                               g["prox_tv_long"], atol=1e-12)
+    with pytest.raises(ValueError):
+        P.TotalVariationPenalty(0)
+    with pytest.raises(ValueError):
+        P.TotalVariationPenalty(1, l1_strength=-1)
+    with pytest.raises(ValueError):
+        P.GeneralizedL2Penalty(np.array([[1.0, 2.0], [0.0, 1.0]]))
+    with pytest.raises(ValueError):
+        P.GeneralizedL2Penalty(-np.eye(3))
+    assert "norm_matrix" in repr(gl2) and "validate=True" in repr(gl2)
+
+
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("R", [1, 5, 20, 32])
+def test_next_penalties_ragged_groups_vs_oracle(R, dtype):
+    """Grouped kernels (one launch over ragged slices, per-slice rho) against the oracle, incl. dual = V - aux,
+    one-row and long groups, a group too long for the shared-memory staging of the simplex kernel."""
+    _lib, _ops, O = _imports()
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    tol = 1e-11 if dtype == "f64" else 3e-5
+    rs = np.random.RandomState(31 + R)
+    sizes = [1, 2, 3, 17, 64, 65, 300, 1200 if R <= 5 else 40, 9]
+    if R == 1:
+        sizes.append(25000)  # > 160 KB of staging: global-memory path of the simplex kernel
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    G, N = len(sizes), int(off[-1])
+    V = rs.standard_normal(size=(N, R)).cumsum(axis=0) * 0.2 + rs.standard_normal(size=(N, R))
+    V = V.astype(np.float32).astype(np.float64) if dtype == "f32" else V
+    rho = rs.uniform(0.3, 3.0, size=G)
+    rho = rho.astype(np.float32).astype(np.float64) if dtype == "f32" else rho
+    offd, rhod = dev(off, torch.int64), dev(rho, tdt)
+    cut = lambda a: [a[i:j] for i, j in zip(off[:-1], off[1:])]  # noqa: E731
+
+    aux, dual = torch.zeros(N, R, dtype=tdt, device="cuda"), dev(V, tdt)
+    _ops.prox_simplex(aux, dual, offd, G, max(sizes), R)
+    ref = np.concatenate([O.UnitSimplexP().prox(v, 1.0, None) for v in cut(V)], 0)
+    np.testing.assert_allclose(aux.double().cpu().numpy(), ref, atol=max(tol, 5e-12))
+    np.testing.assert_allclose(dual.double().cpu().numpy(), V - aux.double().cpu().numpy(), atol=tol)
+
+    for reg, l1 in ((0.4, 0.0), (0.15, 0.3)):
+        aux, dual = torch.zeros(N, R, dtype=tdt, device="cuda"), dev(V, tdt)
+        _ops.prox_tv(aux, dual, offd, G, R, rhod, reg, l1)
+        ref = np.concatenate([O.TotalVariationP(reg, l1).prox(v, r, None) for v, r in zip(cut(V), rho)], 0)
+        np.testing.assert_allclose(aux.double().cpu().numpy(), ref, atol=tol * 10)
+        np.testing.assert_allclose(dual.double().cpu().numpy(), V - aux.double().cpu().numpy(), atol=tol * 10)
+        out = torch.zeros(1, dtype=torch.float64, device="cuda")
+        _ops.tv_norm(dev(V, tdt), offd, G, R, out)
+        np.testing.assert_allclose(out.item(), sum(np.abs(np.diff(v, axis=0)).sum() for v in cut(V)), rtol=1e-10)
+
+    # generalized L2: equal-sized groups (J rows each), random SPD-ish norm matrix with a null space
+    J, Gq = 70, 5
+    L = rs.standard_normal(size=(J - 3, J))
+    Mn = L.T @ L / J
+    Mn = 0.5 * (Mn + Mn.T)
+    Vq = rs.standard_normal(size=(Gq * J, R))
+    Vq = Vq.astype(np.float32).astype(np.float64) if dtype == "f32" else Vq
+    pen = O.GeneralizedL2P(Mn)
+    aux, dual = torch.zeros(Gq * J, R, dtype=tdt, device="cuda"), dev(Vq, tdt)
+    tmp = torch.empty_like(aux)
+    _ops.prox_gl2(aux, dual, Gq, J, R, dev(pen._U, tdt), dev(pen._s, tdt), dev(rho[:Gq], tdt), tmp)
+    ref = np.concatenate([pen.prox(Vq[g * J:(g + 1) * J], rho[g], None) for g in range(Gq)], 0)
+    np.testing.assert_allclose(aux.double().cpu().numpy(), ref, atol=tol * 20)
+    np.testing.assert_allclose(dual.double().cpu().numpy(), Vq - aux.double().cpu().numpy(), atol=tol * 20)
+    out = torch.zeros(1, dtype=torch.float64, device="cuda")
+    _ops.quadform(dev(Mn, tdt), dev(Vq, tdt), Gq, J, R, out, tmp)
+    np.testing.assert_allclose(out.item(), pen.value([Vq[g * J:(g + 1) * J] for g in range(Gq)]),
+                               rtol=1e-10 if dtype == "f64" else 1e-4)
+
+
+def test_tv_kernel_kkt_large():
+    """KKT certificate of the CUDA TV prox on long columns (size-independent property, no oracle involved)."""
+    _lib, _ops, _ = _imports()
+    rs = np.random.RandomState(5)
+    n, R, lam_reg, rho = 20000, 8, 0.7, 1.4
+    V = np.repeat(rs.standard_normal(size=(n // 50, R)), 50, axis=0) * 2 + rs.standard_normal(size=(n, R))
+    aux, dual = torch.zeros(n, R, dtype=torch.float64, device="cuda"), dev(V)
+    _ops.prox_tv(aux, dual, dev(np.array([0, n]), torch.int64), 1, R, dev(np.array([rho])), lam_reg, 0.0)
+    x = aux.cpu().numpy()
+    lam = 2 * lam_reg / rho
+    u = np.cumsum(V - x, axis=0)
+    assert np.abs(u[-1]).max() < 1e-8
+    assert np.all(np.abs(u[:-1]) <= lam * (1 + 1e-9) + 1e-10)
+    d = np.diff(x, axis=0)
+    jump = np.abs(d) > 1e-12
+    np.testing.assert_allclose(u[:-1][jump], -lam * np.sign(d[jump]), atol=1e-8)

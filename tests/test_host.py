@@ -64,8 +64,17 @@ def test_penalty_parsing_order_and_repr():
         P.L1Penalty(-1)
     with pytest.raises(ValueError):
         P.L2Ball(0)
-    with pytest.raises(NotImplementedError):
-        P.UnitSimplex()
+    assert repr(P.UnitSimplex()).endswith("UnitSimplex' with aux_init='random_uniform', dual_init='random_uniform')>")
+    tv = _parse_all_penalties(non_negative=None, lower_bound=None, upper_bound=None, l2_norm_bound=None, unimodal=None,
+                              parafac2=None, l1_penalty={2: 0.5}, tv_penalty={2: 2.0}, generalized_l2_penalty=None,
+                              svd="truncated_svd", regs=None, dual_init="zeros", aux_init="zeros", verbose=False)
+    assert [type(r).__name__ for r in tv[2]] == ["TotalVariationPenalty"]  # the L1 strength moves into the TV penalty
+    assert tv[2][0].reg_strength == 2.0 and tv[2][0].l1_strength == 0.5
+    gl2 = _parse_all_penalties(non_negative=True, lower_bound=None, upper_bound=None, l2_norm_bound=None, unimodal=None,
+                               parafac2=True, l1_penalty=None, tv_penalty=None,
+                               generalized_l2_penalty={1: np.eye(4)}, svd="truncated_svd", regs=None,
+                               dual_init="zeros", aux_init="zeros", verbose=False)
+    assert [type(r).__name__ for r in gl2[1]] == ["Parafac2", "GeneralizedL2Penalty", "NonNegativity"]
 
 
 def test_aux_dual_init_draw_order_matches_oracle():

@@ -27,9 +27,12 @@ def load_case(name):
     off = g["row_offsets"]
     X = [g["X"][a:b] for a, b in zip(off[:-1], off[1:])]
     kw = json.loads(str(g["kwargs"]))
-    for key in ("l1_penalty", "non_negative", "unimodal", "l2_norm_bound", "lower_bound", "upper_bound"):
+    for key in ("l1_penalty", "non_negative", "unimodal", "l2_norm_bound", "lower_bound", "upper_bound", "tv_penalty"):
         if isinstance(kw.get(key), dict):
             kw[key] = {int(k): v for k, v in kw[key].items()}
+    if isinstance(kw.get("generalized_l2_penalty"), dict):  # norm matrices are stored as nested lists
+        kw["generalized_l2_penalty"] = {int(k): np.asarray(v, dtype=np.float64)
+                                        for k, v in kw["generalized_l2_penalty"].items()}
     return g, X, int(g["rank"]), kw
 
 
@@ -84,6 +87,53 @@ def test_prefix_isotonic_vs_sklearn():
                 sk = IsotonicRegression(y_min=0 if nn else None).fit_transform(np.arange(end), y[:end])
                 np.testing.assert_allclose(fit, sk, atol=1e-12)
                 assert abs(err[end] - np.sum((fit - y[:end]) ** 2)) < 1e-9
+
+
+def test_tv_oracle_kkt():
+    """The TV prox is the unique minimiser of 0.5||x - y||^2 + lam TV(x).  KKT certificate: with u = cumsum(y - x),
+    u[-1] = 0, |u[k]| <= lam and u[k] = -lam sign(x[k+1] - x[k]) wherever x jumps.  This pins the oracle's restatement
+    of Condat's algorithm without the (un-installable) condat_tv package."""
+    rs = np.random.RandomState(0)
+    for n in (1, 2, 3, 5, 10, 50, 200, 1000):
+        for lam in (1e-3, 0.1, 1.0, 10.0):
+            y = rs.standard_normal(n) * rs.choice([0.1, 1, 5])
+            if n > 20:
+                y += np.repeat(rs.standard_normal(n // 10 + 1), 10)[:n] * 3
+            x = O.tv_denoise_1d(y, lam)
+            u = np.cumsum(y - x)
+            assert abs(u[-1]) < 1e-9 * max(1.0, np.abs(y).sum())
+            assert np.all(np.abs(u[:-1]) <= lam * (1 + 1e-9) + 1e-12)
+            d = np.diff(x)
+            jump = np.abs(d) > 1e-12
+            np.testing.assert_allclose(u[:-1][jump], -lam * np.sign(d[jump]), atol=1e-9)
+
+
+def test_simplex_oracle_vs_sort_projection():
+    """The bisection of penalties.py:941-969 against the exact sort-based projection onto the unit simplex."""
+    rs = np.random.RandomState(1)
+    for n in (1, 2, 5, 30, 400):
+        M = rs.standard_normal((n, 4)) * 2
+        out = O.UnitSimplexP().prox(M, 1.0, None)
+        for r in range(4):
+            y = np.sort(M[:, r])[::-1]
+            css = np.cumsum(y) - 1
+            k = np.arange(1, n + 1)
+            ok = y - css / k > 0
+            mu = css[ok][-1] / k[ok][-1]
+            assert np.abs(out[:, r] - np.clip(M[:, r] - mu, 0, None)).max() < 1e-11
+        np.testing.assert_allclose(out.sum(0), 1.0, atol=1e-10)
+
+
+def test_next_penalty_operator_goldens():
+    """GeneralizedL2 / UnitSimplex (reference classes) and TV (reference class on the condat_tv stand-in)."""
+    g = np.load(os.path.join(HERE, "golden", "operators.npz"))
+    M = g["prox_in"]
+    np.testing.assert_allclose(O.GeneralizedL2P(g["gl2_matrix"]).prox(M, 1.3, None), g["prox_gl2"], rtol=1e-12)
+    np.testing.assert_allclose(O.GeneralizedL2P(g["gl2_matrix"]).value(M), float(g["gl2_value"]), rtol=1e-12)
+    np.testing.assert_allclose(O.UnitSimplexP().prox(M, 1.3, None), g["prox_simplex"], atol=1e-14)
+    np.testing.assert_allclose(O.TotalVariationP(0.3).prox(M, 1.3, None), g["prox_tv"], atol=1e-14)
+    np.testing.assert_allclose(O.TotalVariationP(0.3, 0.2).value(M), float(g["tv_value"]), rtol=1e-12)
+    np.testing.assert_allclose(O.UnitSimplexP().prox(g["prox_in_long"], 0.7, None), g["prox_simplex_long"], atol=1e-14)
 
 
 def test_closed_form_l2_update():
