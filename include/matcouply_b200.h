@@ -224,6 +224,12 @@ int b2_prox_gl2(void* aux, void* dual, int n_groups, int J, int R, const void* U
 int b2_quadform(const void* M, const void* x, int n_groups, int J, int R, double* out, void* tmp, double* part,
                 int dtype, void* stream);
 
+/* Parafac2(update_basis_matrices=False) (penalties.py:1231-1248): the basis matrices P (packed n x R) stay fixed.
+ * phase 1: num_part[g] = rho_g P_g^T V_g (V in `dual`), the summand b2_pf2_delta reduces;
+ * phase 2: pd = P Delta, dual = V - pd. */
+int b2_pf2_fixed_basis(void* pd, void* dual, const void* P, const void* Delta, const int64_t* row_off, int n_groups,
+                       long long n, int R, const void* rho, double* num_part, int phase, int dtype, void* stream);
+
 /* ---- initial state: device-side continuation of a NumPy RandomState (MT19937) stream ----------------------------
  * out[0:n] = the next n doubles `np.random.RandomState.random_sample` / `uniform(0, 1)` would return for the generator
  * whose state is state_io (device, 625 uint32: the 624 key words and the position, as in RandomState.get_state());

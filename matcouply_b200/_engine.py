@@ -451,16 +451,54 @@ class AOADMMEngine:
             elif kind == _lib.PEN_HOST:
                 self._host_prox(st, p, row_off, n_groups, rho)
             elif kind == _lib.PEN_PARAFAC2:
-                _ops.slice_cross(st.dual[p], None, row_off, n_groups, R, None, self.S, None)
-                _ops.pf2_polar(self.S, self.Delta, rho, n_groups, R, self.Wmat, self.num_part)
-                if self.world > 1:
-                    _ops.pf2_delta(self.num_part, rho, n_groups, R, self.Delta, self.pf2_sums)
-                    self._allreduce(self.pf2_sums)
-                    _ops.pf2_delta(self.num_part, rho, n_groups, R, self.Delta, None, self.pf2_sums)
-                else:
-                    _ops.pf2_delta(self.num_part, rho, n_groups, R, self.Delta, self.pf2_sums)
+                self._pf2_prox_unfused(st, p, row_off, n_groups, rho, gor, n_rows)
+
+    def _pf2_delta_update(self, rho, n_groups):
+        """Delta = sum_g rho_g P_g^T V_g / sum_g rho_g from `num_part` (penalties.py:1240-1245); all-reduced when sharded."""
+        R = self.R
+        _ops.pf2_delta(self.num_part, rho, n_groups, R, self.Delta, self.pf2_sums)
+        if self.world > 1:
+            self._allreduce(self.pf2_sums)
+            _ops.pf2_delta(self.num_part, rho, n_groups, R, self.Delta, None, self.pf2_sums)
+
+    def _pf2_prox_unfused(self, st, p, row_off, n_groups, rho, gor, n_rows):
+        """Parafac2.factor_matrices_update (penalties.py:1224-1250) with all its options: `n_iter` alternations of
+        the basis update (polar factors) and the coordinate-matrix update on the same pre-image V; either update
+        can be frozen (then a single pass, :1247-1248)."""
+        reg, R = st.regs[p], self.R
+        if reg.update_basis_matrices:
+            _ops.slice_cross(st.dual[p], None, row_off, n_groups, R, None, self.S, None)
+            for it in range(max(int(reg.n_iter), 0)):
+                _ops.pf2_polar(self.S, self.Delta, rho, n_groups, R, self.Wmat, self.num_part, self.pf2_Q, warm=it > 0)
+                if not reg.update_coordinate_matrix:
+                    break
+                self._pf2_delta_update(rho, n_groups)
+            if int(reg.n_iter) > 0:
                 _ops.pf2_apply(st.aux[p], st.dual[p], None, self.Wmat, self.Delta, gor, n_rows, R)
                 self.pf2_fresh = True
+                return
+        # frozen basis matrices: P stays what it was given as (aux_init tuple or eye(J_i, R)); with n_iter == 0 the
+        # reference returns the aux unchanged, which the same code covers (Delta untouched, pd = P Delta)
+        P = self._pf2_fixed_basis()
+        if reg.update_coordinate_matrix and int(reg.n_iter) > 0:
+            _ops.pf2_fixed_basis(None, st.dual[p], P, None, row_off, n_groups, n_rows, R, rho, self.num_part, 1)
+            self._pf2_delta_update(rho, n_groups)
+        _ops.pf2_fixed_basis(st.aux[p], st.dual[p], P, self.Delta, row_off, n_groups, n_rows, R, None, None, 2)
+
+    def _pf2_fixed_basis(self):
+        """The initial basis matrices as ONE packed N x R device tensor (built once)."""
+        if getattr(self, "_pf2_P", None) is None:
+            basis = self.pf2_basis0
+            if basis is None or basis.__class__.__name__ == "_EyeBases":
+                P = torch.zeros((self.N, self.R), dtype=self.dtype, device=self.dev)
+                starts, ends = self.row_off[:-1], self.row_off[1:]
+                for j in range(self.R):
+                    ok = (ends - starts) > j
+                    P[(starts + j)[ok], j] = 1
+            else:
+                P = self._up(np.concatenate([np.asarray(b) for b in basis], 0))
+            self._pf2_P = P
+        return self._pf2_P
 
     def _host_prox(self, st, p, row_off, n_groups, rho):
         """Bridge to a user-defined ADMMPenalty subclass (examples/plot_custom_penalty.py:220-231 style): the
@@ -522,7 +560,8 @@ class AOADMMEngine:
                             BtB_out=self.BtB)
             self.w_fresh = True
             return
-        if self.fuse_pf2 and self.n_inner > 0 and st.desc and st.desc[0][0] == _lib.PEN_PARAFAC2:
+        if self.fuse_pf2 and self.n_inner > 0 and st.desc and st.desc[0][0] == _lib.PEN_PARAFAC2 and \
+                st.regs[0].update_basis_matrices and st.regs[0].update_coordinate_matrix and int(st.regs[0].n_iter) >= 1:
             return self._step_B_pf2_fused()
         self._materialize_pf2()
         for _ in range(self.n_inner):
@@ -558,11 +597,10 @@ class AOADMMEngine:
                     self._host_prox(st, p, self.row_off, I, self.rhoB)
             # cold Jacobi start on the first inner iteration (bounds the round-off drift of the accumulated
             # rotations), warm start from the previous inner iteration's eigenvectors afterwards
-            _ops.pf2_polar(self.S, self.Delta, self.rhoB, I, R, self.Wmat, self.num_part, self.pf2_Q, warm=it > 0)
-            _ops.pf2_delta(self.num_part, self.rhoB, I, R, self.Delta, self.pf2_sums)
-            if self.world > 1:
-                self._allreduce(self.pf2_sums)
-                _ops.pf2_delta(self.num_part, self.rhoB, I, R, self.Delta, None, self.pf2_sums)
+            for sub in range(int(st.regs[0].n_iter)):  # Parafac2(n_iter=...): alternations on the same V (penalties.py:1229)
+                _ops.pf2_polar(self.S, self.Delta, self.rhoB, I, R, self.Wmat, self.num_part, self.pf2_Q,
+                               warm=it > 0 or sub > 0)
+                self._pf2_delta_update(self.rhoB, I)
         # P Delta and dual = V - P Delta stay implicit: the next row pass and the gap reduction apply W_g Delta on the fly
         self.pf2_deferred = True
         self.pf2_fresh = True

@@ -54,6 +54,7 @@ _SIGNATURES = {
     "b2_tv_norm": [_vp, _vp, _i, _i, _vp, _vp, _i, _vp],
     "b2_prox_gl2": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp, _i, _vp],
     "b2_quadform": [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _i, _vp],
+    "b2_pf2_fixed_basis": [_vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _vp, _vp, _i, _i, _vp],
     "b2_pf2_polar": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
     "b2_pf2_rowpass": [_vp, _i, _i, _vp, _vp, _vp, _vp, ctypes.POINTER(PenaltyDesc), _i, _i, _vp, _vp, _vp, _vp, _i, _vp,
                        _vp, _i, _vp],

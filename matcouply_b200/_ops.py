@@ -181,6 +181,11 @@ def quadform(M, x, n_groups, J, R, out, tmp):
          _stream())
 
 
+def pf2_fixed_basis(pd, dual, P, Delta, row_off, n_groups, n, R, rho, num_part, phase):
+    call("b2_pf2_fixed_basis", _ptr(pd), _ptr(dual), _ptr(P), _ptr(Delta), _ptr(row_off), n_groups, n, R, _ptr(rho),
+         _ptr(num_part), int(phase), dtype_code(dual.dtype), _stream())
+
+
 def pf2_polar(S, Delta, rho, n_groups, R, Wmat, num_part, Qstore=None, warm=False):
     call("b2_pf2_polar", _ptr(S), _ptr(Delta), _ptr(rho), n_groups, R, _ptr(Wmat), _ptr(num_part), _ptr(Qstore),
          int(bool(warm)), dtype_code(S.dtype), _stream())

@@ -313,6 +313,68 @@ __global__ void __launch_bounds__(256) dot_partial_kernel(const T* __restrict__ 
     if (threadIdx.x == 0) part[blockIdx.x] = acc;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// PARAFAC2 with frozen basis matrices (Parafac2(update_basis_matrices=False), penalties.py:1231-1248): the summand
+// num[g] = rho_g P_g^T V_g of the coordinate-matrix update, and pd = P Delta, dual = V - pd.
+// ---------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256)
+slice_atb_kernel(const T* __restrict__ P, const T* __restrict__ V, const int64_t* __restrict__ row_off, int R,
+                 const T* __restrict__ rho, double* __restrict__ num) {
+    __shared__ double Ps[32][33];
+    __shared__ double Vs[32][33];
+    const int g = blockIdx.x;
+    const long long r0 = row_off[g], r1 = row_off[g + 1];
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};  // outputs e = tid + 256 u -> (i, j) = (e / R, e % R)
+    int oi[4], oj[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int e = threadIdx.x + 256 * u;
+        oi[u] = e < R * R ? e / R : 0;
+        oj[u] = e < R * R ? e % R : 0;
+    }
+    for (long long row0 = r0; row0 < r1; row0 += 32) {
+        for (int e = threadIdx.x; e < 32 * 32; e += 256) {
+            const int rr = e >> 5, c = e & 31;
+            const bool ok = row0 + rr < r1 && c < R;
+            Ps[rr][c] = ok ? (double)P[(size_t)(row0 + rr) * R + c] : 0.0;
+            Vs[rr][c] = ok ? (double)V[(size_t)(row0 + rr) * R + c] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u] = fma(Ps[rr][oi[u]], Vs[rr][oj[u]], acc[u]);
+        __syncthreads();
+    }
+    const double rg = (double)rho[g];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int e = threadIdx.x + 256 * u;
+        if (e < R * R) num[(size_t)g * R * R + e] = rg * acc[u];
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+pf2_apply_fixed_kernel(T* __restrict__ pd, T* __restrict__ dual, const T* __restrict__ P, const T* __restrict__ Delta,
+                       long long n, int R) {
+    __shared__ double D[B2_MAX_RANK * B2_MAX_RANK];
+    for (int e = threadIdx.x; e < R * R; e += blockDim.x) D[e] = (double)Delta[e];
+    __syncthreads();
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n * R;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const long long row = idx / R;
+        const int c = (int)(idx - row * R);
+        double s = 0.0;
+        for (int k = 0; k < R; ++k) s = fma((double)P[row * R + k], D[k * R + c], s);
+        const T z = (T)s;
+        pd[idx] = z;
+        dual[idx] = (T)((double)dual[idx] - (double)z);
+    }
+}
+
 }  // namespace
 
 extern "C" {
@@ -407,6 +469,26 @@ int b2_quadform(const void* M, const void* x, int n_groups, int J, int R, double
     });
     sum_partials_kernel<<<1, 256, 0, st>>>(part, 256, out);
     B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+
+int b2_pf2_fixed_basis(void* pd, void* dual, const void* P, const void* Delta, const int64_t* row_off, int n_groups,
+                       long long n, int R, const void* rho, double* num_part, int phase, int dtype, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
+    B2_REQUIRE(phase == 1 || phase == 2, "b2_pf2_fixed_basis: phase 1 (numerator) or 2 (apply)");
+    if (n_groups == 0 || n == 0) return B2_OK;
+    B2_DISPATCH_DTYPE(dtype, {
+        if (phase == 1) {
+            slice_atb_kernel<T><<<n_groups, 256, 0, st>>>((const T*)P, (const T*)dual, row_off, R, (const T*)rho,
+                                                          num_part);
+        } else {
+            const long long blocks = (n * R + 255) / 256;
+            pf2_apply_fixed_kernel<T><<<(unsigned)(blocks < 65535 ? blocks : 65535), 256, 0, st>>>(
+                (T*)pd, (T*)dual, (const T*)P, (const T*)Delta, n, R);
+        }
+        B2_LAUNCH_CHECK();
+    });
     return B2_OK;
 }
 

@@ -414,11 +414,6 @@ class Parafac2(MatricesPenalty):
         self.n_iter = n_iter
 
     def _descriptor(self):
-        if self.n_iter != 1 or not self.update_basis_matrices or not self.update_coordinate_matrix:
-            raise NotImplementedError(
-                "matcouply_b200 runs the PARAFAC2 prox with n_iter=1 and both updates enabled (the keyword path of "
-                "cmf_aoadmm); other settings are not accelerated yet"
-            )
         return (_lib.PEN_PARAFAC2, False, 0.0, 0.0)
 
     def init_aux(self, matrices, rank, mode, random_state=None):  # penalties.py:1111-1222
@@ -488,7 +483,6 @@ class Parafac2(MatricesPenalty):
 
         from . import _ops
 
-        self._descriptor()
         _, coordinate_matrix = auxes
         devs = [_Dev(fm) for fm in factor_matrices]
         dtype = devs[0].t.dtype
@@ -505,13 +499,27 @@ class Parafac2(MatricesPenalty):
         Wm = torch.empty_like(S)
         num = torch.empty(n_groups, rank, rank, dtype=torch.float64, device="cuda")
         sums = torch.empty(rank * rank + 1, dtype=torch.float64, device="cuda")
-        _ops.slice_cross(V, None, row_off, n_groups, rank, None, S, None)
-        _ops.pf2_polar(S, delta, rho, n_groups, rank, Wm, num)
-        new_delta = torch.empty_like(delta)
-        _ops.pf2_delta(num, rho, n_groups, rank, new_delta, sums)
-        pd, basis = torch.empty_like(V), torch.empty_like(V)
-        _ops.pf2_apply(pd, V, basis, Wm, new_delta, gor, n, rank)
-        bases = [devs[i].back(b) for i, b in enumerate(torch.split(basis, sizes))]
+        basis_in = auxes[0]
+        new_delta = delta.clone()
+        basis = None
+        for it in range(int(self.n_iter)):  # penalties.py:1229-1248
+            if self.update_basis_matrices:
+                if it == 0:
+                    _ops.slice_cross(V, None, row_off, n_groups, rank, None, S, None)
+                _ops.pf2_polar(S, new_delta, rho, n_groups, rank, Wm, num)
+                pd, basis = torch.empty_like(V), torch.empty_like(V)
+                _ops.pf2_apply(pd, V.clone(), basis, Wm, new_delta, gor, n, rank)
+            if self.update_coordinate_matrix:
+                if not self.update_basis_matrices:  # frozen P: numerator rho_g P_g^T V_g from the given bases
+                    P = torch.cat([_Dev(b).t.to(dtype) for b in basis_in], 0).contiguous()
+                    _ops.pf2_fixed_basis(None, V, P, None, row_off, n_groups, n, rank, rho, num, 1)
+                _ops.pf2_delta(num, rho, n_groups, rank, new_delta, sums)
+            if (not self.update_coordinate_matrix) or (not self.update_basis_matrices):
+                break
+        if basis is None:
+            bases = list(basis_in)
+        else:
+            bases = [devs[i].back(b) for i, b in enumerate(torch.split(basis, sizes))]
         return bases, _Dev(coordinate_matrix).back(new_delta)
 
     def subtract_from_aux(self, aux, dual):

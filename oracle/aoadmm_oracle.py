@@ -262,9 +262,14 @@ class UnimodalP(OraclePenalty):  # penalties.py:983-1015
         raise AttributeError("Unimodality has no row update")
 
 
-class Parafac2P(OraclePenalty):  # penalties.py:1018-1324 (n_iter=1, both updates on: the only keyword-reachable setting)
+class Parafac2P(OraclePenalty):  # penalties.py:1018-1324
     name = "parafac2"
     matrixwise = True
+
+    def __init__(self, n_iter=1, update_basis_matrices=True, update_coordinate_matrix=True, **kw):
+        super().__init__(**kw)
+        self.n_iter = n_iter
+        self.update_basis_matrices, self.update_coordinate_matrix = update_basis_matrices, update_coordinate_matrix
 
     def init_aux(self, matrices, rank, mode, rs):  # :1161-1175, tuple init :1176-1220
         if isinstance(self.aux_init, tuple):
@@ -277,18 +282,23 @@ class Parafac2P(OraclePenalty):  # penalties.py:1018-1324 (n_iter=1, both update
         return [np.dot(Pi, delta) - d for Pi, d in zip(P, duals)]
 
     def prox_list(self, Ms, rhos, auxes):  # :1224-1250
-        _, delta = auxes
+        P, delta = auxes
         R = delta.shape[0]
-        P = []
-        for M in Ms:
-            T = np.matmul(M, delta.T)
-            U, _, Vh = np.linalg.svd(T, full_matrices=R > min(T.shape))
-            P.append(np.matmul(U[:, :R], Vh[:R, :]))
-        new_delta = 0
-        for M, Pi, rho in zip(Ms, P, rhos):
-            new_delta += rho * Pi.T @ M
-        new_delta /= sum(rhos)
-        return P, new_delta
+        for _ in range(self.n_iter):
+            if self.update_basis_matrices:
+                P = []
+                for M in Ms:
+                    T = np.matmul(M, delta.T)
+                    U, _, Vh = np.linalg.svd(T, full_matrices=R > min(T.shape))
+                    P.append(np.matmul(U[:, :R], Vh[:R, :]))
+            if self.update_coordinate_matrix:
+                new_delta = 0
+                for M, Pi, rho in zip(Ms, P, rhos):
+                    new_delta += rho * Pi.T @ M
+                delta = new_delta / sum(rhos)
+            if (not self.update_coordinate_matrix) or (not self.update_basis_matrices):
+                break
+        return P, delta
 
     def as_matrices(self, auxes):  # auxes_as_matrices :1287-1304
         P, delta = auxes

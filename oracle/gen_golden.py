@@ -296,6 +296,17 @@ def main():
     make_case("simplex_B_ragged", synth(14, 8, 12, 4, 25, 4), 4,
               dict(non_negative={0: True, 2: True}, regs_spec=[[], [["UnitSimplex", {}]], []], random_state=7,
                    n_iter_max=60))
+    # Parafac2 options (penalties.py:1091-1105, 1229-1248): several alternations per prox call, frozen bases / coordinates
+    make_case("pf2_n_iter3_nn", synth(18, 8, 14, 6, 18, 3, kind="parafac2"), 3,
+              dict(non_negative={0: True, 2: True}, regs_spec=[[], [["Parafac2", {"n_iter": 3}], ["NonNegativity", {}]], []],
+                   random_state=2, n_iter_max=60))
+    make_case("pf2_frozen_basis", synth(19, 7, 12, 5, 15, 3, kind="parafac2"), 3,
+              dict(non_negative=True, regs_spec=[[], [["Parafac2", {"update_basis_matrices": False}]], []],
+                   random_state=3, n_iter_max=40))
+    make_case("pf2_frozen_coordinates", synth(20, 7, 12, 5, 15, 3, kind="parafac2"), 3,
+              dict(non_negative={0: True, 2: True},
+                   regs_spec=[[], [["Parafac2", {"update_coordinate_matrix": False, "n_iter": 2}]], []],
+                   random_state=4, n_iter_max=40))
     make_case("tv_C_l1", synth(15, 7, 30, 6, 12, 3), 3,
               dict(non_negative={0: True, 1: True}, tv_penalty={2: 0.02}, l1_penalty={2: 0.01}, random_state=4,
                    n_iter_max=60))

@@ -843,3 +843,24 @@ def test_tv_kernel_kkt_large():
     d = np.diff(x, axis=0)
     jump = np.abs(d) > 1e-12
     np.testing.assert_allclose(u[:-1][jump], -lam * np.sign(d[jump]), atol=1e-8)
+
+
+@pytest.mark.parametrize("opts", [dict(n_iter=5), dict(update_basis_matrices=False), dict(update_coordinate_matrix=False),
+                                  dict(n_iter=3, update_coordinate_matrix=False), dict(n_iter=0)])
+def test_parafac2_prox_options_vs_oracle(opts):
+    """Parafac2(n_iter, update_basis_matrices, update_coordinate_matrix) (penalties.py:1091-1105, 1229-1248; the
+    reference's own tests: tests/test_penalties.py:439-519) as protocol calls against the oracle."""
+    from matcouply_b200 import penalties as P
+    from oracle import aoadmm_oracle as O
+
+    rs = np.random.RandomState(11)
+    R, Js = 4, [6, 9, 4, 15, 7]
+    fms = [rs.standard_normal(size=(J, R)) for J in Js]
+    rhos = list(rs.uniform(0.5, 2, size=len(Js)))
+    delta = rs.uniform(size=(R, R)) + 0.5 * np.eye(R)
+    bases0 = [np.linalg.qr(rs.standard_normal(size=(J, R)))[0] for J in Js]
+    bases, new_delta = P.Parafac2(**opts).factor_matrices_update(fms, rhos, (bases0, delta))
+    ob, od = O.Parafac2P(**opts).prox_list(fms, rhos, (bases0, delta))
+    for b, o in zip(bases, ob):
+        np.testing.assert_allclose(b, o, atol=1e-10)
+    np.testing.assert_allclose(new_delta, od, atol=1e-10)
