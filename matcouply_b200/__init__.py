@@ -6,12 +6,12 @@ Public modules mirror the reference package (``matcouply/__init__.py:10``):
 ``matcouply_b200/csrc`` behind the C ABI in ``include/matcouply_b200.h``; importing the package does not need a GPU,
 calling it does.
 """
-from . import coupled_matrices, decomposition, penalties  # noqa: F401
+from . import coupled_matrices, data, decomposition, penalties, random  # noqa: F401
 from .coupled_matrices import CoupledMatrixFactorization  # noqa: F401
 from .decomposition import ADMMVars, DiagnosticMetrics, cmf_aoadmm, parafac2_aoadmm  # noqa: F401
 
 __version__ = "0.1.0"
-__all__ = ["coupled_matrices", "decomposition", "penalties", "CoupledMatrixFactorization", "cmf_aoadmm",
+__all__ = ["coupled_matrices", "data", "decomposition", "penalties", "random", "CoupledMatrixFactorization", "cmf_aoadmm",
            "parafac2_aoadmm", "ADMMVars", "DiagnosticMetrics", "PackedMatrices"]
 
 

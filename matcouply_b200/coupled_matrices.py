@@ -111,6 +111,15 @@ class CoupledMatrixFactorization:
     def __repr__(self):  # pragma: nocover
         return "(weights, factors) : rank-{} CoupledMatrixFactorization of shape {}".format(self.rank, self.shape)
 
+    def to_tensor(self):
+        return cmf_to_tensor(self)
+
+    def to_vec(self, pad=True):
+        return cmf_to_vec(self, pad=pad)
+
+    def to_unfolded(self, mode, pad=True):
+        return cmf_to_unfolded(self, mode, pad=pad)
+
     def to_matrices(self):
         return cmf_to_matrices(self)
 
@@ -139,3 +148,32 @@ def cmf_to_matrices(cmf, validate=True):
 
 cmf_to_slice = cmf_to_matrix
 cmf_to_slices = cmf_to_matrices
+cmf_to_slices = cmf_to_matrices
+
+
+def cmf_to_tensor(cmf, validate=True):
+    """Dense ``I x max(J_i) x K`` tensor, shorter matrices zero-padded at the bottom (coupled_matrices.py:517-596)."""
+    _, (A, B_is, C) = cmf
+    matrices = cmf_to_matrices(cmf, validate=validate)
+    lengths = [B_i.shape[0] for B_i in B_is]
+    tensor = np.zeros((A.shape[0], max(lengths), C.shape[0]), dtype=np.asarray(matrices[0]).dtype)
+    for i, (matrix, length) in enumerate(zip(matrices, lengths)):
+        tensor[i, :length] = matrix
+    return tensor
+
+
+def cmf_to_unfolded(cmf, mode, pad=True, validate=True):
+    """Mode-``mode`` unfolding of the (padded) tensor; ``pad=False`` only for mode 2 (coupled_matrices.py:599-714)."""
+    if pad:
+        tensor = cmf_to_tensor(cmf, validate=validate)
+        return np.reshape(np.moveaxis(tensor, mode, 0), (tensor.shape[mode], -1))
+    if mode == 2:
+        return np.transpose(np.concatenate(cmf_to_matrices(cmf, validate=validate), axis=0))
+    raise ValueError(f"Cannot unfold along mode {mode} without padding. ")
+
+
+def cmf_to_vec(cmf, pad=True, validate=True):
+    """Vectorised (padded) tensor, or the concatenated raveled matrices (coupled_matrices.py:717-799)."""
+    if pad:
+        return np.reshape(cmf_to_tensor(cmf, validate=validate), (-1,))
+    return np.concatenate([np.reshape(m, (-1,)) for m in cmf_to_matrices(cmf, validate=validate)])

@@ -163,3 +163,37 @@ def test_cpu_call_fails_loudly():
         pytest.skip("GPU present")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         cmf_aoadmm([np.ones((3, 3))], 1)
+
+
+def test_data_model_sugar_and_simulated_data(golden_dir):
+    """cmf_to_tensor / unfolded / vec (coupled_matrices.py:517-799), random_coupled_matrices (random.py:9-66) and the
+    README data set (data.py:28-95).  The latter is pinned by the golden README case, whose X came from the reference's
+    own get_simple_simulated_data(noise_level=0.2, random_state=1)."""
+    from matcouply_b200.coupled_matrices import cmf_to_tensor, cmf_to_unfolded, cmf_to_vec
+    from matcouply_b200.data import get_simple_simulated_data
+    from matcouply_b200.random import random_coupled_matrices
+
+    shapes = ((5, 10), (3, 10), (2, 10), (4, 10))
+    cmf = random_coupled_matrices(shapes, rank=3, random_state=0)
+    assert cmf.shape == shapes and cmf.rank == 3 and cmf.weights.shape == (3,)
+    T = cmf_to_tensor(cmf)
+    assert T.shape == (4, 5, 10) and (T == 0).sum() == 60
+    for i, M in enumerate(cmf.to_matrices()):
+        np.testing.assert_array_equal(T[i, :M.shape[0]], M)
+    assert cmf_to_unfolded(cmf, 0).shape == (4, 50) and cmf_to_unfolded(cmf, 1).shape == (5, 40)
+    assert cmf_to_unfolded(cmf, 2).shape == (10, 20) and cmf_to_unfolded(cmf, 2, pad=False).shape == (10, 14)
+    np.testing.assert_array_equal(cmf_to_unfolded(cmf, 2)[:, :5], T[0].T)
+    with pytest.raises(ValueError):
+        cmf_to_unfolded(cmf, 1, pad=False)
+    assert cmf_to_vec(cmf).shape == (200,) and cmf.to_vec(pad=False).shape == (140,)
+    full = random_coupled_matrices(shapes, rank=3, random_state=0, full=True)
+    np.testing.assert_allclose(full[1], cmf.to_matrix(1))
+    unnorm = random_coupled_matrices(shapes, 2, random_state=1, normalise_factors=False)
+    np.testing.assert_array_equal(unnorm.weights, np.ones(2))
+    with pytest.raises(ValueError):
+        random_coupled_matrices(((3, 4), (3, 5)), 2)
+
+    X, truth = get_simple_simulated_data(noise_level=0.2, random_state=1)
+    g = np.load(os.path.join(golden_dir, "traj_c0_readme.npz"))
+    np.testing.assert_allclose(np.concatenate(X, 0), g["X"], rtol=1e-12, atol=1e-14)
+    assert truth.shape == tuple((50, 20) for _ in range(15))
