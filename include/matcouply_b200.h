@@ -56,7 +56,7 @@ typedef struct {
 /* kernel-selection switches (process-wide; default 1 = on, except B2_OPT_XSTREAM_HYBRID which is off).  They only choose between equivalent kernels — tests flip
  * them to cross-check the tensor-core formulations against the scalar ones. */
 enum { B2_OPT_PF2_ROWPASS_MMA = 0 /* DMMA row pass of b2_pf2_rowpass */,
-       B2_OPT_POLAR_WARP = 1 /* warp-per-slice Jacobi polar step in b2_pf2_polar (0: CTA-per-slice kernel) */,
+       B2_OPT_POLAR_WARP = 1 /* polar step of b2_pf2_polar: 2 (default) = warp per slice, Jacobi in registers; 1 = warp per slice in shared memory; 0 = CTA per slice */,
        B2_OPT_ADMM_LOCAL_MMA = 2 /* DMMA formulation of b2_admm_local (CTA-per-slice path) */,
        B2_OPT_XSTREAM_HYBRID = 3 /* DMMA blocks + DFMA remainder columns in the fp64 X-stream kernels (R = 8b+1..4);
                                     default OFF: measured 2-6 % slower than padding to a whole block */,

@@ -582,8 +582,13 @@ class AOADMMEngine:
         for it in range(self.n_inner):
             last = it == self.n_inner - 1
             # deferred from the start when the previous outer iteration left (V, W_g, Delta) behind
+            # flag bits: 1 = PARAFAC2 prox deferred; 2 / 4 = the elementwise companions arrive / leave as ONE array
+            # T = x + dual (aux = prox(T) and dual = T - aux are recomputed in registers): explicit (aux, dual) are only
+            # read by the first and written by the last pass of a B-update, which saves two N x R arrays of traffic
+            # per companion in every other pass
+            flags = (1 if (it > 0 or self.pf2_deferred) else 0) | (2 if it > 0 else 0) | (0 if last else 4)
             _ops.pf2_rowpass(self.row_off, I, R, self.Y, A, self.rhoB, self.MinvB, st.descs_c, len(st.desc),
-                             it > 0 or self.pf2_deferred, self.Wmat, self.Delta, st.x if last else None,
+                             flags, self.Wmat, self.Delta, st.x if last else None,
                              self.Wpad if last else None, self.S, self.BtB if last else None)
             for p, (kind, nn, p0, _p1) in enumerate(st.desc):  # column-coupled companions (V is in their dual slot)
                 if kind == _lib.PEN_L2BALL:

@@ -243,7 +243,7 @@ def admm_local(n, R, rhs, rhs_scale, group_mode, group_of_row, rho, Minv, descs,
 def pf2_rowpass(row_off, n_groups, R, Y, A, rho, Minv, descs, n_pen, deferred, Wmat, Delta, x, w_out, S_out,
                 BtB_out=None):
     call("b2_pf2_rowpass", _ptr(row_off), n_groups, R, _ptr(Y), _ptr(A), _ptr(rho), _ptr(Minv), descs, n_pen,
-         int(bool(deferred)), _ptr(Wmat), _ptr(Delta), _ptr(x), _ptr(w_out), 0 if w_out is None else w_out.shape[1],
+         int(deferred), _ptr(Wmat), _ptr(Delta), _ptr(x), _ptr(w_out), 0 if w_out is None else w_out.shape[1],
          _ptr(S_out), _ptr(BtB_out), dtype_code(Y.dtype), _stream())
 
 

@@ -40,7 +40,12 @@ extern unsigned long long g_b2_launches;  // kernels launched through this libra
 
 int b2_num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
 int b2_option_value(int option);  // kernel-selection switches, see b2_set_option
-// warp-per-slice polar step (pf2_polar_warp.cu), selected by B2_OPT_POLAR_WARP inside b2_pf2_polar
+// warp-per-slice polar steps selected by B2_OPT_POLAR_WARP inside b2_pf2_polar: 2 = Jacobi in registers
+// (pf2_polar_reg.cu, ranks 2..B2_POLAR_REG_MAX_RANK, returns -1 otherwise), 1 = shared-memory warp kernel
+// (pf2_polar_warp.cu), 0 = CTA-per-slice kernel (pf2_fused.cu)
+#define B2_POLAR_REG_MAX_RANK 24
+int b2_pf2_polar_reg(const void* S, const void* Delta, const void* rho, int n_groups, int R, void* Wmat,
+                     void* num_part, void* Qstore, int warm, int dtype, cudaStream_t st);
 int b2_pf2_polar_warp(const void* S, const void* Delta, const void* rho, int n_groups, int R, void* Wmat,
                       void* num_part, void* Qstore, int warm, int dtype, cudaStream_t st);
 

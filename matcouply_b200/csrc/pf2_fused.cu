@@ -17,10 +17,12 @@ namespace {
 template <typename T, int CPL>
 __global__ void __launch_bounds__(256, 2)
 pf2_rowpass_kernel(const int64_t* __restrict__ row_off, int R, const T* __restrict__ Y, const T* __restrict__ A,
-                   const T* __restrict__ rho, const T* __restrict__ Minv, PenArgs pa, int deferred,
+                   const T* __restrict__ rho, const T* __restrict__ Minv, PenArgs pa, int deferred_flags,
                    const T* __restrict__ Wmat, const T* __restrict__ Delta, T* __restrict__ x, T* __restrict__ w_out,
                    int ldw, T* __restrict__ S_out, T* __restrict__ BtB_out) {
     using L = RowLayout<T, CPL>;
+    // bit 0: PARAFAC2 prox deferred; bit 1 / 2: elementwise extras arrive / leave as T = x + dual in their dual slot
+    const bool deferred = (deferred_flags & 1) != 0, tin = (deferred_flags & 2) != 0, tout = (deferred_flags & 4) != 0;
     extern __shared__ double rp_smem[];
     const int RR = R * R;
     constexpr int NB = (CPL + 1) / 2;  // == ceil(R / 8) for every R with ceil(R / 4) == CPL
@@ -111,9 +113,21 @@ pf2_rowpass_kernel(const int64_t* __restrict__ row_off, int R, const T* __restri
         for (int p = 1; p < n_pen; ++p) {
             const T* ax = (const T*)pa.aux[p];
             const T* du = (const T*)pa.dual[p];
+            const int kind = pa.kind[p];
+            const bool elementwise = kind == B2_PEN_NONNEG || kind == B2_PEN_BOX || kind == B2_PEN_L1;
+            if (tin && elementwise) {  // T-only state: aux = prox(T), dual = T - aux
 #pragma unroll
-            for (int j = 0; j < CPL; ++j)
-                if (c0 + j < R) sh[j] += ax[base + j] - du[base + j];
+                for (int j = 0; j < CPL; ++j)
+                    if (c0 + j < R) {
+                        const T tv = du[base + j];
+                        const T z = prox_elem<T>(tv, kind, pa.nn[p], (T)pa.p0[p], (T)pa.p1[p], rg);
+                        sh[j] += z - (tv - z);
+                    }
+            } else {
+#pragma unroll
+                for (int j = 0; j < CPL; ++j)
+                    if (c0 + j < R) sh[j] += ax[base + j] - du[base + j];
+            }
         }
         T s_[CPL];
 #pragma unroll
@@ -144,8 +158,12 @@ pf2_rowpass_kernel(const int64_t* __restrict__ row_off, int R, const T* __restri
 #pragma unroll
             for (int j = 0; j < CPL; ++j) {
                 if (valid && c0 + j < R) {
-                    const T v = xv[j] + du[base + j];
-                    if (elementwise) {
+                    T dold = du[base + j];
+                    if (tin && elementwise) dold = dold - prox_elem<T>(dold, kind, nn, p0, p1, rg);
+                    const T v = xv[j] + dold;
+                    if (elementwise && tout) {
+                        du[base + j] = v;  // T-only state: the next pass recomputes aux and dual
+                    } else if (elementwise) {
                         const T z = prox_elem<T>(v, kind, nn, p0, p1, rg);
                         ax[base + j] = z;
                         du[base + j] = v - z;
@@ -556,7 +574,8 @@ int b2_pf2_rowpass(const int64_t* row_off, int n_groups, int R, const void* Y, c
     cudaStream_t st = (cudaStream_t)stream;
     B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
     B2_REQUIRE(n_pen >= 1 && pens[0].kind == B2_PEN_PARAFAC2, "b2_pf2_rowpass: pens[0] must be the PARAFAC2 penalty");
-    B2_REQUIRE(!deferred || (Wmat && Delta), "deferred mode needs Wmat and Delta");
+    B2_REQUIRE(!(deferred & 1) || (Wmat && Delta), "deferred mode needs Wmat and Delta");
+    B2_REQUIRE((deferred & ~7) == 0, "b2_pf2_rowpass: unknown flag bits in `deferred`");
     if (n_groups == 0) return B2_OK;
     PenArgs pa;
     {
@@ -594,6 +613,10 @@ int b2_pf2_polar(const void* S, const void* Delta, const void* rho, int n_groups
     B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
     B2_REQUIRE(!warm || Qstore, "b2_pf2_polar: a warm start needs the eigenvector store");
     if (n_groups == 0) return B2_OK;
+    if (b2_option_value(B2_OPT_POLAR_WARP) >= 2) {
+        const int rc = b2_pf2_polar_reg(S, Delta, rho, n_groups, R, Wmat, num_part, Qstore, warm, dtype, st);
+        if (rc >= 0) return rc;
+    }
     if (b2_option_value(B2_OPT_POLAR_WARP))
         return b2_pf2_polar_warp(S, Delta, rho, n_groups, R, Wmat, num_part, Qstore, warm, dtype, st);
     const size_t smem = (size_t)(5 * R * R + 32) * sizeof(double) + 32 * sizeof(int);

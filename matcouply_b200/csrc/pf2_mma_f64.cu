@@ -18,9 +18,10 @@ int b2_pf2_rowpass_mma_try(const int64_t* row_off, int n_groups, int R, const vo
     in.n = 0;
     in.ptr[in.n++] = Y;
     in.ptr[in.n++] = pa.dual[0];
-    if (!deferred) in.ptr[in.n++] = pa.aux[0];
+    if (!(deferred & 1)) in.ptr[in.n++] = pa.aux[0];
     for (int p = 1; p < pa.n_pen; ++p) {
-        in.ptr[in.n++] = pa.aux[p];
+        const bool elementwise = pa.kind[p] == B2_PEN_NONNEG || pa.kind[p] == B2_PEN_BOX || pa.kind[p] == B2_PEN_L1;
+        if (!((deferred & 2) && elementwise)) in.ptr[in.n++] = pa.aux[p];  // T-only state: the aux slot is not read
         in.ptr[in.n++] = pa.dual[p];
     }
     for (int a = 0; a < in.n; ++a)

@@ -130,7 +130,7 @@ pf2_rowpass_mma_kernel(const int64_t* __restrict__ row_off, int R, RowpassInputs
     // ===== consumers: stage the slice operators while the first tiles are in flight =====
     const int ctid = tid, cthreads = kConsWarps * 32;
     stage_operator<PL, T>(Minv + (size_t)g_slice * RR, R, Ms, ctid, cthreads);
-    if (deferred) {
+    if (deferred & 1) {
         // T_g = W_g Delta, formed in position order directly (R^3 FMAs per CTA)
         const T* Wg = Wmat + (size_t)g_slice * RR;
         for (int e = ctid; e < PL::NPOS * PL::LDM; e += cthreads) {
@@ -152,6 +152,8 @@ pf2_rowpass_mma_kernel(const int64_t* __restrict__ row_off, int R, RowpassInputs
 
     const int g = lane >> 2, t = lane & 3;
     const double rg = (double)rho[g_slice];
+    const bool tin = (deferred & 2) != 0, tout = (deferred & 4) != 0;  // T-only state of the elementwise extras
+    deferred &= 1;
     double sc[NB][2];
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
@@ -197,16 +199,40 @@ pf2_rowpass_mma_kernel(const int64_t* __restrict__ row_off, int R, RowpassInputs
                     sh[b][e] = pd[b][e] - v[b][e];
                 }
         }
+        {
+            int ai = a_idx;
 #pragma unroll
-        for (int p = 0; p < NEXTRA; ++p) {
-            {
-                double ax[NB][2];
-                load_row<PL, T>(st + (uint32_t)(a_idx + 2 * p) * arr_bytes, t, R, valid, ax);
-                load_row<PL, T>(st + (uint32_t)(a_idx + 2 * p + 1) * arr_bytes, t, R, valid, du[p]);
+            for (int p = 0; p < NEXTRA; ++p) {
+                const int kind = pa.kind[p + 1];
+                const bool elementwise = kind == B2_PEN_NONNEG || kind == B2_PEN_BOX || kind == B2_PEN_L1;
+                if (tin && elementwise) {
+                    // T-only state: the dual slot holds the previous prox argument T = x + dual; aux = prox(T) and
+                    // dual = T - aux are recomputed (bit-identical to what the explicit path would have stored)
+                    double tt[NB][2];
+                    load_row<PL, T>(st + (uint32_t)ai * arr_bytes, t, R, valid, tt);
+                    ai += 1;
+                    const int nn = pa.nn[p + 1];
+                    const T p0 = (T)pa.p0[p + 1], p1 = (T)pa.p1[p + 1];
 #pragma unroll
-                for (int b = 0; b < NB; ++b)
+                    for (int b = 0; b < NB; ++b)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) sh[b][e] += ax[b][e] - du[p][b][e];
+                        for (int e = 0; e < 2; ++e) {
+                            const bool ok = valid && reg_col<PL>(b, e, t, R) >= 0;
+                            const T tv = (T)tt[b][e];
+                            const T z = ok ? prox_elem<T>(tv, kind, nn, p0, p1, (T)rg) : T(0);
+                            du[p][b][e] = ok ? (double)(tv - z) : 0.0;
+                            sh[b][e] += (double)z - du[p][b][e];
+                        }
+                } else {
+                    double ax[NB][2];
+                    load_row<PL, T>(st + (uint32_t)ai * arr_bytes, t, R, valid, ax);
+                    load_row<PL, T>(st + (uint32_t)(ai + 1) * arr_bytes, t, R, valid, du[p]);
+                    ai += 2;
+#pragma unroll
+                    for (int b = 0; b < NB; ++b)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) sh[b][e] += ax[b][e] - du[p][b][e];
+                }
             }
         }
         double sv[NB][2], xv[NB][2];
@@ -259,7 +285,15 @@ pf2_rowpass_mma_kernel(const int64_t* __restrict__ row_off, int R, RowpassInputs
                             zo[b][e] = (double)z;
                             dn[b][e] = elementwise ? (double)(vv - z) : (double)vv;
                         }
-                    if (elementwise) store_row<PL, T>((T*)pa.aux[p + 1] + goff, t, R, zo);
+                    if (elementwise && tout) {
+                        // T-only state: keep the prox argument, the next pass recomputes aux and dual from it
+#pragma unroll
+                        for (int b = 0; b < NB; ++b)
+#pragma unroll
+                            for (int e = 0; e < 2; ++e) dn[b][e] = (double)((T)xv[b][e] + (T)du[p][b][e]);
+                    } else if (elementwise) {
+                        store_row<PL, T>((T*)pa.aux[p + 1] + goff, t, R, zo);
+                    }
                     store_row<PL, T>((T*)pa.dual[p + 1] + goff, t, R, dn);  // column-coupled: V, finished later
                 }
             }

@@ -700,7 +700,7 @@ def test_device_mt19937_continues_numpy_randomstate(seed, skip, n):
     np.testing.assert_array_equal(rs.standard_normal(size=3), ref.standard_normal(size=3))
 
 
-@pytest.mark.parametrize("R", [1, 2, 3, 7, 8, 20, 31, 32])
+@pytest.mark.parametrize("R", [1, 2, 3, 4, 5, 7, 8, 13, 16, 17, 20, 21, 24, 25, 31, 32])
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
 def test_parafac2_polar_warp_vs_cta_and_numpy(R, dtype):
     """B2_OPT_POLAR_WARP (default): the warp-per-slice Jacobi polar kernel against the CTA-per-slice one and against
@@ -717,7 +717,7 @@ def test_parafac2_polar_warp_vs_cta_and_numpy(R, dtype):
     Sd, Dd, rd = dev(S, tdt), dev(Delta, tdt), dev(rho, tdt)
     out = {}
     try:
-        for variant in (1, 0):
+        for variant in (2, 1, 0):  # registers (falls back to 1 above rank 24), shared-memory warp, CTA per slice
             lib.b2_set_option(_lib.OPT_POLAR_WARP, variant)
             Wm = torch.zeros(G, R, R, dtype=tdt, device="cuda")
             num = torch.zeros(G, R, R, dtype=torch.float64, device="cuda")
@@ -727,11 +727,13 @@ def test_parafac2_polar_warp_vs_cta_and_numpy(R, dtype):
             _ops.pf2_polar(Sd, Dd, rd, G, R, Wm, num, Q, warm=True)
             out[variant] = cold + (Wm.double().cpu().numpy(), num.cpu().numpy())
     finally:
-        lib.b2_set_option(_lib.OPT_POLAR_WARP, 1)
+        lib.b2_set_option(_lib.OPT_POLAR_WARP, 2)
     tol = 1e-9 if dtype == "f64" else 2e-4
-    for a, b in zip(out[1], out[0]):
-        np.testing.assert_allclose(a, b, rtol=tol, atol=tol)
-    np.testing.assert_allclose(out[1][2], out[1][0], rtol=tol, atol=tol)  # warm == cold
+    for variant in (2, 1):
+        for a, b in zip(out[variant], out[0]):
+            np.testing.assert_allclose(a, b, rtol=tol, atol=tol)
+        np.testing.assert_allclose(out[variant][2], out[variant][0], rtol=tol, atol=tol)  # warm == cold
+    out[1] = out[2]
     if dtype == "f64":
         for g in range(0, G, 37):
             U, _, Vh = np.linalg.svd(V[g] @ Delta.T, full_matrices=False)
