@@ -131,15 +131,24 @@ pf2_rowpass_mma_kernel(const int64_t* __restrict__ row_off, int R, RowpassInputs
     const int ctid = tid, cthreads = kConsWarps * 32;
     stage_operator<PL, T>(Minv + (size_t)g_slice * RR, R, Ms, ctid, cthreads);
     if (deferred & 1) {
-        // T_g = W_g Delta, formed in position order directly (R^3 FMAs per CTA)
+        // T_g = W_g Delta, formed in position order directly (R^3 FMAs per CTA).  W_g and Delta are first staged in
+        // shared memory (the Gram tiles are free until the row loop): ONE global round trip instead of 2 R dependent
+        // ones per thread in the k loop.
+        double* wsm = gtiles;
+        double* dsm = gtiles + RR;
         const T* Wg = Wmat + (size_t)g_slice * RR;
+        for (int e = ctid; e < RR; e += cthreads) {
+            wsm[e] = (double)Wg[e];
+            dsm[e] = (double)Delta[e];
+        }
+        consumer_barrier();
         for (int e = ctid; e < PL::NPOS * PL::LDM; e += cthreads) {
             const int pr = e / PL::LDM, pc = e - pr * PL::LDM;
             double v = 0.0;
             if (pc < PL::NPOS) {
                 const int r = PL::col_of(pr, R), c = PL::col_of(pc, R);
                 if (r >= 0 && c >= 0)
-                    for (int k = 0; k < R; ++k) v = fma((double)Wg[r * R + k], (double)Delta[k * R + c], v);
+                    for (int k = 0; k < R; ++k) v = fma(wsm[r * R + k], dsm[k * R + c], v);
             }
             Ts[e] = v;
         }

@@ -28,9 +28,17 @@ def _load_case(name):
     off = g["row_offsets"]
     X = [g["X"][a:b] for a, b in zip(off[:-1], off[1:])]
     kw = json.loads(str(g["kwargs"]))
-    for key in ("l1_penalty", "non_negative", "unimodal", "l2_norm_bound", "lower_bound", "upper_bound"):
+    for key in ("l1_penalty", "non_negative", "unimodal", "l2_norm_bound", "lower_bound", "upper_bound", "tv_penalty"):
         if isinstance(kw.get(key), dict):
             kw[key] = {int(k): v for k, v in kw[key].items()}
+    if isinstance(kw.get("generalized_l2_penalty"), dict):
+        kw["generalized_l2_penalty"] = {int(k): np.asarray(v, dtype=np.float64)
+                                        for k, v in kw["generalized_l2_penalty"].items()}
+    if "regs_spec" in kw:
+        from matcouply_b200 import penalties as P
+        from oracle.aoadmm_oracle import regs_from_spec
+
+        kw["regs"] = regs_from_spec(kw.pop("regs_spec"), P)
     return g, X, int(g["rank"]), kw
 
 
@@ -63,7 +71,9 @@ def _rel(a, b):
     return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
 
 
-@pytest.mark.parametrize("name", ["c2_nn_pf2_l1_ragged", "c1_nn_cmf", "c3_unimodal_l2ball_pf2", "c0_readme"])
+@pytest.mark.parametrize("name", ["c2_nn_pf2_l1_ragged", "c1_nn_cmf", "c3_unimodal_l2ball_pf2", "c0_readme",
+                                  "gl2_smooth_B_pf2", "tv_B_ragged_constB", "simplex_B_ragged", "pf2_n_iter3_nn",
+                                  "pf2_frozen_basis", "tv_C_l1"])
 def test_two_rank_run_matches_reference_trajectory(name, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
