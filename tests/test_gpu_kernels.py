@@ -866,3 +866,57 @@ def test_parafac2_prox_options_vs_oracle(opts):
     for b, o in zip(bases, ob):
         np.testing.assert_allclose(b, o, atol=1e-10)
     np.testing.assert_allclose(new_delta, od, atol=1e-10)
+
+
+@pytest.mark.parametrize("mma", [1, 0])
+@pytest.mark.parametrize("dtype", ["f64", "f32"])
+@pytest.mark.parametrize("R", [3, 4, 6, 20, 32])
+def test_pf2_rowpass_single_array_companions_bit_identical(R, dtype, mma):
+    """`deferred` flag bits 2 / 4 of b2_pf2_rowpass: elementwise companions carried between passes as ONE array
+    T = x + dual.  Four chained passes (explicit in, T, T, explicit out) must leave bit-identical x, V, aux and dual
+    as four explicit passes, for both formulations of the kernel, with a column-coupled companion left untouched."""
+    _lib, _ops, _ = _imports()
+    lib = _lib.load()
+    tdt = torch.float64 if dtype == "f64" else torch.float32
+    rs = np.random.RandomState(91 + R)
+    G = 6
+    sizes, off, _ = ragged(rs, G, 1, 150, R)
+    N = int(off[-1])
+    f = lambda *s: rs.standard_normal(size=s)  # noqa: E731
+    Y, A, rho = f(N, R), rs.uniform(0.5, 1.5, size=(G, R)), rs.uniform(0.5, 2.0, size=G)
+    Minv = np.stack([np.linalg.inv(m @ m.T + R * np.eye(R)) for m in f(G, R, R)]) * 0.5
+    Wm, Delta = f(G, R, R) / np.sqrt(R), f(R, R) / np.sqrt(R)
+    init = dict(pf_aux=f(N, R), pf_dual=f(N, R), nn_aux=f(N, R), nn_dual=f(N, R), l2_aux=f(N, R), l2_dual=f(N, R))
+    offd = dev(off, torch.int64)
+    results = {}
+    lib.b2_set_option(_lib.OPT_PF2_ROWPASS_MMA, mma)
+    try:
+        for single in (False, True):
+            d = {k: dev(v, tdt) for k, v in init.items()}
+            pens = [(_lib.PEN_PARAFAC2, 0, 0, 0, d["pf_aux"], d["pf_dual"]),
+                    (_lib.PEN_L1, 1, 0.2, 0, d["nn_aux"], d["nn_dual"]),
+                    (_lib.PEN_L2BALL, 0, 1.0, 0, d["l2_aux"], d["l2_dual"])]
+            descs = _ops.make_descs(pens)
+            x = torch.zeros((N, R), dtype=tdt, device="cuda")
+            Wp = _ops.alloc_w(N, R, tdt, "cuda")
+            S = torch.zeros((G, R, R), dtype=tdt, device="cuda")
+            BtB = torch.zeros((G, R, R), dtype=tdt, device="cuda")
+            n_pass = 4
+            for it in range(n_pass):
+                last = it == n_pass - 1
+                flags = 1 if it > 0 else 0
+                if single:
+                    flags |= (2 if it > 0 else 0) | (0 if last else 4)
+                _ops.pf2_rowpass(offd, G, R, dev(Y, tdt), dev(A, tdt), dev(rho, tdt), dev(Minv, tdt), descs, 3, flags,
+                                 dev(Wm, tdt), dev(Delta, tdt), x if last else None, Wp if last else None, S,
+                                 BtB if last else None)
+                # the column-coupled companion is finished by its own kernel after every pass, as in the engine
+                _ops.prox_l2ball(d["l2_aux"], d["l2_dual"], offd, G, R, 1.0, 0)
+            torch.cuda.synchronize()
+            results[single] = {k: v.cpu().numpy().copy() for k, v in d.items() if k != "pf_aux"}
+            results[single]["x"] = x.cpu().numpy().copy()
+            results[single]["S"] = S.cpu().numpy().copy()
+    finally:
+        lib.b2_set_option(_lib.OPT_PF2_ROWPASS_MMA, 1)
+    for k in results[False]:
+        np.testing.assert_array_equal(results[True][k], results[False][k], err_msg=k)
