@@ -40,6 +40,9 @@ CONFIGS = {
     "c3": dict(I=8192, K=256, J=(1024, 1024), R=8, dtype="f64",
                kw=dict(non_negative=True, parafac2=True, unimodal={1: True}, l2_norm_bound=[0, 1, 1]),
                desc="BASELINE config[3]: unimodal + L2Ball PARAFAC2, 8192 slices 1024x256, R=8, fp64"),
+    "c3f32": dict(I=8192, K=256, J=(1024, 1024), R=8, dtype="f32",
+                  kw=dict(non_negative=True, parafac2=True, unimodal={1: True}, l2_norm_bound=[0, 1, 1]),
+                  desc="BASELINE config[3]: unimodal + L2Ball PARAFAC2, 8192 slices 1024x256, R=8, fp32"),
     "c4": dict(I=8192, K=2048, J=(512, 512), R=32, dtype="f64", kw=dict(non_negative=True),
                desc="BASELINE config[4] per-GPU share: nonneg CMF, 8192 slices 512x2048, R=32, fp64"),
 }
