@@ -236,6 +236,91 @@ def _loss(diag, norm_X_sq, l2_penalty, regs, host_factors=None):
     return rec_error, 0.5 * rec_error ** 2 + l2reg + reg_penalty
 
 
+# ----------------------------------------------------------------------------------------------------------
+# the three sub-solvers as stand-alone calls (reference decomposition.py:120-344; the reference's own tests drive
+# them directly, tests/test_decomposition.py:1018-1443)
+# ----------------------------------------------------------------------------------------------------------
+def _single_mode_update(mode, matrices, reg, cmf, aux_list, dual_list, l2_penalty, inner_n_iter_max, inner_tol,
+                        feasibility_penalty_scale, constant_feasibility_penalty):
+    import torch
+
+    from ._engine import AOADMMEngine, PackedMatrices
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("matcouply_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    weights, (A, B_is, C) = cmf
+    if weights is not None:
+        A = A * weights
+    device = torch.device("cuda", torch.cuda.current_device())
+    matrices = list(matrices)
+    all_f32 = all(str(getattr(m, "dtype", "")).endswith("float32") for m in matrices)
+    packed = PackedMatrices.from_list(matrices, torch.float32 if all_f32 else torch.float64, device)
+    regs, l2 = [[], [], []], [0, 0, 0]
+    regs[mode] = list(reg)
+    l2[mode] = l2_penalty if l2_penalty else 0
+    engine = AOADMMEngine(packed, int(np.asarray(C).shape[1]), regs, l2_penalty=l2,
+                          feasibility_penalty_scale=feasibility_penalty_scale,
+                          constant_A=bool(constant_feasibility_penalty) and mode == 0,
+                          constant_B=bool(constant_feasibility_penalty) and mode == 1,
+                          inner_n_iter_max=inner_n_iter_max, update=(mode == 0, mode == 1, mode == 2),
+                          inner_tol=inner_tol)
+    auxes, duals = [[], [], []], [[], [], []]
+    auxes[mode], duals[mode] = list(aux_list), list(dual_list)
+    engine.load_state(np.asarray(A), [np.asarray(b) for b in B_is], np.asarray(C), auxes, duals)
+    engine.prepare()  # Y = X C, B_i^T B_i, cross products and right-hand sides for the given factors
+    (engine.step_A, engine.step_B, engine.step_C)[mode]()
+    A1, B1, C1 = engine.factors()
+    aux_out, dual_out = engine.admm_vars()
+    extra = None
+    if mode == 0:
+        f64 = lambda t: t.detach().to(torch.float64).cpu().numpy()  # noqa: E731
+        extra = (list(f64(engine.rhsA)), list(f64(engine.cross)))
+    return (None, [A1, B1, C1]), aux_out[mode], dual_out[mode], extra
+
+
+def admm_update_A(matrices, reg, cmf, A_aux_list, A_dual_list, l2_penalty, inner_n_iter_max, inner_tol,
+                  feasibility_penalty_scale, constant_feasibility_penalty, svd_fun=None):
+    """One A-mode ADMM update (decomposition.py:120-219) on the CUDA path; also returns ``(rhses, cross_products)``
+    (:219) that the fit term reuses.  ``svd_fun`` is accepted for signature compatibility (the normal matrices are
+    factorised with Cholesky on the device)."""
+    return _single_mode_update(0, matrices, reg, cmf, A_aux_list, A_dual_list, l2_penalty, inner_n_iter_max, inner_tol,
+                               feasibility_penalty_scale, constant_feasibility_penalty)
+
+
+def admm_update_B(matrices, reg, cmf, B_is_aux_list, B_is_dual_list, l2_penalty, inner_n_iter_max, inner_tol,
+                  feasibility_penalty_scale, constant_feasibility_penalty, svd_fun=None):
+    """One B-mode ADMM update (decomposition.py:222-292) on the CUDA path."""
+    return _single_mode_update(1, matrices, reg, cmf, B_is_aux_list, B_is_dual_list, l2_penalty, inner_n_iter_max,
+                               inner_tol, feasibility_penalty_scale, constant_feasibility_penalty)[:3]
+
+
+def admm_update_C(matrices, reg, cmf, C_aux_list, C_dual_list, l2_penalty, inner_n_iter_max, inner_tol,
+                  feasibility_penalty_scale, svd_fun=None):
+    """One C-mode ADMM update (decomposition.py:295-344) on the CUDA path."""
+    return _single_mode_update(2, matrices, reg, cmf, C_aux_list, C_dual_list, l2_penalty, inner_n_iter_max, inner_tol,
+                               feasibility_penalty_scale, False)[:3]
+
+
+def _cmf_reconstruction_error(matrices, cmf, norm_matrices=None, intermediate_A_calculations=None):
+    """||X - X_hat||_F (decomposition.py:420-452), from the expanded form evaluated on the device: one pass over X
+    (Y = X C) plus per-slice R x R products."""
+    import torch
+
+    from ._engine import AOADMMEngine, PackedMatrices
+
+    weights, (A, B_is, C) = cmf
+    if weights is not None:
+        A = A * weights
+    device = torch.device("cuda", torch.cuda.current_device())
+    packed = PackedMatrices.from_list(list(matrices), torch.float64, device)
+    engine = AOADMMEngine(packed, int(np.asarray(C).shape[1]), [[], [], []])
+    engine.load_state(np.asarray(A), [np.asarray(b) for b in B_is], np.asarray(C), [[], [], []], [[], [], []])
+    engine.prepare()
+    inner, quad = engine.diagnostics()["fit"]
+    norm_X_sq = engine.normX_sq if norm_matrices is None else norm_matrices ** 2
+    return float(np.sqrt(max(0, norm_X_sq - 2 * inner + quad)))
+
+
 def cmf_aoadmm(
     matrices,
     rank,

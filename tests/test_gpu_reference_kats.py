@@ -200,3 +200,72 @@ def test_frozen_modes_regs_untouched_and_validation():
     with pytest.raises(AttributeError):
         cmf_aoadmm(mats, 3, n_iter_max=1, l2_norm_bound={0: 1.0})
     cmf_aoadmm(mats, 3, n_iter_max=1, l2_norm_bound={0: 1.0}, constant_feasibility_penalty="A")
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_admm_update_functions_like_the_reference_tests(mode):
+    """admm_update_A / _B / _C called directly with the reference's signature (tests/test_decomposition.py:1018-1100,
+    1263-1361, 1364-1443): (i) exact data + non-negativity + many inner iterations recover the true factor,
+    (ii) one call with random ADMM state equals the oracle's sub-solver, (iii) feasibility gaps of the returned aux."""
+    from matcouply_b200 import decomposition as D
+    from matcouply_b200.penalties import L1Penalty, NonNegativity
+    from oracle import aoadmm_oracle as O
+
+    rs, A, B_is, C, mats = _ragged_cmf(20 + mode, rank=3, I=6, K=7)
+    fun = (D.admm_update_A, D.admm_update_B, D.admm_update_C)[mode]
+    shapes_aux = (A.shape, None, C.shape)
+
+    def rnd_state():
+        if mode == 1:
+            return [rs.uniform(size=b.shape) for b in B_is], [rs.uniform(size=b.shape) for b in B_is]
+        return rs.uniform(size=shapes_aux[mode]), rs.uniform(size=shapes_aux[mode])
+
+    # (i) recovery from a perturbed start, everything else at the truth
+    start = [A.copy(), [b.copy() for b in B_is], C.copy()]
+    if mode == 1:
+        start[1] = [rs.uniform(size=b.shape) for b in B_is]
+    else:
+        start[mode] = rs.uniform(size=start[mode].shape)
+    aux, dual = rnd_state()
+    args = (mats, [NonNegativity()], (None, start), [aux], [dual], 0, 2000, None, 1)
+    out = fun(*args, False, None) if mode != 2 else fun(*args, None)
+    got = out[0][1][mode]
+    if mode == 1:
+        for b, bt in zip(got, B_is):
+            np.testing.assert_allclose(b, bt, rtol=1e-5, atol=1e-7)
+    else:
+        np.testing.assert_allclose(got, (A, None, C)[mode], rtol=1e-5, atol=1e-7)
+    # (ii) five inner iterations from a random state against the oracle's sub-solver, two penalties
+    start = [rs.uniform(size=A.shape), [rs.uniform(size=b.shape) for b in B_is], rs.uniform(size=C.shape)]
+    a1, d1 = rnd_state()
+    a2, d2 = rnd_state()
+    cp = lambda v: [x.copy() for x in v] if isinstance(v, list) else v.copy()  # noqa: E731
+    regs_p = [NonNegativity(), L1Penalty(0.05)]
+    regs_o = [O.NonNeg(), O.L1P(0.05)]
+    args = (mats, regs_p, (None, [start[0].copy(), cp(start[1]), start[2].copy()]), [cp(a1), cp(a2)], [cp(d1), cp(d2)],
+            0.1, 5, None, 1.5)
+    out = fun(*args, False, None) if mode != 2 else fun(*args, None)
+    if mode == 1:
+        ref, raux, rdual = O.solve_mode_B(mats, regs_o, start[0], cp(start[1]), start[2], [cp(a1), cp(a2)],
+                                          [cp(d1), cp(d2)], 0.1, 5, 1.5, False)
+        np.testing.assert_allclose(np.concatenate(out[0][1][1]), np.concatenate(ref), rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(np.concatenate(out[1][1]), np.concatenate(raux[1]), rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(np.concatenate(out[2][0]), np.concatenate(rdual[0]), rtol=1e-9, atol=1e-12)
+    elif mode == 2:
+        ref, raux, rdual = O.solve_mode_C(mats, regs_o, start[0], start[1], start[2].copy(), [a1.copy(), a2.copy()],
+                                          [d1.copy(), d2.copy()], 0.1, 5, 1.5)
+        np.testing.assert_allclose(out[0][1][2], ref, rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(out[1][1], raux[1], rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(out[2][0], rdual[0], rtol=1e-9, atol=1e-12)
+    else:
+        ref, raux, rdual, inter = O.solve_mode_A(mats, regs_o, start[0].copy(), start[1], start[2], [a1.copy(), a2.copy()],
+                                                 [d1.copy(), d2.copy()], 0.1, 5, 1.5, False)
+        np.testing.assert_allclose(out[0][1][0], ref, rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(out[1][1], raux[1], rtol=1e-9, atol=1e-12)
+        rhses, cross = out[3]
+        np.testing.assert_allclose(np.stack(rhses), np.stack(inter[0]), rtol=1e-10)
+        np.testing.assert_allclose(np.stack(cross), np.stack(inter[1]), rtol=1e-10)
+    # fit term helper (decomposition.py:420-452)
+    noisy = [m + 0.05 * rs.standard_normal(size=m.shape) for m in mats]
+    naive = np.sqrt(sum(np.sum((x - (b * a) @ C.T) ** 2) for x, b, a in zip(noisy, B_is, A)))
+    np.testing.assert_allclose(D._cmf_reconstruction_error(noisy, (None, (A, B_is, C))), naive, rtol=1e-9)
