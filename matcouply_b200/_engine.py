@@ -27,7 +27,7 @@ from . import _lib, _ops
 _ENGINE_PROX_KINDS = (_lib.PEN_GL2, _lib.PEN_SIMPLEX, _lib.PEN_TV)
 
 # Kernel-fusion switches (tests flip them to cross-check the fused kernels against the one-kernel-per-step path).
-FUSION_DEFAULTS = {"local": True, "pf2": True}
+FUSION_DEFAULTS = {"local": True, "pf2": True, "overlap": True}
 
 
 def _stack_rows(mats):
@@ -297,6 +297,11 @@ class AOADMMEngine:
         if any(d[0] == _lib.PEN_UNIMODAL for d in self.modes[1].desc):
             uni = (I, R, self.max_rows)
         self.ws = _ops.Workspace(dev, K, R, dt, unimodal_shape=uni)
+        # second stream for the fork/join of the PARAFAC2 inner iteration (see _step_B_pf2_fused)
+        self.overlap_streams = FUSION_DEFAULTS.get("overlap", True) and self.world == 1
+        if self.has_pf2:
+            self._side = torch.cuda.Stream(device=dev)
+            self._ev_fork, self._ev_join = torch.cuda.Event(), torch.cuda.Event()
         self.n_xstream_launches = 0
         self.xstream_events = None  # set to {"y": [], "z": []} to record (start, end) CUDA events per launch
 
@@ -590,7 +595,14 @@ class AOADMMEngine:
             _ops.pf2_rowpass(self.row_off, I, R, self.Y, A, self.rhoB, self.MinvB, st.descs_c, len(st.desc),
                              flags, self.Wmat, self.Delta, st.x if last else None,
                              self.Wpad if last else None, self.S, self.BtB if last else None)
-            for p, (kind, nn, p0, _p1) in enumerate(st.desc):  # column-coupled companions (V is in their dual slot)
+            # The polar step + Delta reduction only need S (from the row pass); the column-coupled companions only
+            # need their own pre-image.  With such companions (Unimodality above all: a latency-bound kernel that
+            # leaves most of the SM idle) the two chains run on two streams and join before the next row pass.
+            coupled = [p for p, d in enumerate(st.desc) if p > 0 and d[0] not in
+                       (_lib.PEN_NONNEG, _lib.PEN_BOX, _lib.PEN_L1)]
+            fork = bool(coupled) and self.overlap_streams
+            def companion(p):  # V is in the companion's dual slot
+                kind, nn, p0, _p1 = st.desc[p]
                 if kind == _lib.PEN_L2BALL:
                     _ops.prox_l2ball(st.aux[p], st.dual[p], self.row_off, I, R, p0, nn)
                 elif kind == _lib.PEN_UNIMODAL:
@@ -600,16 +612,41 @@ class AOADMMEngine:
                                             self.N)
                 elif kind == _lib.PEN_HOST:
                     self._host_prox(st, p, self.row_off, I, self.rhoB)
-            # cold Jacobi start on the first inner iteration (bounds the round-off drift of the accumulated
-            # rotations), warm start from the previous inner iteration's eigenvectors afterwards
-            for sub in range(int(st.regs[0].n_iter)):  # Parafac2(n_iter=...): alternations on the same V (penalties.py:1229)
-                _ops.pf2_polar(self.S, self.Delta, self.rhoB, I, R, self.Wmat, self.num_part, self.pf2_Q,
-                               warm=it > 0 or sub > 0)
-                self._pf2_delta_update(self.rhoB, I)
+
+            if fork:
+                # main stream: the most expensive companion (Unimodality if present); side stream: polar + Delta and
+                # the remaining companions (independent arrays)
+                order = sorted(coupled, key=lambda p: st.desc[p][0] != _lib.PEN_UNIMODAL)
+                device_only = [p for p in order[1:] if st.desc[p][0] != _lib.PEN_HOST]
+                main = torch.cuda.current_stream(self.dev)
+                self._ev_fork.record(main)
+                with torch.cuda.stream(self._side):
+                    self._side.wait_event(self._ev_fork)
+                    self._pf2_polar_delta(st, I, it)
+                    for p in device_only:
+                        companion(p)
+                    self._ev_join.record(self._side)
+                for p in order:
+                    if p == order[0] or p not in device_only:
+                        companion(p)
+                main.wait_event(self._ev_join)
+            else:
+                for p in coupled:
+                    companion(p)
+                self._pf2_polar_delta(st, I, it)
         # P Delta and dual = V - P Delta stay implicit: the next row pass and the gap reduction apply W_g Delta on the fly
         self.pf2_deferred = True
         self.pf2_fresh = True
         self.w_fresh = True
+
+    def _pf2_polar_delta(self, st, I, it):
+        """Polar step + coordinate-matrix update of one inner iteration (penalties.py:1229-1245)."""
+        # cold Jacobi start on the first inner iteration (bounds the round-off drift of the accumulated
+        # rotations), warm start from the previous inner iteration's eigenvectors afterwards
+        for sub in range(int(st.regs[0].n_iter)):  # Parafac2(n_iter=...): alternations on the same V
+            _ops.pf2_polar(self.S, self.Delta, self.rhoB, I, self.R, self.Wmat, self.num_part, self.pf2_Q,
+                           warm=it > 0 or sub > 0)
+            self._pf2_delta_update(self.rhoB, I)
 
     def _row_local(self, st):
         """True when every penalty of the mode is elementwise (the fused b2_admm_local path applies)."""
