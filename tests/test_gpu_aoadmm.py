@@ -276,3 +276,47 @@ def test_user_defined_python_penalty_is_bridged():
     for a, b in zip((ref[1][0], np.concatenate(ref[1][1]), ref[1][2]), (got[1][0], np.concatenate(got[1][1]), got[1][2])):
         assert rel(b, a) < 1e-12
     np.testing.assert_allclose(dgot.regularized_loss, dref.regularized_loss, rtol=1e-12)
+
+
+def test_config2_width_properties_on_device_resident_input():
+    """BASELINE config 2 at full WIDTH (K = 1024, R = 20, ragged J_i in [256, 2048]) on 192 slices (1.8 GB) held as a
+    device-resident PackedMatrices: too big for the oracle, so size-independent properties are checked — orthonormal
+    PARAFAC2 bases, B_i = P_i Delta up to the reported feasibility gap, non-negative auxiliary variables, the expanded
+    fit term against the naive residual, monotone loss once feasible, and bit-identical repeatability."""
+    import bench
+    from matcouply_b200 import cmf_aoadmm
+
+    cfg = dict(bench.CONFIGS["c2"])
+    cfg["I"] = 192
+    sizes = bench.slice_sizes(cfg)
+    dev_ = torch.device("cuda", 0)
+    packed = bench.gen_device_data(cfg, sizes, 0, cfg["I"], torch.float64, dev_)
+    kw = dict(non_negative=True, parafac2=True, l1_penalty={2: 0.1}, random_state=0, n_iter_max=12, tol=None,
+              absolute_tol=None, return_errors=True, return_admm_vars=True)
+    cmf, admm, diag = cmf_aoadmm(packed, cfg["R"], **kw)
+    _, (A, B_is, C) = cmf
+    assert np.all(np.isfinite(diag.regularized_loss)) and diag.n_iter == 12
+    assert diag.regularized_loss[-1] < diag.regularized_loss[1]
+    bases, delta = admm.auxes[1][0]
+    gap_pf2 = diag.feasibility_gaps[-1][1][0]
+    num = den = 0.0
+    for i in (0, 1, 57, 191):
+        P = bases[i]
+        np.testing.assert_allclose(P.T @ P, np.eye(cfg["R"]), atol=1e-9)
+        num += np.sum((P @ delta - B_is[i]) ** 2)
+        den += np.sum(B_is[i] ** 2)
+    assert np.sqrt(num / den) < 3 * gap_pf2 + 1e-12  # sampled slices vs the all-slice gap
+    assert min(a.min() for a in admm.auxes[1][1]) >= 0 and admm.auxes[0][0].min() >= 0
+    # naive residual on the device vs the expanded fit formula (decomposition.py:446-452)
+    X, off = packed.X[:, :packed.K], packed.row_offsets
+    Ct = torch.as_tensor(C, device=dev_).T.contiguous()
+    sse = normx = 0.0
+    for i in range(cfg["I"]):
+        Xi = X[off[i]:off[i + 1]]
+        Bi = torch.as_tensor(B_is[i] * A[i], device=dev_)
+        sse += float(((Xi - Bi @ Ct) ** 2).sum())
+        normx += float((Xi ** 2).sum())
+    np.testing.assert_allclose(diag.rec_errors[-1], np.sqrt(sse / normx), rtol=1e-9)
+    cmf2, _, diag2 = cmf_aoadmm(packed, cfg["R"], **kw)
+    np.testing.assert_array_equal(cmf2[1][2], C)
+    np.testing.assert_array_equal(np.asarray(diag2.regularized_loss), np.asarray(diag.regularized_loss))
