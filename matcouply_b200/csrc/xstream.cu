@@ -285,7 +285,8 @@ struct ZCfg {
     static constexpr int BOX_BYTES = TMZ * 128;
 };
 
-template <typename T, int RP>
+// VECW: the W tile rows are 16-byte aligned and exactly RP wide, so a row is read with 128-bit broadcast loads.
+template <typename T, int RP, bool VECW>
 __global__ void __launch_bounds__(kThreads, 1)
 xstream_z_kernel(const __grid_constant__ CUtensorMap tmap_x, const T* __restrict__ W, int ldw, T* __restrict__ part, int K,
                  int R, int KZ, int num_tiles, int stages) {
@@ -355,11 +356,21 @@ xstream_z_kernel(const __grid_constant__ CUtensorMap tmap_x, const T* __restrict
             T x[EPC];
             *(int4*)x = lds_b128(box + swz128(r, chunk));
             const uint32_t wr = Ws + (uint32_t)(r * ldw * sizeof(T));
+            if constexpr (VECW) {
+                T wv[RP];
 #pragma unroll
-            for (int c = 0; c < RP; ++c) {
-                const T w = (c < R) ? lds_elem<T>(wr + c * (uint32_t)sizeof(T)) : T(0);
+                for (int v = 0; v < (int)(RP * sizeof(T) / 16); ++v) *((int4*)wv + v) = lds_b128(wr + 16 * v);
 #pragma unroll
-                for (int e = 0; e < EPC; ++e) acc[e][c] = fma(x[e], w, acc[e][c]);
+                for (int c = 0; c < RP; ++c)
+#pragma unroll
+                    for (int e = 0; e < EPC; ++e) acc[e][c] = fma(x[e], wv[c], acc[e][c]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < RP; ++c) {
+                    const T w = (c < R) ? lds_elem<T>(wr + c * (uint32_t)sizeof(T)) : T(0);
+#pragma unroll
+                    for (int e = 0; e < EPC; ++e) acc[e][c] = fma(x[e], w, acc[e][c]);
+                }
             }
         }
         int dep = 0;
@@ -713,9 +724,20 @@ int xstream_y_impl(const void* X, long long N, int K, int ldx, const void* C, in
 template <typename T, int RP>
 int launch_z(const CUtensorMap& map, const T* W, int ldw, T* part, int K, int R, int KZ, int num_tiles, dim3 grid,
              int threads, int stages, size_t smem, cudaStream_t st) {
-    auto kern = xstream_z_kernel<T, RP>;
-    B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, threads, smem, st>>>(map, W, ldw, part, K, R, KZ, num_tiles, stages);
+    const bool vecw = RP == R && ((size_t)ldw * sizeof(T)) % 16 == 0 && (RP * sizeof(T)) % 16 == 0;
+    if (vecw) {
+        auto kern = xstream_z_kernel<T, RP, true>;
+        B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                           (int)cudaSharedmemCarveoutMaxShared));
+        kern<<<grid, threads, smem, st>>>(map, W, ldw, part, K, R, KZ, num_tiles, stages);
+    } else {
+        auto kern = xstream_z_kernel<T, RP, false>;
+        B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                           (int)cudaSharedmemCarveoutMaxShared));
+        kern<<<grid, threads, smem, st>>>(map, W, ldw, part, K, R, KZ, num_tiles, stages);
+    }
     B2_LAUNCH_CHECK();
     return B2_OK;
 }
@@ -801,11 +823,22 @@ int xstream_z_impl(const void* X, long long N, int K, int ldx, const void* W, in
     const int cons = ((KZ / Cfg::EPC + 31) / 32) * 32;
     const int threads = cons + 32;
     const int num_tiles = (int)((N + Cfg::TMZ - 1) / Cfg::TMZ);
-    int groups = b2_num_sms() / kblocks;
+    // narrow data (few consumer warps per k-block, e.g. fp32 with K = 256: 64 threads): several CTAs share an SM, each
+    // with its share of the shared memory, instead of one CTA with two busy warps
+    int ctas_per_sm = kConsumerThreads / cons;
+    if (ctas_per_sm > 4) ctas_per_sm = 4;
+    if (ctas_per_sm < 1 || kblocks > 1) ctas_per_sm = 1;
+    int groups = b2_num_sms() * ctas_per_sm / kblocks;
     if (max_ctas > 0 && max_ctas / kblocks < groups) groups = max_ctas / kblocks;
     if (groups < 1) groups = 1;
     if (groups > num_tiles) groups = num_tiles;
-    const size_t part_bytes = (size_t)groups * K * R * sizeof(T);
+    size_t part_bytes = (size_t)groups * K * R * sizeof(T);
+    while (part_bytes > ws_bytes && ctas_per_sm > 1) {  // a caller-sized workspace for one CTA per SM still works
+        --ctas_per_sm;
+        groups = b2_num_sms() * ctas_per_sm / kblocks;
+        if (groups > num_tiles) groups = num_tiles;
+        part_bytes = (size_t)groups * K * R * sizeof(T);
+    }
     B2_REQUIRE(ws_bytes >= part_bytes, "xstream_z workspace too small: need %zu bytes, got %zu", part_bytes, ws_bytes);
 
     alignas(64) CUtensorMap map;
@@ -814,7 +847,7 @@ int xstream_z_impl(const void* X, long long N, int K, int ldx, const void* W, in
     const uint32_t x_bytes = (uint32_t)(KZ / Cfg::EPB) * Cfg::BOX_BYTES;
     const uint32_t w_bytes = (uint32_t)(Cfg::TMZ * ldw * sizeof(T));
     const uint32_t stage_bytes = (x_bytes + w_bytes + 1023u) & ~1023u;
-    int stages = (int)((224 * 1024) / stage_bytes);
+    int stages = (int)(((224 * 1024) / ctas_per_sm - 2048) / stage_bytes);
     if (stages > 8) stages = 8;
     B2_REQUIRE(stages >= 2, "xstream_z: stage does not fit shared memory");
     const size_t smem = (size_t)stages * stage_bytes + 1024 + 2 * stages * sizeof(uint64_t);
@@ -865,7 +898,8 @@ size_t b2_xstream_workspace_bytes(int K, int R, int dtype) {
     const size_t es = dtype == B2_F64 ? 8 : 4;
     const size_t kp = (size_t)((K + 63) / 64) * 64;
     const size_t y = kp * 40 * es;
-    const size_t z = (size_t)b2_num_sms() * K * R * es;
+    // Z partials: one K x R block per CTA; narrow data runs up to 4 CTAs per SM (K <= 1024 elements per SM either way)
+    const size_t z = (size_t)b2_num_sms() * (K < 1024 ? 1024 : K) * R * es;
     return (y > z ? y : z) + 256;
 }
 

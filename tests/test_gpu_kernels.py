@@ -59,7 +59,8 @@ def test_xstream_y(N, K, R, variant, dtype):
     assert np.max(np.abs(got - ref) / scale) < tol, np.max(np.abs(got - ref) / scale)
 
 
-@pytest.mark.parametrize("N,K,R", XSTREAM_SHAPES + [(513, 1024, 8), (64, 1030, 16), (700, 2048, 32), (3000, 1024, 20)])
+@pytest.mark.parametrize("N,K,R", XSTREAM_SHAPES + [(513, 1024, 8), (64, 1030, 16), (700, 2048, 32), (3000, 1024, 20),
+                                                    (20000, 256, 8), (9000, 128, 7)])  # narrow K: several CTAs per SM
 @pytest.mark.parametrize("variant", ["fma", "dmma"])
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
 def test_xstream_z(N, K, R, variant, dtype):
