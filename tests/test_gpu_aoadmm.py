@@ -320,3 +320,27 @@ def test_config2_width_properties_on_device_resident_input():
     cmf2, _, diag2 = cmf_aoadmm(packed, cfg["R"], **kw)
     np.testing.assert_array_equal(cmf2[1][2], C)
     np.testing.assert_array_equal(np.asarray(diag2.regularized_loss), np.asarray(diag.regularized_loss))
+
+
+def test_new_penalties_float32_inputs_track_float64():
+    """float32 inputs run the fp32 kernels end to end (also for GeneralizedL2 / UnitSimplex / TV / Parafac2 options):
+    the factors stay within single-precision distance of the float64 run after 15 iterations."""
+    from matcouply_b200 import cmf_aoadmm
+    from matcouply_b200 import penalties as P
+
+    rs = np.random.RandomState(12)
+    I, K, R, J = 7, 16, 3, 12
+    A, C = rs.uniform(0.2, 1.2, size=(I, R)), rs.uniform(size=(K, R))
+    X = [(rs.uniform(size=(J, R)) * a) @ C.T + 0.05 * rs.standard_normal(size=(J, K)) for a in A]
+    lap = 2 * np.eye(J) - np.eye(J, k=1) - np.eye(J, k=-1)
+    lap[0, 0] = lap[-1, -1] = 1
+    for kw in (dict(non_negative={0: True, 2: True}, generalized_l2_penalty={1: lap}, parafac2=True),
+               dict(non_negative={0: True, 1: True}, tv_penalty={2: 0.05}, l1_penalty={2: 0.01}),
+               dict(non_negative={0: True, 2: True}, regs=[[], [P.UnitSimplex()], []]),
+               dict(non_negative=True, regs=[[], [P.Parafac2(n_iter=2)], []])):
+        common = dict(random_state=0, n_iter_max=15, tol=None, absolute_tol=None)
+        ref = cmf_aoadmm(X, R, **common, **kw)
+        got = cmf_aoadmm([x.astype(np.float32) for x in X], R, **common, **kw)
+        for a, b in zip((ref[1][0], np.concatenate(ref[1][1]), ref[1][2]),
+                        (got[1][0], np.concatenate(got[1][1]), got[1][2])):
+            assert rel(b, a) < 2e-3, (sorted(kw), rel(b, a))
