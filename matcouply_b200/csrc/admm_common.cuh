@@ -103,6 +103,10 @@ int b2_pf2_rowpass_mma_try(const int64_t* row_off, int n_groups, int R, const vo
                            const void* Minv, const PenArgs& pa, int deferred, const void* Wmat, const void* Delta,
                            void* x, void* w_out, int ldw, void* S_out, void* BtB_out, int dtype, cudaStream_t st);
 
+// tensor-core PARAFAC2 gap reduction (pf2_gap_mma.cu); returns -1 when it does not apply
+int b2_pf2_gap_mma_try(const void* V, const void* x, const int64_t* row_off, int n_groups, int R, const void* Wmat,
+                       const void* Delta, double* part, int dtype, cudaStream_t st);
+
 // tensor-core fused row-local ADMM loop (admm_mma.cu); returns -1 when it does not apply
 int b2_admm_local_mma_try(const int64_t* row_off, int n_groups, int R, const void* rhs, const void* rhs_scale,
                           const void* rho, const void* Minv, const PenArgs& pa, int n_inner, void* x, void* w_out,

@@ -499,26 +499,39 @@ pf2_gap_kernel(const int64_t* __restrict__ row_off, int R, const T* __restrict__
     const int c0 = l4 * CPL;
     const T* tseg = Ts + l4 * L::CPLP;
     double d2 = 0.0, x2 = 0.0, ab = 0.0;
-    for (long long row0 = r_begin; row0 < r_end; row0 += kRowsPerPass) {
+    // software pipeline: the rows of pass p + 1 are in flight while pass p is contracted (the kernel is otherwise bound
+    // by the global-load -> shuffle-matvec dependency with nothing to overlap it)
+    T vn[CPL], xn[CPL];
+    auto fetch = [&](long long row0) {
         const long long rowid = row0 + (tid >> 2);
-        const bool valid = rowid < r_end;
-        const size_t base = (size_t)(valid ? rowid : r_end - 1) * R + c0;
-        T v_[CPL], pdv[CPL];
+        const bool ok = rowid < r_end;
+        const size_t base = (size_t)(ok ? rowid : r_end - 1) * R + c0;
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
-            v_[j] = (c0 + j < R) ? V[base + j] : T(0);
+            const bool in = ok && c0 + j < R;
+            vn[j] = in ? V[base + j] : T(0);
+            xn[j] = in ? x[base + j] : T(0);
+        }
+    };
+    fetch(r_begin);
+    for (long long row0 = r_begin; row0 < r_end; row0 += kRowsPerPass) {
+        T v_[CPL], xc[CPL], pdv[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) {
+            v_[j] = vn[j];
+            xc[j] = xn[j];
             pdv[j] = T(0);
         }
+        if (row0 + kRowsPerPass < r_end) fetch(row0 + kRowsPerPass);
         lane_matvec<T, CPL>(v_, tseg, lane, pdv);
 #pragma unroll
         for (int j = 0; j < CPL; ++j) {
-            if (valid && c0 + j < R) {
-                const double xv = (double)x[base + j];
-                const double d = xv - (double)pdv[j];
-                d2 += d * d;
-                x2 += xv * xv;
-                ab += fabs(xv);
-            }
+            // rows past the end and pad columns were fetched as zeros and contribute nothing (pdv of a zero row is zero)
+            const double xv = (double)xc[j];
+            const double d = xv - (double)pdv[j];
+            d2 += d * d;
+            x2 += xv * xv;
+            ab += fabs(xv);
         }
     }
     d2 = block_sum(d2, scratch);
@@ -655,6 +668,15 @@ int b2_pf2_gap(const void* V, const void* x, const int64_t* row_off, int n_group
     if (n_groups == 0) {
         B2_CHECK_CUDA(cudaMemsetAsync(out, 0, 3 * sizeof(double), st));
         return B2_OK;
+    }
+    if (b2_option_value(B2_OPT_PF2_ROWPASS_MMA)) {  // tensor-core formulation (pf2_gap_mma.cu) when it applies
+        const int rc_mma = b2_pf2_gap_mma_try(V, x, row_off, n_groups, R, Wmat, Delta, (double*)ws, dtype, st);
+        if (rc_mma > 0) return rc_mma;
+        if (rc_mma == B2_OK) {
+            pf2_gap_final_kernel<<<1, 256, 0, st>>>((const double*)ws, n_groups, out);
+            B2_LAUNCH_CHECK();
+            return B2_OK;
+        }
     }
     const int CPL = (R + 3) / 4;
     int rc = B2_OK;

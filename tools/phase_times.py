@@ -34,7 +34,7 @@ def wrap(fname):
         acc.setdefault(fname, []).append(e0.elapsed_time(e1)); return r
     setattr(_ops, fname, g)
 for fn in ["xstream_y", "xstream_z", "gram", "scale_gram", "rho_from_trace", "factor_batch", "admm_local", "admm_solve",
-           "pf2_rowpass", "pf2_polar", "pf2_delta", "pf2_apply", "prox_l2ball", "prox_unimodal", "slice_gram",
+           "pf2_rowpass", "pf2_polar", "pf2_delta", "pf2_apply", "pf2_gap", "prox_l2ball", "prox_unimodal", "slice_gram",
            "slice_coldot", "weighted_gram_sum", "hadamard_bcast", "reduce_stats", "fit_terms", "rowscale", "slice_cross"]:
     if hasattr(_ops, fn):
         wrap(fn)
