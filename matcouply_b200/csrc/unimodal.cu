@@ -208,8 +208,15 @@ __device__ __forceinline__ void fill_prefix(T* __restrict__ aux, T* __restrict__
     }
 }
 
+// Residency: measured at config 3 (8 192 slices x 8 columns x 1 024 points): 4 CTAs per SM (<= 128 registers, ~104 KB of
+// shared memory, the rest of the 256 KB stays L1 for the per-thread records) 3.94 ms; 5 CTAs (89 registers, the
+// compiler's own choice) 4.27 ms; 6 CTAs 4.51 ms; 8 CTAs with the maximum shared-memory carve-out 5.50 ms — the record
+// re-reads live on L1 hits, so L1 capacity beats resident warps here.
+#ifndef B2_UNIMODAL_MIN_CTAS
+#define B2_UNIMODAL_MIN_CTAS 4
+#endif
 template <typename T>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, B2_UNIMODAL_MIN_CTAS)
 unimodal_kernel(T* __restrict__ aux, T* __restrict__ dual, const int64_t* __restrict__ row_off, int n_groups, int R,
                 int max_rows, int nn_flag, int32_t* __restrict__ peaks, unsigned char* __restrict__ ws,
                 long long ncolslots, size_t thread_bytes) {
