@@ -159,10 +159,15 @@ size_t b2_unimodal_workspace_bytes(int n_groups, int R, int max_rows);
  *                  optionally basis[row] = V[row] W_g (= P_i). */
 int b2_pf2_polar(const void* S, const void* Delta, const void* rho, int n_groups, int R, void* Wmat, void* num_part,
                  void* Qstore, int warm, int dtype, void* stream);
-/* Fused row pass of one B-mode inner iteration when pens[0] is PARAFAC2 (one CTA per slice):
- *   deferred != 0: pens[0].dual holds the pre-image V of the previous prox; P Delta = V (W_g Delta) and
+/* Fused row pass of one B-mode inner iteration when pens[0] is PARAFAC2 (one CTA per slice).  `deferred` is a bit set:
+ *   bit 0 set:     pens[0].dual holds the pre-image V of the previous prox; P Delta = V (W_g Delta) and
  *                  dual = V - P Delta are formed on the fly (pens[0].aux is not read);
- *   deferred == 0: pens[0].aux = P Delta and pens[0].dual are read as stored.
+ *   bit 0 clear:   pens[0].aux = P Delta and pens[0].dual are read as stored;
+ *   bit 1 set:     the ELEMENTWISE companions (NONNEG, BOX, L1) arrive as ONE array: their dual slot holds the previous
+ *                  prox argument T = x + dual, from which aux = prox(T) and dual = T - aux are recomputed (aux not read);
+ *   bit 2 set:     ... and leave as one array: only T' = x + dual is stored (dual slot), aux is not written.
+ *                  A B-update runs its first pass with bits 1, 2 = (0, 1), the middle passes (1, 1), the last (1, 0), so
+ *                  explicit (aux, dual) exist before and after it (bit-identical to passing them through every pass).
  *   x = (rho_g * sum_p (aux_p - dual_p) + Y o a_g) Minv_g ; pens[0].dual <- V' = x + dual_pf2 ; S_out[g] = V'^T V' ;
  *   other penalties: elementwise kinds are finished (aux = prox, dual update), column-coupled kinds get dual <- x + dual.
  * x / w_out (= x o a_g, row stride ldw) / BtB_out[g] = x_g^T x_g are written only when non-NULL (last inner iteration). */
