@@ -19,7 +19,7 @@ from .coupled_matrices import CoupledMatrixFactorization
 
 __all__ = ["compute_feasibility_gaps", "ADMMVars", "DiagnosticMetrics", "cmf_aoadmm", "parafac2_aoadmm"]
 
-_UNSUPPORTED_INITS = {"svd", "threshold_svd", "parafac2_als", "cp_als", "parafac_als", "cp_hals", "parafac_hals"}
+_UNSUPPORTED_INITS = {"parafac2_als", "cp_als", "parafac_als", "cp_hals", "parafac_hals"}
 
 
 class ADMMVars(NamedTuple):
@@ -171,10 +171,32 @@ def initialize_cmf(matrices, rank, init, random_state=None, _device=None):
         C = random_state.uniform(size=(n_cols, rank))
         B_is = [random_state.uniform(size=(m.shape[0], rank)) for m in matrices]
         return CoupledMatrixFactorization((None, [A, B_is, C]))
+    if init in ("svd", "threshold_svd"):
+        # decomposition.py:42-53: A = 1, B_i = leading left singular vectors of X_i, C = leading right singular vectors
+        # of the stacked data; "threshold_svd" clips both at zero.  Like the random start this
+        # one-off initialisation runs on the HOST with the reference's own LAPACK call (np.linalg.svd = dgesdd): the
+        # signs of singular vectors are LAPACK-implementation-defined, so only the same call gives the same start.
+        # It is not part of the iteration; the data must be host arrays (or is downloaded once).
+        mats = [np.asarray(m.detach().cpu().numpy() if hasattr(m, "detach") else m, dtype=np.float64)
+                for m in matrices]
+        if any(m.ndim != 2 for m in mats):
+            raise ValueError(f'init="{init}" needs the data matrices themselves, not only their shapes')
+
+        def truncated(M, n):  # tensorly.tenalg.svd.truncated_svd
+            U, S, Vh = np.linalg.svd(M, full_matrices=n > min(M.shape))
+            return U[:, :n], S[:n], Vh[:n, :]
+
+        A = np.ones((len(mats), rank))
+        B_is = [truncated(m, rank)[0] for m in mats]
+        C = np.transpose(truncated(np.concatenate(mats, 0), rank)[2])
+        if init == "threshold_svd":
+            B_is = [np.clip(B_i, 0, float("inf")) for B_i in B_is]
+            C = np.clip(C, 0, float("inf"))
+        return CoupledMatrixFactorization((None, [A, B_is, C]))
     if init in _UNSUPPORTED_INITS:
         raise NotImplementedError(
-            f'init="{init}" needs TensorLy decompositions / batched tall SVDs that are not on the B200 hot path yet '
-            '(SURVEY.md §8f); use init="random" or pass a factorization'
+            f'init="{init}" needs TensorLy decompositions (parafac / parafac2 / non_negative_parafac_hals, un-vendored '
+            'third-party code; SURVEY.md §8f); use init="random", "svd", "threshold_svd" or pass a factorization'
         )
     raise ValueError('Initialization method "{}" not recognized'.format(init))
 
@@ -405,7 +427,13 @@ def cmf_aoadmm(
     if init == "random" and dev_draw is not None:
         A0, B0, C0 = initialize_cmf(shape_view, rank, init, random_state=random_state, _device=dev_draw)
     else:
-        _, (A0, B0, C0) = initialize_cmf(shape_view, rank, init, random_state=random_state)
+        init_view = shape_view
+        if init in ("svd", "threshold_svd") and not all(hasattr(m, "ndim") for m in shape_view):
+            if shard is not None:
+                raise NotImplementedError('init="svd" needs the stacked global data; not available for sharded inputs')
+            host = packed.X[:packed.N, :packed.K].detach().to(torch.float64).cpu().numpy()  # device-resident input
+            init_view = [host[a:b] for a, b in zip(packed.row_offsets[:-1], packed.row_offsets[1:])]
+        _, (A0, B0, C0) = initialize_cmf(init_view, rank, init, random_state=random_state)
 
     l2_penalty = [l2 if l2 is not None else 0 for l2 in _listify(l2_penalty, "l2_penalty")]
     regs = _parse_all_penalties(

@@ -779,10 +779,20 @@ def ao_admm(matrices, rank, n_iter_max=1000, l2_penalty=None, l1_penalty=None, n
         np.random.mtrand._rand if random_state is None else np.random.RandomState(random_state))
     matrices = [np.asarray(M, dtype=np.float64) for M in matrices]
     I, K = len(matrices), matrices[0].shape[1]
-    if init is None:  # decomposition.py:31-39 — draw order A, C, B_0..B_{I-1}
+    if init is None or (isinstance(init, str) and init == "random"):  # decomposition.py:31-39 — draw order A, C, B_i
         A = rs.uniform(size=(I, rank))
         C = rs.uniform(size=(K, rank))
         Bs = [rs.uniform(size=(M.shape[0], rank)) for M in matrices]
+    elif isinstance(init, str) and init in ("svd", "threshold_svd"):  # decomposition.py:42-53
+        def truncated(M, n):
+            U, S, Vh = np.linalg.svd(M, full_matrices=n > min(M.shape))
+            return U[:, :n], S[:n], Vh[:n, :]
+        A = np.ones((I, rank))
+        Bs = [truncated(M, rank)[0] for M in matrices]
+        C = np.transpose(truncated(np.concatenate(matrices, 0), rank)[2])
+        if init == "threshold_svd":
+            Bs = [np.clip(B, 0, float("inf")) for B in Bs]
+            C = np.clip(C, 0, float("inf"))
     else:
         A, Bs, C = np.array(init[0]), [np.array(b) for b in init[1]], np.array(init[2])
 

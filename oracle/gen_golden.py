@@ -307,6 +307,10 @@ def main():
               dict(non_negative={0: True, 2: True},
                    regs_spec=[[], [["Parafac2", {"update_coordinate_matrix": False, "n_iter": 2}]], []],
                    random_state=4, n_iter_max=40))
+    # SVD-based initialisations (decomposition.py:42-53)
+    make_case("init_svd_unconstrained", synth(21, 6, 12, 8, 14, 3), 3, dict(init="svd", random_state=1, n_iter_max=40))
+    make_case("init_threshold_svd_nn", synth(22, 7, 14, 6, 16, 3), 3,
+              dict(init="threshold_svd", non_negative=True, random_state=2, n_iter_max=60))
     make_case("tv_C_l1", synth(15, 7, 30, 6, 12, 3), 3,
               dict(non_negative={0: True, 1: True}, tv_penalty={2: 0.02}, l1_penalty={2: 0.01}, random_state=4,
                    n_iter_max=60))
