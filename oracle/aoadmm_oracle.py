@@ -493,12 +493,18 @@ ORACLE_CLASSES = {"NonNegativity": NonNeg, "Box": BoxP, "L1Penalty": L1P, "L2Bal
 def regs_from_spec(spec, classes=None):
     """[[["ClassName", {kwargs}], ...] per mode] -> penalty objects (JSON-safe description of a `regs` argument).
     ``classes``: name -> class mapping (default: the oracle's); array-valued kwargs arrive as nested lists."""
+    oracle_side = classes is None
     classes = ORACLE_CLASSES if classes is None else classes
+    # the spec uses the reference's constructor keywords; the oracle classes name some of them differently
+    rename = {"L2Ball": {"norm_bound": "bound"}, "Box": {"min_val": "lo", "max_val": "hi"},
+              "L1Penalty": {"reg_strength": "strength"}}
     out = []
     for mode_spec in spec:
         mode = []
         for name, kw in mode_spec:
             kw = {k: (np.asarray(v, dtype=np.float64) if isinstance(v, list) else v) for k, v in kw.items()}
+            if oracle_side:
+                kw = {rename.get(name, {}).get(k, k): v for k, v in kw.items()}
             cls = classes[name] if isinstance(classes, dict) else getattr(classes, name)
             mode.append(cls(**kw))
         out.append(mode)
