@@ -248,10 +248,12 @@ class AOADMMEngine:
                         "(or 'A'), as with the reference"
                     )
             if matrixwise and self.world > 1:
-                raise NotImplementedError(
-                    "GeneralizedL2Penalty / TotalVariationPenalty / UnitSimplex / user-defined penalties on a "
-                    "row-sharded mode 0 are not supported (their prox couples all rows of A)"
-                )
+                if kind == _lib.PEN_HOST:
+                    raise NotImplementedError(
+                        "user-defined matrix-wise penalties on a row-sharded mode 0 are not supported (their prox "
+                        "couples all rows of A)")
+                if shard_rows is None:
+                    raise ValueError("matrix-wise penalties on a row-sharded mode 0 need `shard_rows`")
             if kind in (_lib.PEN_L2BALL, _lib.PEN_UNIMODAL):
                 if not self.const_A:
                     raise AttributeError(
@@ -757,6 +759,23 @@ class AOADMMEngine:
                 _ops.prox_unimodal(aux_full, full, off, 1, R, I_glob, nn, self.ws)
                 st.aux[p].copy_(aux_full[lo:lo + I])
                 st.dual[p].copy_(full[lo:lo + I])
+            elif kind in _ENGINE_PROX_KINDS:
+                # GeneralizedL2 / UnitSimplex / TV over all I rows: same gather, prox replicated, own rows kept
+                full = self._gather_A_rows(st.dual[p])
+                aux_full = torch.empty_like(full)
+                off = torch.tensor([0, I_glob], dtype=torch.int64, device=self.dev)
+                st.regs[p]._engine_prox(self, aux_full, full, off, 1, I_glob, self.rhoA[:1] if I > 0 else self.rho_max,
+                                        I_glob)
+                st.aux[p].copy_(aux_full[lo:lo + I])
+                st.dual[p].copy_(full[lo:lo + I])
+
+    def _gather_A_rows(self, local):
+        """The complete I_glob x R matrix from the row shards (all-reduce of disjoint row blocks)."""
+        lo, I_glob = self.shard_rows
+        full = torch.zeros((I_glob, self.R), dtype=self.dtype, device=self.dev)
+        full[lo:lo + self.I] = local
+        self._allreduce(full)
+        return full
 
     def prepare(self):
         """Before the first iteration: ||X||^2 and the products for the initial fit (decomposition.py:906-913)."""
@@ -793,7 +812,7 @@ class AOADMMEngine:
         scal.zero_()
         slot = 2  # [0:2] fit terms
         _ops.fit_terms(self.rhsA, self.cross, self.modes[0].x, self.I, self.R, scal[0:2], self.ws)
-        layout = []
+        layout, deferred_A = [], []
         sizes = (self.I * self.R, self.N * self.R, self.K * self.R)
         # sharded modes first (A, B), replicated mode (C) last
         for m in (0, 1, 2):
@@ -814,11 +833,22 @@ class AOADMMEngine:
                 slot += 3
             for p in range(len(st.desc)):  # values of the penalties that are not hard constraints (loss terms)
                 if st.desc[p][0] in _ENGINE_PROX_KINDS and st.desc[p][0] != _lib.PEN_SIMPLEX:
+                    if m == 0 and self.world > 1:
+                        deferred_A.append(p)  # couples all rows of A: evaluated on the gathered matrix below
+                        continue
                     off_m, n_g, mx = ((self.off_single_I, 1, self.I), (self.row_off, self.I, self.max_rows),
                                       (self.off_single_K, 1, self.K))[m]
                     st.regs[p]._engine_penalty(self, st.x, off_m, n_g, mx, sizes[m] // self.R, scal[slot:slot + 1])
                     layout.append((m, -2 - p, slot))
                     slot += 1
+        if deferred_A:  # replicated values (identical on every rank): after the all-reduced part of the pack
+            I_glob = self.shard_rows[1]
+            full = self._gather_A_rows(self.modes[0].x)
+            off = torch.tensor([0, I_glob], dtype=torch.int64, device=self.dev)
+            for p in deferred_A:
+                self.modes[0].regs[p]._engine_penalty(self, full, off, 1, I_glob, I_glob, scal[slot:slot + 1])
+                layout.append((0, -2 - p, slot))
+                slot += 1
         if self.world > 1:
             self._allreduce(scal[:shard_end])
         return layout, slot

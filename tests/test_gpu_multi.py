@@ -92,7 +92,7 @@ def test_two_rank_run_matches_reference_trajectory(name, tmp_path):
     np.testing.assert_allclose(r0["loss"], g["regularized_loss"][: k + 1], rtol=1e-8)
 
 
-def _mode0_case():
+def _mode0_case(variant=0, oracle=False):
     rs = np.random.RandomState(5)
     I, K, R = 23, 12, 3
     Js = rs.randint(6, 30, size=I)
@@ -101,10 +101,22 @@ def _mode0_case():
     X = [(rs.uniform(size=(J, R)) * A[i]) @ C.T + 0.05 * rs.standard_normal(size=(J, K)) for i, J in enumerate(Js)]
     kw = dict(unimodal={0: True}, l2_norm_bound={0: 2.0}, non_negative=True, constant_feasibility_penalty=True,
               random_state=3)
+    if variant == 1:  # TV + generalized L2 (graph Laplacian over the slice index) on mode 0: values enter the loss
+        lap = 2 * np.eye(I) - np.eye(I, k=1) - np.eye(I, k=-1)
+        lap[0, 0] = lap[-1, -1] = 1
+        kw = dict(tv_penalty={0: 0.02}, generalized_l2_penalty={0: 0.1 * lap}, non_negative={1: True, 2: True},
+                  constant_feasibility_penalty="A", random_state=3)
+    elif variant == 2:  # unit simplex over all rows of A
+        from matcouply_b200 import penalties as P
+        from oracle import aoadmm_oracle as O
+
+        cls = O.UnitSimplexP if oracle else P.UnitSimplex
+        kw = dict(regs=[[cls()], [], []], non_negative={1: True, 2: True}, constant_feasibility_penalty=True,
+                  random_state=3)
     return X, R, kw
 
 
-def _worker_mode0(rank, world, port, k_iter, out_dir):
+def _worker_mode0(rank, world, port, k_iter, out_dir, variant=0):
     if ROOT not in sys.path:
         sys.path.insert(0, ROOT)
     import torch.distributed as dist
@@ -116,7 +128,7 @@ def _worker_mode0(rank, world, port, k_iter, out_dir):
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:
-        X, R, kw = _mode0_case()
+        X, R, kw = _mode0_case(variant)
         sh = make_shard([x.shape[0] for x in X], rank, world)
         cmf, diag = cmf_aoadmm(X[sh.lo:sh.hi], R, n_iter_max=k_iter, tol=None, absolute_tol=None, return_errors=True,
                                process_group=dist.group.WORLD, shard=sh, **kw)
@@ -127,9 +139,11 @@ def _worker_mode0(rank, world, port, k_iter, out_dir):
         dist.destroy_process_group()
 
 
-def test_two_rank_matrix_penalties_on_sharded_mode0(tmp_path):
-    """Unimodality + L2Ball on mode 0 (whole columns of A, whose rows are sharded): all-reduced column norms and the
-    gathered unimodal prox must reproduce the single-process reference algorithm (oracle)."""
+@pytest.mark.parametrize("variant", [0, 1, 2])
+def test_two_rank_matrix_penalties_on_sharded_mode0(tmp_path, variant):
+    """Matrix-wise penalties on mode 0 (whole columns of A, whose rows are sharded): all-reduced column norms (L2Ball),
+    gathered prox (Unimodality, TV, generalized L2, unit simplex) and the loss values of TV / generalized L2 evaluated on
+    the gathered A must reproduce the single-process reference algorithm (oracle)."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
@@ -137,9 +151,9 @@ def test_two_rank_matrix_penalties_on_sharded_mode0(tmp_path):
     from oracle import aoadmm_oracle as O
 
     k = 15
-    X, R, kw = _mode0_case()
+    X, R, kw = _mode0_case(variant, oracle=True)
     o = O.ao_admm(X, R, n_iter_max=k, tol=None, absolute_tol=None, **kw)
-    mp.spawn(_worker_mode0, args=(2, _free_port(), k, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker_mode0, args=(2, _free_port(), k, str(tmp_path), variant), nprocs=2, join=True)
     r0 = np.load(os.path.join(str(tmp_path), "rank0.npz"))
     r1 = np.load(os.path.join(str(tmp_path), "rank1.npz"))
     for key in ("A", "B", "C", "loss"):
