@@ -29,14 +29,33 @@ struct RowpassInputs {
 __device__ __forceinline__ void consumer_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kConsWarps * 32) : "memory"); }
 
 // row in D layout from a shared-memory tile row (shared-space byte address, element type T)
+template <typename T>
+__device__ __forceinline__ void lds_pair(uint32_t saddr, double& a, double& b);
+template <>
+__device__ __forceinline__ void lds_pair<double>(uint32_t saddr, double& a, double& b) {
+    const int4 q = lds_b128(saddr);
+    a = __hiloint2double(q.y, q.x);
+    b = __hiloint2double(q.w, q.z);
+}
+template <>
+__device__ __forceinline__ void lds_pair<float>(uint32_t saddr, double& a, double& b) {
+    a = (double)lds_elem<float>(saddr);
+    b = (double)lds_elem<float>(saddr + 4);
+}
+
 template <class PL, typename T>
 __device__ __forceinline__ void load_row(uint32_t srow, int t, int R, bool valid, double (&v)[PL::NB][2]) {
 #pragma unroll
     for (int b = 0; b < PL::NB; ++b) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const int c = reg_col<PL>(b, e, t, R);
-            v[b][e] = (valid && c >= 0) ? (double)lds_elem<T>(srow + (uint32_t)(c * sizeof(T))) : 0.0;
+        const int c0 = reg_col<PL>(b, 0, t, R), c1 = reg_col<PL>(b, 1, t, R);
+        v[b][0] = v[b][1] = 0.0;
+        if (valid) {
+            if (c0 >= 0 && c1 >= 0) {  // adjacent columns c0, c0 + 1 (c0 even; rows are 16-byte aligned): one load
+                lds_pair<T>(srow + (uint32_t)(c0 * sizeof(T)), v[b][0], v[b][1]);
+            } else {
+                if (c0 >= 0) v[b][0] = (double)lds_elem<T>(srow + (uint32_t)(c0 * sizeof(T)));
+                if (c1 >= 0) v[b][1] = (double)lds_elem<T>(srow + (uint32_t)(c1 * sizeof(T)));
+            }
         }
     }
 }
@@ -61,7 +80,7 @@ __device__ __forceinline__ void store_row(T* __restrict__ grow, int t, int R, co
 // NEXTRA: number of penalties besides PARAFAC2 (compile time: their duals stay in registers).  LAST: the last inner
 // iteration also emits x, W = x o a and B^T B.  Two CTAs per SM (9 warps each: 5 warps on one SM sub-partition x 96 registers fit its 16K-register file) matter: the
 // row loop is latency bound, and a second resident CTA doubles the warps that hide it.
-template <typename T, int NBF, int HALF, int NEXTRA, bool LAST>
+template <typename T, int NBF, int HALF, int NEXTRA, bool LAST, int K1>
 __global__ void __launch_bounds__((kConsWarps + 1) * 32) __maxnreg__((NBF + HALF) <= 3 ? 96 : 168)
 pf2_rowpass_mma_kernel(const int64_t* __restrict__ row_off, int R, RowpassInputs in, const T* __restrict__ A,
                        const T* __restrict__ rho, const T* __restrict__ Minv, PenArgs pa, int deferred,
@@ -212,7 +231,7 @@ pf2_rowpass_mma_kernel(const int64_t* __restrict__ row_off, int R, RowpassInputs
             int ai = a_idx;
 #pragma unroll
             for (int p = 0; p < NEXTRA; ++p) {
-                const int kind = pa.kind[p + 1];
+                const int kind = (K1 >= 0 && p == 0) ? K1 : pa.kind[p + 1];  // K1: compile-time kind of companion 0
                 const bool elementwise = kind == B2_PEN_NONNEG || kind == B2_PEN_BOX || kind == B2_PEN_L1;
                 if (tin && elementwise) {
                     // T-only state: the dual slot holds the previous prox argument T = x + dual; aux = prox(T) and
@@ -280,7 +299,7 @@ pf2_rowpass_mma_kernel(const int64_t* __restrict__ row_off, int R, RowpassInputs
 #pragma unroll
             for (int p = 0; p < NEXTRA; ++p) {
                 {
-                    const int kind = pa.kind[p + 1], nn = pa.nn[p + 1];
+                    const int kind = (K1 >= 0 && p == 0) ? K1 : pa.kind[p + 1], nn = pa.nn[p + 1];
                     const bool elementwise = kind == B2_PEN_NONNEG || kind == B2_PEN_BOX || kind == B2_PEN_L1;
                     const T p0 = (T)pa.p0[p + 1], p1 = (T)pa.p1[p + 1];
                     double zo[NB][2], dn[NB][2];
@@ -329,7 +348,7 @@ pf2_rowpass_mma_kernel(const int64_t* __restrict__ row_off, int R, RowpassInputs
     }
 }
 
-template <typename T, int NBF, int HALF, int NEXTRA, bool LAST>
+template <typename T, int NBF, int HALF, int NEXTRA, bool LAST, int K1>
 int launch_mma_k(const int64_t* row_off, int n_groups, int R, const RowpassInputs& in, const void* A, const void* rho,
                  const void* Minv, const PenArgs& pa, int deferred, const void* Wmat, const void* Delta, void* x,
                  void* w_out, int ldw, void* S_out, void* BtB_out, cudaStream_t st) {
@@ -347,7 +366,7 @@ int launch_mma_k(const int64_t* row_off, int n_groups, int R, const RowpassInput
     if (ring_bytes < red_bytes) ring_bytes = red_bytes;
     const size_t smem = fixed + ring_bytes + 2 * (size_t)stages * sizeof(uint64_t) + 64;
     if (smem > 227 * 1024) return -1;  // too many / too wide input arrays for two stages: use the shuffle kernel
-    auto kern = pf2_rowpass_mma_kernel<T, NBF, HALF, NEXTRA, LAST>;
+    auto kern = pf2_rowpass_mma_kernel<T, NBF, HALF, NEXTRA, LAST, K1>;
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // ask for the largest shared-memory carve-out: otherwise the driver sizes it for ONE resident CTA
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -366,11 +385,19 @@ int launch_mma(const int64_t* row_off, int n_groups, int R, const RowpassInputs&
     const bool last = x != nullptr;
     if (last && !(w_out && BtB_out)) return -1;   // the fused engine always asks for all three on the last iteration
     if (!last && (w_out || BtB_out)) return -1;
-#define B2_MMA_K(NE, LA)                                                                                              \
-    if (n_extra == NE && last == LA)                                                                                  \
-        return launch_mma_k<T, NBF, HALF, NE, LA>(row_off, n_groups, R, in, A, rho, Minv, pa, deferred, Wmat, Delta, x, \
+    // the common companion (non-negativity next to PARAFAC2) gets its kind at compile time: no per-element dispatch
+    const bool nn1 = n_extra == 1 && pa.kind[1] == B2_PEN_NONNEG;
+#define B2_MMA_K(NE, LA, KK)                                                                                          \
+    return launch_mma_k<T, NBF, HALF, NE, LA, KK>(row_off, n_groups, R, in, A, rho, Minv, pa, deferred, Wmat, Delta, x, \
                                                   w_out, ldw, S_out, BtB_out, st);
-    B2_MMA_K(0, false) B2_MMA_K(0, true) B2_MMA_K(1, false) B2_MMA_K(1, true) B2_MMA_K(2, false) B2_MMA_K(2, true)
+    if (n_extra == 0 && !last) { B2_MMA_K(0, false, -1) }
+    if (n_extra == 0 && last) { B2_MMA_K(0, true, -1) }
+    if (nn1 && !last) { B2_MMA_K(1, false, B2_PEN_NONNEG) }
+    if (nn1 && last) { B2_MMA_K(1, true, B2_PEN_NONNEG) }
+    if (n_extra == 1 && !last) { B2_MMA_K(1, false, -1) }
+    if (n_extra == 1 && last) { B2_MMA_K(1, true, -1) }
+    if (n_extra == 2 && !last) { B2_MMA_K(2, false, -1) }
+    if (n_extra == 2 && last) { B2_MMA_K(2, true, -1) }
 #undef B2_MMA_K
     return -1;
 }
