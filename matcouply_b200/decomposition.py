@@ -150,10 +150,12 @@ class _ShapeOnly:
         self.shape = tuple(shape)
 
 
-def initialize_cmf(matrices, rank, init, random_state=None, _device=None):
+def initialize_cmf(matrices, rank, init, svd_fun=None, random_state=None, init_params=None, _device=None):
     """decomposition.py:18-75: a given factorization is used as is, "random" draws A, C, B_0..B_{I-1} (in this
     order) uniformly from one RandomState.  ``_device`` (internal, used by cmf_aoadmm): draw the B_i block on that
-    CUDA device from the same stream and return ``(A, DeviceRows, C)`` instead of a CoupledMatrixFactorization."""
+    CUDA device from the same stream and return ``(A, DeviceRows, C)`` instead of a CoupledMatrixFactorization.
+    ``svd_fun`` / ``init_params`` are accepted for signature compatibility with the reference (the SVD starts use
+    LAPACK's ``gesdd`` like TensorLy's ``truncated_svd``; ``init_params`` only concerns the ALS starts)."""
     random_state = penalties._check_random_state(random_state)
     if _device is not None and init == "random":
         n_slices, n_cols = len(matrices), matrices[0].shape[1]
