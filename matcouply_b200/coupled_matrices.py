@@ -90,6 +90,48 @@ class CoupledMatrixFactorization:
         self.shape = shape
         self.rank = rank
 
+    @classmethod
+    def from_CPTensor(cls, cp_tensor, shapes=None):
+        """A third-order CP tensor ``(weights, (A, B, C))`` (any 2-tuple: TensorLy ``CPTensor`` objects unpack the same
+        way) as a coupled matrix factorization with ``B_i = B[:J_i]`` (coupled_matrices.py:101-151)."""
+        weights, factors = cp_tensor
+        if len(factors) != 3:
+            raise ValueError("Must be a third order CP tensor to convert into a coupled matrix factorization")
+        A, B, C = (np.asarray(f) for f in factors)
+        if shapes is not None:
+            B_is = []
+            if len(shapes) != A.shape[0]:
+                raise ValueError(
+                    f"The first mode has length {A.shape[0]}, which is different "
+                    f"than the length indicated by the shapes argument ({len(shapes)})"
+                )
+            for J_i, K in shapes:
+                if K != C.shape[0]:
+                    raise ValueError(
+                        f"The third mode has length {C.shape[0]}, which is different "
+                        f"than the length indicated by the shapes argument ({K})"
+                    )
+                if J_i > B.shape[0]:
+                    raise ValueError(
+                        f"The second mode of the CP tensor mode has length {B.shape[0]}, which "
+                        f"is smaller than the length indicated by the shape ({J_i}) of matrix"
+                    )
+                B_is.append(np.copy(B)[:J_i, :])
+        else:
+            B_is = [np.copy(B) for _ in range(A.shape[0])]
+        weights = np.ones(A.shape[1]) if weights is None else np.copy(weights)
+        return cls((weights, [np.copy(A), B_is, np.copy(C)]))
+
+    @classmethod
+    def from_Parafac2Tensor(cls, parafac2_tensor):
+        """A PARAFAC2 tensor ``(weights, (A, B, C), projection_matrices)`` as a coupled matrix factorization with
+        ``B_i = P_i B`` (coupled_matrices.py:153-172)."""
+        weights, factors, projection_matrices = parafac2_tensor
+        A, B, C = (np.asarray(f) for f in factors)
+        B_is = [np.dot(np.asarray(P_i), B) for P_i in projection_matrices]
+        weights = np.ones(A.shape[1]) if weights is None else np.copy(weights)
+        return cls((weights, [np.copy(A), B_is, np.copy(C)]))
+
     def __getitem__(self, item):
         if item == 0:
             return self.weights

@@ -197,3 +197,26 @@ def test_data_model_sugar_and_simulated_data(golden_dir):
     g = np.load(os.path.join(golden_dir, "traj_c0_readme.npz"))
     np.testing.assert_allclose(np.concatenate(X, 0), g["X"], rtol=1e-12, atol=1e-14)
     assert truth.shape == tuple((50, 20) for _ in range(15))
+
+
+def test_from_cp_and_parafac2_tensor():
+    """CoupledMatrixFactorization.from_CPTensor / from_Parafac2Tensor (coupled_matrices.py:101-172) on plain tuples."""
+    from matcouply_b200.coupled_matrices import CoupledMatrixFactorization as CMF
+
+    rs = np.random.RandomState(0)
+    A, B, C, w = rs.uniform(size=(4, 3)), rs.uniform(size=(6, 3)), rs.uniform(size=(5, 3)), rs.uniform(size=3)
+    cmf = CMF.from_CPTensor((w, (A, B, C)))
+    dense = np.einsum("r,ir,jr,kr->ijk", w, A, B, C)
+    np.testing.assert_allclose(cmf.to_tensor(), dense, rtol=1e-12)
+    ragged = CMF.from_CPTensor((w, (A, B, C)), shapes=[(6, 5), (4, 5), (2, 5), (5, 5)])
+    assert ragged.shape == ((6, 5), (4, 5), (2, 5), (5, 5))
+    np.testing.assert_allclose(ragged.to_matrix(2), dense[2, :2], rtol=1e-12)
+    for bad in ([(6, 5)] * 3, [(6, 4)] * 4, [(7, 5)] * 4):
+        with pytest.raises(ValueError):
+            CMF.from_CPTensor((w, (A, B, C)), shapes=bad)
+    with pytest.raises(ValueError):
+        CMF.from_CPTensor((w, (A, B)))
+    Ps = [np.linalg.qr(rs.standard_normal(size=(J, 6)))[0] for J in (8, 7, 9, 6)]
+    pf2 = CMF.from_Parafac2Tensor((None, (A, B, C), Ps))
+    assert pf2.shape == ((8, 5), (7, 5), (9, 5), (6, 5))
+    np.testing.assert_allclose(pf2.to_matrix(1), (Ps[1] @ B * A[1]) @ C.T, rtol=1e-12)
