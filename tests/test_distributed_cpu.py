@@ -44,17 +44,29 @@ def _global_state(row_counts, K, R, kw, seed=0):
     cmf = D.initialize_cmf(shapes, R, "random", random_state=rs)
     regs = D._parse_all_penalties(
         non_negative=kw.get("non_negative"), lower_bound=None, upper_bound=None, l2_norm_bound=kw.get("l2_norm_bound"),
-        unimodal=kw.get("unimodal"), parafac2=kw.get("parafac2"), l1_penalty=kw.get("l1_penalty"), tv_penalty=None,
-        generalized_l2_penalty=None, svd="truncated_svd", regs=None, dual_init="random_uniform",
+        unimodal=kw.get("unimodal"), parafac2=kw.get("parafac2"), l1_penalty=kw.get("l1_penalty"),
+        tv_penalty=kw.get("tv_penalty"), generalized_l2_penalty=kw.get("generalized_l2_penalty"), svd="truncated_svd",
+        regs=kw.get("regs"), dual_init="random_uniform",
         aux_init="random_uniform", verbose=False)
     auxes = [[r.init_aux(shapes, R, m, random_state=rs) for r in regs[m]] for m in range(3)]
     duals = [[r.init_dual(shapes, R, m, random_state=rs) for r in regs[m]] for m in range(3)]
     return cmf, regs, auxes, duals
 
 
-def test_shard_state_reassembles_global_draw():
+def _shard_cases():
+    from matcouply_b200 import penalties as P
+
+    lap = 2 * np.eye(11) - np.eye(11, k=1) - np.eye(11, k=-1)
+    return [dict(non_negative=True, parafac2=True, l1_penalty={2: 0.1}),
+            # the penalties added later: TV (mode 1), generalized L2 (mode 2), unit simplex (mode 0), PARAFAC2 options
+            dict(non_negative={2: True}, tv_penalty={1: 0.1}, generalized_l2_penalty={2: lap},
+                 regs=[[P.UnitSimplex()], [P.Parafac2(n_iter=2)], []])]
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_shard_state_reassembles_global_draw(case):
     row_counts, K, R = [7, 3, 9, 4, 6, 8, 5], 11, 3
-    kw = dict(non_negative=True, parafac2=True, l1_penalty={2: 0.1})
+    kw = _shard_cases()[case]
     cmf, regs, auxes, duals = _global_state(row_counts, K, R, kw)
     _, (A, B_is, C) = cmf
     world = 3
