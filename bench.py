@@ -14,6 +14,9 @@ dominant X-stream kernel, timed live with CUDA events inside the timed steps; `c
 (NumPy restatement of the reference, all host threads) on a bounded slice sample; `e2e` = the same metric through the
 public `cmf_aoadmm` call with HOST buffers (pack + H2D + fit + D2H inside the timed region).
 `--impl reference` times the reference algorithm's CPU port (oracle/aoadmm_oracle.py) on the same workload's sample.
+`cpu_baseline_torch` (both arms, N=1) = the same sample under the reference's PyTorch-backend flavour on the host
+cores (oracle/aoadmm_torch_cpu.py, fp64 and fp32) — the north_star's "torch-CPU" column; absent-with-reason for
+penalties that backend cannot run (Unimodality).
 """
 import argparse
 import json
@@ -192,6 +195,38 @@ def oracle_iter_seconds(mats, R, kw):
     return max(((t2 - t1) - (t1 - t0)) / 2.0, 1e-9)
 
 
+def torch_cpu_baseline(mats, R, kw, total_rows, n_slices_total):
+    """The reference under TensorLy's PyTorch backend on the host cores (oracle/aoadmm_torch_cpu.py; float64 and the
+    backend's default float32), same sample and same (t(3 its) - t(1 it)) / 2 rule as the NumPy column.  Only for the
+    penalties that backend can run (no Unimodality); never raises — the line says why it is absent."""
+    try:
+        import torch
+
+        from oracle.aoadmm_torch_cpu import ao_admm_torch_cpu
+
+        pen = {k: v for k, v in kw.items() if k in ("non_negative", "parafac2", "l1_penalty")}
+        if len(pen) != len(kw):
+            return {"unavailable": "the reference's torch backend cannot run " +
+                                   ", ".join(sorted(set(kw) - set(pen))) + " (penalties.py:1008-1009)"}
+        rows = sum(m.shape[0] for m in mats)
+        out = {"unit": "iter/s", "cores": int(torch.get_num_threads()), "kind": "port",
+               "sample": f"first {len(mats)} of {n_slices_total} slices ({rows} of {total_rows} rows), scaled "
+                         "linearly in rows"}
+        ao_admm_torch_cpu(mats[:2], R, n_iter_max=1, **pen)  # warm-up
+        for name, dt in (("f64", torch.float64), ("f32", torch.float32)):
+            t0 = time.perf_counter()
+            ao_admm_torch_cpu(mats, R, n_iter_max=1, dtype=dt, **pen)
+            t1 = time.perf_counter()
+            ao_admm_torch_cpu(mats, R, n_iter_max=3, dtype=dt, **pen)
+            t2 = time.perf_counter()
+            t_s = max(((t2 - t1) - (t1 - t0)) / 2.0, 1e-9)
+            out["value_" + name] = 1.0 / (t_s * total_rows / rows)
+        out["value"] = out["value_f64"]
+        return out
+    except Exception as exc:  # the torch column is an extra; it must never cost the bench line
+        return {"unavailable": f"{type(exc).__name__}: {exc}"}
+
+
 E2E_ITERS = 50  # outer iterations of the timed end-to-end call (the parity horizon of BASELINE.json's north_star)
 
 
@@ -309,6 +344,7 @@ def run_reference(args, cfg, sizes):
                          "sample": f"first {S} of {cfg['I']} slices ({rows} of {total_rows} rows); "
                                    f"{t_iter_sample:.3f} s per outer iteration on the sample, scaled linearly in rows"},
         "e2e": {"value": value, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "cpu_baseline_torch": torch_cpu_baseline(mats, cfg["R"], cfg["kw"], total_rows, cfg["I"]),
     }
     emit(line)
 
@@ -503,6 +539,7 @@ def main():
                 "value": 1.0 / (t_s * total_rows / rows), "unit": "iter/s", "cores": os.cpu_count(), "kind": "port",
                 "sample": f"first {S} of {cfg['I']} slices ({rows} of {total_rows} rows): {t_s:.3f} s per outer "
                           f"iteration, scaled linearly in rows (every reference loop is per slice)"}
+            line["cpu_baseline_torch"] = torch_cpu_baseline(mats, cfg["R"], cfg["kw"], total_rows, cfg["I"])
     if e2e is not None:
         line["e2e"] = e2e
     emit(line)

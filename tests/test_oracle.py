@@ -173,3 +173,36 @@ print("OK")
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
                          env=dict(os.environ, PYTHONDONTWRITEBYTECODE="1"))
     assert out.returncode == 0 and "OK" in out.stdout, out.stderr[-2000:]
+
+
+@pytest.mark.parametrize("kw", [dict(non_negative=True),
+                                dict(non_negative=True, parafac2=True, l1_penalty={2: 0.1}),
+                                dict(parafac2=True, l1_penalty={2: 0.05})])
+def test_torch_cpu_oracle_matches_numpy_oracle(kw):
+    """The torch-CPU column of bench.py (oracle/aoadmm_torch_cpu.py: the reference under TensorLy's PyTorch backend,
+    SURVEY.md §8c) follows the pinned NumPy oracle: to round-off in float64, at single precision in float32 (the
+    backend's default dtype; the reference's own torch tests scale their tolerances by 500, tests/utils.py:6-9)."""
+    import torch
+
+    from oracle.aoadmm_torch_cpu import ao_admm_torch_cpu
+
+    rs = np.random.RandomState(3)
+    R = 3
+    X = [rs.uniform(size=(J, R)) @ rs.uniform(size=(R, 14)) + 0.1 * rs.standard_normal((J, 14))
+         for J in rs.randint(6, 20, size=9)]
+    o = O.ao_admm(X, R, n_iter_max=6, random_state=0, tol=None, absolute_tol=None, **kw)
+    for dtype, tol in ((torch.float64, 1e-11), (torch.float32, 2e-4)):
+        t = ao_admm_torch_cpu(X, R, n_iter_max=6, random_state=0, dtype=dtype, **kw)
+        np.testing.assert_allclose(t["A"], o["A"], rtol=tol, atol=tol)
+        np.testing.assert_allclose(t["C"], o["C"], rtol=tol, atol=tol)
+        for b, ob in zip(t["B_is"], o["B_is"]):
+            np.testing.assert_allclose(b, ob, rtol=tol, atol=tol)
+        np.testing.assert_allclose(t["regularized_loss"], o["regularized_loss"][1:], rtol=tol)
+        np.testing.assert_allclose(t["rec_errors"], o["rec_errors"][1:], rtol=tol)
+
+
+def test_torch_cpu_oracle_refuses_numpy_only_penalties():
+    from oracle.aoadmm_torch_cpu import ao_admm_torch_cpu
+
+    with pytest.raises(TypeError):  # unimodal is not even a keyword of the torch column (penalties.py:1008-1009)
+        ao_admm_torch_cpu([np.ones((4, 3))], 2, unimodal={1: True})
