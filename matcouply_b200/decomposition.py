@@ -19,7 +19,7 @@ from .coupled_matrices import CoupledMatrixFactorization
 
 __all__ = ["compute_feasibility_gaps", "ADMMVars", "DiagnosticMetrics", "cmf_aoadmm", "parafac2_aoadmm"]
 
-_UNSUPPORTED_INITS = {"parafac2_als", "cp_als", "parafac_als", "cp_hals", "parafac_hals"}
+_ALS_INITS = {"parafac2_als", "cp_als", "parafac_als", "cp_hals", "parafac_hals"}  # need TensorLy (host, one-off)
 
 
 class ADMMVars(NamedTuple):
@@ -195,11 +195,38 @@ def initialize_cmf(matrices, rank, init, svd_fun=None, random_state=None, init_p
             B_is = [np.clip(B_i, 0, float("inf")) for B_i in B_is]
             C = np.clip(C, 0, float("inf"))
         return CoupledMatrixFactorization((None, [A, B_is, C]))
-    if init in _UNSUPPORTED_INITS:
-        raise NotImplementedError(
-            f'init="{init}" needs TensorLy decompositions (parafac / parafac2 / non_negative_parafac_hals, un-vendored '
-            'third-party code; SURVEY.md §8f); use init="random", "svd", "threshold_svd" or pass a factorization'
-        )
+    if init in _ALS_INITS:
+        # decomposition.py:55-73: the reference hands these starts to TensorLy's own ALS / HALS algorithms (third-party,
+        # un-vendored).  They are one-off HOST initialisations like the SVD starts, so the same call is
+        # made here when TensorLy is installed; without it there is nothing to restate and the start is refused.
+        try:
+            import tensorly.decomposition as tl_decomposition
+        except ImportError as exc:
+            raise NotImplementedError(
+                f'init="{init}" needs TensorLy decompositions (parafac / parafac2 / non_negative_parafac_hals, '
+                'un-vendored third-party code; SURVEY.md §8f) and TensorLy is not installed; use init="random", "svd", '
+                '"threshold_svd" or pass a factorization'
+            ) from exc
+        mats = [np.asarray(m.detach().cpu().numpy() if hasattr(m, "detach") else m) for m in matrices]
+        if any(m.ndim != 2 for m in mats):
+            raise ValueError(f'init="{init}" needs the data matrices themselves, not only their shapes')
+        if init_params is None:
+            init_params = {}
+        if "n_iter_max" not in init_params:
+            init_params["n_iter_max"] = 50
+        if init == "parafac2_als":
+            pf2 = tl_decomposition.parafac2(mats, rank, **init_params, random_state=random_state)
+            return CoupledMatrixFactorization.from_Parafac2Tensor(pf2)
+        # PARAFAC starts work on the zero-padded tensor (_utils.py:49-54)
+        shapes = [tuple(m.shape) for m in mats]
+        tensor = np.zeros((len(mats), max(j for j, _ in shapes), shapes[0][1]), dtype=mats[0].dtype)
+        for i, m in enumerate(mats):
+            tensor[i, :m.shape[0]] = m
+        if init in ("cp_als", "parafac_als"):
+            cp = tl_decomposition.parafac(tensor, rank, **init_params, random_state=random_state)
+        else:
+            cp = tl_decomposition.non_negative_parafac_hals(tensor, rank, **init_params, random_state=random_state)
+        return CoupledMatrixFactorization.from_CPTensor(cp, shapes=shapes)
     raise ValueError('Initialization method "{}" not recognized'.format(init))
 
 
@@ -430,12 +457,17 @@ def cmf_aoadmm(
         A0, B0, C0 = initialize_cmf(shape_view, rank, init, random_state=random_state, _device=dev_draw)
     else:
         init_view = shape_view
-        if init in ("svd", "threshold_svd") and not all(hasattr(m, "ndim") for m in shape_view):
+        needs_data = isinstance(init, str) and (init in ("svd", "threshold_svd") or init in _ALS_INITS)
+        if needs_data and not all(hasattr(m, "ndim") for m in shape_view):
             if shard is not None:
-                raise NotImplementedError('init="svd" needs the stacked global data; not available for sharded inputs')
+                raise NotImplementedError(
+                    f'init="{init}" needs the stacked global data; not available for sharded inputs')
             host = packed.X[:packed.N, :packed.K].detach().to(torch.float64).cpu().numpy()  # device-resident input
             init_view = [host[a:b] for a, b in zip(packed.row_offsets[:-1], packed.row_offsets[1:])]
-        _, (A0, B0, C0) = initialize_cmf(init_view, rank, init, random_state=random_state)
+        w0, (A0, B0, C0) = initialize_cmf(init_view, rank, init, random_state=random_state,
+                                         init_params=init_params)
+        if w0 is not None:  # TensorLy starts carry weights; absorbed like a given factorization (:22-25)
+            A0 = np.asarray(w0) * np.asarray(A0)
 
     l2_penalty = [l2 if l2 is not None else 0 for l2 in _listify(l2_penalty, "l2_penalty")]
     regs = _parse_all_penalties(

@@ -220,3 +220,66 @@ def test_from_cp_and_parafac2_tensor():
     pf2 = CMF.from_Parafac2Tensor((None, (A, B, C), Ps))
     assert pf2.shape == ((8, 5), (7, 5), (9, 5), (6, 5))
     np.testing.assert_allclose(pf2.to_matrix(1), (Ps[1] @ B * A[1]) @ C.T, rtol=1e-12)
+
+
+def test_als_inits_delegate_to_tensorly_when_installed(monkeypatch):
+    """decomposition.py:55-73: the ALS / HALS starts are TensorLy's own algorithms.  Without TensorLy they are refused
+    (NotImplementedError); with it the reference's call is made on the host: same function, same arguments
+    (``n_iter_max`` defaulting to 50, the caller's RandomState), zero-padded tensor for the CP starts."""
+    import sys
+    import types
+
+    from matcouply_b200.decomposition import initialize_cmf
+
+    rs = np.random.RandomState(0)
+    mats = [rs.uniform(size=(J, 5)) for J in (4, 7, 3)]
+    if "tensorly" not in sys.modules:
+        try:
+            import tensorly  # noqa: F401
+        except ImportError:
+            with pytest.raises(NotImplementedError, match="TensorLy"):
+                initialize_cmf(mats, 2, "cp_als", random_state=rs)
+
+    calls = []
+    A, B, C = rs.uniform(size=(3, 2)), rs.uniform(size=(7, 2)), rs.uniform(size=(5, 2))
+    P = [np.linalg.qr(rs.standard_normal((m.shape[0], 2)))[0] for m in mats]
+
+    def parafac2(matrices, rank, **kw):
+        calls.append(("parafac2", matrices, rank, kw))
+        return None, (A, B[:2], C), P
+
+    def parafac(tensor, rank, **kw):
+        calls.append(("parafac", tensor, rank, kw))
+        return np.array([2.0, 3.0]), (A, B, C)
+
+    def hals(tensor, rank, **kw):
+        calls.append(("hals", tensor, rank, kw))
+        return None, (A, B, C)
+
+    fake = types.ModuleType("tensorly")
+    fake.decomposition = types.ModuleType("tensorly.decomposition")
+    fake.decomposition.parafac2, fake.decomposition.parafac = parafac2, parafac
+    fake.decomposition.non_negative_parafac_hals = hals
+    monkeypatch.setitem(sys.modules, "tensorly", fake)
+    monkeypatch.setitem(sys.modules, "tensorly.decomposition", fake.decomposition)
+
+    state = np.random.RandomState(5)
+    cmf = initialize_cmf(mats, 2, "parafac2_als", random_state=state)
+    name, arg, rank, kw = calls[-1]
+    assert name == "parafac2" and rank == 2 and kw["n_iter_max"] == 50 and kw["random_state"] is state
+    assert all(np.array_equal(a, m) for a, m in zip(arg, mats))
+    for B_i, P_i in zip(cmf[1][1], P):
+        np.testing.assert_allclose(B_i, P_i @ B[:2])
+
+    for init, which in (("cp_als", "parafac"), ("parafac_als", "parafac"), ("cp_hals", "hals"), ("parafac_hals", "hals")):
+        cmf = initialize_cmf(mats, 2, init, random_state=state, init_params={"n_iter_max": 7, "tol": 1e-3})
+        name, tensor, rank, kw = calls[-1]
+        assert name == which and kw["n_iter_max"] == 7 and kw["tol"] == 1e-3
+        assert tensor.shape == (3, 7, 5)
+        for i, m in enumerate(mats):
+            assert np.array_equal(tensor[i, :m.shape[0]], m) and not tensor[i, m.shape[0]:].any()
+        assert [b.shape for b in cmf[1][1]] == [(4, 2), (7, 2), (3, 2)]
+        np.testing.assert_allclose(cmf[1][1][0], B[:4])
+    assert np.array_equal(initialize_cmf(mats, 2, "cp_als", random_state=state)[0], [2.0, 3.0])
+    with pytest.raises(ValueError, match="not recognized"):
+        initialize_cmf(mats, 2, "no_such_init", random_state=state)
