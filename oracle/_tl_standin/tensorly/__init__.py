@@ -86,3 +86,49 @@ def index_update(t, idx, val):
 
 
 SVD_FUNS = ["truncated_svd", "symeig_svd", "randomized_svd"]
+
+
+def unfold(t, mode):  # tensorly.base.unfold: mode-`mode` unfolding, remaining modes in C order
+    return np.reshape(np.moveaxis(t, mode, 0), (t.shape[mode], -1))
+
+
+def tensor_to_vec(t):  # tensorly.base.tensor_to_vec
+    return np.reshape(t, (-1,))
+
+
+class _CPTensor:
+    """tensorly.cp_tensor.CPTensor as the reference uses it (coupled_matrices.py:121-122): unpacks as
+    (weights, factors), weights defaulting to ones(rank)."""
+
+    def __init__(self, cp_tensor):
+        weights, factors = cp_tensor
+        rank = np.shape(factors[0])[1]
+        self.weights = np.ones(rank) if weights is None else weights
+        self.factors = factors
+
+    def __iter__(self):
+        yield self.weights
+        yield self.factors
+
+
+class _Parafac2Tensor:
+    """tensorly.parafac2_tensor.Parafac2Tensor (coupled_matrices.py:168-169): (weights, factors, projections)."""
+
+    def __init__(self, parafac2_tensor):
+        weights, factors, projections = parafac2_tensor
+        rank = np.shape(factors[0])[1]
+        self.weights = np.ones(rank) if weights is None else weights
+        self.factors, self.projections = factors, projections
+
+    def __iter__(self):
+        yield self.weights
+        yield self.factors
+        yield self.projections
+
+
+class cp_tensor:  # namespace stand-ins for the two sub-modules
+    CPTensor = _CPTensor
+
+
+class parafac2_tensor:
+    Parafac2Tensor = _Parafac2Tensor
