@@ -219,4 +219,26 @@ def host_cases(cm, rnd, dec, pen):
     case("pen/pf2/aux_tuple_wrong_count", lambda: pen.Parafac2(aux_init=(eyes[:2], np.eye(rank))).init_aux(mats, rank, 1))
     case("pen/pf2/aux_tuple_wrong_rows",
          lambda: pen.Parafac2(aux_init=([np.eye(j + 1, rank) for j, _ in shapes], np.eye(rank))).init_aux(mats, rank, 1))
+
+    # the host half of the penalty protocol (penalties.py:268-343, 469-485, 1256-1324)
+    aux_A, dual_A = rs.uniform(size=(4, rank)), rs.uniform(size=(4, rank))
+    aux_B = [rs.uniform(size=(j, rank)) for j, _ in shapes]
+    dual_B = [rs.uniform(size=(j, rank)) for j, _ in shapes]
+    nn, pf2 = pen.NonNegativity(), pen.Parafac2()
+    case("protocol/nn/subtract_from_aux", lambda: nn.subtract_from_aux(aux_A, dual_A))
+    case("protocol/nn/subtract_from_auxes", lambda: nn.subtract_from_auxes(aux_B, dual_B))
+    case("protocol/nn/aux_as_matrix", lambda: nn.aux_as_matrix(aux_A))
+    case("protocol/nn/auxes_as_matrices", lambda: nn.auxes_as_matrices(aux_B))
+    case("protocol/nn/penalty_matrix", lambda: nn.penalty(aux_A))
+    case("protocol/nn/penalty_list", lambda: nn.penalty(aux_B))
+    case("protocol/box/penalty", lambda: pen.Box(0, 1).penalty(aux_A))
+    case("protocol/l2ball/penalty", lambda: pen.L2Ball(1.0).penalty(aux_B))
+    case("protocol/unimodal/penalty", lambda: pen.Unimodality().penalty(aux_A))
+    delta = rs.uniform(size=(rank, rank))
+    case("protocol/pf2/subtract_from_auxes", lambda: pf2.subtract_from_auxes((eyes, delta), dual_B))
+    case("protocol/pf2/auxes_as_matrices", lambda: pf2.auxes_as_matrices((eyes, delta)))
+    case("protocol/pf2/subtract_from_aux", lambda: pf2.subtract_from_aux(aux_A, dual_A))
+    case("protocol/pf2/aux_as_matrix", lambda: pf2.aux_as_matrix(aux_A))
+    case("protocol/pf2/penalty_list", lambda: pf2.penalty(aux_B))
+    case("protocol/pf2/penalty_matrix", lambda: pf2.penalty(aux_A))
     return out
