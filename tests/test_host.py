@@ -24,6 +24,40 @@ def test_library_exports_every_declared_symbol():
     assert lib.b2_version() >= 100
 
 
+def test_ctypes_table_matches_header_prototypes():
+    """ABI drift guard: every prototype of include/matcouply_b200.h is parsed and compared, parameter by parameter,
+    with the ctypes argtypes / restype the Python host binds (a mismatch would corrupt a call silently)."""
+    import ctypes
+
+    from matcouply_b200 import _lib
+
+    header = open(os.path.join(ROOT, "include", "matcouply_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", " ", header, flags=re.S)
+    header = re.sub(r"//[^\n]*", " ", header)
+    protos = re.findall(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(b2_[a-z0-9_]+)\s*\(([^()]*)\)\s*;", header)
+    assert len(protos) == len(_lib.EXPORTED_SYMBOLS)
+
+    def ctype_of(decl):
+        decl = re.sub(r"\bconst\b", " ", decl).strip()
+        if "*" in decl:
+            return ctypes.c_char_p if re.match(r"char\s*\*$", decl) else ctypes.c_void_p
+        words = decl.split()
+        base = " ".join(words[:-1]) if len(words) > 1 and words[-1] not in ("int", "long", "double", "size_t") else decl
+        return {"int": ctypes.c_int, "long long": ctypes.c_longlong, "size_t": ctypes.c_size_t,
+                "double": ctypes.c_double, "unsigned long long": ctypes.c_ulonglong, "void": None}[base]
+
+    for ret, name, params in protos:
+        params = params.strip()
+        want = [] if params in ("", "void") else [ctype_of(q) for q in params.split(",")]
+        if name in _lib._SIGNATURES:
+            got, res = _lib._SIGNATURES[name], ctypes.c_int
+        else:
+            got, res = _lib._OTHER[name]
+        got = [ctypes.c_void_p if isinstance(g, type) and issubclass(g, ctypes._Pointer) else g for g in got]  # typed
+        assert got == want, (name, got, want)                                      # struct pointers are pointers
+        assert ctype_of(ret.strip()) == res, (name, ret, res)
+
+
 def test_no_product_import_of_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "matcouply_b200")):
         for f in files:
