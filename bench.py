@@ -181,6 +181,30 @@ class ClockSampler:
         return out
 
 
+def use_all_host_threads():
+    """CPU legs: give BLAS / OpenMP / torch every core this process may run on (torchrun exports OMP_NUM_THREADS=1,
+    which would silently make the baseline single-threaded) and return the thread count ACTUALLY in effect."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    used = 1
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+
+        threadpool_limits(limits=n)  # called as a function: stays in effect
+        used = max([int(lib.get("num_threads", 1)) for lib in threadpool_info() if lib.get("user_api") == "blas"] or [1])
+    except Exception:
+        pass
+    try:
+        import torch
+
+        torch.set_num_threads(n)
+    except Exception:
+        pass
+    return used
+
+
 def oracle_iter_seconds(mats, R, kw):
     """Reference algorithm on the CPU (oracle port): seconds per outer iteration = (t(3 its) - t(1 it)) / 2."""
     from oracle import aoadmm_oracle as O
@@ -325,6 +349,7 @@ def run_reference(args, cfg, sizes):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cores = use_all_host_threads()
     S = cpu_sample_size(cfg)
     mats = gen_host_sample(cfg, sizes, S)
     rows = sum(m.shape[0] for m in mats)
@@ -340,7 +365,7 @@ def run_reference(args, cfg, sizes):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * t_full,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": cfg["desc"], "sample": f"first {S} slices ({rows} rows), time scaled by rows"},
-        "cpu_baseline": {"value": value, "unit": "iter/s", "cores": os.cpu_count(), "kind": "port",
+        "cpu_baseline": {"value": value, "unit": "iter/s", "cores": cores, "kind": "port",
                          "sample": f"first {S} of {cfg['I']} slices ({rows} of {total_rows} rows); "
                                    f"{t_iter_sample:.3f} s per outer iteration on the sample, scaled linearly in rows"},
         "e2e": {"value": value, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -534,9 +559,10 @@ def main():
         rows = sum(m.shape[0] for m in mats)
         total_rows = int(sizes.sum())
         if world == 1:
+            cores = use_all_host_threads()
             t_s = oracle_iter_seconds(mats, cfg["R"], cfg["kw"])
             line["cpu_baseline"] = {
-                "value": 1.0 / (t_s * total_rows / rows), "unit": "iter/s", "cores": os.cpu_count(), "kind": "port",
+                "value": 1.0 / (t_s * total_rows / rows), "unit": "iter/s", "cores": cores, "kind": "port",
                 "sample": f"first {S} of {cfg['I']} slices ({rows} of {total_rows} rows): {t_s:.3f} s per outer "
                           f"iteration, scaled linearly in rows (every reference loop is per slice)"}
             line["cpu_baseline_torch"] = torch_cpu_baseline(mats, cfg["R"], cfg["kw"], total_rows, cfg["I"])
