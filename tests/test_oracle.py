@@ -206,3 +206,21 @@ def test_torch_cpu_oracle_refuses_numpy_only_penalties():
 
     with pytest.raises(TypeError):  # unimodal is not even a keyword of the torch column (penalties.py:1008-1009)
         ao_admm_torch_cpu([np.ones((4, 3))], 2, unimodal={1: True})
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_oracle_matches_reference_on_random_configs(seed):
+    """The 24 seeded random combinations of all penalty kinds / Parafac2 options / feasibility-penalty modes / inits of
+    the GPU differential test (tests/test_gpu_aoadmm.py::test_random_penalty_combinations_match_oracle), run through
+    the UNMODIFIED reference by oracle/gen_golden_random.py: the oracle reproduces the reference's final factors and
+    its whole loss / error history, which closes the chain CUDA path == oracle == reference on these problems."""
+    from oracle.random_configs import random_config, reference_safe
+
+    g = np.load(os.path.join(HERE, "golden", "random_configs.npz"))
+    X, R, kw = random_config(seed)
+    o = O.ao_admm(X, R, **reference_safe(kw))
+    np.testing.assert_allclose(o["regularized_loss"], g[f"s{seed}_loss"], rtol=1e-9)
+    np.testing.assert_allclose(o["rec_errors"], g[f"s{seed}_rec"], rtol=1e-9)
+    for got, key in ((o["A"], "A"), (np.concatenate(o["B_is"], 0), "B"), (o["C"], "C")):
+        ref = g[f"s{seed}_{key}"]
+        assert np.linalg.norm(got - ref) <= 1e-9 * np.linalg.norm(ref), (seed, key)
