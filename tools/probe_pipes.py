@@ -1,7 +1,7 @@
 """Do the DMMA and DFMA pipes overlap on B200?  Times microbench kinds 0 (DFMA), 1 (DMMA), 3 (8 DMMA + 16 DFMA interleaved)
 with the same iteration count.  If t3 ~= t1 the pipes are independent; if t3 ~= t1 + t0 * (1024/8192) ... they share."""
 import json, os, sys
-import numpy as np, torch
+import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from matcouply_b200 import _ops  # noqa: E402

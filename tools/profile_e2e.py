@@ -1,6 +1,6 @@
 """Where does the host-facing cmf_aoadmm call spend its time? (bench.py's e2e leg on the c2 sample)"""
 import cProfile, io, os, pstats, sys, time
-import numpy as np, torch
+import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
