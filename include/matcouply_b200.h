@@ -241,6 +241,11 @@ int b2_pf2_fixed_basis(void* pd, void* dual, const void* P, const void* Delta, c
  * state_io is advanced so the host generator can continue the stream (decomposition.py:31-39, 78-89;
  * penalties.py:125-147, 239-261 draw everything from one RandomState). */
 int b2_mt19937_uniform(void* state_io, double* out, long long n, void* stream);
+/* HOST function (state_io is a HOST pointer, no CUDA call): advance the same 625-word state by n_words 32-bit outputs
+ * (2 per double) in O(1) of n_words — MT19937 jump-ahead, t^J mod the characteristic polynomial applied by Horner's
+ * rule.  Lets a rank of a sharded run skip the rows of other ranks in the reference's single RandomState stream
+ * (decomposition.py:31-39, 78-89) instead of walking them; bit-identical to drawing and discarding. */
+int b2_mt19937_jump_host(unsigned* state_io, unsigned long long n_words);
 
 /* ---- measurement helpers (bench.py / DESIGN.md roofline denominators) -------------------------------------------
  * kind 0: fp64 FMA pipe, 1: DMMA.8x8x4, 2: fp32 FMA, 3: DMMA + DFMA interleaved (pipe overlap probe). Runs `iters` dependent-chain-free iterations on every SM and

@@ -178,6 +178,29 @@ class DeviceRows:
         return DeviceRows(self.tensor[int(off[lo]):int(off[hi])], off[lo:hi + 1] - off[lo])
 
 
+class ShardRows:
+    """A mode-1 variable of a SHARDED run of which only this rank's slices ``[lo, hi)`` were drawn (the rest of the
+    reference's RandomState stream was skipped with the MT19937 jump-ahead, `_ops.mt19937_skip`).  Stands in for the
+    global list until `distributed.shard_state` cuts the rank's share out of it."""
+
+    def __init__(self, local, lo, hi, n_global):
+        self.local, self.lo, self.hi, self.n_global = local, int(lo), int(hi), int(n_global)
+
+    def __len__(self):
+        return self.n_global
+
+    def cut(self, lo, hi):
+        if (int(lo), int(hi)) != (self.lo, self.hi):
+            raise ValueError(f"only slices [{self.lo}, {self.hi}) were drawn on this rank, not [{lo}, {hi})")
+        return self.local
+
+    def __getitem__(self, i):
+        raise RuntimeError(f"only slices [{self.lo}, {self.hi}) of this variable exist on this rank")
+
+    def __iter__(self):
+        raise RuntimeError(f"only slices [{self.lo}, {self.hi}) of this variable exist on this rank")
+
+
 class _ModeState:
     """Factor matrix + per-penalty aux/dual of one mode, all flat (n x R) device tensors."""
 

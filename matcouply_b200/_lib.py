@@ -70,6 +70,7 @@ _SIGNATURES = {
     "b2_prox_elementwise": [_vp, _vp, _ll, _i, _i, _d, _d, _d, _i, _vp],
     "b2_microbench_flops": [_i, _i, ctypes.POINTER(_d), _vp, _vp],
     "b2_mt19937_uniform": [_vp, _vp, _ll, _vp],
+    "b2_mt19937_jump_host": [_vp, ctypes.c_ulonglong],
     "b2_set_option": [_i, _i],
 }
 _OTHER = {

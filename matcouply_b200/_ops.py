@@ -293,6 +293,19 @@ def mt19937_uniform(random_state, n, device):
     return out
 
 
+def mt19937_skip(random_state, n):
+    """Advance ``random_state`` (legacy MT19937 ``np.random.RandomState``) exactly as ``random_state.uniform(size=n)``
+    would, without drawing: host-side jump-ahead (``b2_mt19937_jump_host``), cost independent of ``n``."""
+    name, key, pos, has_gauss, cached = random_state.get_state(legacy=True)
+    if name != "MT19937":
+        raise TypeError("skipping needs a MT19937 RandomState")
+    st = np.empty(625, dtype=np.uint32)
+    st[:624] = key
+    st[624] = pos
+    call("b2_mt19937_jump_host", st.ctypes.data, 2 * int(n))
+    random_state.set_state(("MT19937", st[:624].copy(), int(st[624]), has_gauss, cached))
+
+
 _SIDE_STREAMS = {}
 
 

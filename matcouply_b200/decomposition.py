@@ -19,6 +19,7 @@ from .coupled_matrices import CoupledMatrixFactorization
 
 __all__ = ["compute_feasibility_gaps", "ADMMVars", "DiagnosticMetrics", "cmf_aoadmm", "parafac2_aoadmm"]
 
+_MT_JUMP_DEFAULT = "0"  # sharded initial state: "1" = jump-ahead draws of the local rows only (see _device_rows_uniform)
 _ALS_INITS = {"parafac2_als", "cp_als", "parafac_als", "cp_hals", "parafac_hals"}  # need TensorLy (host, one-off)
 
 
@@ -453,8 +454,17 @@ def cmf_aoadmm(
     # default path: the big B-mode blocks (B_i, aux, dual) are drawn on the device from random_state's own MT19937
     # stream (bit-identical to host draws, see csrc/rng.cu); B2_HOST_RNG=1 forces the host draws
     dev_draw = None if os.environ.get("B2_HOST_RNG") else device
+    # sharded run: draw only this rank's rows of every device-drawn variable and jump over the others in the stream
+    # (B2_MT_JUMP=0 walks the whole global stream on every rank instead; same bits either way)
+    draw_window = None
+    if shard is not None and dev_draw is not None and os.environ.get("B2_MT_JUMP", _MT_JUMP_DEFAULT) != "0":
+        draw_window = (shard.lo, shard.hi)
     if init == "random" and dev_draw is not None:
-        A0, B0, C0 = initialize_cmf(shape_view, rank, init, random_state=random_state, _device=dev_draw)
+        penalties._DEVICE_DRAW["window"] = draw_window
+        try:
+            A0, B0, C0 = initialize_cmf(shape_view, rank, init, random_state=random_state, _device=dev_draw)
+        finally:
+            penalties._DEVICE_DRAW["window"] = None
     else:
         init_view = shape_view
         needs_data = isinstance(init, str) and (init in ("svd", "threshold_svd") or init in _ALS_INITS)
@@ -485,11 +495,13 @@ def cmf_aoadmm(
 
     # aux first, then dual, each in mode order from the same RandomState (decomposition.py:78-89)
     penalties._DEVICE_DRAW["device"] = dev_draw
+    penalties._DEVICE_DRAW["window"] = draw_window
     try:
         auxes = [[reg.init_aux(shape_view, rank, m, random_state=random_state) for reg in regs[m]] for m in range(3)]
         duals = [[reg.init_dual(shape_view, rank, m, random_state=random_state) for reg in regs[m]] for m in range(3)]
     finally:
         penalties._DEVICE_DRAW["device"] = None
+        penalties._DEVICE_DRAW["window"] = None
 
     if isinstance(constant_feasibility_penalty, str) and constant_feasibility_penalty not in {"A", "B"}:
         raise ValueError(

@@ -42,7 +42,7 @@ def _check_random_state(seed):
 
 
 # set by cmf_aoadmm around its own init_aux / init_dual calls (see _init_variable); None = draw on the host
-_DEVICE_DRAW = {"device": None}
+_DEVICE_DRAW = {"device": None, "window": None}  # window: (lo, hi) slices of this rank in a sharded run, or None
 
 
 def _device_rows_uniform(random_state, matrices, rank, device):
@@ -51,6 +51,18 @@ def _device_rows_uniform(random_state, matrices, rank, device):
     from ._engine import DeviceRows
 
     off = np.concatenate([[0], np.cumsum([int(m.shape[0]) for m in matrices])]).astype(np.int64)
+    window = _DEVICE_DRAW.get("window")
+    if window is not None:
+        # sharded run: skip the rows of the other ranks in the stream (MT19937 jump-ahead on the host, O(1) in the
+        # number of skipped draws) and draw only this rank's rows; the generator ends where the global draw would
+        from ._engine import ShardRows
+
+        lo, hi = window
+        n_local = int(off[hi] - off[lo])
+        _ops.mt19937_skip(random_state, int(off[lo]) * rank)
+        flat = _ops.mt19937_uniform(random_state, n_local * rank, device)
+        _ops.mt19937_skip(random_state, int(off[-1] - off[hi]) * rank)
+        return ShardRows(DeviceRows(flat.view(n_local, rank), off[lo:hi + 1] - off[lo]), lo, hi, len(matrices))
     flat = _ops.mt19937_uniform(random_state, int(off[-1]) * rank, device)
     return DeviceRows(flat.view(int(off[-1]), rank), off)
 

@@ -344,3 +344,66 @@ def test_host_contract_matches_reference(golden_dir):
         else:
             assert ours[name] == ref[name], (name, ref[name], ours[name])
     assert len(ref) >= 160 and sum(isinstance(v, str) and v.split(":")[0].endswith("Error") for v in ref.values()) >= 70
+
+
+def test_mt19937_jump_matches_numpy_stream():
+    """b2_mt19937_jump_host (host function of the C ABI, no GPU needed): jumping over n draws leaves the RandomState
+    in EXACTLY the state drawing them would — key words, position, and therefore every later draw — from any
+    starting position, across block boundaries and over distances where the polynomial path is taken."""
+    from matcouply_b200 import _ops
+
+    for seed, pre, n in [(0, 0, 1), (0, 0, 312), (1, 5, 311), (2, 100, 624 * 30), (3, 7, 624 * 33 + 17),
+                         (4, 1, 50_000), (5, 311, 1_000_000), (6, 0, 6_000_000), (7, 12345, 20_000_003)]:
+        a, b = np.random.RandomState(seed), np.random.RandomState(seed)
+        a.random_sample(pre), b.random_sample(pre)
+        a.random_sample(n)
+        _ops.mt19937_skip(b, n)
+        sa, sb = a.get_state(), b.get_state()
+        assert np.array_equal(sa[1], sb[1]) and sa[2] == sb[2], (seed, pre, n)
+        assert np.array_equal(a.random_sample(100), b.random_sample(100))
+        assert np.array_equal(a.standard_normal(5), b.standard_normal(5))
+    c = np.random.RandomState(3)
+    c.standard_normal(3)  # a cached Gaussian must survive the jump like it survives uniform draws
+    d = np.random.RandomState(3)
+    d.standard_normal(3)
+    c.random_sample(1000)
+    _ops.mt19937_skip(d, 1000)
+    assert np.array_equal(c.standard_normal(4), d.standard_normal(4))
+
+
+def test_sharded_device_draw_window_equals_cut_of_global_draw(monkeypatch):
+    """Sharded initial state: drawing only this rank's rows of a mode-1 variable (jump over the other ranks' rows in
+    the stream) gives the same rows as cutting them out of the global draw, and leaves the generator where the
+    global draw leaves it.  The device generator is replaced by NumPy's here (it is bit-identical to it on the GPU:
+    tests/test_gpu_kernels.py), so the host logic runs on the CPU."""
+    import torch
+
+    from matcouply_b200 import _ops, penalties
+    from matcouply_b200._engine import ShardRows
+    from matcouply_b200.distributed import make_shard, shard_state
+
+    monkeypatch.setattr(_ops, "mt19937_uniform",
+                        lambda rs, n, device: torch.from_numpy(rs.random_sample(int(n))))
+    rows = [7, 3, 12, 5, 9, 4, 11, 6]
+    mats = [np.empty((j, 5)) for j in rows]
+    rank = 4
+    for world in (2, 3):
+        for r in range(world):
+            shard = make_shard(rows, r, world)
+            g, w = np.random.RandomState(11), np.random.RandomState(11)
+            g.uniform(size=3), w.uniform(size=3)
+            full = penalties._device_rows_uniform(g, mats, rank, "cpu")
+            monkeypatch.setitem(penalties._DEVICE_DRAW, "window", (shard.lo, shard.hi))
+            part = penalties._device_rows_uniform(w, mats, rank, "cpu")
+            monkeypatch.setitem(penalties._DEVICE_DRAW, "window", None)
+            assert isinstance(part, ShardRows) and len(part) == len(rows)
+            want, got = full.cut(shard.lo, shard.hi), part.cut(shard.lo, shard.hi)
+            assert torch.equal(want.tensor, got.tensor) and np.array_equal(want.row_offsets, got.row_offsets)
+            assert np.array_equal(g.get_state()[1], w.get_state()[1]) and g.get_state()[2] == w.get_state()[2]
+            with pytest.raises(ValueError):
+                part.cut(0, len(rows) + 1)
+            # through shard_state, as cmf_aoadmm does it (NonNegativity aux / dual on mode 1 + the factor itself)
+            regs = [[], [penalties.NonNegativity()], []]
+            A = np.ones((len(rows), rank))
+            A1, B1, aux1, dual1 = shard_state(A, part, [[], [part], []], [[], [part], []], regs, shard)
+            assert B1 is got and aux1[1][0] is got and dual1[1][0] is got and A1.shape[0] == shard.hi - shard.lo
