@@ -19,7 +19,7 @@ from .coupled_matrices import CoupledMatrixFactorization
 
 __all__ = ["compute_feasibility_gaps", "ADMMVars", "DiagnosticMetrics", "cmf_aoadmm", "parafac2_aoadmm"]
 
-_MT_JUMP_DEFAULT = "0"  # sharded initial state: "1" = jump-ahead draws of the local rows only (see _device_rows_uniform)
+_MT_JUMP_DEFAULT = "1"  # sharded initial state: "1" = jump-ahead draws of the local rows only (see _device_rows_uniform)
 _ALS_INITS = {"parafac2_als", "cp_als", "parafac_als", "cp_hals", "parafac_hals"}  # need TensorLy (host, one-off)
 
 

@@ -161,3 +161,67 @@ def test_two_rank_matrix_penalties_on_sharded_mode0(tmp_path, variant):
     errs = (_rel(r0["A"], o["A"]), _rel(r0["B"], np.concatenate(o["B_is"], 0)), _rel(r0["C"], o["C"]))
     assert max(errs) < 1e-8, errs
     np.testing.assert_allclose(r0["loss"], o["regularized_loss"][: k + 1], rtol=1e-8)
+
+
+def _jump_worker(rank, port, name, out_path):
+    """One GPU, a one-rank NCCL group: play rank 0 and rank 1 of a two-rank sharding one after the other (the
+    all-reduces are identities, so the numbers are not the global solution — but the INITIAL STATE path is the sharded
+    one) with the global stream walk (B2_MT_JUMP=0) and with the jump-ahead draw of the local rows (B2_MT_JUMP=1)."""
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+
+    from matcouply_b200 import cmf_aoadmm
+    from matcouply_b200.distributed import make_shard
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(0)
+    dist.init_process_group("nccl", rank=0, world_size=1, device_id=torch.device("cuda", 0))
+
+    def flat(v, out):
+        if isinstance(v, np.ndarray):
+            out.append(np.array(v))
+        elif isinstance(v, (list, tuple)) or hasattr(v, "__iter__"):
+            for u in v:
+                flat(u, out)
+        return out
+
+    try:
+        g, X, R, kw = _load_case(name)
+        kw = dict(kw)
+        kw.pop("n_iter_max", None)
+        worst, n_arrays = 0.0, 0
+        for fake_rank in (0, 1):
+            sh = make_shard([x.shape[0] for x in X], fake_rank, 2)
+            runs = {}
+            for mode in ("0", "1"):
+                os.environ["B2_MT_JUMP"] = mode
+                cmf, admm, diag = cmf_aoadmm(X[sh.lo:sh.hi], R, n_iter_max=2, tol=None, absolute_tol=None,
+                                             return_errors=True, return_admm_vars=True,
+                                             process_group=dist.group.WORLD, shard=sh, **kw)
+                arrays = flat([cmf[1][0], list(cmf[1][1]), cmf[1][2]], [])
+                flat([list(admm[0]), list(admm[1])], arrays)
+                arrays.append(np.asarray(diag.regularized_loss))
+                runs[mode] = arrays
+            assert len(runs["0"]) == len(runs["1"])
+            for a, b in zip(runs["0"], runs["1"]):
+                assert a.shape == b.shape
+                worst = max(worst, float(np.max(np.abs(a - b))) if a.size else 0.0)
+                n_arrays += 1
+        with open(out_path, "w") as f:
+            json.dump({"worst": worst, "arrays": n_arrays}, f)
+    finally:
+        os.environ.pop("B2_MT_JUMP", None)
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["c2_nn_pf2_l1_ragged", "c3_unimodal_l2ball_pf2"])
+def test_sharded_jump_ahead_draw_is_bit_identical_to_the_global_walk(name, tmp_path):
+    """Runs on ONE GPU.  The sharded initial state drawn with the MT19937 jump-ahead (local rows only) leads to
+    bit-identical factors, ADMM variables and losses as walking the whole global RandomState stream."""
+    import torch.multiprocessing as mp
+
+    out = str(tmp_path / "jump.json")
+    mp.spawn(_jump_worker, args=(_free_port(), name, out), nprocs=1, join=True)
+    res = json.load(open(out))
+    assert res["arrays"] > 10 and res["worst"] == 0.0, res
