@@ -4,6 +4,7 @@ torch is plumbing only (device memory + stream); every computation below is a ha
 ``matcouply_b200/csrc``.  All functions require CUDA tensors and raise otherwise (no CPU fallback).
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -278,6 +279,12 @@ def mt19937_uniform(random_state, n, device):
     st = np.empty(625, dtype=np.uint32)
     st[:624] = key
     st[624] = pos
+    n_chunks = int(os.environ.get("B2_MT_CHUNKS", "1"))  # opt-in until measured on the GPU
+    if n_chunks > 1 and int(n) >= _MT_CHUNK_MIN_DRAWS:
+        bounds, starts, final = mt_chunk_plan(st, int(n), n_chunks)
+        out = _mt19937_uniform_chunked(bounds, starts, device)
+        random_state.set_state(("MT19937", final[:624].copy(), int(final[624]), has_gauss, cached))
+        return out
     # a side stream: the generator kernel (one CTA) overlaps whatever the caller's stream is doing (cmf_aoadmm: the
     # H2D copy of the data), and reading back the advanced state only waits for the generator
     main = torch.cuda.current_stream(device)
@@ -290,6 +297,45 @@ def mt19937_uniform(random_state, n, device):
     main.wait_stream(side)
     out.record_stream(main)
     random_state.set_state(("MT19937", new[:624].copy(), int(new[624]), has_gauss, cached))
+    return out
+
+
+_MT_CHUNK_MIN_DRAWS = 1 << 20
+
+
+def mt_chunk_plan(state, n, n_chunks):
+    """Cut the next ``n`` doubles of the MT19937 stream whose 625-word state is ``state`` into ``n_chunks`` consecutive
+    chunks: returns (bounds [n_chunks + 1], start state of every chunk [n_chunks x 625], state after all n draws),
+    each start obtained from the previous one with the host jump-ahead (``b2_mt19937_jump_host``, 2 ms per jump)."""
+    bounds = np.linspace(0, int(n), int(n_chunks) + 1).astype(np.int64)
+    cur = np.array(state, dtype=np.uint32)
+    starts = np.empty((int(n_chunks), 625), dtype=np.uint32)
+    for c in range(int(n_chunks)):
+        starts[c] = cur
+        call("b2_mt19937_jump_host", cur.ctypes.data, 2 * int(bounds[c + 1] - bounds[c]))
+    return bounds, starts, cur
+
+
+def _mt19937_uniform_chunked(bounds, starts, device):
+    """The chunks of `mt_chunk_plan` generated concurrently: the sequential one-CTA generator kernel of csrc/rng.cu once
+    per chunk, every launch on its own stream and from its own jumped start state (same bits as one long walk)."""
+    n_chunks, n = len(starts), int(bounds[-1])
+    main = torch.cuda.current_stream(device)
+    streams = [_side_stream(device, c) for c in range(n_chunks)]
+    with torch.cuda.stream(streams[0]):
+        dstates = torch.from_numpy(np.ascontiguousarray(starts).view(np.int32)).to(device)
+        out = torch.empty(n, dtype=torch.float64, device=device)
+    for c, side in enumerate(streams):
+        if c:
+            side.wait_stream(streams[0])  # the allocation and the state upload belong to the first side stream
+        lo, cnt = int(bounds[c]), int(bounds[c + 1] - bounds[c])
+        if cnt:
+            with torch.cuda.stream(side):
+                call("b2_mt19937_uniform", _ptr(dstates[c]), ctypes.c_void_p(out.data_ptr() + 8 * lo), cnt, _stream())
+        main.wait_stream(side)
+        out.record_stream(side)
+        dstates.record_stream(side)
+    out.record_stream(main)
     return out
 
 
@@ -309,8 +355,9 @@ def mt19937_skip(random_state, n):
 _SIDE_STREAMS = {}
 
 
-def _side_stream(device):
-    key = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+def _side_stream(device, which=0):
+    dev = torch.device(device).index if torch.device(device).index is not None else torch.cuda.current_device()
+    key = dev if which == 0 else (dev, which)
     if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = torch.cuda.Stream(device=key)
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device=dev)
     return _SIDE_STREAMS[key]

@@ -701,6 +701,23 @@ def test_device_mt19937_continues_numpy_randomstate(seed, skip, n):
     np.testing.assert_array_equal(rs.standard_normal(size=3), ref.standard_normal(size=3))
 
 
+@pytest.mark.skipif(not os.environ.get("B2_TEST_EXPERIMENTAL"),
+                    reason="opt-in path written after the round's GPU budget ended: validate it first (DESIGN.md §7)")
+@pytest.mark.parametrize("n_chunks,n", [(2, 1 << 20), (8, 3_000_001), (16, 5_000_000)])
+def test_device_mt19937_chunked_generation(monkeypatch, n_chunks, n):
+    """B2_MT_CHUNKS (opt-in): the stream cut into chunks with the host jump-ahead, one generator launch per chunk on
+    its own CUDA stream — same doubles and same final generator state as one sequential walk."""
+    _lib, _ops, _ = _imports()
+    monkeypatch.setenv("B2_MT_CHUNKS", str(n_chunks))
+    ref, rs = np.random.RandomState(5), np.random.RandomState(5)
+    ref.uniform(size=13), rs.uniform(size=13)
+    want = ref.uniform(size=n)
+    got = _ops.mt19937_uniform(rs, n, torch.device("cuda"))
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(got.cpu().numpy(), want)
+    np.testing.assert_array_equal(rs.uniform(size=7), ref.uniform(size=7))
+
+
 @pytest.mark.parametrize("R", [1, 2, 3, 4, 5, 7, 8, 13, 16, 17, 20, 21, 24, 25, 31, 32])
 @pytest.mark.parametrize("dtype", ["f64", "f32"])
 def test_parafac2_polar_warp_vs_cta_and_numpy(R, dtype):

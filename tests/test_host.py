@@ -407,3 +407,26 @@ def test_sharded_device_draw_window_equals_cut_of_global_draw(monkeypatch):
             A = np.ones((len(rows), rank))
             A1, B1, aux1, dual1 = shard_state(A, part, [[], [part], []], [[], [part], []], regs, shard)
             assert B1 is got and aux1[1][0] is got and dual1[1][0] is got and A1.shape[0] == shard.hi - shard.lo
+
+
+def test_mt_chunk_plan_states_match_the_sequential_walk():
+    """Chunked generation plan (opt-in B2_MT_CHUNKS): every chunk's start state is the state NumPy's generator has
+    after the draws of the chunks before it, and the final state is the one after all n draws."""
+    from matcouply_b200 import _ops
+
+    rs = np.random.RandomState(21)
+    rs.uniform(size=77)
+    name, key, pos, _, _ = rs.get_state()
+    st = np.empty(625, dtype=np.uint32)
+    st[:624], st[624] = key, pos
+    n, n_chunks = 2_000_003, 7
+    bounds, starts, final = _ops.mt_chunk_plan(st, n, n_chunks)
+    assert bounds[0] == 0 and bounds[-1] == n and len(starts) == n_chunks
+    walk = np.random.RandomState(21)
+    walk.uniform(size=77)
+    for c in range(n_chunks):
+        k, p = walk.get_state()[1:3]
+        assert np.array_equal(starts[c, :624], k) and int(starts[c, 624]) == p, c
+        walk.random_sample(int(bounds[c + 1] - bounds[c]))
+    k, p = walk.get_state()[1:3]
+    assert np.array_equal(final[:624], k) and int(final[624]) == p
