@@ -79,18 +79,20 @@ void reduce(uint64_t* p) {
     }
 }
 
-uint16_t g_spread[256];
-bool g_spread_ready = false;
-
-void square(uint64_t* p) {  // p (degree < 19937, words 0..311) <- p^2 (bits interleaved with zeros)
-    if (!g_spread_ready) {
+struct SpreadTable {  // byte -> its 8 bits interleaved with zeros (squaring over GF(2))
+    uint16_t v[256];
+    SpreadTable() {
         for (int b = 0; b < 256; ++b) {
             uint16_t s = 0;
             for (int i = 0; i < 8; ++i) s |= (uint16_t)(((b >> i) & 1) << (2 * i));
-            g_spread[b] = s;
+            v[b] = s;
         }
-        g_spread_ready = true;
     }
+};
+
+void square(uint64_t* p) {  // p (degree < 19937, words 0..311) <- p^2 (bits interleaved with zeros)
+    static const SpreadTable table;  // thread-safe one-time initialisation
+    const uint16_t* g_spread = table.v;
     for (int wi = kPolyWords / 2 - 1; wi >= 0; --wi) {
         const uint64_t v = p[wi];
         uint64_t lo = 0, hi = 0;
