@@ -430,3 +430,27 @@ def test_mt_chunk_plan_states_match_the_sequential_walk():
         walk.random_sample(int(bounds[c + 1] - bounds[c]))
     k, p = walk.get_state()[1:3]
     assert np.array_equal(final[:624], k) and int(final[624]) == p
+
+
+def test_mt19937_characteristic_polynomial_table():
+    """The 135-term table of csrc/mt_jump.cu really is the characteristic polynomial of NumPy's MT19937: the raw
+    (untempered) word sequence x_k of a RandomState satisfies XOR_{e in phi} x_{k+e} = 0 for every k >= 1 (k = 0 only
+    in its top bit: the low 31 bits of the first word never enter the recurrence)."""
+    src = open(os.path.join(ROOT, "matcouply_b200", "csrc", "mt_jump.cu")).read()
+    body = re.search(r"kPhiExps\[135\] = \{(.*?)\};", src, re.S).group(1)
+    exps = np.array([int(t) for t in re.findall(r"\d+", body)], dtype=np.int64)
+    assert len(exps) == 135 and exps[0] == 0 and exps[-1] == 19937 and np.all(np.diff(exps) > 0)
+    rs = np.random.RandomState(2024)
+    blocks = [rs.get_state()[1].copy()]
+    for _ in range(34):
+        rs.bytes(4 * 624)  # consumes exactly one block
+        key, pos = rs.get_state()[1:3]
+        assert pos == 624
+        blocks.append(key.copy())
+    x = np.concatenate(blocks).astype(np.uint32)
+    ks = np.arange(0, 1200)
+    acc = np.bitwise_xor.reduce(x[ks[None, :] + exps[:, None]], axis=0)
+    assert not acc[1:].any()
+    assert (acc[0] & np.uint32(0x80000000)) == 0
+    # and it is not satisfied by a shifted table (the check has teeth)
+    assert np.bitwise_xor.reduce(x[ks[None, :] + (exps[:, None] + (exps[:, None] > 0))], axis=0)[1:].any()
