@@ -188,9 +188,14 @@ def cmf_to_matrices(cmf, validate=True):
     return [cmf_to_matrix((None, (A, B_is, C)), i, validate=False) for i in range(A.shape[0])]
 
 
-cmf_to_slice = cmf_to_matrix
-cmf_to_slices = cmf_to_matrices
-cmf_to_slices = cmf_to_matrices
+def cmf_to_slice(cmf, slice_idx, validate=True):
+    """Alias of ``cmf_to_matrix`` with the reference's keyword name (coupled_matrices.py:431)."""
+    return cmf_to_matrix(cmf, slice_idx, validate=validate)
+
+
+def cmf_to_slices(cmf, validate=True):
+    """Alias of ``cmf_to_matrices`` (coupled_matrices.py:507)."""
+    return cmf_to_matrices(cmf, validate=validate)
 
 
 def cmf_to_tensor(cmf, validate=True):

@@ -231,6 +231,22 @@ def initialize_cmf(matrices, rank, init, svd_fun=None, random_state=None, init_p
     raise ValueError('Initialization method "{}" not recognized'.format(init))
 
 
+def initialize_aux(matrices, rank, reg, random_state):
+    """decomposition.py:78-82: the auxiliary variables of every penalty, mode by mode, from ONE RandomState."""
+    A_aux_list = [A_reg.init_aux(matrices, rank, 0, random_state=random_state) for A_reg in reg[0]]
+    B_aux_list = [B_reg.init_aux(matrices, rank, 1, random_state=random_state) for B_reg in reg[1]]
+    C_aux_list = [C_reg.init_aux(matrices, rank, 2, random_state=random_state) for C_reg in reg[2]]
+    return A_aux_list, B_aux_list, C_aux_list
+
+
+def initialize_dual(matrices, rank, reg, random_state):
+    """decomposition.py:85-89: the scaled dual variables, same order."""
+    A_dual_list = [A_reg.init_dual(matrices, rank, 0, random_state=random_state) for A_reg in reg[0]]
+    B_dual_list = [B_reg.init_dual(matrices, rank, 1, random_state=random_state) for B_reg in reg[1]]
+    C_dual_list = [C_reg.init_dual(matrices, rank, 2, random_state=random_state) for C_reg in reg[2]]
+    return A_dual_list, B_dual_list, C_dual_list
+
+
 def _check_feasibility(feasibility_gaps, feasibility_tol):  # decomposition.py:630-640
     worst = -float("inf")
     for mode_gaps in feasibility_gaps:

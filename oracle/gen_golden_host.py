@@ -1,5 +1,6 @@
 """Run oracle/host_cases.py against the UNMODIFIED reference (build container only) and write the outcomes — return
-value summaries and "<ExceptionType>: <message>" strings — to tests/golden/host_contract.json.
+value summaries and "<ExceptionType>: <message>" strings — to tests/golden/host_contract.json, and the signatures of the public callables to
+tests/golden/host_signatures.json.
 
     python oracle/gen_golden_host.py
 
@@ -18,9 +19,9 @@ sys.path.insert(0, os.path.join(HERE, "_condat_standin"))
 sys.path.insert(0, "/root/reference/src")
 sys.path.insert(0, ROOT)
 
-from matcouply import coupled_matrices, decomposition, penalties, random  # noqa: E402  (the reference)
+from matcouply import coupled_matrices, data, decomposition, penalties, random  # noqa: E402  (the reference)
 
-from oracle.host_cases import host_cases  # noqa: E402
+from oracle.host_cases import host_cases, public_signatures  # noqa: E402
 
 if __name__ == "__main__":
     out = host_cases(coupled_matrices, random, decomposition, penalties)
@@ -29,3 +30,9 @@ if __name__ == "__main__":
         json.dump(out, f, indent=1, sort_keys=True)
     n_err = sum(isinstance(v, str) and ": " in v and v.split(":")[0].endswith(("Error", "Exception")) for v in out.values())
     print(f"{len(out)} cases ({n_err} raising) -> {path}")
+    sigs = public_signatures(dict(coupled_matrices=coupled_matrices, data=data, decomposition=decomposition,
+                                  penalties=penalties, random=random))
+    path = os.path.join(ROOT, "tests", "golden", "host_signatures.json")
+    with open(path, "w") as f:
+        json.dump(sigs, f, indent=1, sort_keys=True)
+    print(f"{len(sigs)} signatures -> {path}")

@@ -220,6 +220,13 @@ def host_cases(cm, rnd, dec, pen):
     case("pen/pf2/aux_tuple_wrong_rows",
          lambda: pen.Parafac2(aux_init=([np.eye(j + 1, rank) for j, _ in shapes], np.eye(rank))).init_aux(mats, rank, 1))
 
+    # keyword names of the aliases and the state initialisers (decomposition.py:78-89)
+    case("to_slice/keyword", lambda: cm.cmf_to_slice((w, (A, Bs, C)), slice_idx=2))
+    case("to_matrix/keyword", lambda: cm.cmf_to_matrix((w, (A, Bs, C)), matrix_idx=2))
+    regs3 = [[pen.NonNegativity()], [pen.Parafac2(), pen.L1Penalty(0.1)], [pen.Box(0, 1, aux_init="zeros")]]
+    case("initialize_aux", lambda: dec.initialize_aux(mats, rank, regs3, np.random.RandomState(5)))
+    case("initialize_dual", lambda: dec.initialize_dual(mats, rank, regs3, random_state=np.random.RandomState(5)))
+
     # the host half of the penalty protocol (penalties.py:268-343, 469-485, 1256-1324)
     aux_A, dual_A = rs.uniform(size=(4, rank)), rs.uniform(size=(4, rank))
     aux_B = [rs.uniform(size=(j, rank)) for j, _ in shapes]
@@ -241,4 +248,45 @@ def host_cases(cm, rnd, dec, pen):
     case("protocol/pf2/aux_as_matrix", lambda: pf2.aux_as_matrix(aux_A))
     case("protocol/pf2/penalty_list", lambda: pf2.penalty(aux_B))
     case("protocol/pf2/penalty_matrix", lambda: pf2.penalty(aux_A))
+    return out
+
+
+PUBLIC_CALLABLES = {
+    "decomposition": ["cmf_aoadmm", "parafac2_aoadmm", "initialize_cmf", "initialize_aux", "initialize_dual",
+                      "admm_update_A", "admm_update_B", "admm_update_C", "compute_feasibility_gaps",
+                      "_cmf_reconstruction_error", "_listify", "_parse_all_penalties", "_check_feasibility"],
+    "penalties": ["ADMMPenalty", "MatricesPenalty", "MatrixPenalty", "RowVectorPenalty", "NonNegativity", "Box",
+                  "L1Penalty", "L2Ball", "Unimodality", "Parafac2", "GeneralizedL2Penalty", "TotalVariationPenalty",
+                  "UnitSimplex"],
+    "coupled_matrices": ["CoupledMatrixFactorization", "cmf_to_matrix", "cmf_to_matrices", "cmf_to_slice",
+                         "cmf_to_slices", "cmf_to_tensor", "cmf_to_unfolded", "cmf_to_vec", "_validate_cmf"],
+    "random": ["random_coupled_matrices"],
+    "data": ["get_simple_simulated_data"],
+}
+PROTOCOL_METHODS = ["__init__", "init_aux", "init_dual", "penalty", "subtract_from_aux", "subtract_from_auxes",
+                    "aux_as_matrix", "auxes_as_matrices", "factor_matrix_row_update", "factor_matrix_update",
+                    "factor_matrices_update", "from_CPTensor", "from_Parafac2Tensor", "to_matrix", "to_matrices",
+                    "to_tensor", "to_unfolded", "to_vec"]
+
+
+def public_signatures(modules):
+    """{"module.callable[.method]": [[parameter name, default repr or "<required>"], ...]} for the public surface
+    (modules: dict name -> module).  Positional order, names and defaults are the drop-in contract of a Python API."""
+    import inspect
+
+    def sig(f):
+        return [[n, "<required>" if p.default is inspect.Parameter.empty else repr(p.default)]
+                for n, p in inspect.signature(f).parameters.items()
+                if p.kind not in (p.VAR_KEYWORD, p.VAR_POSITIONAL)]
+
+    out = {}
+    for mod_name, names in PUBLIC_CALLABLES.items():
+        for name in names:
+            obj = getattr(modules[mod_name], name)
+            if inspect.isclass(obj):
+                for m in PROTOCOL_METHODS:
+                    if callable(getattr(obj, m, None)):
+                        out[f"{mod_name}.{name}.{m}"] = sig(getattr(obj, m))
+            else:
+                out[f"{mod_name}.{name}"] = sig(obj)
     return out

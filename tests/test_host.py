@@ -320,7 +320,7 @@ def test_als_inits_delegate_to_tensorly_when_installed(monkeypatch):
 
 
 def test_host_contract_matches_reference(golden_dir):
-    """161 host-side calls (result container, _validate_cmf, cmf_to_*, from_CPTensor / from_Parafac2Tensor,
+    """165 host-side calls (result container, _validate_cmf, cmf_to_*, from_CPTensor / from_Parafac2Tensor,
     random_coupled_matrices, keyword parsing, penalty constructors and aux / dual initialisation) give the outcome the
     unmodified reference gave — same values, same exception TYPES and MESSAGES (tests/golden/host_contract.json, written
     by oracle/gen_golden_host.py from oracle/host_cases.py; the cases restate the reference's own host tests,
@@ -454,3 +454,28 @@ def test_mt19937_characteristic_polynomial_table():
     assert (acc[0] & np.uint32(0x80000000)) == 0
     # and it is not satisfied by a shifted table (the check has teeth)
     assert np.bitwise_xor.reduce(x[ks[None, :] + (exps[:, None] + (exps[:, None] > 0))], axis=0)[1:].any()
+
+
+def test_public_signatures_match_reference(golden_dir):
+    """Every public callable of the host surface (161 functions / constructors / protocol methods) takes the
+    reference's parameters in the reference's order with the reference's defaults (tests/golden/host_signatures.json,
+    dumped from the unmodified reference by oracle/gen_golden_host.py).  Allowed differences: extra trailing
+    parameters (device, process_group, shard, ...) and a default where the reference requires a value (`svd_fun`,
+    unused here) — every call the reference accepts is accepted."""
+    import json
+
+    from matcouply_b200 import coupled_matrices, data, decomposition, penalties, random
+    from oracle.host_cases import public_signatures
+
+    with open(os.path.join(golden_dir, "host_signatures.json")) as f:
+        ref = json.load(f)
+    ours = public_signatures(dict(coupled_matrices=coupled_matrices, data=data, decomposition=decomposition,
+                                  penalties=penalties, random=random))
+    assert len(ref) >= 160
+    for name, want in ref.items():
+        assert name in ours, name
+        got = ours[name]
+        assert [p[0] for p in got[:len(want)]] == [p[0] for p in want], (name, want, got)
+        for (pname, d_ref), (_, d_our) in zip(want, got):
+            assert d_ref == d_our or d_ref == "<required>", (name, pname, d_ref, d_our)
+        assert all(d != "<required>" for _, d in got[len(want):]), (name, got[len(want):])
