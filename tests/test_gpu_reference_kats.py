@@ -269,3 +269,49 @@ def test_admm_update_functions_like_the_reference_tests(mode):
     noisy = [m + 0.05 * rs.standard_normal(size=m.shape) for m in mats]
     naive = np.sqrt(sum(np.sum((x - (b * a) @ C.T) ** 2) for x, b, a in zip(noisy, B_is, A)))
     np.testing.assert_allclose(D._cmf_reconstruction_error(noisy, (None, (A, B_is, C))), naive, rtol=1e-9)
+
+
+def test_custom_penalty_example_imports_work():
+    """The import lines of the reference's custom-penalty example (examples/plot_custom_penalty.py:213-231) work with
+    the package name changed: `_doc_utils.copy_ancestor_docstring`, `_unimodal_regression.unimodal_regression`
+    (vector, matrix and 3-D input, reference tests/test_unimodal_regression.py:44-115), and a penalty built from them
+    runs through `cmf_aoadmm` via `regs` and stays unimodal in all but the last column."""
+    from matcouply_b200 import cmf_aoadmm
+    from matcouply_b200._doc_utils import copy_ancestor_docstring
+    from matcouply_b200._unimodal_regression import unimodal_regression
+    from matcouply_b200.penalties import HardConstraintMixin, MatrixPenalty
+    from oracle import aoadmm_oracle as O
+
+    rs = np.random.RandomState(0)
+    for nn in (False, True):
+        Y = rs.standard_normal(size=(40, 5))
+        want = O.unimodal_regression(Y, non_negativity=nn)
+        np.testing.assert_allclose(unimodal_regression(Y, non_negativity=nn), want, rtol=1e-12, atol=1e-13)
+        np.testing.assert_allclose(unimodal_regression(Y[:, 2], non_negativity=nn), want[:, 2], rtol=1e-12, atol=1e-13)
+        T = rs.standard_normal(size=(30, 3, 2))
+        got = unimodal_regression(T, non_negativity=nn)
+        assert got.shape == T.shape
+        np.testing.assert_allclose(got.reshape(30, 6), O.unimodal_regression(T.reshape(30, 6), non_negativity=nn),
+                                   rtol=1e-12, atol=1e-13)
+    up = np.arange(10.0)
+    np.testing.assert_allclose(unimodal_regression(up), up)  # a monotone vector is unimodal already
+
+    class UnimodalAllExceptLast(HardConstraintMixin, MatrixPenalty):
+        def __init__(self, non_negativity=False, aux_init="random_uniform", dual_init="random_uniform"):
+            super().__init__(aux_init, dual_init)
+            self.non_negativity = non_negativity
+
+        @copy_ancestor_docstring
+        def factor_matrix_update(self, factor_matrix, feasibility_penalty, aux):
+            new = np.copy(factor_matrix)
+            new[:, :-1] = unimodal_regression(factor_matrix[:, :-1], non_negativity=self.non_negativity)
+            if self.non_negativity:
+                new = np.clip(new, 0, None)
+            return new
+
+    _, A, B_is, C, mats = _ragged_cmf(3)
+    pen = UnimodalAllExceptLast(non_negativity=True)
+    cmf, admm = cmf_aoadmm(mats, 3, regs=[[], [pen], []], n_iter_max=5, random_state=0, return_admm_vars=True)
+    for aux in admm[0][1][0]:
+        body = np.asarray(aux)[:, :-1]
+        np.testing.assert_allclose(body, O.unimodal_regression(body, non_negativity=True), rtol=1e-10, atol=1e-12)
