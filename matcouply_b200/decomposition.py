@@ -231,6 +231,18 @@ def initialize_cmf(matrices, rank, init, svd_fun=None, random_state=None, init_p
     raise ValueError('Initialization method "{}" not recognized'.format(init))
 
 
+_SVD_NAMES = ("truncated_svd", "symeig_svd", "randomized_svd", "numpy_svd")  # tensorly.SVD_FUNS, NumPy backend
+
+
+def _check_svd_name(svd):
+    """_utils.py:15-26 (get_svd): an unknown ``svd`` name is refused up front.  The name does not select a code path
+    here — every use of the SVD in the reference is basis-invariant (inverse of an SPD matrix, polar factor) and runs
+    as Cholesky / Jacobi kernels."""
+    if svd not in _SVD_NAMES:
+        raise ValueError(f"Got svd={svd}. However, for the current backend (numpy), the possible choices are "
+                         f"{list(_SVD_NAMES[:3])}")
+
+
 def initialize_aux(matrices, rank, reg, random_state):
     """decomposition.py:78-82: the auxiliary variables of every penalty, mode by mode, from ONE RandomState."""
     A_aux_list = [A_reg.init_aux(matrices, rank, 0, random_state=random_state) for A_reg in reg[0]]
@@ -447,6 +459,7 @@ def cmf_aoadmm(
 
     from ._engine import AOADMMEngine, PackedMatrices
 
+    _check_svd_name(svd)
     if not torch.cuda.is_available():
         raise RuntimeError("matcouply_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)

@@ -479,3 +479,12 @@ def test_public_signatures_match_reference(golden_dir):
         for (pname, d_ref), (_, d_our) in zip(want, got):
             assert d_ref == d_our or d_ref == "<required>", (name, pname, d_ref, d_our)
         assert all(d != "<required>" for _, d in got[len(want):]), (name, got[len(want):])
+
+
+def test_unknown_svd_name_is_refused_before_anything_runs():
+    """_utils.py:15-26: `svd` must name one of TensorLy's SVD functions (checked before the device is touched)."""
+    from matcouply_b200 import cmf_aoadmm, parafac2_aoadmm
+
+    for fn in (cmf_aoadmm, parafac2_aoadmm):
+        with pytest.raises(ValueError, match="Got svd=nonsense"):
+            fn([np.ones((3, 3))], 1, svd="nonsense")
