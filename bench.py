@@ -1,6 +1,6 @@
 """Benchmark of the AO-ADMM hot path (BASELINE.json metric: outer iterations/s at 16k slices + X-stream GB/s).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c1|c3|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c1|c3|c3f32|c4|c4w]
 
 A *step* is one outer AO-ADMM iteration (B-, C-, A-mode ADMM updates + feasibility gaps + fit/loss with the small
 device->host read the stopping rule needs; reference decomposition.py:945-1053) over the whole synthetic data set.
@@ -49,6 +49,11 @@ CONFIGS = {
     "c4": dict(I=8192, K=2048, J=(512, 512), R=32, dtype="f64", kw=dict(non_negative=True),
                desc="BASELINE config[4] per-GPU share: nonneg CMF, 8192 slices 512x2048, R=32, fp64"),
 }
+# config[4] as the weak-scaling sweep BASELINE.json describes: 8192 slices PER GPU (65,536 at 8 GPUs: 550 GB of X, which
+# no single GPU holds).  `value` stays outer iterations/s of the N-times larger problem; `slice_iterations_per_s` =
+# value x slices is the aggregate that should grow with N.
+CONFIGS["c4w"] = dict(CONFIGS["c4"], weak=True,
+                      desc="BASELINE config[4] weak scaling: nonneg CMF, 8192 slices 512x2048 PER GPU, R=32, fp64")
 
 
 def slice_sizes(cfg, seed=1):
@@ -363,7 +368,8 @@ def run_reference(args, cfg, sizes):
     line = {
         "impl": "reference", "metric": "AO-ADMM outer iterations per second", "value": value, "unit": "iter/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * t_full,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak" if cfg.get("weak") else "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
         "config": {"workload": cfg["desc"], "sample": f"first {S} slices ({rows} rows), time scaled by rows"},
         "cpu_baseline": {"value": value, "unit": "iter/s", "cores": cores, "kind": "port",
                          "sample": f"first {S} of {cfg['I']} slices ({rows} of {total_rows} rows); "
@@ -371,6 +377,8 @@ def run_reference(args, cfg, sizes):
         "e2e": {"value": value, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "cpu_baseline_torch": torch_cpu_baseline(mats, cfg["R"], cfg["kw"], total_rows, cfg["I"]),
     }
+    if cfg.get("weak"):
+        line["slice_iterations_per_s"] = value * int(cfg["I"])
     emit(line)
 
 
@@ -409,6 +417,10 @@ def main():
     if args.slices:
         cfg["I"] = args.slices
         cfg["desc"] += f" [REDUCED to {args.slices} slices]"
+    if cfg.get("weak"):  # per-GPU work fixed: the problem grows with the number of ranks
+        n_ranks = int(os.environ.get("WORLD_SIZE", "1"))
+        cfg["I"] *= n_ranks
+        cfg["desc"] += f" [{cfg['I']} slices on {n_ranks} GPU(s)]"
     sizes = slice_sizes(cfg)
     if args.impl == "reference":
         return run_reference(args, cfg, sizes)
@@ -539,8 +551,8 @@ def main():
     line = {
         "metric": "AO-ADMM outer iterations per second", "value": 1000.0 / ms_step, "unit": "iter/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": cfg["dtype"],
-        "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak" if cfg.get("weak") else "strong", "vs_baseline": None,
+        "dtype": cfg["dtype"], "data": "synthetic",
         "config": {"workload": cfg["desc"] + (" [REDUCED: shard did not fit HBM]" if reduced else ""),
                    "slices_total": int(cfg["I"]) if not reduced else int(hi - lo), "rows_rank0": rows_rank0,
                    "x_bytes_rank0": int(x_bytes_local), "x_passes_per_iteration": 2,
@@ -568,6 +580,8 @@ def main():
             line["cpu_baseline_torch"] = torch_cpu_baseline(mats, cfg["R"], cfg["kw"], total_rows, cfg["I"])
     if e2e is not None:
         line["e2e"] = e2e
+    if cfg.get("weak"):
+        line["slice_iterations_per_s"] = line["value"] * int(cfg["I"])
     emit(line)
     if world > 1:
         dist.destroy_process_group()

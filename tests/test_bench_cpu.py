@@ -63,3 +63,13 @@ def test_shard_bounds_balance_rows_and_cover_all_slices():
         assert b[0][0] == 0 and b[-1][1] == len(sizes) and all(x[1] == y[0] for x, y in zip(b, b[1:]))
         rows = np.array([sizes[lo:hi].sum() for lo, hi in b], dtype=np.float64)
         assert rows.max() / rows.mean() < 1.001  # balanced by row count, not by slice count
+
+
+def test_weak_scaling_config_grows_with_the_rank_count():
+    """--config c4w (BASELINE config[4] as the weak-scaling sweep): slices per GPU fixed, problem x WORLD_SIZE."""
+    d1 = json.loads(_run_reference("--config", "c4w", "--slices", "8")[0])
+    d2 = json.loads(_run_reference("--config", "c4w", "--slices", "8", "--gpus", "2",
+                                   env={"RANK": "0", "WORLD_SIZE": "2"})[0])
+    assert d1["scaling"] == d2["scaling"] == "weak"
+    assert "[8 slices on 1 GPU(s)]" in d1["config"]["workload"] and "[16 slices on 2 GPU(s)]" in d2["config"]["workload"]
+    assert abs(d2["slice_iterations_per_s"] - 16 * d2["value"]) < 1e-9 * d2["slice_iterations_per_s"]
