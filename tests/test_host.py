@@ -488,3 +488,25 @@ def test_unknown_svd_name_is_refused_before_anything_runs():
     for fn in (cmf_aoadmm, parafac2_aoadmm):
         with pytest.raises(ValueError, match="Got svd=nonsense"):
             fn([np.ones((3, 3))], 1, svd="nonsense")
+
+
+def test_mt19937_jump_random_distances():
+    """Property check of the jump-ahead over random start positions and distances (including the brute-force /
+    polynomial switch-over around 64 blocks and exact block boundaries)."""
+    from matcouply_b200 import _ops
+
+    rs = np.random.RandomState(99)
+    cases = [(int(rs.randint(0, 700)), int(n)) for n in rs.randint(1, 200_000, size=12)]
+    cases += [(0, 312 * k) for k in (1, 2, 63, 64, 65, 66, 130)]  # 624-word block boundaries (2 words per double)
+    cases += [(1, 312 * 64 - 1), (1, 312 * 65 - 1), (311, 312 * 65 + 1)]
+    for pre, n in cases:
+        a, b = np.random.RandomState(7), np.random.RandomState(7)
+        a.random_sample(pre), b.random_sample(pre)
+        a.random_sample(n)
+        _ops.mt19937_skip(b, n)
+        sa, sb = a.get_state(), b.get_state()
+        assert np.array_equal(sa[1], sb[1]) and sa[2] == sb[2], (pre, n)
+    z = np.random.RandomState(7)
+    before = z.get_state()
+    _ops.mt19937_skip(z, 0)
+    assert np.array_equal(before[1], z.get_state()[1]) and before[2] == z.get_state()[2]
