@@ -95,12 +95,15 @@ int b2_sumsq(const void* X, long long n_rows, int K, int ldx, int dtype, double*
 int b2_gram(const void* M, long long n, int R, int ld, void* G, int dtype, void* ws, size_t ws_bytes, void* stream);
 /* lhs[g] = G o (a_g a_g^T), g < n_groups  (decomposition.py:243). */
 int b2_scale_gram(const void* G, const void* A, int n_groups, int R, void* lhs, int dtype, void* stream);
-/* rho[g] = 0.5 * trace(lhs[g]) * scale ; rho_max[0] = max_g rho[g]  (decomposition.py:162-165, 247-250, 319). */
+/* rho[g] = 0.5 * trace(lhs[g]) * scale ; rho_max[0] = max_g rho[g]  (decomposition.py:162-165, 247-250, 319).
+ * n_groups == 0 (empty shard): rho_max[0] = -inf, the identity of the MAX all-reduce that follows. */
 int b2_rho_from_trace(const void* lhs, int n_groups, int R, double scale, void* rho, void* rho_max, int dtype,
                       void* stream);
 /* If rho_max != NULL every rho[g] is first overwritten by rho_max[0] (constant_feasibility_penalty).
  * Minv[g] = inverse(lhs[g] + (rho[g]*n_reg + l2) * I) via Cholesky; replaces the SVD solve of :168-172, :252-256,
- * :320-321 (x (U/s) Uh == x lhs^-1 for symmetric positive definite lhs). */
+ * :320-321 (x (U/s) Uh == x lhs^-1 for symmetric positive definite lhs).  A matrix whose Cholesky pivot is <= 0 or
+ * NaN (no penalty and no ridge on a rank-deficient Gram, or a negative l2) takes a Jacobi eigen-decomposition instead,
+ * Minv = Q diag(1/lam) Q^T — what the reference's SVD route computes for ANY symmetric lhs — so there is no silent NaN. */
 int b2_factor_batch(const void* lhs, int n_groups, int R, void* rho, const void* rho_max, int n_reg, double l2,
                     void* Minv, int dtype, void* stream);
 /* Per slice g: rhs[g][r] = sum_j B[j][r]*Y[j][r] (= diag(B_i^T X_i C), :158) and

@@ -59,6 +59,11 @@ class PackedMatrices:
         return [(int(j), self.K) for j in np.diff(self.row_offsets)]
 
     @classmethod
+    def empty(cls, K, dtype, device):
+        """No slice at all: the shard of a rank beyond the last slice of a sharded run."""
+        return cls(torch.empty((0, _ops.padded_ld(int(K), dtype)), dtype=dtype, device=device), [0], int(K))
+
+    @classmethod
     def from_list(cls, matrices, dtype, device):
         K = int(matrices[0].shape[1])
         sizes = [int(m.shape[0]) for m in matrices]
@@ -314,6 +319,7 @@ class AOADMMEngine:
             # deferred state: the PARAFAC2 dual slot holds the pre-image V of the last prox and (aux, dual) =
             # (V W_g Delta, V - V W_g Delta) exist only implicitly; _materialize_pf2() writes them out on demand
             self.pf2_deferred = False
+            self.pf2_delta_zero = False  # Delta == 0 exactly (aux_init="zeros"): see _pf2_prox_unfused
             self.pf2_gap_part = torch.zeros(3 * max(I, 1), dtype=torch.float64, device=dev)
             self.pf2_Q = torch.zeros(I, R, R, dtype=torch.float64, device=dev)  # Jacobi eigenvectors (warm start)
         self.scal = torch.zeros(64, dtype=torch.float64, device=dev)
@@ -365,6 +371,7 @@ class AOADMMEngine:
                     basis, delta = aux
                     self.pf2_fresh = False
                     self.pf2_deferred = False
+                    self.pf2_delta_zero = not np.any(np.asarray(delta))
                     self.Delta.copy_(self._up(delta))
                     if basis.__class__.__name__ == "_EyeBases":
                         # P_i = eye(J_i, R): row j < R of slice i of P_i Delta is Delta[j]; built on the device
@@ -411,7 +418,7 @@ class AOADMMEngine:
                         ok = (self.row_off[1:] - starts) > j
                         pd[(starts + j)[ok]] = self.Delta[j]
                     st[m].aux.append(pd)
-                    self.pf2_basis0, self.pf2_fresh, self.pf2_deferred = None, False, False
+                    self.pf2_basis0, self.pf2_fresh, self.pf2_deferred, self.pf2_delta_zero = None, False, False, False
                 else:
                     st[m].aux.append(rnd(n, R))
                 st[m].dual.append(rnd(n, R))
@@ -498,14 +505,35 @@ class AOADMMEngine:
         reg, R = st.regs[p], self.R
         if reg.update_basis_matrices:
             _ops.slice_cross(st.dual[p], None, row_off, n_groups, R, None, self.S, None)
-            for it in range(max(int(reg.n_iter), 0)):
-                _ops.pf2_polar(self.S, self.Delta, rho, n_groups, R, self.Wmat, self.num_part, self.pf2_Q, warm=it > 0)
+            n_it, polar_done = max(int(reg.n_iter), 0), False
+            for it in range(n_it):
+                if it == 0 and self.pf2_delta_zero:
+                    # Delta == 0 (aux_init="zeros"): the reference takes the SVD of the ZERO matrix V_i Delta^T, for
+                    # which LAPACK returns identity factors, i.e. P_i = eye(J_i, R) (penalties.py:1233-1235); the
+                    # coordinate update then runs on that basis (:1240-1245)
+                    if not reg.update_coordinate_matrix:
+                        break
+                    _ops.pf2_fixed_basis(None, st.dual[p], self._pf2_eye(), None, row_off, n_groups, n_rows, R, rho,
+                                         self.num_part, 1)
+                    self._pf2_delta_update(rho, n_groups)
+                    self.pf2_delta_zero = False
+                    continue
+                _ops.pf2_polar(self.S, self.Delta, rho, n_groups, R, self.Wmat, self.num_part, self.pf2_Q,
+                               warm=polar_done)
+                polar_done = True
                 if not reg.update_coordinate_matrix:
                     break
                 self._pf2_delta_update(rho, n_groups)
-            if int(reg.n_iter) > 0:
+            if polar_done:
                 _ops.pf2_apply(st.aux[p], st.dual[p], None, self.Wmat, self.Delta, gor, n_rows, R)
                 self.pf2_fresh = True
+                return
+            if n_it > 0:  # only the identity-basis step ran: P = eye(J_i, R), pd = P Delta
+                from .penalties import _EyeBases
+
+                self.pf2_basis0, self.pf2_fresh = _EyeBases(np.diff(self.p.row_offsets), R), False
+                _ops.pf2_fixed_basis(st.aux[p], st.dual[p], self._pf2_eye(), self.Delta, row_off, n_groups, n_rows, R,
+                                     None, None, 2)
                 return
         # frozen basis matrices: P stays what it was given as (aux_init tuple or eye(J_i, R)); with n_iter == 0 the
         # reference returns the aux unchanged, which the same code covers (Delta untouched, pd = P Delta)
@@ -515,19 +543,25 @@ class AOADMMEngine:
             self._pf2_delta_update(rho, n_groups)
         _ops.pf2_fixed_basis(st.aux[p], st.dual[p], P, self.Delta, row_off, n_groups, n_rows, R, None, None, 2)
 
+    def _pf2_eye(self):
+        """eye(J_i, R) of every slice as ONE packed N x R device tensor (built once)."""
+        if getattr(self, "_pf2_eye_P", None) is None:
+            P = torch.zeros((self.N, self.R), dtype=self.dtype, device=self.dev)
+            starts, ends = self.row_off[:-1], self.row_off[1:]
+            for j in range(self.R):
+                ok = (ends - starts) > j
+                P[(starts + j)[ok], j] = 1
+            self._pf2_eye_P = P
+        return self._pf2_eye_P
+
     def _pf2_fixed_basis(self):
         """The initial basis matrices as ONE packed N x R device tensor (built once)."""
         if getattr(self, "_pf2_P", None) is None:
             basis = self.pf2_basis0
             if basis is None or basis.__class__.__name__ == "_EyeBases":
-                P = torch.zeros((self.N, self.R), dtype=self.dtype, device=self.dev)
-                starts, ends = self.row_off[:-1], self.row_off[1:]
-                for j in range(self.R):
-                    ok = (ends - starts) > j
-                    P[(starts + j)[ok], j] = 1
+                self._pf2_P = self._pf2_eye()
             else:
-                P = self._up(np.concatenate([np.asarray(b) for b in basis], 0))
-            self._pf2_P = P
+                self._pf2_P = self._up(np.concatenate([np.asarray(b) for b in basis], 0))
         return self._pf2_P
 
     def _host_prox(self, st, p, row_off, n_groups, rho):
@@ -591,7 +625,8 @@ class AOADMMEngine:
             self.w_fresh = True
             return
         if self.fuse_pf2 and self.n_inner > 0 and st.desc and st.desc[0][0] == _lib.PEN_PARAFAC2 and \
-                st.regs[0].update_basis_matrices and st.regs[0].update_coordinate_matrix and int(st.regs[0].n_iter) >= 1:
+                not self.pf2_delta_zero and st.regs[0].update_basis_matrices and \
+                st.regs[0].update_coordinate_matrix and int(st.regs[0].n_iter) >= 1:
             return self._step_B_pf2_fused()
         self._materialize_pf2()
         for _ in range(self.n_inner):
@@ -782,6 +817,11 @@ class AOADMMEngine:
                 _ops.prox_unimodal(aux_full, full, off, 1, R, I_glob, nn, self.ws)
                 st.aux[p].copy_(aux_full[lo:lo + I])
                 st.dual[p].copy_(full[lo:lo + I])
+            elif kind == _lib.PEN_HOST:
+                # user-defined ROW-wise penalty (matrix-wise ones are refused for a sharded mode 0 in __init__): rows
+                # are rank-local, the bridge runs on this rank's rows
+                if I > 0:
+                    self._host_prox(st, p, self.off_single_I, 1, self.rhoA)
             elif kind in _ENGINE_PROX_KINDS:
                 # GeneralizedL2 / UnitSimplex / TV over all I rows: same gather, prox replicated, own rows kept
                 full = self._gather_A_rows(st.dual[p])

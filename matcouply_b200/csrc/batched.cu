@@ -95,10 +95,69 @@ __global__ void max_kernel(const T* __restrict__ v, int n, T* __restrict__ out) 
     }
 }
 
+template <typename T>
+__global__ void fill_kernel(T* __restrict__ out, int n, double value) {
+    for (int i = threadIdx.x; i < n; i += blockDim.x) out[i] = (T)value;
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Batched SPD inverse by Cholesky, one warp per matrix (lane = column). fp64 internally.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int kFactorWarps = 4;
+
+// Fallback of factor_batch_kernel for a matrix that is not (numerically) positive definite: the reference applies
+// lhs^-1 through an SVD, `x (U / s) Uh` (decomposition.py:172, 256, 321), which for a symmetric matrix equals
+// Q diag(1 / lam) Q^T of its eigen-decomposition whatever the signs of lam — it does not need definiteness.  Cyclic
+// Jacobi by one warp on the R x R matrix in shared memory (lane = row in the column pass, column in the row pass);
+// only reached when a Cholesky pivot is <= 0 or NaN (no penalty and no ridge on a rank-deficient Gram matrix, or a
+// negative l2_penalty), so it is written for clarity, not speed.  G: the matrix (destroyed), Q: R x R scratch.
+template <typename T>
+__device__ void eig_inverse_warp(double* __restrict__ G, double* __restrict__ Q, int R, int lane, T* __restrict__ dst) {
+    for (int e = lane; e < R * R; e += 32) Q[e] = (e / R == e % R) ? 1.0 : 0.0;
+    __syncwarp();
+    for (int sweep = 0; sweep < 60 && R > 1; ++sweep) {
+        double off = 0.0, dg = 0.0;
+        if (lane < R)
+            for (int i = 0; i < R; ++i) {
+                const double v = G[i * R + lane];
+                if (i == lane) dg += v * v; else off += v * v;
+            }
+        off = warp_sum(off);
+        dg = warp_sum(dg);
+        if (!(off > 1e-30 * dg && off > 0.0)) break;
+        for (int p = 0; p < R - 1; ++p)
+            for (int q = p + 1; q < R; ++q) {
+                const double apq = G[p * R + q], app = G[p * R + p], aqq = G[q * R + q];
+                __syncwarp();  // every lane has read the pivot entries before anyone rotates them
+                if (!(fabs(apq) > 1e-300 && fabs(apq) > 1e-20 * sqrt(fabs(app * aqq)))) continue;  // warp-uniform
+                const double tau = (aqq - app) / (2.0 * apq);
+                const double t = (tau >= 0.0 ? 1.0 : -1.0) / (fabs(tau) + sqrt(1.0 + tau * tau));
+                const double c = 1.0 / sqrt(1.0 + t * t), sn = t * c;
+                if (lane < R) {  // G <- G J, Q <- Q J (lane = row)
+                    const double gp = G[lane * R + p], gq = G[lane * R + q];
+                    G[lane * R + p] = c * gp - sn * gq;
+                    G[lane * R + q] = sn * gp + c * gq;
+                    const double qp = Q[lane * R + p], qq = Q[lane * R + q];
+                    Q[lane * R + p] = c * qp - sn * qq;
+                    Q[lane * R + q] = sn * qp + c * qq;
+                }
+                __syncwarp();
+                if (lane < R) {  // G <- J^T G (lane = column)
+                    const double gp = G[p * R + lane], gq = G[q * R + lane];
+                    G[p * R + lane] = c * gp - sn * gq;
+                    G[q * R + lane] = sn * gp + c * gq;
+                }
+                __syncwarp();
+            }
+    }
+    __syncwarp();
+    if (lane < R)  // Minv = Q diag(1 / lam) Q^T ; lane = column s
+        for (int r = 0; r < R; ++r) {
+            double acc = 0.0;
+            for (int k = 0; k < R; ++k) acc += Q[r * R + k] * Q[lane * R + k] / G[k * R + k];
+            dst[r * R + lane] = (T)acc;
+        }
+}
 
 template <typename T>
 __global__ void factor_batch_kernel(const T* __restrict__ lhs, int n_groups, int R, T* __restrict__ rho,
@@ -119,8 +178,14 @@ __global__ void factor_batch_kernel(const T* __restrict__ lhs, int n_groups, int
     }
     __syncwarp();
     // in-place Cholesky (lower), right-looking; lane owns row `lane`
+    bool spd = true;
     for (int k = 0; k < R; ++k) {
-        const double d = sqrt(L[k * R + k]);
+        const double dd = L[k * R + k];
+        if (!(dd > 0.0)) {  // same value in every lane: warp-uniform exit
+            spd = false;
+            break;
+        }
+        const double d = sqrt(dd);
         __syncwarp();
         if (lane == k) L[k * R + k] = d;
         if (lane > k && lane < R) L[lane * R + k] /= d;
@@ -130,6 +195,16 @@ __global__ void factor_batch_kernel(const T* __restrict__ lhs, int n_groups, int
             for (int j = k + 1; j <= lane; ++j) L[lane * R + j] -= lik * L[j * R + k];
         }
         __syncwarp();
+    }
+    if (!spd) {  // not positive definite: inverse through the eigen-decomposition, like the reference's SVD route
+        __syncwarp();
+        for (int e = lane; e < R * R; e += 32) {
+            const int r = e / R, c = e - r * R;
+            L[e] = 0.5 * ((double)src[e] + (double)src[c * R + r]) + (r == c ? shift : 0.0);
+        }
+        __syncwarp();
+        eig_inverse_warp<T>(L, Z, R, lane, Minv + (size_t)g * R * R);
+        return;
     }
     // Z = L^-1 (lower): lane = column c, forward substitution
     if (lane < R) {
@@ -295,7 +370,17 @@ int b2_scale_gram(const void* G, const void* A, int n_groups, int R, void* lhs, 
 int b2_rho_from_trace(const void* lhs, int n_groups, int R, double scale, void* rho, void* rho_max, int dtype,
                       void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    if (n_groups == 0) return B2_OK;
+    if (n_groups == 0) {
+        // an empty shard contributes the identity of the MAX all-reduce that follows (a value left over from the
+        // previous mode's update would otherwise take part in it)
+        if (rho_max) {
+            B2_DISPATCH_DTYPE(dtype, {
+                fill_kernel<T><<<1, 32, 0, st>>>((T*)rho_max, 1, -INFINITY);
+                B2_LAUNCH_CHECK();
+            });
+        }
+        return B2_OK;
+    }
     B2_DISPATCH_DTYPE(dtype, {
         rho_trace_kernel<T><<<(n_groups + 127) / 128, 128, 0, st>>>((const T*)lhs, n_groups, R, scale, (T*)rho);
         B2_LAUNCH_CHECK();

@@ -457,12 +457,86 @@ def cmf_aoadmm(
     """
     import torch
 
-    from ._engine import AOADMMEngine, PackedMatrices
+    from ._engine import PackedMatrices
 
     _check_svd_name(svd)
     if not torch.cuda.is_available():
         raise RuntimeError("matcouply_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
-    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if device is not None:
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise ValueError(f"matcouply_b200 runs on CUDA devices only, got device={device}")
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+    if isinstance(matrices, PackedMatrices):
+        if device is not None and device != matrices.X.device:
+            raise ValueError(f"`matrices` is resident on {matrices.X.device}, but device={device} was requested")
+        device = matrices.X.device
+    elif device is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    # every kernel launch, workspace allocation and stream / event of the fit binds to `device`, whatever the caller's
+    # current device is (the C ABI launches on torch's current stream, which belongs to the current device)
+    with torch.cuda.device(device):
+        return _cmf_aoadmm_on_device(
+            matrices=matrices, rank=rank, init=init, n_iter_max=n_iter_max, l2_penalty=l2_penalty,
+            tv_penalty=tv_penalty, l1_penalty=l1_penalty, non_negative=non_negative, unimodal=unimodal,
+            generalized_l2_penalty=generalized_l2_penalty, l2_norm_bound=l2_norm_bound,
+            lower_bound=lower_bound, upper_bound=upper_bound, parafac2=parafac2, regs=regs,
+            feasibility_penalty_scale=feasibility_penalty_scale,
+            constant_feasibility_penalty=constant_feasibility_penalty, aux_init=aux_init,
+            dual_init=dual_init, svd=svd, init_params=init_params, random_state=random_state, tol=tol,
+            absolute_tol=absolute_tol, feasibility_tol=feasibility_tol, inner_tol=inner_tol,
+            inner_n_iter_max=inner_n_iter_max, update_A=update_A, update_B_is=update_B_is,
+            update_C=update_C, return_admm_vars=return_admm_vars, return_errors=return_errors,
+            verbose=verbose, process_group=process_group, shard=shard, gather_factors=gather_factors,
+            use_cuda_graph=use_cuda_graph, device=device,
+        )
+
+
+def _cmf_aoadmm_on_device(
+    matrices,
+    rank,
+    init="random",
+    n_iter_max=1000,
+    l2_penalty=None,
+    tv_penalty=None,
+    l1_penalty=None,
+    non_negative=None,
+    unimodal=None,
+    generalized_l2_penalty=None,
+    l2_norm_bound=None,
+    lower_bound=None,
+    upper_bound=None,
+    parafac2=None,
+    regs=None,
+    feasibility_penalty_scale=1,
+    constant_feasibility_penalty=False,
+    aux_init="random_uniform",
+    dual_init="random_uniform",
+    svd="truncated_svd",
+    init_params=None,
+    random_state=None,
+    tol=1e-8,
+    absolute_tol=1e-10,
+    feasibility_tol=1e-4,
+    inner_tol=None,
+    inner_n_iter_max=5,
+    update_A=True,
+    update_B_is=True,
+    update_C=True,
+    return_admm_vars=False,
+    return_errors=False,
+    verbose=False,
+    device=None,
+    process_group=None,
+    shard=None,
+    gather_factors=True,
+    use_cuda_graph=None,
+):
+    """Body of :func:`cmf_aoadmm`; runs with ``device`` as the current CUDA device."""
+    import torch
+
+    from ._engine import AOADMMEngine, PackedMatrices
 
     random_state = penalties._check_random_state(random_state)
     if isinstance(matrices, PackedMatrices):
@@ -470,8 +544,16 @@ def cmf_aoadmm(
         shape_view = [_ShapeOnly(s) for s in packed.shapes]
     else:
         matrices = list(matrices)
-        all_f32 = all(str(getattr(m, "dtype", "")).endswith("float32") for m in matrices)
-        packed = PackedMatrices.from_list(matrices, torch.float32 if all_f32 else torch.float64, device)
+        if not matrices and shard is not None and shard.lo == shard.hi:
+            # a rank of a sharded run with no slice at all (more ranks than slices): it still takes part in every
+            # all-reduce and computes the replicated C-mode state, on a 0 x K shard
+            if not shard.n_cols:
+                raise ValueError("an empty shard needs ShardSpec.n_cols (make_shard(..., n_cols=K))")
+            packed = PackedMatrices.empty(shard.n_cols, torch.float32 if shard.dtype == "float32" else torch.float64,
+                                          device)
+        else:
+            all_f32 = all(str(getattr(m, "dtype", "")).endswith("float32") for m in matrices)
+            packed = PackedMatrices.from_list(matrices, torch.float32 if all_f32 else torch.float64, device)
         shape_view = matrices
     if shard is not None:
         if process_group is None:

@@ -33,6 +33,8 @@ class ShardSpec(NamedTuple):
     row_counts: Tuple[int, ...]  # J_i of EVERY slice of the global problem
     lo: int
     hi: int
+    n_cols: int = 0  # K of the data matrices; only needed by a rank whose range is EMPTY (it has no matrix to ask)
+    dtype: str = "float64"  # "float32" selects the fp32 kernels on such a rank (the others see it from their data)
 
     @property
     def n_global(self):
@@ -55,9 +57,12 @@ def partition_slices(row_counts: Sequence[int], world_size: int) -> List[Tuple[i
     return [(cuts[r], cuts[r + 1]) for r in range(world_size)]
 
 
-def make_shard(row_counts: Sequence[int], rank: int, world_size: int) -> ShardSpec:
+def make_shard(row_counts: Sequence[int], rank: int, world_size: int, n_cols: int = 0,
+               dtype: str = "float64") -> ShardSpec:
+    """``n_cols`` / ``dtype``: the column count K and the element type of the data; pass them when ``world_size`` can
+    exceed the number of slices, so that a rank with an empty range still knows the shape of the problem."""
     lo, hi = partition_slices(row_counts, world_size)[rank]
-    return ShardSpec(tuple(int(j) for j in row_counts), lo, hi)
+    return ShardSpec(tuple(int(j) for j in row_counts), lo, hi, int(n_cols), str(dtype))
 
 
 def shard_state(A, B_is, auxes, duals, regs, shard: ShardSpec):

@@ -518,9 +518,15 @@ class Parafac2(MatricesPenalty):
             if self.update_basis_matrices:
                 if it == 0:
                     _ops.slice_cross(V, None, row_off, n_groups, rank, None, S, None)
-                _ops.pf2_polar(S, new_delta, rho, n_groups, rank, Wm, num)
-                pd, basis = torch.empty_like(V), torch.empty_like(V)
-                _ops.pf2_apply(pd, V.clone(), basis, Wm, new_delta, gor, n, rank)
+                if not bool(torch.any(new_delta != 0)):
+                    # zero coordinate matrix (aux_init="zeros"): the reference's SVD of the zero matrix V_i Delta^T
+                    # returns LAPACK's identity factors, i.e. P_i = eye(J_i, rank) (penalties.py:1233-1235)
+                    basis = torch.cat([torch.eye(j, rank, dtype=dtype, device="cuda") for j in sizes], 0).contiguous()
+                    _ops.pf2_fixed_basis(None, V, basis, None, row_off, n_groups, n, rank, rho, num, 1)
+                else:
+                    _ops.pf2_polar(S, new_delta, rho, n_groups, rank, Wm, num)
+                    pd, basis = torch.empty_like(V), torch.empty_like(V)
+                    _ops.pf2_apply(pd, V.clone(), basis, Wm, new_delta, gor, n, rank)
             if self.update_coordinate_matrix:
                 if not self.update_basis_matrices:  # frozen P: numerator rho_g P_g^T V_g from the given bases
                     P = torch.cat([_Dev(b).t.to(dtype) for b in basis_in], 0).contiguous()
@@ -625,9 +631,12 @@ class GeneralizedL2Penalty(_EnginePenaltyMixin, MatrixPenalty):
             self._dev[dtype] = (up(self._U), up(self._s), up(self._M))
         return self._dev[dtype]
 
-    def _check_rows(self, n_rows, n_groups):
+    def _check_rows(self, n_rows, n_groups, max_rows):
+        # b2_prox_gl2 / b2_quadform address slice g as rows [g J, (g + 1) J): EVERY slice must have exactly J rows
+        # (heights that merely sum to n_groups * J would be processed in misaligned blocks; the reference fails with
+        # a shape error in that case).  All heights <= max_rows and their sum == n_groups * J  <=>  all equal J.
         J = self._M.shape[0]
-        if n_groups * J != n_rows:
+        if n_groups * J != n_rows or (n_groups > 0 and int(max_rows) != J):
             raise ValueError(
                 f"GeneralizedL2Penalty with a {J} x {J} norm matrix needs factor matrices with {J} rows each "
                 f"(got {n_rows} rows in {n_groups} matrices)")
@@ -636,7 +645,7 @@ class GeneralizedL2Penalty(_EnginePenaltyMixin, MatrixPenalty):
     def _engine_prox(self, eng, aux, dual, row_off, n_groups, max_rows, rho, n_rows):
         from . import _ops
 
-        J = self._check_rows(n_rows, n_groups)
+        J = self._check_rows(n_rows, n_groups, max_rows)
         U, s, _ = self._device_operands(aux.dtype)
         tmp = aux.new_empty((n_rows, aux.shape[1]))
         _ops.prox_gl2(aux, dual, n_groups, J, aux.shape[1], U, s, rho, tmp)
@@ -644,7 +653,7 @@ class GeneralizedL2Penalty(_EnginePenaltyMixin, MatrixPenalty):
     def _engine_penalty(self, eng, x, row_off, n_groups, max_rows, n_rows, out):
         from . import _ops
 
-        J = self._check_rows(n_rows, n_groups)
+        J = self._check_rows(n_rows, n_groups, max_rows)
         _, _, M = self._device_operands(x.dtype)
         _ops.quadform(M, x, n_groups, J, x.shape[1], out, x.new_empty((n_rows, x.shape[1])))
 

@@ -394,3 +394,48 @@ def test_random_penalty_combinations_match_oracle(seed):
     errs = (rel(A, o["A"]), rel(np.concatenate(B_is, 0), np.concatenate(o["B_is"], 0)), rel(C, o["C"]))
     assert max(errs) < 1e-7, (seed, kw["regs_spec"], kw["constant_feasibility_penalty"], errs)
     np.testing.assert_allclose(diag.regularized_loss, o["regularized_loss"], rtol=1e-7)
+
+
+def test_indefinite_normal_matrix_follows_the_reference_svd_route():
+    """No penalty on B and a NEGATIVE l2_penalty there make the B-mode normal matrix `C^T C o a a^T + l2 I`
+    indefinite (the smallest eigenvalue of the Gram is below |l2|): Cholesky does not exist, the reference's SVD
+    solve (decomposition.py:252-256) still applies the inverse.  Same iterates as the oracle, no NaN."""
+    from matcouply_b200 import cmf_aoadmm
+    from oracle import aoadmm_oracle as O
+
+    rs = np.random.RandomState(8)
+    I, K, R = 6, 3, 4  # K < R: C^T C has rank <= 3, so lhs_B = G o aa^T - 0.05 I has a negative eigenvalue
+    X = [rs.uniform(size=(J, K)) for J in (7, 9, 8, 12, 6, 10)]
+    kw = dict(l2_penalty=[0.0, -0.05, 0.1], non_negative={0: True}, random_state=4, n_iter_max=3, tol=None,
+              absolute_tol=None)
+    o = O.ao_admm(X, R, **kw)
+    cmf = cmf_aoadmm(X, R, **kw)
+    _, (A, B_is, C) = cmf
+    assert np.all(np.isfinite(C)) and all(np.all(np.isfinite(b)) for b in B_is)
+    errs = (rel(A, o["A"]), rel(np.concatenate(B_is, 0), np.concatenate(o["B_is"], 0)), rel(C, o["C"]))
+    assert max(errs) < 1e-7, errs
+
+
+@pytest.mark.parametrize("kw", [dict(parafac2=True), dict(regs_spec=[[], [["Parafac2", {"n_iter": 2}]], []]),
+                                dict(regs_spec=[[], [["Parafac2", {"update_coordinate_matrix": False}]], []])])
+def test_parafac2_from_a_zero_coordinate_matrix(kw):
+    """aux_init="zeros" gives PARAFAC2 the coordinate matrix Delta = 0: the reference's first Procrustes step is then
+    the SVD of a zero matrix, for which LAPACK returns identity factors, i.e. P_i = eye(J_i, R) (penalties.py:1233-1235;
+    pinned against the live reference by tests/test_oracle.py::test_oracle_vs_live_reference).  The engine takes the
+    same step (fixed identity basis for that one update) instead of dropping every direction of the zero Gram."""
+    from matcouply_b200 import cmf_aoadmm
+    from oracle import aoadmm_oracle as O
+
+    rs = np.random.RandomState(21)
+    X = [rs.uniform(size=(J, 11)) for J in (8, 13, 9, 10, 21, 7)]
+    common = dict(non_negative={0: True, 2: True}, aux_init="zeros", random_state=2, n_iter_max=15, tol=None,
+                  absolute_tol=None)
+    o = O.ao_admm(X, 3, **common, **kw)
+    cmf, admm, diag = cmf_aoadmm(X, 3, return_errors=True, return_admm_vars=True, **common, **product_kwargs(kw))
+    _, (A, B_is, C) = cmf
+    errs = (rel(A, o["A"]), rel(np.concatenate(B_is, 0), np.concatenate(o["B_is"], 0)), rel(C, o["C"]))
+    assert max(errs) < 1e-8, errs
+    np.testing.assert_allclose(diag.regularized_loss, o["regularized_loss"], rtol=1e-8)
+    bases, delta = admm.auxes[1][0]
+    assert rel(delta, o["aux"][1][0][1]) < 1e-7
+    assert rel(np.concatenate(bases, 0), np.concatenate(o["aux"][1][0][0], 0)) < 1e-6

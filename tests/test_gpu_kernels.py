@@ -167,6 +167,35 @@ def test_factor_batch(R, constant):
         np.testing.assert_allclose(Minv[g].cpu().numpy(), ref, rtol=1e-11, atol=1e-13 * np.abs(ref).max())
 
 
+@pytest.mark.parametrize("R", [2, 5, 16, 20, 32])
+def test_factor_batch_not_positive_definite_takes_the_eigen_route(R):
+    """A symmetric lhs that is NOT positive definite (negative l2_penalty, or round-off on a rank-deficient Gram): the
+    reference's `x (U / s) Uh` (decomposition.py:172, 256, 321) is the plain inverse for ANY invertible symmetric
+    matrix.  The Cholesky pivot test must route such matrices to the Jacobi eigen-inverse (no silent NaN), leave the
+    positive definite ones of the same batch on the Cholesky path, and agree with the reference's SVD route."""
+    _lib, _ops, _ = _imports()
+    rs = np.random.RandomState(100 + R)
+    G = 11
+    lhs = []
+    for g in range(G):
+        Q, _ = np.linalg.qr(rs.standard_normal(size=(R, R)))
+        lam = rs.uniform(0.5, 3.0, size=R)
+        if g % 2 == 0:  # indefinite, well conditioned
+            lam[rs.randint(R)] *= -1.0
+        lhs.append((Q * lam) @ Q.T)
+    lhs = np.stack(lhs)
+    lhs = 0.5 * (lhs + lhs.transpose(0, 2, 1))
+    rho_d = dev(np.zeros(G))
+    Minv = torch.empty((G, R, R), dtype=torch.float64, device="cuda")
+    _ops.factor_batch(dev(lhs), G, R, rho_d, None, 0, 0.0, Minv)
+    got = Minv.cpu().numpy()
+    assert np.all(np.isfinite(got))
+    for g in range(G):
+        U, s, Uh = np.linalg.svd(lhs[g])
+        ref = (U / s) @ Uh
+        np.testing.assert_allclose(got[g], ref, rtol=1e-9, atol=1e-11 * np.abs(ref).max())
+
+
 def ragged(rs, G, lo, hi, R):
     sizes = rs.randint(lo, hi + 1, size=G)
     off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)

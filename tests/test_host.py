@@ -510,3 +510,29 @@ def test_mt19937_jump_random_distances():
     before = z.get_state()
     _ops.mt19937_skip(z, 0)
     assert np.array_equal(before[1], z.get_state()[1]) and before[2] == z.get_state()[2]
+
+
+def test_generalized_l2_rejects_ragged_slices_whose_heights_only_sum_up():
+    """b2_prox_gl2 addresses slice g as rows [g J, (g + 1) J): heights (3, 5) sum to 2 x 4 but are not 4 x 4 blocks;
+    the reference raises a shape error there, a total-rows check alone would run on misaligned blocks."""
+    from matcouply_b200.penalties import GeneralizedL2Penalty
+
+    pen = GeneralizedL2Penalty(np.eye(4))
+    assert pen._check_rows(8, 2, 4) == 4
+    assert pen._check_rows(0, 0, 0) == 4  # empty shard
+    with pytest.raises(ValueError):
+        pen._check_rows(8, 2, 5)
+    with pytest.raises(ValueError):
+        pen._check_rows(9, 2, 4)
+
+
+def test_shard_spec_carries_the_problem_shape_for_empty_ranges():
+    """More ranks than slices: the ranks beyond the last slice get an empty range and learn K / dtype from the spec."""
+    from matcouply_b200.distributed import make_shard, partition_slices
+
+    parts = partition_slices([5, 7, 6], 8)
+    assert parts[0][0] == 0 and parts[-1][1] == 3 and all(a <= b for a, b in parts)
+    assert sum(b - a for a, b in parts) == 3 and sum(1 for a, b in parts if a == b) >= 5
+    sh = make_shard([5, 7, 6], 7, 8, n_cols=11, dtype="float32")
+    assert (sh.n_cols, sh.dtype, sh.n_global) == (11, "float32", 3)
+    assert make_shard([5, 7, 6], 0, 2).n_cols == 0  # optional: ranks with data read K from their matrices

@@ -168,6 +168,14 @@ o = ao_admm(X, 3, **kw)
 assert d.n_iter == o["n_iter"]
 np.testing.assert_allclose(o["regularized_loss"], d.regularized_loss, rtol=1e-11)
 np.testing.assert_allclose(o["A"], cmf[1][0], rtol=1e-9, atol=1e-13)
+# PARAFAC2 from a ZERO coordinate matrix (aux_init="zeros"): the reference's first Procrustes step is the SVD of a zero
+# matrix, whose LAPACK factors are identities (P_i = eye(J_i, R)); the oracle must take the same path
+kw = dict(parafac2=True, non_negative={0: True, 2: True}, aux_init="zeros", random_state=2, n_iter_max=15, tol=None,
+          absolute_tol=None)
+cmf, d = cmf_aoadmm(X, 3, return_errors=True, **kw)
+o = ao_admm(X, 3, **kw)
+np.testing.assert_allclose(o["regularized_loss"], d.regularized_loss, rtol=1e-11)
+np.testing.assert_allclose(o["C"], cmf[1][2], rtol=1e-9, atol=1e-13)
 print("OK")
 """ % (os.path.join(ROOT, "oracle", "_tl_standin"), ROOT)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True,
