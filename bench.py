@@ -224,6 +224,31 @@ def oracle_iter_seconds(mats, R, kw):
     return max(((t2 - t1) - (t1 - t0)) / 2.0, 1e-9)
 
 
+def reference_iter_seconds(mats, R, kw):
+    """Seconds per outer iteration of the reference's OWN code on the host cores, and which code that was:
+    ("reference") the unmodified `matcouply.decomposition.cmf_aoadmm` staged under oracle/_ref (oracle/stage_ref.py;
+    NumPy backend through the tensorly stand-in, numba-jitted unimodal regression when numba is importable, as in the
+    reference), or ("port") the oracle restatement when nothing is staged.  Same (t(3 its) - t(1 it)) / 2 rule."""
+    ref = None
+    if os.environ.get("B2_REFERENCE_ARM") != "port":  # "port" forces the restatement (A/B of the two CPU arms)
+        try:
+            from oracle.stage_ref import load_reference
+
+            ref = load_reference()
+        except Exception:
+            ref = None
+    if ref is None:
+        return oracle_iter_seconds(mats, R, kw), "port"
+    base = dict(random_state=0, tol=None, absolute_tol=None, return_errors=True, **kw)
+    ref.cmf_aoadmm(mats[:2], R, n_iter_max=2, **base)  # warm-up (imports, BLAS threads, numba JIT)
+    t0 = time.perf_counter()
+    ref.cmf_aoadmm(mats, R, n_iter_max=1, **base)
+    t1 = time.perf_counter()
+    ref.cmf_aoadmm(mats, R, n_iter_max=3, **base)
+    t2 = time.perf_counter()
+    return max(((t2 - t1) - (t1 - t0)) / 2.0, 1e-9), "reference"
+
+
 def torch_cpu_baseline(mats, R, kw, total_rows, n_slices_total):
     """The reference under TensorLy's PyTorch backend on the host cores (oracle/aoadmm_torch_cpu.py; float64 and the
     backend's default float32), same sample and same (t(3 its) - t(1 it)) / 2 rule as the NumPy column.  Only for the
@@ -259,7 +284,26 @@ def torch_cpu_baseline(mats, R, kw, total_rows, n_slices_total):
 E2E_ITERS = 50  # outer iterations of the timed end-to-end call (the parity horizon of BASELINE.json's north_star)
 
 
-def e2e_sample_size(cfg, es, budget_bytes=8 << 30):
+E2E_BYTES_PER_RANK = 64 << 30   # page-locked host data of the e2e leg per rank ...
+E2E_BYTES_TOTAL = 128 << 30      # ... and over all ranks of the box (pinning and generating it is untimed but not free)
+
+
+def e2e_budget_bytes(world):
+    """Bytes of X per rank for the e2e leg: 64 GB at 1-2 ranks, 128 GB / N beyond, never more than ~40 % of the host's
+    available memory (B2_E2E_GB overrides the per-rank figure)."""
+    if os.environ.get("B2_E2E_GB"):
+        return int(float(os.environ["B2_E2E_GB"]) * (1 << 30))
+    budget = min(E2E_BYTES_PER_RANK, E2E_BYTES_TOTAL // max(world, 1))
+    try:
+        with open("/proc/meminfo") as f:
+            avail_kb = next(int(line.split()[1]) for line in f if line.startswith("MemAvailable"))
+        budget = min(budget, int(0.4 * avail_kb * 1024 / max(world, 1)))
+    except Exception:
+        pass
+    return max(budget, 1 << 30)
+
+
+def e2e_sample_size(cfg, es, budget_bytes):
     """Slices of the e2e leg: about `budget_bytes` of X in page-locked host memory."""
     mean_j = sum(cfg["J"]) / 2
     return int(max(8, min(cfg["I"], budget_bytes // (mean_j * cfg["K"] * es))))
@@ -294,7 +338,7 @@ def run_e2e(cfg, sizes, dtype, es, device, world, rank, group, regs):
     from matcouply_b200.distributed import make_shard
 
     kw = dict(cfg["kw"], random_state=0, tol=None, absolute_tol=None)
-    S2 = min(cfg["I"], e2e_sample_size(cfg, es) * world)
+    S2 = min(cfg["I"], e2e_sample_size(cfg, es, e2e_budget_bytes(world)) * world)
     sub = dict(cfg, I=S2)
     sizes2 = sizes[:S2]
     if world > 1:
@@ -331,12 +375,15 @@ def run_e2e(cfg, sizes, dtype, es, device, world, rank, group, regs):
     return {
         "value": 1.0 / (t_call / k_e2e * total_rows / rows2), "unit": "iter/s",
         "h2d_bytes_per_step": int(h2d / k_e2e), "d2h_bytes_per_step": int(d2h / k_e2e),
+        "unscaled": {"call_seconds": t_call, "iterations": k_e2e, "rows": rows2, "rows_full_workload": total_rows,
+                     "x_gbytes": rows2 * cfg["K"] * es / 1e9, "iter_per_s_on_sample": k_e2e / t_call,
+                     "seconds_per_iteration": t_iter, "fixed_seconds": times[5] - 5 * t_iter},
         "note": f"cmf_aoadmm(list of page-locked host arrays, n_iter_max={k_e2e}, return_errors=True) on the first "
                 f"{S2} slices ({rows2} rows, {rows2 * cfg['K'] * es / 1e9:.1f} GB of X) sharded over {world} GPU(s): whole "
                 f"call timed, max over ranks ({t_call:.3f} s: initial state drawn from the RandomState stream, H2D of X, {k_e2e} "
                 f"outer iterations with the per-iteration diagnostics D2H, D2H of the factors), iterations/s = {k_e2e} / "
-                f"t_call, scaled linearly in rows to the full workload (155 GB of host data cannot be staged inside a "
-                f"few-minute run). The same call with n_iter_max=5 takes {times[5]:.3f} s, i.e. {1000 * t_iter:.2f} ms "
+                f"t_call, scaled linearly in rows to the full workload (the sample is the largest page-locked host "
+                f"buffer a few-minute run can stage: 64 GB per rank, 128 GB per box). The same call with n_iter_max=5 takes {times[5]:.3f} s, i.e. {1000 * t_iter:.2f} ms "
                 f"per iteration + {times[5] - 5 * t_iter:.3f} s of fixed cost (upload + init + download)"}
 
 
@@ -348,9 +395,9 @@ def cpu_sample_size(cfg):
 
 
 def run_reference(args, cfg, sizes):
-    """--impl reference: the reference's CPU algorithm (oracle port; the reference itself is pure Python + TensorLy and
-    cannot travel to the GPU box) on a bounded slice sample, extrapolated linearly in the slice count (every reference
-    loop is per slice)."""
+    """--impl reference: the reference's own CPU implementation — the unmodified package staged under oracle/_ref by
+    `__graft_entry__.build()` (kind "reference"; the oracle port only if nothing is staged) — on a bounded slice
+    sample, extrapolated linearly in the row count (every reference loop is per slice)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -358,9 +405,10 @@ def run_reference(args, cfg, sizes):
     S = cpu_sample_size(cfg)
     mats = gen_host_sample(cfg, sizes, S)
     rows = sum(m.shape[0] for m in mats)
-    secs = []
+    secs, kind = [], "port"
     for _ in range(max(1, min(args.steps, 3))):
-        secs.append(oracle_iter_seconds(mats, cfg["R"], cfg["kw"]))
+        t_s, kind = reference_iter_seconds(mats, cfg["R"], cfg["kw"])
+        secs.append(t_s)
     t_iter_sample = float(np.median(secs))
     total_rows = int(sizes.sum())
     t_full = t_iter_sample * total_rows / rows
@@ -371,9 +419,11 @@ def run_reference(args, cfg, sizes):
         "higher_is_better": True, "scaling": "weak" if cfg.get("weak") else "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
         "config": {"workload": cfg["desc"], "sample": f"first {S} slices ({rows} rows), time scaled by rows"},
-        "cpu_baseline": {"value": value, "unit": "iter/s", "cores": cores, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": "iter/s", "cores": cores, "kind": kind,
                          "sample": f"first {S} of {cfg['I']} slices ({rows} of {total_rows} rows); "
-                                   f"{t_iter_sample:.3f} s per outer iteration on the sample, scaled linearly in rows"},
+                                   f"{t_iter_sample:.3f} s per outer iteration on the sample, scaled linearly in rows"
+                                   + ("; unmodified reference package (oracle/_ref) on the NumPy backend"
+                                      if kind == "reference" else "; oracle port (no staged reference)")},
         "e2e": {"value": value, "unit": "iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "cpu_baseline_torch": torch_cpu_baseline(mats, cfg["R"], cfg["kw"], total_rows, cfg["I"]),
     }
@@ -480,7 +530,7 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    eng.xstream_events = {"y": [], "z": []}
+    eng.xstream_events = {}
     launches0 = int(_lib.load().b2_launch_count())
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -495,13 +545,17 @@ def main():
     launches = int(_lib.load().b2_launch_count()) - launches0
     ev = eng.xstream_events
     eng.xstream_events = None
-    t_y = float(np.mean([a.elapsed_time(b) for a, b in ev["y"]]))
-    t_z = float(np.mean([a.elapsed_time(b) for a, b in ev["z"]]))
-    tmax = torch.tensor([ms_total, t_y, t_z], dtype=torch.float64, device=device)
+    fam = {k: (float(np.mean([a.elapsed_time(b) for a, b in v])), len(v) / args.steps) for k, v in ev.items() if v}
+    t_y, t_z = fam["y"][0], fam["z"][0]
+    keys = ["y", "z", "rowpass", "polar", "unimodal", "local"]
+    tmax = torch.tensor([ms_total] + [fam.get(k, (0.0, 0.0))[0] for k in keys], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dist.barrier()
-    ms_total, t_y, t_z = (float(v) for v in tmax.cpu())
+    vals = [float(v) for v in tmax.cpu()]
+    ms_total = vals[0]
+    fam = {k: (vals[1 + i], fam[k][1]) for i, k in enumerate(keys) if k in fam}
+    t_y, t_z = fam["y"][0], fam["z"][0]
     ms_step = ms_total / args.steps
     window_note = "timed region"
     need = torch.tensor([1.0 if sampler.n_in(t_host0, t_host1 + 0.12) < 2 else 0.0], device=device)
@@ -538,16 +592,48 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs, copy kernel)" if "hbm_gbs" in peaks else "fallback 6650"
-    dom, t_dom = ("xstream_z", t_z) if t_z >= t_y else ("xstream_y", t_y)
-    achieved = x_bytes_local / t_dom / 1e6  # GB/s: algorithmic bytes = the X shard read once per launch
+    # ---- roofline of the DOMINANT kernel of this config's step (largest time per step over the kernel families) ----
+    # algorithmic bytes per launch: X-stream = the X shard once; the B-state kernels = the N x R arrays
+    # they must read and write once (row pass: Y, V, T in / V', T' out in a middle pass; unimodal: V in, aux + dual out;
+    # fused local loop: Y + x + (aux, dual) per penalty in, x + W + (aux, dual) out)
+    nr_bytes = rows_rank0 * cfg["R"] * es
+    n_b_pen = len(regs[1])
+    algo = {"y": x_bytes_local, "z": x_bytes_local, "rowpass": (3 + 2 * max(n_b_pen - 1, 0)) * nr_bytes,
+            "unimodal": 3 * nr_bytes, "local": (4 + 4 * n_b_pen) * nr_bytes, "polar": 3 * cfg["R"] ** 2 * 8 * (hi - lo)}
+    names = {"y": "xstream_y", "z": "xstream_z", "rowpass": "pf2_rowpass_mma_kernel", "polar": "pf2_polar_reg_kernel",
+             "unimodal": "unimodal_kernel", "local": "admm_local_mma_kernel"}
+    kernels = {names[k]: {"ms_per_launch": t, "launches_per_step": n, "ms_per_step": t * n,
+                          "algorithmic_bytes_per_launch": int(algo[k]), "gbs": algo[k] / t / 1e6 if t > 0 else None}
+               for k, (t, n) in fam.items()}
+    dom_key = max(fam, key=lambda k: fam[k][0] * fam[k][1])
+    dom, t_dom = names[dom_key], fam[dom_key][0]
+    achieved = algo[dom_key] / t_dom / 1e6  # GB/s
     traffic, traffic_src = None, None
     try:  # DRAM bytes per algorithmic byte from the committed `ncu --set full` capture, scaled to this launch
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj[dom]["ratio"] * x_bytes_local
+        traffic = tj[dom]["ratio"] * algo[dom_key]
         traffic_src = (f"(dram__bytes_read.sum + dram__bytes_write.sum) / algorithmic bytes = {tj[dom]['ratio']:.4f} in "
-                       f"the {tj['source']}, times this launch's algorithmic bytes")
+                       f"the {tj.get(dom, {}).get('source', tj.get('source'))}, times this launch's algorithmic bytes")
     except Exception:
         pass
+    # second roof of the fp64 X-stream kernels: the fp64 tensor pipe (DMMA.8x8x4), measured live (burst, idle GPU)
+    fp64 = None
+    if cfg["dtype"] == "f64":
+        try:
+            from matcouply_b200 import _ops
+
+            flops, ms = _ops.microbench_flops(1, 4096)
+            peak_tf = flops / ms / 1e9
+            r_pad = (cfg["R"] + 7) // 8 * 8
+            t_x = max(t_y, t_z)
+            ach_tf = 2.0 * r_pad * cfg["K"] * rows_rank0 / t_x / 1e9
+            fp64 = {"kernel": "xstream_y" if t_y >= t_z else "xstream_z", "achieved": ach_tf, "peak": peak_tf,
+                    "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
+                    "note": f"2*{r_pad}*K*N padded DMMA.8x8x4 flops per launch / CUDA-event time; peak = "
+                            "b2_microbench_flops(DMMA) in this run at the clock of an otherwise idle GPU "
+                            f"(the timed steps ran at {clocks.get('sm_mhz')} of {clocks.get('sm_max_mhz')} MHz)"}
+        except Exception as exc:
+            fp64 = {"unavailable": f"{type(exc).__name__}: {exc}"}
     line = {
         "metric": "AO-ADMM outer iterations per second", "value": 1000.0 / ms_step, "unit": "iter/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -557,8 +643,10 @@ def main():
                    "slices_total": int(cfg["I"]) if not reduced else int(hi - lo), "rows_rank0": rows_rank0,
                    "x_bytes_rank0": int(x_bytes_local), "x_passes_per_iteration": 2,
                    "l2_flush": "not needed: X shard >> 126 MB L2", "parallelism": f"slices sharded over {world} GPU(s)"},
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm+fp64" if (fp64 and "frac" in fp64 and dom_key in ("y", "z")) else "hbm",
+                     "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "fp64": fp64, "kernels": kernels,
                      "xstream_y_ms": t_y, "xstream_z_ms": t_z,
                      "xstream_y_gbs": x_bytes_local / t_y / 1e6, "xstream_z_gbs": x_bytes_local / t_z / 1e6,
                      "iteration_stream_gbs": 2 * x_bytes_local / ms_step / 1e6},
@@ -572,9 +660,9 @@ def main():
         total_rows = int(sizes.sum())
         if world == 1:
             cores = use_all_host_threads()
-            t_s = oracle_iter_seconds(mats, cfg["R"], cfg["kw"])
+            t_s, kind = reference_iter_seconds(mats, cfg["R"], cfg["kw"])
             line["cpu_baseline"] = {
-                "value": 1.0 / (t_s * total_rows / rows), "unit": "iter/s", "cores": cores, "kind": "port",
+                "value": 1.0 / (t_s * total_rows / rows), "unit": "iter/s", "cores": cores, "kind": kind,
                 "sample": f"first {S} of {cfg['I']} slices ({rows} of {total_rows} rows): {t_s:.3f} s per outer "
                           f"iteration, scaled linearly in rows (every reference loop is per slice)"}
             line["cpu_baseline_torch"] = torch_cpu_baseline(mats, cfg["R"], cfg["kw"], total_rows, cfg["I"])

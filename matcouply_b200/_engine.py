@@ -17,6 +17,8 @@ X-stream schedule (exact Gauss-Seidel order of the reference, two passes instead
 Sharding: with a process group, every rank holds a contiguous range of slices (X, B-state, A rows are rank-local);
 C, Delta and all scalars are replicated through a few small all-reduces per outer iteration.
 """
+import os
+
 import numpy as np
 import torch
 
@@ -28,6 +30,25 @@ _ENGINE_PROX_KINDS = (_lib.PEN_GL2, _lib.PEN_SIMPLEX, _lib.PEN_TV)
 
 # Kernel-fusion switches (tests flip them to cross-check the fused kernels against the one-kernel-per-step path).
 FUSION_DEFAULTS = {"local": True, "pf2": True, "overlap": True}
+
+
+class _Phase:
+    """NVTX range around one phase of the outer iteration: makes nsys / ncu launch lists self-describing.
+    A push/pop costs ~0.1 us without a profiler attached; B2_NVTX=0 turns the ranges off."""
+
+    enabled = os.environ.get("B2_NVTX", "1") != "0"
+
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if _Phase.enabled:
+            torch.cuda.nvtx.range_push(self.name)
+
+    def __exit__(self, *exc):
+        if _Phase.enabled:
+            torch.cuda.nvtx.range_pop()
+        return False
 
 
 def _stack_rows(mats):
@@ -596,14 +617,17 @@ class AOADMMEngine:
             self.pf2_deferred = False
 
     def _timed(self, key, fn):
-        self.n_xstream_launches += 1
+        """Run one kernel-family call; with `xstream_events` set (bench.py) bracket it with CUDA events on the
+        launching stream.  Keys: "y" / "z" (X-stream passes), "rowpass", "polar", "unimodal", "local"."""
+        if key in ("y", "z"):
+            self.n_xstream_launches += 1
         if self.xstream_events is None:
             return fn()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         fn()
         e1.record()
-        self.xstream_events[key].append((e0, e1))
+        self.xstream_events.setdefault(key, []).append((e0, e1))
 
     def step_B(self):
         """admm_update_B (decomposition.py:222-292); rhs_i = Y_i o a_i with the cached Y = X C."""
@@ -619,9 +643,9 @@ class AOADMMEngine:
         self.w_fresh = False
         if self._row_local(st):  # whole inner loop in one fused pass, W = B o a emitted for the Z pass
             # W = B o a stays valid for the C-step: A only changes after the C-step (decomposition.py:948-988)
-            _ops.admm_local(self.N, R, self.Y, A, _lib.GROUP_INDEXED, self.gor, self.rhoB, self.MinvB, st.descs_c,
-                            len(st.desc), self.n_inner, st.x, self.Wpad, row_off=self.row_off, n_groups=I,
-                            BtB_out=self.BtB)
+            self._timed("local", lambda: _ops.admm_local(
+                self.N, R, self.Y, A, _lib.GROUP_INDEXED, self.gor, self.rhoB, self.MinvB, st.descs_c, len(st.desc),
+                self.n_inner, st.x, self.Wpad, row_off=self.row_off, n_groups=I, BtB_out=self.BtB))
             self.w_fresh = True
             return
         if self.fuse_pf2 and self.n_inner > 0 and st.desc and st.desc[0][0] == _lib.PEN_PARAFAC2 and \
@@ -652,9 +676,9 @@ class AOADMMEngine:
             # read by the first and written by the last pass of a B-update, which saves two N x R arrays of traffic
             # per companion in every other pass
             flags = (1 if (it > 0 or self.pf2_deferred) else 0) | (2 if it > 0 else 0) | (0 if last else 4)
-            _ops.pf2_rowpass(self.row_off, I, R, self.Y, A, self.rhoB, self.MinvB, st.descs_c, len(st.desc),
-                             flags, self.Wmat, self.Delta, st.x if last else None,
-                             self.Wpad if last else None, self.S, self.BtB if last else None)
+            self._timed("rowpass", lambda: _ops.pf2_rowpass(
+                self.row_off, I, R, self.Y, A, self.rhoB, self.MinvB, st.descs_c, len(st.desc), flags, self.Wmat,
+                self.Delta, st.x if last else None, self.Wpad if last else None, self.S, self.BtB if last else None))
             # The polar step + Delta reduction only need S (from the row pass); the column-coupled companions only
             # need their own pre-image.  With such companions (Unimodality above all: a latency-bound kernel that
             # leaves most of the SM idle) the two chains run on two streams and join before the next row pass.
@@ -666,7 +690,8 @@ class AOADMMEngine:
                 if kind == _lib.PEN_L2BALL:
                     _ops.prox_l2ball(st.aux[p], st.dual[p], self.row_off, I, R, p0, nn)
                 elif kind == _lib.PEN_UNIMODAL:
-                    _ops.prox_unimodal(st.aux[p], st.dual[p], self.row_off, I, R, self.max_rows, nn, self.ws)
+                    self._timed("unimodal", lambda: _ops.prox_unimodal(st.aux[p], st.dual[p], self.row_off, I, R,
+                                                                       self.max_rows, nn, self.ws))
                 elif kind in _ENGINE_PROX_KINDS:
                     st.regs[p]._engine_prox(self, st.aux[p], st.dual[p], self.row_off, I, self.max_rows, self.rhoB,
                                             self.N)
@@ -704,8 +729,8 @@ class AOADMMEngine:
         # cold Jacobi start on the first inner iteration (bounds the round-off drift of the accumulated
         # rotations), warm start from the previous inner iteration's eigenvectors afterwards
         for sub in range(int(st.regs[0].n_iter)):  # Parafac2(n_iter=...): alternations on the same V
-            _ops.pf2_polar(self.S, self.Delta, self.rhoB, I, self.R, self.Wmat, self.num_part, self.pf2_Q,
-                           warm=it > 0 or sub > 0)
+            self._timed("polar", lambda: _ops.pf2_polar(self.S, self.Delta, self.rhoB, I, self.R, self.Wmat,
+                                                        self.num_part, self.pf2_Q, warm=it > 0 or sub > 0))
             self._pf2_delta_update(self.rhoB, I)
 
     def _row_local(self, st):
@@ -852,13 +877,17 @@ class AOADMMEngine:
     def outer_iteration(self):
         """One pass of decomposition.py:945-988."""
         if self.update_B:
-            self.step_B()
+            with _Phase("b2:admm_update_B"):
+                self.step_B()
         if self.update_C:
-            self.step_C()
+            with _Phase("b2:admm_update_C"):
+                self.step_C()
         if self.update_B or self.update_C:
-            self.refresh_products()
+            with _Phase("b2:xstream_y+products"):
+                self.refresh_products()
         if self.update_A:
-            self.step_A()
+            with _Phase("b2:admm_update_A"):
+                self.step_A()
 
     # ------------------------------------------------------------------------------------------------------
     # diagnostics: one fused scalar pack, one device->host copy
@@ -871,6 +900,10 @@ class AOADMMEngine:
 
     def _launch_diagnostics(self):
         """Launch the fused reductions into the scalar pack `self.scal`; returns (layout, n_slots). No host sync."""
+        with _Phase("b2:gaps+fit"):
+            return self._launch_diagnostics_impl()
+
+    def _launch_diagnostics_impl(self):
         scal = self.scal
         scal.zero_()
         slot = 2  # [0:2] fit terms

@@ -209,8 +209,8 @@ int b2_admm_solve(long long n, int R, const void* rhs, const void* rhs_scale, in
                   void* x, int dtype, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
+    if (n == 0) return B2_OK;  // empty shard: zero-size buffers may arrive as NULL
     B2_REQUIRE(group_mode != B2_GROUP_INDEXED || group_of_row != nullptr, "group_of_row required");
-    if (n == 0) return B2_OK;
     PenArgs pa;
     {
         const int rc = b2_pack_penalties(pens, n_pen, &pa);

@@ -103,6 +103,8 @@ struct GramAcc {
         const int d = max(dep(), extra_dep);
         const unsigned never = __any_sync(0xffffffffu, d == 0x7ff7a5a5) ? 1u : 0u;
         double* tl = tile + never;
+        __syncwarp();  // the memory-model barrier between the previous call's fragment reads and these stores (the vote
+                       // above only pins the INSTRUCTION order; compute-sanitizer racecheck needs the real barrier)
 #pragma unroll
         for (int b = 0; b < PL::NB; ++b) *(double2*)(tl + g * LDT + 8 * b + 2 * t) = make_double2(v[b][0], v[b][1]);
         __syncwarp();

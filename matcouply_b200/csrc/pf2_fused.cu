@@ -587,9 +587,9 @@ int b2_pf2_rowpass(const int64_t* row_off, int n_groups, int R, const void* Y, c
     cudaStream_t st = (cudaStream_t)stream;
     B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
     B2_REQUIRE(n_pen >= 1 && pens[0].kind == B2_PEN_PARAFAC2, "b2_pf2_rowpass: pens[0] must be the PARAFAC2 penalty");
-    B2_REQUIRE(!(deferred & 1) || (Wmat && Delta), "deferred mode needs Wmat and Delta");
     B2_REQUIRE((deferred & ~7) == 0, "b2_pf2_rowpass: unknown flag bits in `deferred`");
-    if (n_groups == 0) return B2_OK;
+    if (n_groups == 0) return B2_OK;  // empty shard: zero-size buffers may arrive as NULL
+    B2_REQUIRE(!(deferred & 1) || (Wmat && Delta), "deferred mode needs Wmat and Delta");
     PenArgs pa;
     {
         const int rc = b2_pack_penalties(pens, n_pen, &pa);
@@ -624,8 +624,8 @@ int b2_pf2_polar(const void* S, const void* Delta, const void* rho, int n_groups
                  void* Qstore, int warm, int dtype, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
+    if (n_groups == 0) return B2_OK;  // empty shard: zero-size buffers may arrive as NULL
     B2_REQUIRE(!warm || Qstore, "b2_pf2_polar: a warm start needs the eigenvector store");
-    if (n_groups == 0) return B2_OK;
     if (b2_option_value(B2_OPT_POLAR_WARP) >= 2) {
         const int rc = b2_pf2_polar_reg(S, Delta, rho, n_groups, R, Wmat, num_part, Qstore, warm, dtype, st);
         if (rc >= 0) return rc;

@@ -401,8 +401,8 @@ int b2_prox_tv(void* aux, void* dual, const int64_t* row_off, int n_groups, int 
     cudaStream_t st = (cudaStream_t)stream;
     B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
     B2_REQUIRE(reg_strength > 0.0 && l1_strength >= 0.0, "TV strength must be > 0 and the L1 strength >= 0");
+    if (n_groups == 0) return B2_OK;  // empty shard: zero-size buffers may arrive as NULL
     B2_REQUIRE(rho != nullptr && (rho_stride == 0 || rho_stride == 1), "b2_prox_tv: rho (device) with stride 0 or 1");
-    if (n_groups == 0) return B2_OK;
     const long long threads = (long long)n_groups * 32;
     const int block = 128;
     B2_DISPATCH_DTYPE(dtype, {
@@ -434,9 +434,9 @@ int b2_prox_gl2(void* aux, void* dual, int n_groups, int J, int R, const void* U
                 int rho_stride, void* tmp, int dtype, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
+    if (n_groups == 0 || J == 0) return B2_OK;  // empty shard: zero-size buffers may arrive as NULL
     B2_REQUIRE(tmp != nullptr, "b2_prox_gl2 needs n_groups * J * R elements of scratch");
     B2_REQUIRE(rho != nullptr && (rho_stride == 0 || rho_stride == 1), "b2_prox_gl2: rho (device) with stride 0 or 1");
-    if (n_groups == 0 || J == 0) return B2_OK;
     const dim3 grid((J + 63) / 64, n_groups);
     B2_DISPATCH_DTYPE(dtype, {
         gl2_gemm_kernel<T, true><<<grid, 256, 0, st>>>((const T*)U, (const T*)s, (const T*)rho, rho_stride,
@@ -453,11 +453,11 @@ int b2_quadform(const void* M, const void* x, int n_groups, int J, int R, double
                 int dtype, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
-    B2_REQUIRE(tmp != nullptr && part != nullptr, "b2_quadform needs scratch (n_groups*J*R elements, 256 doubles)");
-    if (n_groups == 0 || J == 0) {
+    if (n_groups == 0 || J == 0) {  // empty shard: zero-size buffers may arrive as NULL
         B2_CHECK_CUDA(cudaMemsetAsync(out, 0, sizeof(double), st));
         return B2_OK;
     }
+    B2_REQUIRE(tmp != nullptr && part != nullptr, "b2_quadform needs scratch (n_groups*J*R elements, 256 doubles)");
     const dim3 grid((J + 63) / 64, n_groups);
     const long long n = (long long)n_groups * J * R;
     B2_DISPATCH_DTYPE(dtype, {

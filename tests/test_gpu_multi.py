@@ -302,3 +302,25 @@ def test_sharded_jump_ahead_draw_is_bit_identical_to_the_global_walk(name, tmp_p
     mp.spawn(_jump_worker, args=(_free_port(), name, out), nprocs=1, join=True)
     res = json.load(open(out))
     assert res["arrays"] > 10 and res["worst"] == 0.0, res
+
+
+def test_device_keyword_binds_every_launch_to_that_device():
+    """`cmf_aoadmm(..., device="cuda:1")` while device 0 is current: streams, workspaces, events and kernel launches
+    must all bind to device 1 (the C ABI launches on torch's current stream).  Needs 2 GPUs."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from matcouply_b200 import PackedMatrices, cmf_aoadmm
+
+    g, X, R, kw = _load_case("c2_nn_pf2_l1_ragged")
+    kw = dict(kw, n_iter_max=8, tol=None, absolute_tol=None)
+    torch.cuda.set_device(0)
+    ref = cmf_aoadmm(X, R, **kw)
+    got = cmf_aoadmm(X, R, device="cuda:1", **kw)
+    assert torch.cuda.current_device() == 0
+    for a, b in zip((ref[1][0], np.concatenate(ref[1][1]), ref[1][2]), (got[1][0], np.concatenate(got[1][1]), got[1][2])):
+        np.testing.assert_array_equal(a, b)
+    packed = PackedMatrices.from_list(X, torch.float64, torch.device("cuda", 1))
+    got2 = cmf_aoadmm(packed, R, **kw)  # device-resident input: the fit follows the data
+    np.testing.assert_array_equal(got2[1][2], ref[1][2])
+    with pytest.raises(ValueError):
+        cmf_aoadmm(packed, R, device="cuda:0", **kw)
