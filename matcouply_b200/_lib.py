@@ -14,6 +14,8 @@ VARIANT_AUTO, VARIANT_FMA, VARIANT_DMMA = 0, 1, 2
 PEN_NONNEG, PEN_BOX, PEN_L1, PEN_L2BALL, PEN_UNIMODAL, PEN_PARAFAC2, PEN_GL2, PEN_SIMPLEX, PEN_TV, PEN_HOST = range(10)
 GROUP_SINGLE, GROUP_INDEXED, GROUP_IDENTITY = 0, 1, 2
 OPT_PF2_ROWPASS_MMA, OPT_POLAR_WARP, OPT_ADMM_LOCAL_MMA, OPT_XSTREAM_HYBRID = 0, 1, 2, 3
+# B2_OPT_PF2_ROWPASS_MMA: 0 = shuffle kernel, 1 = DMMA tile kernel, 2 (default) = + the steady-state specialisation
+PF2_ROWPASS_DEFAULT = 2
 MAX_RANK = 32
 MAX_PENALTIES_PER_MODE = 4
 

@@ -595,6 +595,11 @@ int b2_pf2_rowpass(const int64_t* row_off, int n_groups, int R, const void* Y, c
         const int rc = b2_pack_penalties(pens, n_pen, &pa);
         if (rc != B2_OK) return rc;
     }
+    if (b2_option_value(B2_OPT_PF2_ROWPASS_MMA) >= 2) {  // steady-state specialisation (pf2_rowpass_v2.cu)
+        const int rc = b2_pf2_rowpass_v2_try(row_off, n_groups, R, Y, A, rho, Minv, pa, deferred, Wmat, Delta, x, w_out,
+                                             ldw, S_out, BtB_out, dtype, st);
+        if (rc >= 0) return rc;
+    }
     if (b2_option_value(B2_OPT_PF2_ROWPASS_MMA)) {  // tensor-core formulation (pf2_mma.cu) when it applies
         const int rc = b2_pf2_rowpass_mma_try(row_off, n_groups, R, Y, A, rho, Minv, pa, deferred, Wmat, Delta, x, w_out,
                                               ldw, S_out, BtB_out, dtype, st);

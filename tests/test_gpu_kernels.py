@@ -581,7 +581,85 @@ def test_pf2_rowpass_both_formulations(R, dtype, mma):
                     Bref = np.stack([xr[off[g]:off[g + 1]].T @ xr[off[g]:off[g + 1]] for g in range(G)])
                     np.testing.assert_allclose(BtB.double().cpu().numpy(), Bref, rtol=tol * 10, atol=tol * 1e3)
     finally:
-        lib.b2_set_option(_lib.OPT_PF2_ROWPASS_MMA, 1)
+        lib.b2_set_option(_lib.OPT_PF2_ROWPASS_MMA, _lib.PF2_ROWPASS_DEFAULT)
+
+
+@pytest.mark.parametrize("R", [4, 8, 12, 16, 20, 24, 28, 32])
+@pytest.mark.parametrize("n_extra", [0, 1])
+def test_pf2_rowpass_steady_state_kernel_bit_identical(R, n_extra):
+    """The steady-state specialisation of the row pass (csrc/pf2_rowpass_v2.cuh: compile-time rank, deferred prox,
+    PARAFAC2 alone or with non-negativity, full-tile fast path, last-releaser refill) performs the same operations in
+    the same order as the general DMMA tile kernel: a whole B-update (first / middle / middle / last pass, the flag
+    sequence of `_engine._step_B_pf2_fused`) must leave BIT-identical V, T / (aux, dual), x, W, S and B^T B.  Slices of
+    0, 1, 63, 64, 65, 128 and ~1000 rows cover the empty, ragged-only, full-only and mixed tile paths and ring wrap."""
+    _lib, _ops, _ = _imports()
+    lib = _lib.load()
+    rs = np.random.RandomState(300 + R + n_extra)
+    sizes = np.array([0, 1, 63, 64, 65, 128, 700 + 37 * (R % 5), 5, 1029, 64], dtype=np.int64)
+    G = len(sizes)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    N = int(off[-1])
+    f = lambda *s: rs.standard_normal(size=s)  # noqa: E731
+    Y, A, rho = f(N, R), rs.uniform(0.5, 1.5, size=(G, R)), rs.uniform(0.5, 2.0, size=G)
+    Minv = np.stack([np.linalg.inv(m @ m.T + R * np.eye(R)) for m in f(G, R, R)]) * 0.5
+    Wm, Delta = f(G, R, R) / np.sqrt(R), f(R, R) / np.sqrt(R)
+    init = dict(pf_aux=f(N, R), pf_dual=f(N, R), nn_aux=f(N, R), nn_dual=f(N, R))
+    offd = dev(off, torch.int64)
+    gor = np.repeat(np.arange(G), sizes)
+    results = {}
+    try:
+        for opt in (1, 2):
+            lib.b2_set_option(_lib.OPT_PF2_ROWPASS_MMA, opt)
+            d = {k: dev(v) for k, v in init.items()}
+            pens = [(_lib.PEN_PARAFAC2, 0, 0, 0, d["pf_aux"], d["pf_dual"])]
+            if n_extra:
+                pens.append((_lib.PEN_NONNEG, 0, 0, 0, d["nn_aux"], d["nn_dual"]))
+            descs = _ops.make_descs(pens)
+            x = torch.full((N, R), float("nan"), dtype=torch.float64, device="cuda")
+            Wp = _ops.alloc_w(N, R, torch.float64, "cuda")
+            BtB = torch.full((G, R, R), float("nan"), dtype=torch.float64, device="cuda")
+            S_all = []
+            n_pass = 4
+            launches0 = int(lib.b2_launch_count())
+            for it in range(n_pass):
+                last = it == n_pass - 1
+                flags = 1 | (2 if it > 0 else 0) | (0 if last else 4)
+                S = torch.full((G, R, R), float("nan"), dtype=torch.float64, device="cuda")
+                _ops.pf2_rowpass(offd, G, R, dev(Y), dev(A), dev(rho), dev(Minv), descs, len(pens), flags, dev(Wm),
+                                 dev(Delta), x if last else None, Wp if last else None, S, BtB if last else None)
+                S_all.append(S.cpu().numpy())
+            torch.cuda.synchronize()
+            assert int(lib.b2_launch_count()) - launches0 == n_pass  # one kernel per pass on either path
+            results[opt] = dict(x=x.cpu().numpy(), W=Wp.cpu().numpy(), BtB=BtB.cpu().numpy(), S=np.stack(S_all),
+                                **{k: v.cpu().numpy() for k, v in d.items()})
+    finally:
+        lib.b2_set_option(_lib.OPT_PF2_ROWPASS_MMA, _lib.PF2_ROWPASS_DEFAULT)
+    for key in results[1]:
+        if n_extra == 0 and key.startswith("nn_"):
+            continue
+        np.testing.assert_array_equal(results[2][key], results[1][key], err_msg=key)
+    # and one pass against NumPy (deferred, first pass of a B-update)
+    lib.b2_set_option(_lib.OPT_PF2_ROWPASS_MMA, 2)
+    d = {k: dev(v) for k, v in init.items()}
+    pens = [(_lib.PEN_PARAFAC2, 0, 0, 0, d["pf_aux"], d["pf_dual"])]
+    if n_extra:
+        pens.append((_lib.PEN_NONNEG, 0, 0, 0, d["nn_aux"], d["nn_dual"]))
+    S = torch.full((G, R, R), float("nan"), dtype=torch.float64, device="cuda")
+    _ops.pf2_rowpass(offd, G, R, dev(Y), dev(A), dev(rho), dev(Minv), _ops.make_descs(pens), len(pens), 1 | 4, dev(Wm),
+                     dev(Delta), None, None, S, None)
+    T = np.einsum("gik,kj->gij", Wm, Delta)
+    pd = np.einsum("nk,nkj->nj", init["pf_dual"], T[gor])
+    dpf = init["pf_dual"] - pd
+    sh = pd - dpf
+    if n_extra:
+        sh = sh + init["nn_aux"] - init["nn_dual"]
+    xr = np.einsum("nk,nkj->nj", rho[gor][:, None] * sh + Y * A[gor], Minv[gor])
+    vn = xr + dpf
+    np.testing.assert_allclose(d["pf_dual"].cpu().numpy(), vn, rtol=1e-11, atol=1e-10)
+    if n_extra:
+        np.testing.assert_allclose(d["nn_dual"].cpu().numpy(), xr + init["nn_dual"], rtol=1e-11, atol=1e-10)  # T' = x + dual
+    Sref = np.stack([vn[off[g]:off[g + 1]].T @ vn[off[g]:off[g + 1]] for g in range(G)])
+    np.testing.assert_allclose(S.cpu().numpy(), Sref, rtol=1e-10, atol=1e-8)
 
 
 @pytest.mark.parametrize("R", [4, 8, 20, 32])
@@ -964,6 +1042,6 @@ def test_pf2_rowpass_single_array_companions_bit_identical(R, dtype, mma):
             results[single]["x"] = x.cpu().numpy().copy()
             results[single]["S"] = S.cpu().numpy().copy()
     finally:
-        lib.b2_set_option(_lib.OPT_PF2_ROWPASS_MMA, 1)
+        lib.b2_set_option(_lib.OPT_PF2_ROWPASS_MMA, _lib.PF2_ROWPASS_DEFAULT)
     for k in results[False]:
         np.testing.assert_array_equal(results[True][k], results[False][k], err_msg=k)
