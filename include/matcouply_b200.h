@@ -55,12 +55,17 @@ typedef struct {
 
 /* kernel-selection switches (process-wide; default 1 = on, except B2_OPT_XSTREAM_HYBRID which is off).  They only choose between equivalent kernels — tests flip
  * them to cross-check the tensor-core formulations against the scalar ones. */
-enum { B2_OPT_PF2_ROWPASS_MMA = 0 /* DMMA row pass of b2_pf2_rowpass */,
+enum { B2_OPT_PF2_ROWPASS_MMA = 0 /* row pass of b2_pf2_rowpass: 0 = shuffle kernel, 1 = DMMA tile kernel, 2 (default) = DMMA tile
+                                     kernel + its steady-state specialisation (fp64, R % 4 == 0, deferred prox, PARAFAC2
+                                     alone or with non-negativity) */,
        B2_OPT_POLAR_WARP = 1 /* polar step of b2_pf2_polar: 2 (default) = warp per slice, Jacobi in registers; 1 = warp per slice in shared memory; 0 = CTA per slice */,
        B2_OPT_ADMM_LOCAL_MMA = 2 /* DMMA formulation of b2_admm_local (CTA-per-slice path) */,
        B2_OPT_XSTREAM_HYBRID = 3 /* DMMA blocks + DFMA remainder columns in the fp64 X-stream kernels (R = 8b+1..4);
                                     default OFF: measured 2-6 % slower than padding to a whole block */,
-       B2_OPT_COUNT = 4 };
+       B2_OPT_UNIMODAL_VARIANT = 4 /* b2_prox_unimodal: (column ring depth, shared-memory stack-cache depth, CTAs per
+                                      SM) of the PAVA kernel: 0 = (8, 4, 4), 1 = (4, 8, 4), 2 = (8, 8, 4), 3 = (4, 16, 3),
+                                      4 = (4, 8, 5), 5 = (4, 12, 4); same results, different residency */,
+       B2_OPT_COUNT = 5 };
 int b2_set_option(int option, int value);
 int b2_get_option(int option);
 
@@ -173,11 +178,20 @@ int b2_pf2_polar(const void* S, const void* Delta, const void* rho, int n_groups
  *                  explicit (aux, dual) exist before and after it (bit-identical to passing them through every pass).
  *   x = (rho_g * sum_p (aux_p - dual_p) + Y o a_g) Minv_g ; pens[0].dual <- V' = x + dual_pf2 ; S_out[g] = V'^T V' ;
  *   other penalties: elementwise kinds are finished (aux = prox, dual update), column-coupled kinds get dual <- x + dual.
- * x / w_out (= x o a_g, row stride ldw) / BtB_out[g] = x_g^T x_g are written only when non-NULL (last inner iteration). */
+ * x / w_out (= x o a_g, row stride ldw) / BtB_out[g] = x_g^T x_g are written only when non-NULL (last inner iteration).
+ * comp_stats_part (optional, 3 * n_groups doubles; last pass = x non-NULL, exactly one companion): per slice
+ *   [sum (aux_1 - x)^2, sum x^2, sum |x|] of the companion, the terms of its feasibility gap and penalty value
+ *   (decomposition.py:406-415, penalties.py:589-592), taken while aux and x are in registers instead of a further pass
+ *   over both arrays; reduce them with b2_group_stats_sum.  Only the steady-state kernel serves it — ask
+ *   b2_pf2_rowpass_fused_stats_supported(R, dtype, n_pen, kind of pens[1], deferred) first; in that case bit 2 may also
+ *   stay set on the last pass (the companion is kept as ONE array T across outer iterations: aux = prox(T), dual = T - aux). */
 int b2_pf2_rowpass(const int64_t* row_off, int n_groups, int R, const void* Y, const void* A, const void* rho,
                    const void* Minv, const b2_penalty_desc* pens_host, int n_pen, int deferred, const void* Wmat,
-                   const void* Delta, void* x, void* w_out, int ldw, void* S_out, void* BtB_out, int dtype,
-                   void* stream);
+                   const void* Delta, void* x, void* w_out, int ldw, void* S_out, void* BtB_out,
+                   double* comp_stats_part, int dtype, void* stream);
+int b2_pf2_rowpass_fused_stats_supported(int R, int dtype, int n_pen, int companion_kind, int deferred);
+/* out[0:3] = sum over groups of part[3 g + 0:3], fixed order (per-slice partials of b2_pf2_rowpass / b2_pf2_gap). */
+int b2_group_stats_sum(const double* part, int n_groups, double* out, void* stream);
 
 /* ---- per-slice Gram bookkeeping shared by the C- and A-updates (decomposition.py:155, 158, 312-314) ---------------
  * b2_slice_gram:        BtB[g] = B_g^T B_g                       (DMMA, one CTA per slice)

@@ -341,6 +341,15 @@ class AOADMMEngine:
             # (V W_g Delta, V - V W_g Delta) exist only implicitly; _materialize_pf2() writes them out on demand
             self.pf2_deferred = False
             self.pf2_delta_zero = False  # Delta == 0 exactly (aux_init="zeros"): see _pf2_prox_unfused
+            # One elementwise companion next to PARAFAC2 served by the steady-state row-pass kernel: the companion stays
+            # ONE array T = x + dual across outer iterations too (`comp_T_state`: its dual slot holds T, aux is stale;
+            # _materialize_companion() writes the pair out on demand) and its gap terms come out of the last row pass
+            # (`comp_stats_fresh`: per-slice partials in comp_stats_part) instead of a pass over x and aux.
+            d1 = self.modes[1].desc
+            self.comp_keep_T = (len(d1) == 2 and d1[0][0] == _lib.PEN_PARAFAC2 and self.inner_tol is None and
+                                _ops.pf2_rowpass_fused_stats_supported(R, dt, 2, d1[1][0], 1))
+            self.comp_T_state = self.comp_stats_fresh = False
+            self.comp_stats_part = torch.zeros(3 * max(I, 1), dtype=torch.float64, device=dev)
             self.pf2_gap_part = torch.zeros(3 * max(I, 1), dtype=torch.float64, device=dev)
             self.pf2_Q = torch.zeros(I, R, R, dtype=torch.float64, device=dev)  # Jacobi eigenvectors (warm start)
         self.scal = torch.zeros(64, dtype=torch.float64, device=dev)
@@ -393,6 +402,7 @@ class AOADMMEngine:
                     self.pf2_fresh = False
                     self.pf2_deferred = False
                     self.pf2_delta_zero = not np.any(np.asarray(delta))
+                    self.comp_T_state = self.comp_stats_fresh = False
                     self.Delta.copy_(self._up(delta))
                     if basis.__class__.__name__ == "_EyeBases":
                         # P_i = eye(J_i, R): row j < R of slice i of P_i Delta is Delta[j]; built on the device
@@ -440,6 +450,7 @@ class AOADMMEngine:
                         pd[(starts + j)[ok]] = self.Delta[j]
                     st[m].aux.append(pd)
                     self.pf2_basis0, self.pf2_fresh, self.pf2_deferred, self.pf2_delta_zero = None, False, False, False
+                    self.comp_T_state = self.comp_stats_fresh = False
                 else:
                     st[m].aux.append(rnd(n, R))
                 st[m].dual.append(rnd(n, R))
@@ -462,6 +473,7 @@ class AOADMMEngine:
     def admm_vars(self):
         """(auxes, duals) in the reference's ADMMVars layout (decomposition.py:1077-1081)."""
         f64 = lambda t: t.detach().to(torch.float64).cpu().numpy()  # noqa: E731
+        self._materialize_companion()
         auxes, duals = ([], [], []), ([], [], [])
         for m in range(3):
             st = self.modes[m]
@@ -616,6 +628,16 @@ class AOADMMEngine:
             _ops.pf2_apply(st.aux[p], st.dual[p], None, self.Wmat, self.Delta, self.gor, self.N, self.R)
             self.pf2_deferred = False
 
+    def _materialize_companion(self):
+        """Write out (aux, dual) = (prox(T), T - prox(T)) of the one-array companion if it is held as T."""
+        if self.has_pf2 and self.comp_T_state:
+            st = self.modes[1]
+            kind, nn, p0, p1 = st.desc[1]
+            # only rho-independent kinds are kept as T across outer iterations (non-negativity): rho = 1 is a dummy
+            _ops.prox_elementwise(st.dual[1], st.aux[1], kind, nn, p0, p1, 1.0)
+            st.dual[1].sub_(st.aux[1])
+            self.comp_T_state = False
+
     def _timed(self, key, fn):
         """Run one kernel-family call; with `xstream_events` set (bench.py) bracket it with CUDA events on the
         launching stream.  Keys: "y" / "z" (X-stream passes), "rowpass", "polar", "unimodal", "local"."""
@@ -641,6 +663,8 @@ class AOADMMEngine:
         _ops.factor_batch(self.lhsB, I, R, self.rhoB, self.rho_max if self.const_B else None, len(st.desc), self.l2[1],
                           self.MinvB)
         self.w_fresh = False
+        if self.has_pf2:
+            self.comp_stats_fresh = False
         if self._row_local(st):  # whole inner loop in one fused pass, W = B o a emitted for the Z pass
             # W = B o a stays valid for the C-step: A only changes after the C-step (decomposition.py:948-988)
             self._timed("local", lambda: _ops.admm_local(
@@ -653,6 +677,7 @@ class AOADMMEngine:
                 st.regs[0].update_coordinate_matrix and int(st.regs[0].n_iter) >= 1:
             return self._step_B_pf2_fused()
         self._materialize_pf2()
+        self._materialize_companion()
         for _ in range(self.n_inner):
             x_old = st.x.clone() if self.inner_tol is not None else None
             _ops.admm_solve(self.N, R, self.Y, A, _lib.GROUP_INDEXED, self.gor, self.rhoB, self.MinvB, st.descs_c,
@@ -675,10 +700,19 @@ class AOADMMEngine:
             # T = x + dual (aux = prox(T) and dual = T - aux are recomputed in registers): explicit (aux, dual) are only
             # read by the first and written by the last pass of a B-update, which saves two N x R arrays of traffic
             # per companion in every other pass
-            flags = (1 if (it > 0 or self.pf2_deferred) else 0) | (2 if it > 0 else 0) | (0 if last else 4)
+            deferred = it > 0 or self.pf2_deferred
+            # the steady-state kernel (deferred prox) can leave the companion as T on the last pass too and emit its
+            # gap terms; otherwise the last pass writes the explicit (aux, dual) pair
+            keep_T = last and self.comp_keep_T and deferred
+            tin = it > 0 or self.comp_T_state
+            flags = (1 if deferred else 0) | (2 if tin else 0) | (4 if (not last or keep_T) else 0)
+            stats = self.comp_stats_part if keep_T else None
             self._timed("rowpass", lambda: _ops.pf2_rowpass(
                 self.row_off, I, R, self.Y, A, self.rhoB, self.MinvB, st.descs_c, len(st.desc), flags, self.Wmat,
-                self.Delta, st.x if last else None, self.Wpad if last else None, self.S, self.BtB if last else None))
+                self.Delta, st.x if last else None, self.Wpad if last else None, self.S, self.BtB if last else None,
+                stats))
+            if last:
+                self.comp_T_state = self.comp_stats_fresh = keep_T
             # The polar step + Delta reduction only need S (from the row pass); the column-coupled companions only
             # need their own pre-image.  With such companions (Unimodality above all: a latency-bound kernel that
             # leaves most of the SM idle) the two chains run on two streams and join before the next row pass.
@@ -923,7 +957,11 @@ class AOADMMEngine:
                 if m == 1 and st.desc[p][0] == _lib.PEN_PARAFAC2 and self.pf2_deferred:
                     _ops.pf2_gap(st.dual[p], st.x, self.row_off, self.I, self.R, self.Wmat, self.Delta,
                                  scal[slot:slot + 3], self.pf2_gap_part)
+                elif m == 1 and p == 1 and self.has_pf2 and self.comp_stats_fresh:
+                    _ops.group_stats_sum(self.comp_stats_part, self.I, scal[slot:slot + 3])  # from the last row pass
                 else:
+                    if m == 1 and p == 1 and self.has_pf2:
+                        self._materialize_companion()
                     _ops.reduce_stats(st.x, st.aux[p], sizes[m], scal[slot:slot + 3], self.ws)
                 layout.append((m, p, slot))
                 slot += 3

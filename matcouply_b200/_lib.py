@@ -13,7 +13,7 @@ F32, F64 = 0, 1
 VARIANT_AUTO, VARIANT_FMA, VARIANT_DMMA = 0, 1, 2
 PEN_NONNEG, PEN_BOX, PEN_L1, PEN_L2BALL, PEN_UNIMODAL, PEN_PARAFAC2, PEN_GL2, PEN_SIMPLEX, PEN_TV, PEN_HOST = range(10)
 GROUP_SINGLE, GROUP_INDEXED, GROUP_IDENTITY = 0, 1, 2
-OPT_PF2_ROWPASS_MMA, OPT_POLAR_WARP, OPT_ADMM_LOCAL_MMA, OPT_XSTREAM_HYBRID = 0, 1, 2, 3
+OPT_PF2_ROWPASS_MMA, OPT_POLAR_WARP, OPT_ADMM_LOCAL_MMA, OPT_XSTREAM_HYBRID, OPT_UNIMODAL_VARIANT = 0, 1, 2, 3, 4
 # B2_OPT_PF2_ROWPASS_MMA: 0 = shuffle kernel, 1 = DMMA tile kernel, 2 (default) = + the steady-state specialisation
 PF2_ROWPASS_DEFAULT = 2
 MAX_RANK = 32
@@ -59,7 +59,8 @@ _SIGNATURES = {
     "b2_pf2_fixed_basis": [_vp, _vp, _vp, _vp, _vp, _i, _ll, _i, _vp, _vp, _i, _i, _vp],
     "b2_pf2_polar": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _i, _vp],
     "b2_pf2_rowpass": [_vp, _i, _i, _vp, _vp, _vp, _vp, ctypes.POINTER(PenaltyDesc), _i, _i, _vp, _vp, _vp, _vp, _i, _vp,
-                       _vp, _i, _vp],
+                       _vp, _vp, _i, _vp],
+    "b2_group_stats_sum": [_vp, _i, _vp, _vp],
     "b2_pf2_delta": [_vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp],
     "b2_pf2_apply": [_vp, _vp, _vp, _vp, _vp, _vp, _ll, _i, _i, _vp],
     "b2_pf2_gap": [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _i, _vp, _sz, _vp],
@@ -81,6 +82,7 @@ _OTHER = {
     "b2_device_sm_count": ([], _i),
     "b2_launch_count": ([], ctypes.c_ulonglong),
     "b2_get_option": ([_i], _i),
+    "b2_pf2_rowpass_fused_stats_supported": ([_i, _i, _i, _i, _i], _i),
     "b2_xstream_workspace_bytes": ([_i, _i, _i], _sz),
     "b2_xstream_z_ldw": ([_i, _i, _i], _i),
     "b2_unimodal_workspace_bytes": ([_i, _i, _i], _sz),

@@ -242,10 +242,21 @@ def admm_local(n, R, rhs, rhs_scale, group_mode, group_of_row, rho, Minv, descs,
 
 
 def pf2_rowpass(row_off, n_groups, R, Y, A, rho, Minv, descs, n_pen, deferred, Wmat, Delta, x, w_out, S_out,
-                BtB_out=None):
+                BtB_out=None, comp_stats_part=None):
     call("b2_pf2_rowpass", _ptr(row_off), n_groups, R, _ptr(Y), _ptr(A), _ptr(rho), _ptr(Minv), descs, n_pen,
          int(deferred), _ptr(Wmat), _ptr(Delta), _ptr(x), _ptr(w_out), 0 if w_out is None else w_out.shape[1],
-         _ptr(S_out), _ptr(BtB_out), dtype_code(Y.dtype), _stream())
+         _ptr(S_out), _ptr(BtB_out), _ptr(comp_stats_part), dtype_code(Y.dtype), _stream())
+
+
+def pf2_rowpass_fused_stats_supported(R, dtype, n_pen, companion_kind, deferred):
+    """True when b2_pf2_rowpass serves `comp_stats_part` (and the one-array companion on the last pass) for such a call."""
+    return bool(_lib.load().b2_pf2_rowpass_fused_stats_supported(int(R), dtype_code(dtype), int(n_pen),
+                                                                   int(companion_kind), int(deferred)))
+
+
+def group_stats_sum(part, n_groups, out):
+    """out[0:3] = sum over groups of the per-slice partials part[3 g + 0:3] (fixed order)."""
+    call("b2_group_stats_sum", _ptr(part), int(n_groups), _ptr(out), _stream())
 
 
 def pf2_gap(V, x, row_off, n_groups, R, Wmat, Delta, out, part):

@@ -107,7 +107,9 @@ int b2_pf2_rowpass_mma_try(const int64_t* row_off, int n_groups, int R, const vo
 // non-negativity companion); returns -1 when it does not apply
 int b2_pf2_rowpass_v2_try(const int64_t* row_off, int n_groups, int R, const void* Y, const void* A, const void* rho,
                           const void* Minv, const PenArgs& pa, int deferred, const void* Wmat, const void* Delta,
-                          void* x, void* w_out, int ldw, void* S_out, void* BtB_out, int dtype, cudaStream_t st);
+                          void* x, void* w_out, int ldw, void* S_out, void* BtB_out, double* stats_part, int dtype,
+                          cudaStream_t st);
+int b2_pf2_rowpass_v2_applies(int R, int dtype, int n_pen, int companion_kind, int deferred);
 
 // tensor-core PARAFAC2 gap reduction (pf2_gap_mma.cu); returns -1 when it does not apply
 int b2_pf2_gap_mma_try(const void* V, const void* x, const int64_t* row_off, int n_groups, int R, const void* Wmat,

@@ -580,10 +580,14 @@ int launch_slice_gram(const void* B, const int64_t* row_off, int n_groups, int R
 
 extern "C" {
 
+int b2_pf2_rowpass_fused_stats_supported(int R, int dtype, int n_pen, int companion_kind, int deferred) {
+    return b2_pf2_rowpass_v2_applies(R, dtype, n_pen, companion_kind, deferred);
+}
+
 int b2_pf2_rowpass(const int64_t* row_off, int n_groups, int R, const void* Y, const void* A, const void* rho,
                    const void* Minv, const b2_penalty_desc* pens, int n_pen, int deferred, const void* Wmat,
-                   const void* Delta, void* x, void* w_out, int ldw, void* S_out, void* BtB_out, int dtype,
-                   void* stream) {
+                   const void* Delta, void* x, void* w_out, int ldw, void* S_out, void* BtB_out,
+                   double* comp_stats_part, int dtype, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
     B2_REQUIRE(n_pen >= 1 && pens[0].kind == B2_PEN_PARAFAC2, "b2_pf2_rowpass: pens[0] must be the PARAFAC2 penalty");
@@ -595,11 +599,19 @@ int b2_pf2_rowpass(const int64_t* row_off, int n_groups, int R, const void* Y, c
         const int rc = b2_pack_penalties(pens, n_pen, &pa);
         if (rc != B2_OK) return rc;
     }
+    if (comp_stats_part != nullptr) {
+        B2_REQUIRE(x != nullptr && n_pen == 2, "b2_pf2_rowpass: comp_stats_part belongs to the last pass with one companion");
+        B2_REQUIRE(b2_pf2_rowpass_v2_applies(R, dtype, n_pen, pa.kind[1], deferred),
+                   "b2_pf2_rowpass: comp_stats_part needs the steady-state kernel "
+                   "(check b2_pf2_rowpass_fused_stats_supported first)");
+    }
     if (b2_option_value(B2_OPT_PF2_ROWPASS_MMA) >= 2) {  // steady-state specialisation (pf2_rowpass_v2.cu)
         const int rc = b2_pf2_rowpass_v2_try(row_off, n_groups, R, Y, A, rho, Minv, pa, deferred, Wmat, Delta, x, w_out,
-                                             ldw, S_out, BtB_out, dtype, st);
+                                             ldw, S_out, BtB_out, comp_stats_part, dtype, st);
         if (rc >= 0) return rc;
     }
+    B2_REQUIRE(comp_stats_part == nullptr, "b2_pf2_rowpass: the steady-state kernel did not take this call "
+                                           "(unaligned buffers?), comp_stats_part cannot be served");
     if (b2_option_value(B2_OPT_PF2_ROWPASS_MMA)) {  // tensor-core formulation (pf2_mma.cu) when it applies
         const int rc = b2_pf2_rowpass_mma_try(row_off, n_groups, R, Y, A, rho, Minv, pa, deferred, Wmat, Delta, x, w_out,
                                               ldw, S_out, BtB_out, dtype, st);
@@ -702,6 +714,17 @@ int b2_pf2_gap(const void* V, const void* x, const int64_t* row_off, int n_group
 #undef B2_CASE_CPL
     if (rc != B2_OK) return rc;
     pf2_gap_final_kernel<<<1, 256, 0, st>>>((const double*)ws, n_groups, out);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+
+int b2_group_stats_sum(const double* part, int n_groups, double* out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_groups == 0) {
+        B2_CHECK_CUDA(cudaMemsetAsync(out, 0, 3 * sizeof(double), st));
+        return B2_OK;
+    }
+    pf2_gap_final_kernel<<<1, 256, 0, st>>>(part, n_groups, out);
     B2_LAUNCH_CHECK();
     return B2_OK;
 }

@@ -35,6 +35,7 @@ struct Args {
     double *x_out, *w_out;
     int ldw;
     double *S_out, *BtB_out;
+    double* stats_part;  // optional (LAST, one companion): per slice [sum (aux1 - x)^2, sum x^2, sum |x|]
     int stages;
 };
 
@@ -99,6 +100,7 @@ pf2_rowpass_v2_kernel(const Args a) {
             a.S_out[(size_t)g_slice * RR + e] = 0.0;
             if (LAST) a.BtB_out[(size_t)g_slice * RR + e] = 0.0;
         }
+        if (LAST && K1 >= 0 && a.stats_part != nullptr && tid < 3) a.stats_part[(size_t)g_slice * 3 + tid] = 0.0;
         return;
     }
     const int n_tiles = (int)((r_end - r_begin + kTile - 1) / kTile);
@@ -163,6 +165,7 @@ pf2_rowpass_v2_kernel(const Args a) {
     GA accS, accB;
     accS.clear();
     if (LAST) accB.clear();
+    double gap_d2 = 0.0, gap_x2 = 0.0, gap_ab = 0.0;
     double* tileG = gtiles + (size_t)warp * 8 * GA::LDT;
     const uint32_t lane_row_off = (uint32_t)((warp * 8 + g) * R * sizeof(double));
 
@@ -253,6 +256,14 @@ pf2_rowpass_v2_kernel(const Args a) {
                         const double z = prox_elem<double>(vv, K1, 0, 0.0, 0.0, rg);
                         zo[b][e] = z;
                         dn[b][e] = TOUT ? vv : vv - z;
+                        if constexpr (LAST) {
+                            // feasibility-gap terms of the companion (decomposition.py:406-415) while aux and x are in
+                            // registers; padding positions hold x = aux = 0
+                            const double df = z - xv[b][e];
+                            gap_d2 = fma(df, df, gap_d2);
+                            gap_x2 = fma(xv[b][e], xv[b][e], gap_x2);
+                            gap_ab += fabs(xv[b][e]);
+                        }
                     }
                 if constexpr (!TOUT) st_row<PL>(a.c_aux + goff, t, zo);
                 st_row<PL>(a.c_dual + goff, t, dn);
@@ -292,6 +303,23 @@ pf2_rowpass_v2_kernel(const Args a) {
         __syncthreads();
         gram_reduce_store<PL, double>(accB, red, warp, lane, kWarps, tid, kThreads, R, a.BtB_out + (size_t)g_slice * RR,
                                       sync);
+        if (K1 >= 0 && a.stats_part != nullptr) {  // fixed-order reduction: lanes (shuffle tree), then warps 0..7
+            gap_d2 = warp_sum(gap_d2);
+            gap_x2 = warp_sum(gap_x2);
+            gap_ab = warp_sum(gap_ab);
+            __syncthreads();
+            if (lane == 0) {
+                red[3 * warp] = gap_d2;
+                red[3 * warp + 1] = gap_x2;
+                red[3 * warp + 2] = gap_ab;
+            }
+            __syncthreads();
+            if (tid < 3) {
+                double sum = 0.0;
+                for (int w = 0; w < kWarps; ++w) sum += red[3 * w + tid];
+                a.stats_part[(size_t)g_slice * 3 + tid] = sum;
+            }
+        }
     }
 }
 
@@ -336,13 +364,17 @@ int launch_pass(const Args& a, int n_groups, bool tin, bool tout, bool last, cud
     if (tin && tout && !last) return launch<NBF, HALF, K1, true, true, false>(a, n_groups, st);
     if (tin && !tout && last) return launch<NBF, HALF, K1, true, false, true>(a, n_groups, st);
     if (!tin && !tout && last) return launch<NBF, HALF, K1, false, false, true>(a, n_groups, st);  // inner_n_iter_max = 1
+    // the companion stays ONE array across outer iterations too (T in the dual slot; the engine materialises
+    // (aux, dual) on demand and takes the gap terms from stats_part)
+    if (tin && tout && last) return launch<NBF, HALF, K1, true, true, true>(a, n_groups, st);
+    if (!tin && tout && last) return launch<NBF, HALF, K1, false, true, true>(a, n_groups, st);
     return -1;
 }
 
 // Returns B2_OK after launching, a positive error code, or -1 when this specialisation does not apply.
 inline int try_launch(const int64_t* row_off, int n_groups, int R, const void* Y, const void* A, const void* rho,
                       const void* Minv, const PenArgs& pa, int deferred, const void* Wmat, const void* Delta, void* x,
-                      void* w_out, int ldw, void* S_out, void* BtB_out, cudaStream_t st) {
+                      void* w_out, int ldw, void* S_out, void* BtB_out, double* stats_part, cudaStream_t st) {
     if (!(deferred & 1) || R % 4 != 0 || R < 4 || R > 32) return -1;
     const int n_extra = pa.n_pen - 1;
     if (n_extra > 1) return -1;
@@ -375,6 +407,7 @@ inline int try_launch(const int64_t* row_off, int n_groups, int R, const void* Y
     a.ldw = ldw;
     a.S_out = (double*)S_out;
     a.BtB_out = (double*)BtB_out;
+    a.stats_part = stats_part;
     const int NBF = R / 8, HALF = (R % 8) ? 1 : 0;
 #define B2_RP2_CASE(F, H)                                                                              \
     if (NBF == F && HALF == H) {                                                                       \

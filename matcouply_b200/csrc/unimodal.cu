@@ -36,15 +36,18 @@ struct __align__(16) Rec {
 };
 
 constexpr int kThreads = 128;
-constexpr int kYRing = 8;   // elements of the column in flight ahead of the PAVA front (cp.async into shared memory)
-constexpr int kStack = 4;   // most recent stack blocks (below the register-resident top) cached in shared memory
+// YRING: elements of the column in flight ahead of the PAVA front (cp.async into shared memory);
+// STACK: most recent stack blocks (below the register-resident top) cached in shared memory — a pop below the cached
+// window re-reads the recorded block end from global memory, and since a warp trip costs the slowest of its 32 lanes,
+// a few per cent of such pops per lane put a global-memory round trip into a quarter of all trips.
 
 // shared memory, all arrays [depth][thread] so that a warp access is conflict free
+template <int YRING, int STACK>
 struct SharedState {
-    double y[kYRing][kThreads];
-    double2 sums[kStack][kThreads];   // sy, sy2
-    double2 lvl_err[kStack][kThreads];  // level, err_after
-    int start[kStack][kThreads];
+    double y[YRING][kThreads];
+    double2 sums[STACK][kThreads];   // sy, sy2
+    double2 lvl_err[STACK][kThreads];  // level, err_after
+    int start[STACK][kThreads];
 };
 
 template <typename T>
@@ -63,9 +66,9 @@ __device__ __forceinline__ void store_rec(Rec* r, double err_after, double sy, d
 __device__ __forceinline__ int rec_start(const Rec* r) { return r->start; }
 
 // Prefix-isotonic PAVA over seq(j) = col[(rev ? n-1-j : j) * ld], j in [0, n); fills rec[0..n).
-template <typename T>
+template <typename T, int kYRing, int kStack>
 __device__ __forceinline__ void pava_prefix(const T* __restrict__ col, long long ld, int n, bool rev, bool nn,
-                                            Rec* __restrict__ rec, SharedState& sh, int tid) {
+                                            Rec* __restrict__ rec, SharedState<kYRing, kStack>& sh, int tid) {
     const long long step = rev ? -ld : ld;
     const T* p = col + (rev ? (long long)(n - 1) * ld : 0LL);
     // element j lands in ring slot j % kYRing, stored as T in the first sizeof(T) bytes of the slot
@@ -208,20 +211,18 @@ __device__ __forceinline__ void fill_prefix(T* __restrict__ aux, T* __restrict__
     }
 }
 
-// Residency: measured at config 3 (8 192 slices x 8 columns x 1 024 points): 4 CTAs per SM (<= 128 registers, ~104 KB of
-// shared memory, the rest of the 256 KB stays L1 for the per-thread records) 3.94 ms; 5 CTAs (89 registers, the
-// compiler's own choice) 4.27 ms; 6 CTAs 4.51 ms; 8 CTAs with the maximum shared-memory carve-out 5.50 ms — the record
-// re-reads live on L1 hits, so L1 capacity beats resident warps here.
-#ifndef B2_UNIMODAL_MIN_CTAS
-#define B2_UNIMODAL_MIN_CTAS 4
-#endif
-template <typename T>
-__global__ void __launch_bounds__(kThreads, B2_UNIMODAL_MIN_CTAS)
+// Residency: measured at config 3 (8 192 slices x 8 columns x 1 024 points) in round 1 with YRING = 8, STACK = 4: 4 CTAs
+// per SM (<= 128 registers, ~104 KB of shared memory, the rest of the 256 KB stays L1 for the per-thread records)
+// 3.94 ms; 5 CTAs (89 registers, the compiler's own choice) 4.27 ms; 6 CTAs 4.51 ms; 8 CTAs with the maximum
+// shared-memory carve-out 5.50 ms.  The variant (ring depth, stack-cache depth, CTAs per SM) is a template parameter
+// pack selected by B2_OPT_UNIMODAL_VARIANT so that alternatives can be A/B-ed inside one process.
+template <typename T, int YRING, int STACK, int MINCTAS>
+__global__ void __launch_bounds__(kThreads, MINCTAS)
 unimodal_kernel(T* __restrict__ aux, T* __restrict__ dual, const int64_t* __restrict__ row_off, int n_groups, int R,
                 int max_rows, int nn_flag, int32_t* __restrict__ peaks, unsigned char* __restrict__ ws,
                 long long ncolslots, size_t thread_bytes) {
     extern __shared__ __align__(16) unsigned char uni_smem[];
-    SharedState& sh = *(SharedState*)uni_smem;
+    SharedState<YRING, STACK>& sh = *(SharedState<YRING, STACK>*)uni_smem;
     const int tid = threadIdx.x, lane = tid & 31;
     const int rev = lane >> 4;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -243,7 +244,7 @@ unimodal_kernel(T* __restrict__ aux, T* __restrict__ dual, const int64_t* __rest
             n = (int)(row_off[g + 1] - r0);
             base = r0 * R + c;
         }
-        if (active && n > 0) pava_prefix<T>(dual + base, R, n, rev != 0, nn, mine, sh, tid);
+        if (active && n > 0) pava_prefix<T, YRING, STACK>(dual + base, R, n, rev != 0, nn, mine, sh, tid);
         __syncwarp();  // the partner lane's prefix errors are read below
         // peak: first strict minimum of errL[i] + errR[n - i], i = 0..n (:84-92); the pair splits the range.
         // error[0] = 0 is implicit, error[k] = rec[k-1].err_after.
@@ -323,13 +324,25 @@ int b2_prox_unimodal(void* aux, void* dual, const int64_t* row_off, int n_groups
     B2_REQUIRE(((uintptr_t)ws) % 16 == 0, "workspace must be 16-byte aligned");
     const long long threads = ncolslots * 2;  // 16 column slots per warp
     const int grid = (int)((threads + kThreads - 1) / kThreads);
-    B2_DISPATCH_DTYPE(dtype, {
-        auto kern = unimodal_kernel<T>;
-        B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SharedState)));
-        kern<<<grid, kThreads, sizeof(SharedState), st>>>((T*)aux, (T*)dual, row_off, n_groups, R, max_rows, non_negativity,
-                                                 peaks, (unsigned char*)ws, ncolslots, tb);
-        B2_LAUNCH_CHECK();
-    });
+    const int variant = b2_option_value(B2_OPT_UNIMODAL_VARIANT);
+#define B2_UNI_LAUNCH(YR, SK, MC)                                                                                     \
+    B2_DISPATCH_DTYPE(dtype, {                                                                                        \
+        auto kern = unimodal_kernel<T, YR, SK, MC>;                                                                   \
+        const int smem = (int)sizeof(SharedState<YR, SK>);                                                            \
+        B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                 \
+        kern<<<grid, kThreads, smem, st>>>((T*)aux, (T*)dual, row_off, n_groups, R, max_rows, non_negativity, peaks,  \
+                                           (unsigned char*)ws, ncolslots, tb);                                        \
+        B2_LAUNCH_CHECK();                                                                                            \
+    })
+    switch (variant) {
+        case 1: B2_UNI_LAUNCH(4, 8, 4); break;    // deeper stack cache, shorter ring: 40 KB per CTA
+        case 2: B2_UNI_LAUNCH(8, 8, 4); break;    // deeper stack cache: 44 KB per CTA
+        case 3: B2_UNI_LAUNCH(4, 16, 3); break;   // stack cache covers noise-like data completely: 76 KB per CTA
+        case 4: B2_UNI_LAUNCH(4, 8, 5); break;
+        case 5: B2_UNI_LAUNCH(4, 12, 4); break;
+        default: B2_UNI_LAUNCH(8, 4, 4); break;   // round-1 configuration
+    }
+#undef B2_UNI_LAUNCH
     return B2_OK;
 }
 

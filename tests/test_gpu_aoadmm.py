@@ -439,3 +439,40 @@ def test_parafac2_from_a_zero_coordinate_matrix(kw):
     bases, delta = admm.auxes[1][0]
     assert rel(delta, o["aux"][1][0][1]) < 1e-7
     assert rel(np.concatenate(bases, 0), np.concatenate(o["aux"][1][0][0], 0)) < 1e-6
+
+
+@pytest.mark.parametrize("R", [4, 8, 20])
+def test_one_array_companion_and_fused_gap_terms_match_the_oracle(R):
+    """Non-negativity next to PARAFAC2 at a rank the steady-state row pass serves (fp64, R % 4 == 0): between outer
+    iterations the companion lives as ONE array T = x + dual and its feasibility-gap terms come out of the last row
+    pass (csrc/pf2_rowpass_v2.cuh).  The reported gaps, the losses and the materialised ADMM variables (aux = prox(T),
+    dual = T - aux on demand) must equal the reference algorithm's, also when the stopping rule reads them every
+    iteration, and a run that materialises in between (return_admm_vars) must not disturb the iterates."""
+    from matcouply_b200 import cmf_aoadmm
+    from oracle import aoadmm_oracle as O
+
+    rs = np.random.RandomState(60 + R)
+    I, K = 9, 3 * R + 5
+    Js = list(rs.randint(R, 200, size=I - 1)) + [64]
+    A, C = rs.uniform(0.2, 1.2, size=(I, R)), rs.uniform(size=(K, R))
+    X = [(rs.uniform(size=(J, R)) * a) @ C.T + 0.1 * rs.standard_normal(size=(J, K)) for J, a in zip(Js, A)]
+    kw = dict(non_negative=True, parafac2=True, random_state=1, n_iter_max=9, tol=None, absolute_tol=None)
+    o = O.ao_admm(X, R, **kw)
+    cmf, admm, diag = cmf_aoadmm(X, R, return_errors=True, return_admm_vars=True, **kw)
+    _, (Ag, Bg, Cg) = cmf
+    assert rel(Ag, o["A"]) < 1e-8 and rel(Cg, o["C"]) < 1e-8
+    assert rel(np.concatenate(Bg, 0), np.concatenate(o["B_is"], 0)) < 1e-8
+    np.testing.assert_allclose(diag.regularized_loss, o["regularized_loss"], rtol=1e-8)
+    gaps = np.array([[v for mode in it for v in mode] for it in diag.feasibility_gaps])
+    ogaps = np.array([[v for mode in it for v in mode] for it in o["feasibility_gaps"]])
+    np.testing.assert_allclose(gaps, ogaps, rtol=1e-6, atol=1e-13)
+    nn_aux, nn_dual = admm.auxes[1][1], admm.duals[1][1]
+    assert rel(np.concatenate(nn_aux, 0), np.concatenate(o["aux"][1][1], 0)) < 1e-7
+    assert rel(np.concatenate(nn_dual, 0), np.concatenate(o["dual"][1][1], 0)) < 1e-6
+    assert min(a.min() for a in nn_aux) >= 0
+    # one- and two-iteration runs (first B-update starts from explicit state, the second from T) also agree
+    for k in (1, 2):
+        ok = O.ao_admm(X, R, **dict(kw, n_iter_max=k))
+        ck, ak = cmf_aoadmm(X, R, return_admm_vars=True, **dict(kw, n_iter_max=k))
+        assert rel(np.concatenate(ck[1][1], 0), np.concatenate(ok["B_is"], 0)) < 1e-9
+        assert rel(np.concatenate(ak.duals[1][1], 0), np.concatenate(ok["dual"][1][1], 0)) < 1e-8
