@@ -63,7 +63,7 @@ enum { B2_OPT_PF2_ROWPASS_MMA = 0 /* row pass of b2_pf2_rowpass: 0 = shuffle ker
        B2_OPT_XSTREAM_HYBRID = 3 /* DMMA blocks + DFMA remainder columns in the fp64 X-stream kernels (R = 8b+1..4);
                                     default OFF: measured 2-6 % slower than padding to a whole block */,
        B2_OPT_UNIMODAL_VARIANT = 4 /* b2_prox_unimodal: (column ring depth, shared-memory stack-cache depth, CTAs per
-                                      SM) of the PAVA kernel: 0 = (8, 4, 4), 1 = (4, 8, 4), 2 = (8, 8, 4), 3 = (4, 16, 3),
+                                      SM) of the PAVA kernel: 0 = (8, 4, 4) round 1, 1 = (4, 8, 4) default, 2 = (8, 8, 4), 3 = (4, 16, 3),
                                       4 = (4, 8, 5), 5 = (4, 12, 4); same results, different residency */,
        B2_OPT_COUNT = 5 };
 int b2_set_option(int option, int value);

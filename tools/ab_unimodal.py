@@ -40,6 +40,6 @@ for dtype in (torch.float64, torch.float32):
             rec = {"dtype": str(dtype), "input": name, "variant": variant, "ms": ms, "bit_identical_to_variant0": same,
                    "algorithmic_gbs": 3 * V.numel() * V.element_size() / ms / 1e6}
             out["runs"].append(rec); print(rec)
-lib.b2_set_option(_lib.OPT_UNIMODAL_VARIANT, 0)
+lib.b2_set_option(_lib.OPT_UNIMODAL_VARIANT, 1)
 os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "ab_unimodal.json"), "w"), indent=1)
