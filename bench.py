@@ -462,6 +462,8 @@ def main():
     ap.add_argument("--config", default=os.environ.get("B2_BENCH_CONFIG", "c2"), choices=sorted(CONFIGS))
     ap.add_argument("--slices", type=int, default=0, help="override the slice count (debug only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / e2e legs (debug only)")
+    ap.add_argument("--x1", default="auto", choices=["auto", "off"],
+                    help="off = force the two-pass X-stream schedule where the single-read fused pass would apply (A/B)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.slices:
@@ -506,7 +508,7 @@ def main():
     while True:
         try:
             packed = gen_device_data(cfg, sizes, lo, hi, dtype, device)
-            eng = AOADMMEngine(packed, cfg["R"], regs, group=group)
+            eng = AOADMMEngine(packed, cfg["R"], regs, group=group, fuse_x1=None if args.x1 == "auto" else False)
             eng.load_state_device(seed=rank)
             eng.prepare()
             break
@@ -546,8 +548,8 @@ def main():
     ev = eng.xstream_events
     eng.xstream_events = None
     fam = {k: (float(np.mean([a.elapsed_time(b) for a, b in v])), len(v) / args.steps) for k, v in ev.items() if v}
-    t_y, t_z = fam["y"][0], fam["z"][0]
-    keys = ["y", "z", "rowpass", "polar", "unimodal", "local"]
+    keys = ["y", "z", "fused", "rowpass", "polar", "unimodal", "local"]
+    x_passes = 1 if eng.fused_x1 else 2
     tmax = torch.tensor([ms_total] + [fam.get(k, (0.0, 0.0))[0] for k in keys], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -555,7 +557,7 @@ def main():
     vals = [float(v) for v in tmax.cpu()]
     ms_total = vals[0]
     fam = {k: (vals[1 + i], fam[k][1]) for i, k in enumerate(keys) if k in fam}
-    t_y, t_z = fam["y"][0], fam["z"][0]
+    t_y, t_z = fam.get("y", (None,))[0], fam.get("z", (None,))[0]
     ms_step = ms_total / args.steps
     window_note = "timed region"
     need = torch.tensor([1.0 if sampler.n_in(t_host0, t_host1 + 0.12) < 2 else 0.0], device=device)
@@ -598,9 +600,13 @@ def main():
     # fused local loop: Y + x + (aux, dual) per penalty in, x + W + (aux, dual) out)
     nr_bytes = rows_rank0 * cfg["R"] * es
     n_b_pen = len(regs[1])
-    algo = {"y": x_bytes_local, "z": x_bytes_local, "rowpass": (3 + 2 * max(n_b_pen - 1, 0)) * nr_bytes,
+    # single-read fused pass: X once (its second read of every 64-row chunk is served by L2; the B-state and G_i = X_i^T B_i
+    # traffic is not counted — conservative, like the side operands of the two-pass kernels)
+    algo = {"y": x_bytes_local, "z": x_bytes_local, "fused": x_bytes_local,
+            "rowpass": (3 + 2 * max(n_b_pen - 1, 0)) * nr_bytes,
             "unimodal": 3 * nr_bytes, "local": (4 + 4 * n_b_pen) * nr_bytes, "polar": 3 * cfg["R"] ** 2 * 8 * (hi - lo)}
-    names = {"y": "xstream_y", "z": "xstream_z", "rowpass": "pf2_rowpass_mma_kernel", "polar": "pf2_polar_reg_kernel",
+    names = {"y": "xstream_y", "z": "xstream_z", "fused": "xfused_local_kernel", "rowpass": "pf2_rowpass_mma_kernel",
+             "polar": "pf2_polar_reg_kernel",
              "unimodal": "unimodal_kernel", "local": "admm_local_mma_kernel"}
     kernels = {names[k]: {"ms_per_launch": t, "launches_per_step": n, "ms_per_step": t * n,
                           "algorithmic_bytes_per_launch": int(algo[k]), "gbs": algo[k] / t / 1e6 if t > 0 else None}
@@ -625,11 +631,14 @@ def main():
             flops, ms = _ops.microbench_flops(1, 4096)
             peak_tf = flops / ms / 1e9
             r_pad = (cfg["R"] + 7) // 8 * 8
-            t_x = max(t_y, t_z)
-            ach_tf = 2.0 * r_pad * cfg["K"] * rows_rank0 / t_x / 1e9
-            fp64 = {"kernel": "xstream_y" if t_y >= t_z else "xstream_z", "achieved": ach_tf, "peak": peak_tf,
+            if "fused" in fam:  # both contractions (Y = X C and G = X^T B) in the one launch
+                t_x, n_contr, kname = fam["fused"][0], 2, "xfused_local_kernel"
+            else:
+                t_x, n_contr, kname = max(t_y, t_z), 1, "xstream_y" if t_y >= t_z else "xstream_z"
+            ach_tf = n_contr * 2.0 * r_pad * cfg["K"] * rows_rank0 / t_x / 1e9
+            fp64 = {"kernel": kname, "achieved": ach_tf, "peak": peak_tf,
                     "unit": "TFLOP/s", "frac": ach_tf / peak_tf,
-                    "note": f"2*{r_pad}*K*N padded DMMA.8x8x4 flops per launch / CUDA-event time; peak = "
+                    "note": f"{n_contr}*2*{r_pad}*K*N padded DMMA.8x8x4 flops per launch / CUDA-event time; peak = "
                             "b2_microbench_flops(DMMA) in this run at the clock of an otherwise idle GPU "
                             f"(the timed steps ran at {clocks.get('sm_mhz')} of {clocks.get('sm_max_mhz')} MHz)"}
         except Exception as exc:
@@ -641,15 +650,16 @@ def main():
         "dtype": cfg["dtype"], "data": "synthetic",
         "config": {"workload": cfg["desc"] + (" [REDUCED: shard did not fit HBM]" if reduced else ""),
                    "slices_total": int(cfg["I"]) if not reduced else int(hi - lo), "rows_rank0": rows_rank0,
-                   "x_bytes_rank0": int(x_bytes_local), "x_passes_per_iteration": 2,
+                   "x_bytes_rank0": int(x_bytes_local), "x_passes_per_iteration": x_passes,
                    "l2_flush": "not needed: X shard >> 126 MB L2", "parallelism": f"slices sharded over {world} GPU(s)"},
-        "roofline": {"bound": "hbm+fp64" if (fp64 and "frac" in fp64 and dom_key in ("y", "z")) else "hbm",
+        "roofline": {"bound": "hbm+fp64" if (fp64 and "frac" in fp64 and dom_key in ("y", "z", "fused")) else "hbm",
                      "kernel": dom, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "fp64": fp64, "kernels": kernels,
                      "xstream_y_ms": t_y, "xstream_z_ms": t_z,
-                     "xstream_y_gbs": x_bytes_local / t_y / 1e6, "xstream_z_gbs": x_bytes_local / t_z / 1e6,
-                     "iteration_stream_gbs": 2 * x_bytes_local / ms_step / 1e6},
+                     "xstream_y_gbs": x_bytes_local / t_y / 1e6 if t_y else None,
+                     "xstream_z_gbs": x_bytes_local / t_z / 1e6 if t_z else None,
+                     "iteration_stream_gbs": x_passes * x_bytes_local / ms_step / 1e6},
         "gpu_launches": launches, "clocks": clocks,
     }
     if not args.no_cpu:

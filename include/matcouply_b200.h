@@ -94,6 +94,28 @@ size_t b2_xstream_workspace_bytes(int K, int R, int dtype);
 int b2_sumsq(const void* X, long long n_rows, int K, int ldx, int dtype, double* out, void* ws, size_t ws_bytes,
              void* stream);
 
+/* ---- single-read fused X-stream pass for slice-local CMF (SURVEY.md §8b `b2_xstream_fused_local`) ----------------
+ * ONE pass over X per outer iteration for problems whose B-mode penalties are all row-local (NONNEG, BOX, L1;
+ * n_pen <= 2), fp64: per slice g (rows row_off[g] .. row_off[g+1])
+ *     Y_g = X_g C;  B_g <- n_inner ADMM iterations on rhs = Y_g * a_g with Minv_g, rho_g (decomposition.py:242, 259-289;
+ *     aux/dual of `pens_host` updated in place);  G[g] = X_g^T B_g (K x R);  Z = sum_g G[g] diag(a_g) (K x R,
+ *     decomposition.py:312-315);  BtB[g] = B_g^T B_g.
+ * The A-update's diag(B_g^T X_g C_new) (decomposition.py:145-158) then comes from b2_slice_gdot(G, C_new) without
+ * another pass over X.  The reference reads X three times per outer iteration (:242, :315, :148-152).
+ * sched: device array [n_ctas x rounds] of slice ids (-1 = none): CTA c processes sched[c*rounds + 0 ..] in order;
+ *   every slice must appear exactly once (the host balances rows per CTA); n_ctas <= b2_device_sm_count().
+ * ws: >= b2_xstream_fused_workspace_bytes(K, R, n_ctas) bytes, 16-byte aligned.
+ * b2_xstream_fused_local_supported: 1 when the kernel applies (fp64, K * ceil(R/8) <= 1024, C fits shared memory). */
+int b2_xstream_fused_local_supported(int K, int R, int dtype, int n_pen);
+size_t b2_xstream_fused_workspace_bytes(int K, int R, int n_ctas);
+int b2_xstream_fused_local(const void* X, long long n_rows, int K, int ldx, const int64_t* row_off, int n_slices,
+                           const int32_t* sched, int n_ctas, int rounds, const void* C, const void* A,
+                           const void* rho, const void* Minv, const b2_penalty_desc* pens_host, int n_pen,
+                           int n_inner, int R, void* B, void* Z, void* G, void* BtB, int dtype, void* ws,
+                           size_t ws_bytes, void* stream);
+/* rhs[g][c] = sum_k G[g][k][c] * C[k][c]  (= diag(B_g^T X_g C) from G[g] = X_g^T B_g), fp64 */
+int b2_slice_gdot(const void* G, const void* C, int n_groups, int K, int R, void* rhs, int dtype, void* stream);
+
 /* ---- small dense / batched per-slice math --------------------------------------------------------------------*/
 /* G (R x R) = M^T M for a dense n x R matrix with row stride ld >= R (C^T C :138,:240 ; sum_i (B_i a_i)^T (B_i a_i)
  * :314). ws >= 16*R*R*SMs bytes. */

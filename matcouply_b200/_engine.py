@@ -13,6 +13,9 @@ Data layout in HBM (reference symbols: I slices X_i of J_i x K, N = sum J_i):
 X-stream schedule (exact Gauss-Seidel order of the reference, two passes instead of its three):
   Y = X C^(t)   (after the C-update; serves the A-update of iteration t and the B-update of iteration t+1)
   Z = X^T W     (after the B-update; serves the C-update)
+Slice-local problems (every B-mode penalty row-local, fp64) run ONE pass per outer iteration (`fused_x1`, csrc/xfused.cu):
+  per slice  Y_i = X_i C -> inner loop of the B-update -> G_i = X_i^T B_i -> Z += G_i diag(a_i)   while X_i is L2-resident;
+  the A-update's diag(B_i^T X_i C_new) = colsum(G_i o C_new) then needs no further pass over X.
 
 Sharding: with a process group, every rank holds a contiguous range of slices (X, B-state, A rows are rank-local);
 C, Delta and all scalars are replicated through a few small all-reduces per outer iteration.
@@ -29,7 +32,9 @@ from . import _lib, _ops
 _ENGINE_PROX_KINDS = (_lib.PEN_GL2, _lib.PEN_SIMPLEX, _lib.PEN_TV)
 
 # Kernel-fusion switches (tests flip them to cross-check the fused kernels against the one-kernel-per-step path).
-FUSION_DEFAULTS = {"local": True, "pf2": True, "overlap": True}
+# "x1": the single-read fused X-stream pass for slice-local B-updates (csrc/xfused.cu): one pass over X per outer
+# iteration instead of two
+FUSION_DEFAULTS = {"local": True, "pf2": True, "overlap": True, "x1": True}
 
 
 class _Phase:
@@ -242,7 +247,7 @@ class _ModeState:
 class AOADMMEngine:
     def __init__(self, packed, rank, regs, l2_penalty=(0, 0, 0), feasibility_penalty_scale=1.0, constant_A=False,
                  constant_B=False, inner_n_iter_max=5, update=(True, True, True), group=None, xstream_variant=None,
-                 fuse_local=None, fuse_pf2=None, shard_rows=None, inner_tol=None):
+                 fuse_local=None, fuse_pf2=None, shard_rows=None, inner_tol=None, fuse_x1=None):
         _lib.load()
         self.p = packed
         self.dev = packed.X.device
@@ -352,6 +357,19 @@ class AOADMMEngine:
             self.comp_stats_part = torch.zeros(3 * max(I, 1), dtype=torch.float64, device=dev)
             self.pf2_gap_part = torch.zeros(3 * max(I, 1), dtype=torch.float64, device=dev)
             self.pf2_Q = torch.zeros(I, R, R, dtype=torch.float64, device=dev)  # Jacobi eigenvectors (warm start)
+        # Single-read fused pass: applies when the whole B-update is slice-local and row-local.
+        # The extra traffic is G (I x K x R, written by the pass and read once by the A-update), 2 R / mean(J_i) of X:
+        # not worth it for very short slices.
+        d1 = self.modes[1].desc
+        want_x1 = FUSION_DEFAULTS.get("x1", True) if fuse_x1 is None else bool(fuse_x1)
+        self.fused_x1 = bool(
+            want_x1 and self.fuse_local and self.update_B and I > 0 and N > 0 and dt == torch.float64
+            and self.n_inner > 0 and len(d1) <= 2 and all(d[0] in (_lib.PEN_NONNEG, _lib.PEN_BOX, _lib.PEN_L1) for d in d1)
+            and N >= 4 * R * I and _ops.xstream_fused_supported(K, R, dt, len(d1)))
+        self.z_fresh = self.g_fresh = False
+        if self.fused_x1:
+            self.G = z(I, K, R)
+            self.fws = _ops.FusedWorkspace(packed.row_offsets, K, R, dev)
         self.scal = torch.zeros(64, dtype=torch.float64, device=dev)
         self.normX_sq = None
         uni = None
@@ -390,6 +408,7 @@ class AOADMMEngine:
     def load_state(self, A, B_is, C, auxes, duals):
         """A: I x R, B_is: list of J_i x R (or packed N x R), C: K x R; auxes/duals: 3 lists as in ADMMVars."""
         st = self.modes
+        self.z_fresh = self.g_fresh = False
         st[0].x = self._up(A)
         st[1].x = self._up_rows(B_is)
         st[2].x = self._up(C)
@@ -436,6 +455,7 @@ class AOADMMEngine:
         gen = torch.Generator(device=self.dev).manual_seed(int(seed))
         rnd = lambda *s: torch.rand(s, dtype=self.dtype, device=self.dev, generator=gen)  # noqa: E731
         st, R = self.modes, self.R
+        self.z_fresh = self.g_fresh = False
         st[0].x, st[1].x, st[2].x = rnd(self.I, R), rnd(self.N, R), rnd(self.K, R)
         for m, n in ((0, self.I), (1, self.N), (2, self.K)):
             st[m].aux, st[m].dual = [], []
@@ -665,6 +685,14 @@ class AOADMMEngine:
         self.w_fresh = False
         if self.has_pf2:
             self.comp_stats_fresh = False
+        if self.fused_x1:  # ONE pass over X: Y = X C, the inner loop, G_i = X_i^T B_i, Z and B_i^T B_i (csrc/xfused.cu)
+            self._timed("fused", lambda: _ops.xstream_fused_local(
+                self.p.X, self.N, self.K, self.row_off, I, self.fws, C, A, self.rhoB, self.MinvB, st.descs_c,
+                len(st.desc), self.n_inner, st.x, self.Z, self.G, self.BtB))
+            self.n_xstream_launches += 1
+            self.z_fresh = self.g_fresh = True
+            return
+        self.z_fresh = self.g_fresh = False
         if self._row_local(st):  # whole inner loop in one fused pass, W = B o a emitted for the Z pass
             # W = B o a stays valid for the C-step: A only changes after the C-step (decomposition.py:948-988)
             self._timed("local", lambda: _ops.admm_local(
@@ -775,10 +803,13 @@ class AOADMMEngine:
     def step_C(self):
         """admm_update_C (decomposition.py:295-344); one X pass: Z = X^T (B o a)."""
         st, R, K = self.modes[2], self.R, self.K
-        if not getattr(self, "w_fresh", False):
-            _ops.rowscale(self.modes[1].x, self.modes[0].x, self.gor, self.N, R, self.Wpad)
+        if self.z_fresh:  # Z = sum_i G_i diag(a_i) came out of the fused pass (A has not changed since)
+            self.z_fresh = False
+        else:
+            if not getattr(self, "w_fresh", False):
+                _ops.rowscale(self.modes[1].x, self.modes[0].x, self.gor, self.N, R, self.Wpad)
+            self._timed("z", lambda: _ops.xstream_z(self.p.X, self.N, K, self.Wpad, self.Z, self.ws, self.variant))
         self.w_fresh = False
-        self._timed("z", lambda: _ops.xstream_z(self.p.X, self.N, K, self.Wpad, self.Z, self.ws, self.variant))
         _ops.weighted_gram_sum(self.BtB, self.modes[0].x, self.I, R, self.lhsC)  # sum_i (B_i a_i)^T (B_i a_i)
         self._allreduce(self.ZL)
         _ops.rho_from_trace(self.lhsC, 1, R, self.scale, self.rhoC, None)
@@ -799,9 +830,14 @@ class AOADMMEngine:
         """Y = X C (one X pass), CtC, cross_i = (B_i^T B_i) o CtC, rhsA_i = colsum(B_i o Y_i)
         (decomposition.py:138-158).  Also what the fit term needs (:446-449)."""
         C, B = self.modes[2].x, self.modes[1].x
-        self._timed("y", lambda: _ops.xstream_y(self.p.X, self.N, self.K, C, self.Y, self.ws, self.variant))
         _ops.gram(C, self.K, self.CtC, self.ws)
         _ops.hadamard_bcast(self.BtB, self.CtC, self.I, self.R, self.cross)
+        if self.g_fresh:
+            # G_i = X_i^T B_i of the current B is at hand (fused pass): diag(B_i^T X_i C) = colsum_k(G_i o C), no X pass.
+            # The next B-update is a fused pass again and computes its own Y = X C.
+            _ops.slice_gdot(self.G, C, self.I, self.K, self.R, self.rhsA)
+            return
+        self._timed("y", lambda: _ops.xstream_y(self.p.X, self.N, self.K, C, self.Y, self.ws, self.variant))
         _ops.slice_coldot(B, self.Y, self.row_off, self.I, self.R, self.rhsA)
 
     def step_A(self):
@@ -1025,13 +1061,15 @@ class AOADMMEngine:
             self._graphs = {}
         entry = self._graphs.get(key)
         if entry is None:
-            flags = (self.w_fresh, getattr(self, "pf2_deferred", None), getattr(self, "pf2_fresh", None))
+            flags = (self.w_fresh, self.z_fresh, self.g_fresh, getattr(self, "pf2_deferred", None),
+                     getattr(self, "pf2_fresh", None))
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
             with torch.cuda.graph(g):
                 self.outer_iteration()
                 launched = self._launch_diagnostics() if with_diagnostics else None
-            after = (self.w_fresh, getattr(self, "pf2_deferred", None), getattr(self, "pf2_fresh", None))
+            after = (self.w_fresh, self.z_fresh, self.g_fresh, getattr(self, "pf2_deferred", None),
+                     getattr(self, "pf2_fresh", None))
             if flags != after:
                 raise RuntimeError("graph capture outside the steady state of the engine")
             entry = self._graphs[key] = (g, launched)

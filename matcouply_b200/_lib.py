@@ -40,6 +40,9 @@ _SIGNATURES = {
     "b2_xstream_y": [_vp, _ll, _i, _i, _vp, _i, _vp, _i, _vp, _sz, _i, _i, _vp],
     "b2_xstream_z": [_vp, _ll, _i, _i, _vp, _i, _i, _vp, _i, _vp, _sz, _i, _i, _vp],
     "b2_sumsq": [_vp, _ll, _i, _i, _i, _vp, _vp, _sz, _vp],
+    "b2_xstream_fused_local": [_vp, _ll, _i, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _vp, _vp, ctypes.POINTER(PenaltyDesc),
+                               _i, _i, _i, _vp, _vp, _vp, _vp, _i, _vp, _sz, _vp],
+    "b2_slice_gdot": [_vp, _vp, _i, _i, _i, _vp, _i, _vp],
     "b2_gram": [_vp, _ll, _i, _i, _vp, _i, _vp, _sz, _vp],
     "b2_scale_gram": [_vp, _vp, _i, _i, _vp, _i, _vp],
     "b2_rho_from_trace": [_vp, _i, _i, _d, _vp, _vp, _i, _vp],
@@ -84,6 +87,8 @@ _OTHER = {
     "b2_get_option": ([_i], _i),
     "b2_pf2_rowpass_fused_stats_supported": ([_i, _i, _i, _i, _i], _i),
     "b2_xstream_workspace_bytes": ([_i, _i, _i], _sz),
+    "b2_xstream_fused_local_supported": ([_i, _i, _i, _i], _i),
+    "b2_xstream_fused_workspace_bytes": ([_i, _i, _i], _sz),
     "b2_xstream_z_ldw": ([_i, _i, _i], _i),
     "b2_unimodal_workspace_bytes": ([_i, _i, _i], _sz),
 }

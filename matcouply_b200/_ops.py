@@ -68,6 +68,54 @@ def xstream_z(X, n_rows, K, W, Z, ws, variant=_lib.VARIANT_AUTO, max_ctas=0):
          _ptr(ws.xs), ws.xs_bytes, resolve_variant(variant, X.dtype), max_ctas, _stream())
 
 
+def xstream_fused_supported(K, R, dtype, n_pen):
+    """True when the single-read fused pass (csrc/xfused.cu) applies to such a problem."""
+    return bool(_lib.load().b2_xstream_fused_local_supported(int(K), int(R), dtype_code(dtype), int(n_pen)))
+
+
+def fused_schedule(row_offsets, n_ctas):
+    """Balanced static schedule of the fused pass: slices sorted by height, each handed to the least loaded CTA
+    (longest-processing-time rule).  Returns an int32 array [n_ctas x rounds], -1 padded."""
+    import heapq
+
+    sizes = np.diff(np.asarray(row_offsets, dtype=np.int64))
+    n_ctas = max(1, min(int(n_ctas), len(sizes)))
+    lists = [[] for _ in range(n_ctas)]
+    heap = [(0, c) for c in range(n_ctas)]
+    for g in np.argsort(-sizes, kind="stable"):
+        load, c = heapq.heappop(heap)
+        lists[c].append(int(g))
+        heapq.heappush(heap, (load + int(sizes[g]), c))
+    rounds = max(len(l) for l in lists) if len(sizes) else 0
+    sched = np.full((n_ctas, max(rounds, 1)), -1, dtype=np.int32)
+    for c, l in enumerate(lists):
+        sched[c, :len(l)] = l
+    return sched
+
+
+class FusedWorkspace:
+    """Schedule + scratch of the fused pass for one packed data set."""
+
+    def __init__(self, row_offsets, K, R, device):
+        lib = _lib.load()
+        self.sched_host = fused_schedule(row_offsets, int(lib.b2_device_sm_count()))
+        self.n_ctas, self.rounds = self.sched_host.shape
+        self.sched = torch.as_tensor(self.sched_host).to(device)
+        self.bytes = int(lib.b2_xstream_fused_workspace_bytes(int(K), int(R), self.n_ctas))
+        self.buf = torch.empty(self.bytes, dtype=torch.uint8, device=device)
+
+
+def xstream_fused_local(X, n_rows, K, row_off, n_slices, fws, C, A, rho, Minv, descs, n_pen, n_inner, B, Z, G, BtB):
+    R = C.shape[1]
+    call("b2_xstream_fused_local", _ptr(X), n_rows, K, X.shape[1], _ptr(row_off), n_slices, _ptr(fws.sched), fws.n_ctas,
+         fws.rounds, _ptr(C), _ptr(A), _ptr(rho), _ptr(Minv), descs, n_pen, n_inner, R, _ptr(B), _ptr(Z), _ptr(G),
+         _ptr(BtB), dtype_code(X.dtype), _ptr(fws.buf), fws.bytes, _stream())
+
+
+def slice_gdot(G, C, n_groups, K, R, rhs):
+    call("b2_slice_gdot", _ptr(G), _ptr(C), n_groups, K, R, _ptr(rhs), dtype_code(G.dtype), _stream())
+
+
 def z_ldw(R, dtype, variant=_lib.VARIANT_AUTO):
     return int(_lib.load().b2_xstream_z_ldw(R, dtype_code(dtype), resolve_variant(variant, dtype)))
 

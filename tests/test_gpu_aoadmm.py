@@ -476,3 +476,48 @@ def test_one_array_companion_and_fused_gap_terms_match_the_oracle(R):
         ck, ak = cmf_aoadmm(X, R, return_admm_vars=True, **dict(kw, n_iter_max=k))
         assert rel(np.concatenate(ck[1][1], 0), np.concatenate(ok["B_is"], 0)) < 1e-9
         assert rel(np.concatenate(ak.duals[1][1], 0), np.concatenate(ok["dual"][1][1], 0)) < 1e-8
+
+
+@pytest.mark.parametrize("kw", [
+    dict(non_negative=True),
+    dict(non_negative=True, l1_penalty={1: 0.05, 2: 0.02}),
+    dict(non_negative={0: True, 2: True}),                       # no penalty on the B-mode
+    dict(lower_bound={1: -0.2}, upper_bound={1: 0.7}, l2_penalty=0.01),
+    dict(non_negative=True, l2_norm_bound={0: 1.0}, constant_feasibility_penalty=True),
+])
+def test_single_read_fused_pass_matches_two_pass_schedule(kw, monkeypatch):
+    """with row-local B-mode penalties the engine runs ONE pass over X per outer iteration
+    (csrc/xfused.cu).  Same iterates, ADMM variables and diagnostics as the two-pass schedule (round-off apart: the
+    products are summed in another order)."""
+    from matcouply_b200 import _engine, _ops, cmf_aoadmm
+
+    rs = np.random.RandomState(5)
+    I, K, R = 23, 70, 5
+    Js = list(rs.randint(4 * R, 160, size=I - 1)) + [64]
+    X = [rs.uniform(size=(J, K)) for J in Js]
+    calls = {"fused": 0, "y": 0}
+    real_fused, real_y = _ops.xstream_fused_local, _ops.xstream_y
+    monkeypatch.setattr(_ops, "xstream_fused_local", lambda *a, **k: (calls.__setitem__("fused", calls["fused"] + 1),
+                                                                       real_fused(*a, **k))[1])
+    monkeypatch.setattr(_ops, "xstream_y", lambda *a, **k: (calls.__setitem__("y", calls["y"] + 1), real_y(*a, **k))[1])
+    out = []
+    for x1 in (True, False):
+        _engine.FUSION_DEFAULTS.update(x1=x1)
+        calls.update(fused=0, y=0)
+        try:
+            cmf, admm, diag = cmf_aoadmm(X, R, n_iter_max=8, tol=None, absolute_tol=None, random_state=3,
+                                         return_admm_vars=True, return_errors=True, **kw)
+        finally:
+            _engine.FUSION_DEFAULTS.update(x1=True)
+        # fused: one pass per iteration (+ the Y pass of the initial fit); two-pass: no fused launch at all
+        assert (calls["fused"], calls["y"]) == ((8, 1) if x1 else (0, 9))
+        out.append((cmf, admm, diag))
+    (c1, a1, d1), (c2, a2, d2) = out
+    tol = 1e-9
+    assert rel(c1[1][0], c2[1][0]) < tol and rel(c1[1][2], c2[1][2]) < tol
+    assert rel(np.concatenate(c1[1][1], 0), np.concatenate(c2[1][1], 0)) < tol
+    np.testing.assert_allclose(d1.regularized_loss, d2.regularized_loss, rtol=1e-9)
+    np.testing.assert_allclose(d1.rec_errors, d2.rec_errors, rtol=1e-9)
+    for m in range(3):
+        for x1_, x2_ in zip(a1.duals[m] + a1.auxes[m], a2.duals[m] + a2.auxes[m]):
+            assert rel(np.concatenate(x1_, 0) if m == 1 else x1_, np.concatenate(x2_, 0) if m == 1 else x2_) < 10 * tol

@@ -1045,3 +1045,82 @@ def test_pf2_rowpass_single_array_companions_bit_identical(R, dtype, mma):
         lib.b2_set_option(_lib.OPT_PF2_ROWPASS_MMA, _lib.PF2_ROWPASS_DEFAULT)
     for k in results[False]:
         np.testing.assert_array_equal(results[True][k], results[False][k], err_msg=k)
+
+
+@pytest.mark.parametrize("K,R", [(512, 16), (100, 8), (64, 5), (1024, 8), (256, 24), (130, 16), (96, 3), (40, 32)])
+@pytest.mark.parametrize("n_pen", [0, 1, 2])
+@pytest.mark.parametrize("n_slices,lo,hi", [(9, 0, 150), (400, 1, 40), (150, 60, 70)])
+def test_xstream_fused_local_equals_two_pass(K, R, n_pen, n_slices, lo, hi):
+    """The single-read fused pass (csrc/xfused.cu: Y = X C, B-update inner loop, G_i = X_i^T B_i, Z, B_i^T B_i in ONE
+    pass over X) against the two-pass composition xstream_y -> admm_local -> xstream_z and NumPy."""
+    _lib, _ops, O = _imports()
+    assert _ops.xstream_fused_supported(K, R, torch.float64, n_pen)
+    rs = np.random.RandomState(K + 7 * R + n_pen + n_slices)
+    sizes = rs.randint(lo, hi + 1, size=n_slices)
+    if lo == 0:
+        sizes[[0, n_slices // 2]] = 0  # empty slices
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    N = int(off[-1])
+    Xh, X = packed_x(N, K, torch.float64, rs)
+    C = rs.uniform(size=(K, R))
+    A = rs.uniform(0.5, 1.5, size=(n_slices, R))
+    A[rs.uniform(size=A.shape) < 0.1] = 0.0  # clipped entries of a non-negative A
+    rho = rs.uniform(0.5, 2.0, size=n_slices)
+    Ms = rs.standard_normal(size=(n_slices, 2 * R, R))
+    Minv = np.stack([np.linalg.inv(m.T @ m + np.eye(R)) for m in Ms])
+    cases = [(_lib.PEN_NONNEG, False, 0.0, 0.0), (_lib.PEN_L1, False, 0.2, 0.0)][:n_pen]
+    aux0 = [rs.standard_normal(size=(N, R)) for _ in cases]
+    dual0 = [rs.standard_normal(size=(N, R)) for _ in cases]
+    gor = dev(np.repeat(np.arange(n_slices), sizes).astype(np.int32), torch.int32)
+    off_d = dev(off, torch.int64)
+    ws = _ops.Workspace("cuda", K, R, torch.float64)
+
+    # two-pass composition
+    aux, dual = [dev(a) for a in aux0], [dev(d) for d in dual0]
+    descs = _ops.make_descs([(c[0], c[1], c[2], c[3], a, d) for c, a, d in zip(cases, aux, dual)])
+    Y = torch.zeros((N, R), dtype=torch.float64, device="cuda")
+    _ops.xstream_y(X, N, K, dev(C), Y, ws)
+    x_ref = torch.zeros((N, R), dtype=torch.float64, device="cuda")
+    W = _ops.alloc_w(N, R, torch.float64, "cuda")
+    BtB_ref = torch.zeros((n_slices, R, R), dtype=torch.float64, device="cuda")
+    _ops.admm_local(N, R, Y, dev(A), _lib.GROUP_INDEXED, gor, dev(rho), dev(Minv), descs, n_pen, 5, x_ref, W,
+                    row_off=off_d, n_groups=n_slices, BtB_out=BtB_ref)
+    Z_ref = torch.zeros((K, R), dtype=torch.float64, device="cuda")
+    _ops.xstream_z(X, N, K, W, Z_ref, ws)
+    ref = [x_ref] + aux + dual
+
+    # fused pass
+    aux_f, dual_f = [dev(a) for a in aux0], [dev(d) for d in dual0]
+    descs_f = _ops.make_descs([(c[0], c[1], c[2], c[3], a, d) for c, a, d in zip(cases, aux_f, dual_f)])
+    fws = _ops.FusedWorkspace(off, K, R, "cuda")
+    assert sorted(int(g) for g in fws.sched_host.ravel() if g >= 0) == list(range(n_slices))
+    x = torch.full((N, R), np.nan, dtype=torch.float64, device="cuda")
+    Z = torch.full((K, R), np.nan, dtype=torch.float64, device="cuda")
+    G = torch.full((n_slices, K, R), np.nan, dtype=torch.float64, device="cuda")
+    BtB = torch.full((n_slices, R, R), np.nan, dtype=torch.float64, device="cuda")
+    _ops.xstream_fused_local(X, N, K, off_d, n_slices, fws, dev(C), dev(A), dev(rho), dev(Minv), descs_f, n_pen, 5, x, Z,
+                             G, BtB)
+    torch.cuda.synchronize()
+    for a, b in zip([x] + aux_f + dual_f, ref):
+        np.testing.assert_allclose(a.cpu().numpy(), b.cpu().numpy(), rtol=1e-10, atol=1e-10)
+    scale = max(1.0, float(Z_ref.abs().max()))
+    np.testing.assert_allclose(Z.cpu().numpy(), Z_ref.cpu().numpy(), rtol=1e-10, atol=1e-11 * scale)
+    np.testing.assert_allclose(BtB.cpu().numpy(), BtB_ref.cpu().numpy(), rtol=1e-10, atol=1e-10)
+    xh = x.cpu().numpy()
+    G_ref = np.stack([Xh[off[g]:off[g + 1]].T @ xh[off[g]:off[g + 1]] for g in range(n_slices)])
+    np.testing.assert_allclose(G.cpu().numpy(), G_ref, rtol=1e-10, atol=1e-10 * max(1.0, np.abs(G_ref).max()))
+    # the A-update's right-hand side from G: diag(B_g^T X_g C2) for another C
+    C2 = rs.uniform(size=(K, R))
+    rhs = torch.full((n_slices, R), np.nan, dtype=torch.float64, device="cuda")
+    _ops.slice_gdot(G, dev(C2), n_slices, K, R, rhs)
+    rhs_ref = np.stack([np.einsum("jr,jr->r", xh[off[g]:off[g + 1]], Xh[off[g]:off[g + 1]] @ C2) for g in range(n_slices)])
+    np.testing.assert_allclose(rhs.cpu().numpy(), rhs_ref, rtol=1e-10, atol=1e-10 * max(1.0, np.abs(rhs_ref).max()))
+
+
+def test_xstream_fused_local_limits():
+    """Shapes whose G_i accumulators do not fit the registers (config 4: K = 2048, R = 32) are refused, not mangled."""
+    _lib, _ops, O = _imports()
+    assert not _ops.xstream_fused_supported(2048, 32, torch.float64, 1)
+    assert not _ops.xstream_fused_supported(512, 16, torch.float32, 1)
+    assert not _ops.xstream_fused_supported(512, 16, torch.float64, 3)
+    assert _ops.xstream_fused_supported(512, 16, torch.float64, 1)
