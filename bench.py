@@ -52,6 +52,9 @@ CONFIGS = {
 # config[4] as the weak-scaling sweep BASELINE.json describes: 8192 slices PER GPU (65,536 at 8 GPUs: 550 GB of X, which
 # no single GPU holds).  `value` stays outer iterations/s of the N-times larger problem; `slice_iterations_per_s` =
 # value x slices is the aggregate that should grow with N.
+# diagnostic (not a BASELINE config): config 1 at half the rank — the regime where the contraction is HBM-bound, not
+# fp64-pipe-bound, i.e. where reading X once instead of twice pays in full
+CONFIGS["c1r8"] = dict(CONFIGS["c1"], R=8, desc="config[1] shapes at R=8 (diagnostic): nonneg CMF, 4096 slices 256x512, fp64")
 CONFIGS["c4w"] = dict(CONFIGS["c4"], weak=True,
                       desc="BASELINE config[4] weak scaling: nonneg CMF, 8192 slices 512x2048 PER GPU, R=32, fp64")
 
@@ -462,8 +465,9 @@ def main():
     ap.add_argument("--config", default=os.environ.get("B2_BENCH_CONFIG", "c2"), choices=sorted(CONFIGS))
     ap.add_argument("--slices", type=int, default=0, help="override the slice count (debug only)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline / e2e legs (debug only)")
-    ap.add_argument("--x1", default="auto", choices=["auto", "off"],
-                    help="off = force the two-pass X-stream schedule where the single-read fused pass would apply (A/B)")
+    ap.add_argument("--x1", default="auto", choices=["auto", "on", "off"],
+                    help="single-read fused X-stream pass: auto = the engine's policy (ranks <= 8), on = wherever the "
+                         "kernel applies, off = always the two-pass schedule (A/B)")
     args = ap.parse_args()
     cfg = dict(CONFIGS[args.config])
     if args.slices:
@@ -508,7 +512,7 @@ def main():
     while True:
         try:
             packed = gen_device_data(cfg, sizes, lo, hi, dtype, device)
-            eng = AOADMMEngine(packed, cfg["R"], regs, group=group, fuse_x1=None if args.x1 == "auto" else False)
+            eng = AOADMMEngine(packed, cfg["R"], regs, group=group, fuse_x1={"auto": None, "on": True, "off": False}[args.x1])
             eng.load_state_device(seed=rank)
             eng.prepare()
             break

@@ -33,8 +33,14 @@ _ENGINE_PROX_KINDS = (_lib.PEN_GL2, _lib.PEN_SIMPLEX, _lib.PEN_TV)
 
 # Kernel-fusion switches (tests flip them to cross-check the fused kernels against the one-kernel-per-step path).
 # "x1": the single-read fused X-stream pass for slice-local B-updates (csrc/xfused.cu): one pass over X per outer
-# iteration instead of two
-FUSION_DEFAULTS = {"local": True, "pf2": True, "overlap": True, "x1": True}
+# iteration instead of two.  True = wherever the kernel applies, False = never, "auto" = where it is measured faster than
+# the two-pass schedule: ranks <= 8 (one tensor-core column block), where the contraction is HBM-bound; from R = 9 on
+# the two contractions of one launch are bound by the fp64 tensor pipe and the serial B-update between them is exposed
+# (config 1, R = 16: 1.79 ms fused vs 1.57 ms for Y + Z + the fused ADMM loop; R = 8: 0.99 vs 1.44 ms; profiles/).
+# Environment: B2_X1=1 / 0 / auto.
+FUSION_DEFAULTS = {"local": True, "pf2": True, "overlap": True,
+                   "x1": {"1": True, "0": False}.get(os.environ.get("B2_X1", "auto"), "auto")}
+X1_AUTO_MAX_RANK = 8
 
 
 class _Phase:
@@ -361,7 +367,9 @@ class AOADMMEngine:
         # The extra traffic is G (I x K x R, written by the pass and read once by the A-update), 2 R / mean(J_i) of X:
         # not worth it for very short slices.
         d1 = self.modes[1].desc
-        want_x1 = FUSION_DEFAULTS.get("x1", True) if fuse_x1 is None else bool(fuse_x1)
+        want_x1 = FUSION_DEFAULTS.get("x1", "auto") if fuse_x1 is None else fuse_x1
+        if want_x1 == "auto":
+            want_x1 = R <= X1_AUTO_MAX_RANK
         self.fused_x1 = bool(
             want_x1 and self.fuse_local and self.update_B and I > 0 and N > 0 and dt == torch.float64
             and self.n_inner > 0 and len(d1) <= 2 and all(d[0] in (_lib.PEN_NONNEG, _lib.PEN_BOX, _lib.PEN_L1) for d in d1)

@@ -3,8 +3,8 @@
 //
 //     Y_i = X_i C                                   (rhs of the B-update, decomposition.py:242:  X_i (C o a_i) = Y_i o a_i)
 //     B_i <- inner ADMM loop of admm_update_B       (decomposition.py:259-289, row-local penalties: NonNegativity, Box, L1)
-//     G_i = X_i^T B_i                               (K x R per slice)
-//     Z  += G_i diag(a_i)                           (rhs of the C-update, decomposition.py:312-315)
+//     G_i = X_i^T B_i                               (K x R per slice; Z = sum_i G_i diag(a_i), the rhs of the C-update
+//                                                    decomposition.py:312-315, is summed from the stored G_i right after)
 //     B_i^T B_i                                     (lhs of the C-update :310 and cross products of the A-update :138-143)
 //
 // The A-update of the same outer iteration (which needs diag(B_i^T X_i C_new), decomposition.py:145-158) is served
@@ -23,6 +23,8 @@
 //            256 KB at K = 512, so this read is served by L2 — 148 CTAs keep 37 MB live) and consumer warp w
 //            accumulates G_i[k-block + 16 w .. + 16][:] in registers.
 // fp64 only (DMMA); the register-resident G_i / Z accumulators bound K * ceil(R/8) <= 1024.
+#include <stddef.h>
+
 #include "admm_common.cuh"
 #include "mma_tiles.cuh"
 #include "xstream_common.cuh"
@@ -31,7 +33,7 @@ namespace {
 
 constexpr int kCons = 8;  // consumer warps
 constexpr int kThreadsF = (kCons + 1) * 32;
-constexpr int kCR = 64;  // rows per chunk
+constexpr int kCR = 128;  // rows per chunk
 constexpr int kBoxBytesF = 32 * 128;
 constexpr int kStageBytesF = 8 * kBoxBytesF;
 
@@ -48,11 +50,22 @@ struct FusedArgs {
     PenArgs pa;
     int n_inner, R, K, Kp;
     double* B;      // N x R (out)
-    double* Zpart;  // gridDim.x x K x R (out)
     double* G;      // n_slices x K x R (out)
     double* BtB;    // n_slices x R x R (out)
     int stages;
 };
+
+__device__ __forceinline__ double2 lds_f64x2(uint32_t saddr) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(saddr));
+    return v;
+}
+// volatile: the B-state rows are requested where the call stands (ahead of the Y-phase), not where they are used
+__device__ __forceinline__ double2 ldg_f64x2(const double* p) {
+    double2 v;
+    asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
 
 template <class PL>
 __device__ __forceinline__ void load_row_g(const double* __restrict__ base, long long row, int R, int t, bool valid,
@@ -64,7 +77,7 @@ __device__ __forceinline__ void load_row_g(const double* __restrict__ base, long
         v[b][0] = v[b][1] = 0.0;
         if (valid) {
             if (vec && c0 >= 0 && c1 >= 0) {
-                const double2 pr = *(const double2*)(base + (size_t)row * R + c0);
+                const double2 pr = ldg_f64x2(base + (size_t)row * R + c0);
                 v[b][0] = pr.x;
                 v[b][1] = pr.y;
             } else {
@@ -91,24 +104,68 @@ __device__ __forceinline__ void store_row_g(double* __restrict__ base, long long
     }
 }
 
+// per-slice operands of the B-update (Minv_g in MMA position order, a_g, rho_g), double buffered: the next slice's set is
+// fetched with cp.async while the current slice is processed
+// TMA tile load with an L2 eviction-priority hint: the Y-phase read of a chunk is marked evict_last (the Z-phase reads
+// the same rows a few microseconds later), the Z-phase read evict_first (the rows are dead afterwards)
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar,
+                                                 uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], "
+        "[%2], %5;" ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
+        : "memory");
+}
+
+template <class PL>
+struct SliceOps {
+    double Ms[PL::NPOS * PL::LDM];
+    double a[PL::NPOS];
+    double rho[2];
+};
+
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <class PL>
+__device__ __forceinline__ void fetch_slice_ops(SliceOps<PL>* so, const FusedArgs& fa, int g, int tid) {
+    const int R = fa.R;
+    for (int e = tid; e < R * R; e += kCons * 32) {  // PosLayout<NBLK, 0>: position == column, pad rows/columns stay 0
+        const int r = e / R, c = e - r * R;
+        cp_async8(&so->Ms[r * PL::LDM + c], fa.Minv + (size_t)g * R * R + e);
+    }
+    if (tid < R) cp_async8(&so->a[tid], fa.A + (size_t)g * R + tid);
+    if (tid == 32) cp_async8(&so->rho[0], fa.rho + g);
+}
+
 template <int NBLK, int KB, int NP>
 __global__ void __launch_bounds__(kThreadsF, 1)
 xfused_local_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedArgs fa) {
     using PL = PosLayout<NBLK, 0>;
     using GA = GramAcc<PL>;
+    using SO = SliceOps<PL>;
     constexpr int NB = NBLK;
-    constexpr int LDC = 8 * NBLK + 4, LDR = 8 * NBLK + 2, LDW = 8 * NBLK + 2;
+    constexpr int LDC = 8 * NBLK + 4, LDR = 8 * NBLK + 2;
     constexpr int NPm = NP > 0 ? NP : 1;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    // carve: ring [stages x 32 KB] | Cp_s [Kp x LDC] | red [4 x 64 x LDR] | Wt [64 x LDW] | Ms | a_s | full | empty
+    // carve: ring [stages x 32 KB] | Cp_s [Kp x LDC] | red [2 x 128 x LDR] | slice operands x 2 | full | empty
     unsigned char* base = (unsigned char*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int stages = fa.stages, Kp = fa.Kp, R = fa.R, K = fa.K;
     double* Cp_s = (double*)(base + (size_t)stages * kStageBytesF);
     double* red = Cp_s + (size_t)Kp * LDC;
-    double* Wt = red + 4 * kCR * LDR;
-    double* Ms = Wt + kCR * LDW;
-    double* a_s = Ms + PL::NPOS * PL::LDM;
-    uint64_t* full = (uint64_t*)(a_s + PL::NPOS);
+    SO* sops = (SO*)(red + 2 * kCR * LDR);
+    uint64_t* full = (uint64_t*)(sops + 2);
     uint64_t* empty = full + stages;
     const uint32_t base_s = smem_u32(base);
 
@@ -121,13 +178,14 @@ xfused_local_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedArgs 
         fence_mbar_init();
     }
     __syncthreads();
-    const int nks = Kp / 64, nkb = Kp / 128;
+    const int nks = Kp / 32, nkb = Kp / 128;
     const int32_t* my_sched = fa.sched + (size_t)blockIdx.x * fa.rounds;
 
     if (warp == kCons) {
         // ===== producer warp: one elected lane issues all TMA traffic =====
         if (lane == 0) {
             prefetch_tmap(&tmap_x);
+            const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
             int s = 0;
             uint32_t ph = 0;
             for (int i = 0; i < fa.rounds; ++i) {
@@ -135,30 +193,31 @@ xfused_local_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedArgs 
                 if (g < 0) continue;
                 const long long r_begin = fa.row_off[g], r_end = fa.row_off[g + 1];
                 for (long long row0 = r_begin; row0 < r_end; row0 += kCR) {
-                    const int nrh = (r_end - row0) > 32 ? 2 : 1;
-                    for (int ks = 0; ks < nks; ++ks) {  // Y-phase: box (rh, kq)
+                    const long long left = r_end - row0;
+                    const int nrq = left >= kCR ? 4 : (int)((left + 31) >> 5);  // 32-row quarters in this chunk
+                    for (int ks = 0; ks < nks; ++ks) {  // Y-phase: box (rq, kh) = rows 32 rq.., k's 32 ks + 16 kh..
                         mbar_wait(&empty[s], ph ^ 1);
                         unsigned char* st = base + (size_t)s * kStageBytesF;
-                        mbar_arrive_expect_tx(&full[s], (uint32_t)(nrh * 4 * kBoxBytesF));
-                        for (int rh = 0; rh < nrh; ++rh)
+                        mbar_arrive_expect_tx(&full[s], (uint32_t)(nrq * 2 * kBoxBytesF));
+                        for (int rq = 0; rq < nrq; ++rq)
 #pragma unroll
-                            for (int kq = 0; kq < 4; ++kq)
-                                tma_load_2d(st + (rh * 4 + kq) * kBoxBytesF, &tmap_x, ks * 64 + kq * 16,
-                                            (int)(row0 + rh * 32), &full[s]);
+                            for (int kh = 0; kh < 2; ++kh)
+                                tma_load_2d_hint(st + (rq * 2 + kh) * kBoxBytesF, &tmap_x, ks * 32 + kh * 16,
+                                                 (int)(row0 + rq * 32), &full[s], pol_keep);
                         if (++s == stages) {
                             s = 0;
                             ph ^= 1;
                         }
                     }
-                    for (int rt = 0; rt < nrh; ++rt) {  // Z-phase: box = 16 k's of a 128-k block
+                    for (int rt = 0; rt < nrq; ++rt) {  // Z-phase: box = 16 k's of a 128-k block, rows 32 rt..
                         for (int kb = 0; kb < nkb; ++kb) {
                             mbar_wait(&empty[s], ph ^ 1);
                             unsigned char* st = base + (size_t)s * kStageBytesF;
                             mbar_arrive_expect_tx(&full[s], (uint32_t)kStageBytesF);
 #pragma unroll
                             for (int b = 0; b < 8; ++b)
-                                tma_load_2d(st + b * kBoxBytesF, &tmap_x, kb * 128 + b * 16, (int)(row0 + rt * 32),
-                                            &full[s]);
+                                tma_load_2d_hint(st + b * kBoxBytesF, &tmap_x, kb * 128 + b * 16,
+                                                 (int)(row0 + rt * 32), &full[s], pol_drop);
                             if (++s == stages) {
                                 s = 0;
                                 ph ^= 1;
@@ -173,18 +232,31 @@ xfused_local_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedArgs 
 
     // ===== consumers =====
     for (int e = tid; e < Kp * LDC; e += kCons * 32) Cp_s[e] = fa.Cp[e];
+    for (int e = tid; e < (int)(2 * sizeof(SO) / sizeof(double)); e += kCons * 32) ((double*)sops)[e] = 0.0;
     const int g_ = lane >> 2, t = lane & 3;
-    const int kq = warp & 3, rh = warp >> 2;
+    const int kh = warp & 1, rq = warp >> 1;
     const uint32_t a_chunk0 = 4u * (t >> 1), a_half = (t & 1) * 8u;
     const uint32_t cp_addr = smem_u32(Cp_s) + (uint32_t)(g_ * sizeof(double));
-    const uint32_t wt_addr = smem_u32(Wt) + (uint32_t)(g_ * sizeof(double));
+    const uint32_t red_addr = smem_u32(red);
+    const uint32_t sops_addr = smem_u32(sops);
+    const uint32_t wt_addr = red_addr + (uint32_t)(g_ * sizeof(double));  // the new rows of B_i live in partial 0 of `red`
     const int RR = R * R;
     const int iters = NP == 0 ? 1 : fa.n_inner;
-    // running Z of this CTA: K x R partial in HBM / L2, updated once per slice (the G_i accumulators take the registers)
-    double* zp = fa.Zpart + (size_t)blockIdx.x * K * R;
-    bool first = true;
     int s = 0;
     uint32_t ph = 0;
+    int buf = 0;
+    // first non-empty slice of this CTA: fetch its operands
+    int i_next = 0;
+    auto advance_next = [&]() {
+        while (i_next < fa.rounds) {
+            const int g = my_sched[i_next];
+            if (g >= 0 && fa.row_off[g + 1] > fa.row_off[g]) break;
+            ++i_next;
+        }
+    };
+    advance_next();
+    cons_barrier();  // the zero fill of the operand buffers is complete
+    if (i_next < fa.rounds) fetch_slice_ops<PL>(&sops[0], fa, my_sched[i_next], tid);
 
     for (int i = 0; i < fa.rounds; ++i) {
         const int g = my_sched[i];
@@ -196,23 +268,23 @@ xfused_local_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedArgs 
             for (int e = tid; e < K * R; e += kCons * 32) Gg[e] = 0.0;
             continue;
         }
-        cons_barrier();  // every warp is done with the previous slice's operator, scale and reduction scratch
-        stage_operator<PL, double>(fa.Minv + (size_t)g * RR, R, Ms, tid, kCons * 32);
-        for (int e = tid; e < PL::NPOS; e += kCons * 32) {
-            const int c = PL::col_of(e, R);
-            a_s[e] = c >= 0 ? fa.A[(size_t)g * R + c] : 0.0;
-        }
-        cons_barrier();
-        const double rg = fa.rho[g];
+        cp_async_wait_all();  // this slice's operands (requested one slice ago) have landed
+        cons_barrier();       // ... in every thread; and every warp is done with the previous slice's scratch
+        const uint32_t so_addr = sops_addr + (uint32_t)(buf * sizeof(SO));
+        i_next = i + 1;
+        advance_next();
+        if (i_next < fa.rounds) fetch_slice_ops<PL>(&sops[buf ^ 1], fa, my_sched[i_next], tid);
+        buf ^= 1;
+        const double rg = lds_f64(so_addr + (uint32_t)offsetof(SO, rho));
         double sc[NB][2];
 #pragma unroll
         for (int b = 0; b < NB; ++b) {
-            sc[b][0] = a_s[8 * b + 2 * t];
-            sc[b][1] = a_s[8 * b + 2 * t + 1];
+            const double2 a2 = lds_f64x2(so_addr + (uint32_t)(offsetof(SO, a) + (8 * b + 2 * t) * sizeof(double)));
+            sc[b][0] = a2.x;
+            sc[b][1] = a2.y;
         }
         GA accB;
         accB.clear();
-        double* tileG = red + (size_t)warp * 8 * LDR;  // rows [8 warp, +8) of partial 0: read by this warp only
         double Gacc[KB][2][NBLK][2];
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb)
@@ -222,18 +294,22 @@ xfused_local_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedArgs 
                 for (int n = 0; n < NBLK; ++n) Gacc[kb][m][n][0] = Gacc[kb][m][n][1] = 0.0;
 
         for (long long row0 = r_begin; row0 < r_end; row0 += kCR) {
-            const int nrh = (r_end - row0) > 32 ? 2 : 1;
-            const long long brow = row0 + warp * 8 + g_;  // this lane's row in the B-update
-            const bool valid = brow < r_end;
+            const long long left = r_end - row0;
+            const int nrq = left >= kCR ? 4 : (int)((left + 31) >> 5);
+            // this lane's two rows in the B-update (m-blocks 2 warp, 2 warp + 1 of the chunk)
+            const long long brow0 = row0 + warp * 16 + g_, brow1 = brow0 + 8;
+            const bool valid0 = brow0 < r_end, valid1 = brow1 < r_end;
             // the B-state rows of the B-update are requested now and arrive behind the Y-phase
-            double ax[NPm][NB][2], du[NPm][NB][2];
+            double ax[2][NPm][NB][2], du[2][NPm][NB][2];
 #pragma unroll
             for (int p = 0; p < NP; ++p) {
-                load_row_g<PL>((const double*)fa.pa.aux[p], brow, R, t, valid, ax[p]);
-                load_row_g<PL>((const double*)fa.pa.dual[p], brow, R, t, valid, du[p]);
+                load_row_g<PL>((const double*)fa.pa.aux[p], brow0, R, t, valid0, ax[0][p]);
+                load_row_g<PL>((const double*)fa.pa.dual[p], brow0, R, t, valid0, du[0][p]);
+                load_row_g<PL>((const double*)fa.pa.aux[p], brow1, R, t, valid1, ax[1][p]);
+                load_row_g<PL>((const double*)fa.pa.dual[p], brow1, R, t, valid1, du[1][p]);
             }
 
-            // ---- Y-phase: acc[m][n] = partial of Y[row0 + 32 rh + 8 m + g][8 n + 2 t (+1)] over k-quarter kq ----
+            // ---- Y-phase: acc[m][n] = partial of Y[row0 + 32 rq + 8 m + g][8 n + 2 t (+1)] over k-half kh ----
             double acc[4][NBLK][2];
 #pragma unroll
             for (int m = 0; m < 4; ++m)
@@ -241,9 +317,9 @@ xfused_local_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedArgs 
                 for (int n = 0; n < NBLK; ++n) acc[m][n][0] = acc[m][n][1] = 0.0;
             for (int ks = 0; ks < nks; ++ks) {
                 mbar_wait(&full[s], ph);
-                if (rh < nrh) {
-                    const uint32_t box = base_s + (uint32_t)s * kStageBytesF + (uint32_t)(rh * 4 + kq) * kBoxBytesF;
-                    const uint32_t crow0 = cp_addr + (uint32_t)((ks * 64 + kq * 16 + t) * LDC * sizeof(double));
+                if (rq < nrq) {
+                    const uint32_t box = base_s + (uint32_t)s * kStageBytesF + (uint32_t)(rq * 2 + kh) * kBoxBytesF;
+                    const uint32_t crow0 = cp_addr + (uint32_t)((ks * 32 + kh * 16 + t) * LDC * sizeof(double));
 #pragma unroll
                     for (int k4 = 0; k4 < 4; ++k4) {
                         double a[4], bf[NBLK];
@@ -270,83 +346,109 @@ xfused_local_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedArgs 
                     ph ^= 1;
                 }
             }
-            // k-quarter partials -> shared memory; rows of the second half of a short chunk are zeros
+            cons_barrier();  // every warp has left the previous chunk's Z-phase, which reads partial 0 of `red`
+            // k-half partials -> shared memory; quarters past the end of a short chunk are zeros
 #pragma unroll
             for (int m = 0; m < 4; ++m)
 #pragma unroll
                 for (int n = 0; n < NBLK; ++n)
-                    *(double2*)(red + (size_t)(kq * kCR + 32 * rh + 8 * m + g_) * LDR + 8 * n + 2 * t) =
+                    *(double2*)(red + (size_t)(kh * kCR + 32 * rq + 8 * m + g_) * LDR + 8 * n + 2 * t) =
                         make_double2(acc[m][n][0], acc[m][n][1]);
             cons_barrier();
-            double r_[NB][2], xv[NB][2];
+            double r_[2][NB][2], xv[2][NB][2];
 #pragma unroll
-            for (int b = 0; b < NB; ++b) {
-                double2 y = *(const double2*)(red + (size_t)(8 * warp + g_) * LDR + 8 * b + 2 * t);
+            for (int mb = 0; mb < 2; ++mb) {
+                const uint32_t row = red_addr + (uint32_t)(((16 * warp + 8 * mb + g_) * LDR + 2 * t) * sizeof(double));
 #pragma unroll
-                for (int q = 1; q < 4; ++q) {
-                    const double2 u = *(const double2*)(red + (size_t)(q * kCR + 8 * warp + g_) * LDR + 8 * b + 2 * t);
-                    y.x += u.x;
-                    y.y += u.y;
+                for (int b = 0; b < NB; ++b) {
+                    const double2 y0 = lds_f64x2(row + b * 64);
+                    const double2 y1 = lds_f64x2(row + (uint32_t)(kCR * LDR * sizeof(double)) + b * 64);
+                    r_[mb][b][0] = (y0.x + y1.x) * sc[b][0];
+                    r_[mb][b][1] = (y0.y + y1.y) * sc[b][1];
                 }
-                r_[b][0] = y.x * sc[b][0];
-                r_[b][1] = y.y * sc[b][1];
             }
-            __syncwarp();  // tileG aliases this warp's rows of partial 0: all lanes have read them
+            __syncwarp();  // the Gram tiles alias this warp's rows of partial 0: all lanes have read them
 
-            // ---- B-update: the whole inner loop on this warp's 8 rows (decomposition.py:259-289) ----
+            // ---- B-update: the whole inner loop on this warp's 2 x 8 rows (decomposition.py:259-289) ----
+            // B fragments of Minv_g for all k-steps: loaded once, reused by the n_inner iterations and both row blocks
+            double mf[PL::KS][NB];
+#pragma unroll
+            for (int ks = 0; ks < PL::KS; ++ks)
+#pragma unroll
+                for (int nb = 0; nb < NB; ++nb)
+                    mf[ks][nb] = lds_f64(so_addr + (uint32_t)(((8 * (ks >> 1) + 2 * t + (ks & 1)) * PL::LDM + g_ + 8 * nb) *
+                                                             sizeof(double)));
             for (int it = 0; it < iters; ++it) {
-                double sv[NB][2];
+                double sv[2][NB][2];
 #pragma unroll
-                for (int b = 0; b < NB; ++b)
+                for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-                    for (int e = 0; e < 2; ++e) {
-                        double sh = 0.0;
+                    for (int b = 0; b < NB; ++b)
 #pragma unroll
-                        for (int p = 0; p < NP; ++p) sh += ax[p][b][e] - du[p][b][e];
-                        sv[b][e] = NP > 0 ? fma(rg, sh, r_[b][e]) : r_[b][e];
+                        for (int e = 0; e < 2; ++e) {
+                            double sh = 0.0;
+#pragma unroll
+                            for (int p = 0; p < NP; ++p) sh += ax[mb][p][b][e] - du[mb][p][b][e];
+                            sv[mb][b][e] = NP > 0 ? fma(rg, sh, r_[mb][b][e]) : r_[mb][b][e];
+                        }
+#pragma unroll
+                for (int mb = 0; mb < 2; ++mb)
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) xv[mb][nb][0] = xv[mb][nb][1] = 0.0;
+#pragma unroll
+                for (int ks = 0; ks < PL::KS; ++ks)  // x = s Minv_g: the two row blocks are independent chains
+#pragma unroll
+                    for (int nb = 0; nb < NB; ++nb) {
+                        dmma884(xv[0][nb][0], xv[0][nb][1], sv[0][ks >> 1][ks & 1], mf[ks][nb]);
+                        dmma884(xv[1][nb][0], xv[1][nb][1], sv[1][ks >> 1][ks & 1], mf[ks][nb]);
                     }
-                mma_rowmat<PL>(sv, Ms, g_, t, xv);
 #pragma unroll
                 for (int p = 0; p < NP; ++p) {
                     const int kind = fa.pa.kind[p], nn = fa.pa.nn[p];
                     const double p0 = fa.pa.p0[p], p1 = fa.pa.p1[p];
 #pragma unroll
-                    for (int b = 0; b < NB; ++b)
+                    for (int mb = 0; mb < 2; ++mb)
 #pragma unroll
-                        for (int e = 0; e < 2; ++e) {
-                            const double vv = xv[b][e] + du[p][b][e];
-                            const double z = prox_elem<double>(vv, kind, nn, p0, p1, rg);
-                            ax[p][b][e] = z;
-                            du[p][b][e] = vv - z;
-                        }
-                }
-            }
-            double xz[NB][2];
+                        for (int b = 0; b < NB; ++b)
 #pragma unroll
-            for (int b = 0; b < NB; ++b)
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    const bool pad = reg_col<PL>(b, e, t, R) < 0;
-                    xz[b][e] = (valid && !pad) ? xv[b][e] : 0.0;
-                }
-            if (valid) {
-                store_row_g<PL>(fa.B, brow, R, t, xv);
-#pragma unroll
-                for (int p = 0; p < NP; ++p) {
-                    store_row_g<PL>((double*)fa.pa.aux[p], brow, R, t, ax[p]);
-                    store_row_g<PL>((double*)fa.pa.dual[p], brow, R, t, du[p]);
+                            for (int e = 0; e < 2; ++e) {
+                                const double vv = xv[mb][b][e] + du[mb][p][b][e];
+                                const double z = prox_elem<double>(vv, kind, nn, p0, p1, rg);
+                                ax[mb][p][b][e] = z;
+                                du[mb][p][b][e] = vv - z;
+                            }
                 }
             }
 #pragma unroll
-            for (int b = 0; b < NB; ++b)  // the new rows of B_i (zero rows past the end of the slice, zero pad columns)
-                *(double2*)(Wt + (size_t)(8 * warp + g_) * LDW + 8 * b + 2 * t) = make_double2(xz[b][0], xz[b][1]);
-            accB.add(xz, tileG, g_, t);
+            for (int mb = 0; mb < 2; ++mb) {
+                const bool valid = mb ? valid1 : valid0;
+                const long long brow = mb ? brow1 : brow0;
+                double xz[NB][2];
+#pragma unroll
+                for (int b = 0; b < NB; ++b)
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const bool pad = reg_col<PL>(b, e, t, R) < 0;
+                        xz[b][e] = (valid && !pad) ? xv[mb][b][e] : 0.0;
+                    }
+                if (valid) {
+                    store_row_g<PL>(fa.B, brow, R, t, xv[mb]);
+#pragma unroll
+                    for (int p = 0; p < NP; ++p) {
+                        store_row_g<PL>((double*)fa.pa.aux[p], brow, R, t, ax[mb][p]);
+                        store_row_g<PL>((double*)fa.pa.dual[p], brow, R, t, du[mb][p]);
+                    }
+                }
+                // B_i^T B_i; the tile the rows are staged in (zero rows past the end of the slice, zero pad columns)
+                // is at the same time the operand of the Z-phase
+                accB.add(xz, red + (size_t)(16 * warp + 8 * mb) * LDR, g_, t);
+            }
             cons_barrier();
 
             // ---- Z-phase: Gacc[kb][m][n] += X[rows, k]^T x[rows, :]  for k = 128 kb + 16 warp + 8 m + g ----
-            // (contracts with the UNSCALED rows: G_i = X_i^T B_i also serves the A-update; a_i is applied once per
-            // slice below — dividing X_i^T (B_i o a_i) by a_i afterwards would hit the zeros of a clipped a_i)
-            for (int rt = 0; rt < nrh; ++rt) {
+            // (contracts with the UNSCALED rows: G_i = X_i^T B_i also serves the A-update; a_i is applied when Z is
+            // summed from the G_i — dividing X_i^T (B_i o a_i) by a_i afterwards would hit the zeros of a clipped a_i)
+            for (int rt = 0; rt < nrq; ++rt) {
 #pragma unroll
                 for (int kb = 0; kb < KB; ++kb) {
                     if (kb < nkb) {
@@ -363,7 +465,7 @@ xfused_local_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedArgs 
                                     const uint32_t kk = 8 * m + g_;
                                     a[m] = lds_f64(box + swz128(row, kk >> 1) + (kk & 1) * 8);
                                 }
-                                const uint32_t wrow = wt_addr + (uint32_t)((rt * 32 + row) * LDW * sizeof(double));
+                                const uint32_t wrow = wt_addr + (uint32_t)((rt * 32 + row) * LDR * sizeof(double));
 #pragma unroll
                                 for (int n = 0; n < NBLK; ++n) bf[n] = lds_f64(wrow + n * 64);
 #pragma unroll
@@ -388,7 +490,7 @@ xfused_local_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedArgs 
             }
         }
 
-        // ---- end of slice: Z += G_i diag(a_i), G_i -> HBM, B_i^T B_i -> HBM ----
+        // ---- end of slice: G_i -> HBM (fire-and-forget stores), B_i^T B_i -> HBM ----
         const bool vec = (R & 1) == 0;
 #pragma unroll
         for (int kb = 0; kb < KB; ++kb) {
@@ -401,37 +503,22 @@ xfused_local_kernel(const __grid_constant__ CUtensorMap tmap_x, const FusedArgs 
                         for (int n = 0; n < NBLK; ++n) {
                             const int c = 8 * n + 2 * t;
                             const size_t o = (size_t)k * R + c;
-                            const double g0 = Gacc[kb][m][n][0], g1 = Gacc[kb][m][n][1];
                             if (vec) {
-                                if (c < R) {
-                                    double2 z = first ? make_double2(0.0, 0.0) : *(const double2*)(zp + o);
-                                    z.x = fma(g0, sc[n][0], z.x);
-                                    z.y = fma(g1, sc[n][1], z.y);
-                                    *(double2*)(zp + o) = z;
-                                    *(double2*)(Gg + o) = make_double2(g0, g1);
-                                }
+                                if (c < R) *(double2*)(Gg + o) = make_double2(Gacc[kb][m][n][0], Gacc[kb][m][n][1]);
                             } else {
-                                if (c < R) {
-                                    zp[o] = fma(g0, sc[n][0], first ? 0.0 : zp[o]);
-                                    Gg[o] = g0;
-                                }
-                                if (c + 1 < R) {
-                                    zp[o + 1] = fma(g1, sc[n][1], first ? 0.0 : zp[o + 1]);
-                                    Gg[o + 1] = g1;
-                                }
+                                if (c < R) Gg[o] = Gacc[kb][m][n][0];
+                                if (c + 1 < R) Gg[o + 1] = Gacc[kb][m][n][1];
                             }
                         }
                     }
                 }
             }
         }
-        first = false;
+        cons_barrier();  // every warp has left the last Z-phase: `red` becomes the reduction scratch
         gram_reduce_store<PL, double>(accB, red, warp, lane, kCons, tid, kCons * 32, R, fa.BtB + (size_t)g * RR,
                                       cons_barrier);
     }
-
-    if (first)  // this CTA had no (non-empty) slice: its partial is all zeros
-        for (int e = tid; e < K * R; e += kCons * 32) zp[e] = 0.0;
+    cp_async_wait_all();
 }
 
 // rhs[g][c] = sum_k G[g][k][c] * C[k][c]   (= diag(B_g^T X_g C), decomposition.py:145-158, from G_g = X_g^T B_g)
@@ -453,6 +540,28 @@ __global__ void __launch_bounds__(256) slice_gdot_kernel(const double* __restric
     }
 }
 
+// Zpart[s][e] = sum over the slices i of slab s of G[i][e] * A[i][e % R]   (Z = sum_i G_i diag(a_i), fixed order)
+__global__ void __launch_bounds__(256) gsum_z_kernel(const double* __restrict__ G, const double* __restrict__ A,
+                                                     int n_slices, int KR, int R, int per_slab,
+                                                     double* __restrict__ Zpart) {
+    const int e = blockIdx.x * 256 + threadIdx.x;
+    if (e >= KR) return;
+    const int c = e % R;
+    const int i0 = blockIdx.y * per_slab, i1 = min(n_slices, i0 + per_slab);
+    double acc = 0.0;
+    int i = i0;
+    for (; i + 4 <= i1; i += 4) {  // 4 independent loads in flight
+        const double g0 = G[(size_t)i * KR + e], g1 = G[(size_t)(i + 1) * KR + e];
+        const double g2 = G[(size_t)(i + 2) * KR + e], g3 = G[(size_t)(i + 3) * KR + e];
+        acc = fma(g0, A[(size_t)i * R + c], acc);
+        acc = fma(g1, A[(size_t)(i + 1) * R + c], acc);
+        acc = fma(g2, A[(size_t)(i + 2) * R + c], acc);
+        acc = fma(g3, A[(size_t)(i + 3) * R + c], acc);
+    }
+    for (; i < i1; ++i) acc = fma(G[(size_t)i * KR + e], A[(size_t)i * R + c], acc);
+    Zpart[(size_t)blockIdx.y * KR + e] = acc;
+}
+
 struct FusedPlan {
     int NBLK, KB, Kp, stages;
     size_t smem;
@@ -467,8 +576,8 @@ int fused_plan(int K, int R, int dtype, int n_pen, FusedPlan* pl) {
     int KB = 1;
     while (KB < nkb) KB *= 2;
     if (NBLK * KB > 8) return 0;  // register-resident G_i and Z accumulators: 8 NBLK KB doubles per thread
-    const int LDC = 8 * NBLK + 4, LDR = 8 * NBLK + 2, LDW = 8 * NBLK + 2, NPOS = 8 * NBLK, LDM = 8 * NBLK + 2;
-    const size_t fixed = 1024 + ((size_t)Kp * LDC + 4 * kCR * LDR + kCR * LDW + NPOS * LDM + NPOS) * sizeof(double) + 64;
+    const int LDC = 8 * NBLK + 4, LDR = 8 * NBLK + 2, NPOS = 8 * NBLK, LDM = 8 * NBLK + 2;
+    const size_t fixed = 1024 + ((size_t)Kp * LDC + 2 * kCR * LDR + 2 * (NPOS * LDM + NPOS + 2)) * sizeof(double) + 64;
     const size_t budget = 227 * 1024;
     if (fixed + 2 * (kStageBytesF + 16) > budget) return 0;
     int stages = (int)((budget - fixed) / (kStageBytesF + 16));
@@ -561,7 +670,6 @@ int b2_xstream_fused_local(const void* X, long long n_rows, int K, int ldx, cons
     fa.K = K;
     fa.Kp = pl.Kp;
     fa.B = (double*)B;
-    fa.Zpart = Zpart;
     fa.G = (double*)G;
     fa.BtB = (double*)BtB;
     fa.stages = pl.stages;
@@ -574,8 +682,14 @@ int b2_xstream_fused_local(const void* X, long long n_rows, int K, int ldx, cons
     B2_F_CASE(4, 1) B2_F_CASE(4, 2)
 #undef B2_F_CASE
     if (rc != B2_OK) return rc;
+    // Z = sum_i G_i diag(a_i): slabs of slices in parallel, then the fixed-order sum of the slab partials
     const int n = K * R;
-    reduce_partials_kernel<double><<<(n + 255) / 256, 256, 0, st>>>(Zpart, (double*)Z, n, n_ctas);
+    const int slabs = n_slices < n_ctas ? n_slices : n_ctas;
+    const int per_slab = (n_slices + slabs - 1) / slabs;
+    gsum_z_kernel<<<dim3((n + 255) / 256, slabs), 256, 0, st>>>((const double*)G, (const double*)A, n_slices, n, R,
+                                                                 per_slab, Zpart);
+    B2_LAUNCH_CHECK();
+    reduce_partials_kernel<double><<<(n + 255) / 256, 256, 0, st>>>(Zpart, (double*)Z, n, slabs);
     B2_LAUNCH_CHECK();
     return B2_OK;
 }

@@ -501,6 +501,7 @@ def test_single_read_fused_pass_matches_two_pass_schedule(kw, monkeypatch):
                                                                        real_fused(*a, **k))[1])
     monkeypatch.setattr(_ops, "xstream_y", lambda *a, **k: (calls.__setitem__("y", calls["y"] + 1), real_y(*a, **k))[1])
     out = []
+    default = _engine.FUSION_DEFAULTS["x1"]
     for x1 in (True, False):
         _engine.FUSION_DEFAULTS.update(x1=x1)
         calls.update(fused=0, y=0)
@@ -508,7 +509,7 @@ def test_single_read_fused_pass_matches_two_pass_schedule(kw, monkeypatch):
             cmf, admm, diag = cmf_aoadmm(X, R, n_iter_max=8, tol=None, absolute_tol=None, random_state=3,
                                          return_admm_vars=True, return_errors=True, **kw)
         finally:
-            _engine.FUSION_DEFAULTS.update(x1=True)
+            _engine.FUSION_DEFAULTS.update(x1=default)
         # fused: one pass per iteration (+ the Y pass of the initial fit); two-pass: no fused launch at all
         assert (calls["fused"], calls["y"]) == ((8, 1) if x1 else (0, 9))
         out.append((cmf, admm, diag))

@@ -97,6 +97,44 @@ def test_fp64_trajectory_at_baseline_width(name):
           f"final loss rel diff = {abs(diag.regularized_loss[-1] - losses[-1]) / losses[-1]:.3e}")
 
 
+@pytest.mark.parametrize("rank", [16, 8])
+def test_fp64_trajectory_config1_single_read_pass(rank, monkeypatch):
+    """SURVEY.md §8 row X1 at the config-1 width (K = 512, J = 256; R = 16 and the HBM-bound R = 8): the single-read
+    fused pass (csrc/xfused.cu, forced on: at R = 16 the engine's own policy picks the two-pass schedule) against the
+    oracle, 1e-8 per checkpoint over 50 iterations, and really ONE pass over X per outer iteration."""
+    from matcouply_b200 import _engine, _ops, cmf_aoadmm
+    from oracle import aoadmm_oracle as O
+
+    cfg, X = twin("c1")
+    traj = _Checkpoints(CHECKPOINTS)
+    o = O.ao_admm(X, rank, n_iter_max=max(CHECKPOINTS), tol=None, absolute_tol=None, random_state=0, trajectory=traj,
+                  **cfg["kw"])
+    calls = {"fused": 0, "y": 0, "z": 0}
+    for key in ("fused", "y", "z"):
+        real = getattr(_ops, {"fused": "xstream_fused_local", "y": "xstream_y", "z": "xstream_z"}[key])
+        monkeypatch.setattr(_ops, real.__name__, lambda *a, _k=key, _f=real, **kw: (
+            calls.__setitem__(_k, calls[_k] + 1), _f(*a, **kw))[1])
+    default = _engine.FUSION_DEFAULTS["x1"]
+    _engine.FUSION_DEFAULTS.update(x1=True)
+    try:
+        worst = 0.0
+        for k, A_o, B_o, C_o in traj:
+            calls.update(fused=0, y=0, z=0)
+            cmf, diag = cmf_aoadmm(X, rank, n_iter_max=k, tol=None, absolute_tol=None, random_state=0,
+                                   return_errors=True, **cfg["kw"])
+            assert (calls["fused"], calls["y"], calls["z"]) == (k, 1, 0)  # + the Y pass of the initial fit
+            _, (A, B_is, C) = cmf
+            errs = (rel(A, A_o), rel(np.concatenate(B_is, 0), B_o), rel(C, C_o))
+            worst = max(worst, *errs)
+            assert max(errs) < 1e-8, (rank, k, errs)
+    finally:
+        _engine.FUSION_DEFAULTS.update(x1=default)
+    np.testing.assert_allclose(diag.regularized_loss, o["regularized_loss"], rtol=1e-8)
+    np.testing.assert_allclose(diag.rec_errors, o["rec_errors"], rtol=1e-8)
+    print(f"[width parity] c1 single-read pass, R={rank}: worst relative factor difference over checkpoints "
+          f"{CHECKPOINTS} = {worst:.3e}")
+
+
 @pytest.mark.parametrize("name", ["c1", "c2", "c3", "c4"])
 def test_same_stopping_iteration_at_baseline_width(name):
     """Run to the stopping rule (loosened so that it fires within a few dozen iterations): same `n_iter`, message and
