@@ -63,8 +63,10 @@ enum { B2_OPT_PF2_ROWPASS_MMA = 0 /* row pass of b2_pf2_rowpass: 0 = shuffle ker
        B2_OPT_XSTREAM_HYBRID = 3 /* DMMA blocks + DFMA remainder columns in the fp64 X-stream kernels (R = 8b+1..4);
                                     default OFF: measured 2-6 % slower than padding to a whole block */,
        B2_OPT_UNIMODAL_VARIANT = 4 /* b2_prox_unimodal: (column ring depth, shared-memory stack-cache depth, CTAs per
-                                      SM) of the PAVA kernel: 0 = (8, 4, 4) round 1, 1 = (4, 8, 4) default, 2 = (8, 8, 4), 3 = (4, 16, 3),
-                                      4 = (4, 8, 5), 5 = (4, 12, 4); same results, different residency */,
+                                      SM) of the PAVA kernel: 0 = (8, 4, 4) round 1, 1 = (4, 8, 4), 2 = (8, 8, 4), 3 = (4, 16, 3),
+                                      4 = (4, 8, 5), 5 = (4, 12, 4); 6 = variant 1 with the exact reciprocal-based division
+                                      and 256-bit record loads / stores; 9 (default) = 6 with merge + finalisation in one
+                                      trip; same results, different speed */,
        B2_OPT_COUNT = 5 };
 int b2_set_option(int option, int value);
 int b2_get_option(int option);
@@ -169,6 +171,11 @@ int b2_admm_local(long long n, int R, const void* rhs, const void* rhs_scale, in
  * squares to colsq_io (n_groups x R doubles), the caller all-reduces them, phase 2 scales with the reduced sums. */
 int b2_prox_l2ball(void* aux, void* dual, const int64_t* row_off, int n_groups, int R, double bound, int non_negativity,
                    double* colsq_io, int phase, int dtype, void* stream);
+/* Self-test of the exact integer-divisor division the unimodal kernel uses (reciprocal + two Markstein corrections)
+ * against the IEEE division: n pseudo-random numerators x divisors 1..max_cnt; *mismatches_dev (device, 8 bytes)
+ * receives the number of differing results (must be 0). */
+int b2_selftest_div_count(long long n, unsigned long long seed, int max_cnt, unsigned long long* mismatches_dev,
+                          void* stream);
 /* Unimodality (penalties.py:1014-1015 -> _unimodal_regression.py:24-141): per group and column aux = unimodal
  * regression of V (PAVA prefix/suffix isotonic fits, `<=` pooling, first strict minimum peak); dual = V - aux.
  * peaks (may be NULL): n_groups x R int32 peak indices t*.  ws >= b2_unimodal_workspace_bytes(). fp64 arithmetic. */

@@ -54,6 +54,7 @@ _SIGNATURES = {
                       _vp, _i, _vp],
     "b2_prox_l2ball": [_vp, _vp, _vp, _i, _i, _d, _i, _vp, _i, _i, _vp],
     "b2_prox_unimodal": [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _i, _vp, _sz, _vp],
+    "b2_selftest_div_count": [_ll, ctypes.c_ulonglong, _i, _vp, _vp],
     "b2_prox_simplex": [_vp, _vp, _vp, _i, _i, _i, _i, _vp],
     "b2_prox_tv": [_vp, _vp, _vp, _i, _i, _vp, _i, _d, _d, _i, _vp],
     "b2_tv_norm": [_vp, _vp, _i, _i, _vp, _vp, _i, _vp],

@@ -42,12 +42,12 @@ constexpr int kThreads = 128;
 // a few per cent of such pops per lane put a global-memory round trip into a quarter of all trips.
 
 // shared memory, all arrays [depth][thread] so that a warp access is conflict free
-template <int YRING, int STACK>
+template <int YRING, int STACK, int NT = kThreads>
 struct SharedState {
-    double y[YRING][kThreads];
-    double2 sums[STACK][kThreads];   // sy, sy2
-    double2 lvl_err[STACK][kThreads];  // level, err_after
-    int start[STACK][kThreads];
+    double y[YRING][NT];
+    double2 sums[STACK][NT];   // sy, sy2
+    double2 lvl_err[STACK][NT];  // level, err_after
+    int start[STACK][NT];
 };
 
 template <typename T>
@@ -58,17 +58,59 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
+// FAST variants: one 256-bit store / load per record (STG.256 / LDG.256 on sm_100a; records are 32-byte aligned)
+template <bool FAST>
 __device__ __forceinline__ void store_rec(Rec* r, double err_after, double sy, double sy2, int start) {
-    double2* q = (double2*)r;
-    q[0] = make_double2(err_after, sy);
-    q[1] = make_double2(sy2, __hiloint2double(0, start));
+    if constexpr (FAST) {
+        asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(r), "d"(err_after), "d"(sy), "d"(sy2),
+                     "d"(__hiloint2double(0, start))
+                     : "memory");
+    } else {
+        double2* q = (double2*)r;
+        q[0] = make_double2(err_after, sy);
+        q[1] = make_double2(sy2, __hiloint2double(0, start));
+    }
 }
-__device__ __forceinline__ int rec_start(const Rec* r) { return r->start; }
+template <bool FAST>
+__device__ __forceinline__ void load_rec(const Rec* r, double& err_after, double& sy, double& sy2, int& start) {
+    if constexpr (FAST) {
+        double w;
+        asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(err_after), "=d"(sy), "=d"(sy2), "=d"(w) : "l"(r) : "memory");
+        start = __double2loint(w);
+    } else {
+        start = r->start;
+        sy = r->sy;
+        sy2 = r->sy2;
+        err_after = r->err_after;
+    }
+}
+
+// a / cnt, correctly rounded (== __ddiv_rn), for an integer-valued divisor.  y = RN(1 / cnt) and two Markstein
+// correction steps: q1 = q0 + y (a - cnt q0) is a faithful quotient, and for a faithful q1 and a correctly rounded
+// reciprocal RN(q1 + y (a - cnt q1)) is the correctly rounded quotient (Markstein 1990; checked against exact rational
+// arithmetic and on the device against __ddiv_rn, tests/test_gpu_kernels.py).  5 fp64 operations after the reciprocal
+// instead of the ~35-instruction IEEE division sequence with its slow-path branch.  Tiny numerators (the residuals
+// could go subnormal) and non-finite ones take the IEEE division.
+template <bool FAST>
+__device__ __forceinline__ double div_count(double a, double cnt) {
+    if constexpr (FAST) {
+        const unsigned e = ((unsigned)__double2hiint(a) >> 20) & 0x7ffu;
+        if (e - 128u < 1919u) {  // 2^-895 <= |a| < 2^1024 (finite): residuals stay normal
+            const double y = __drcp_rn(cnt);
+            const double q0 = __dmul_rn(a, y);
+            const double r0 = __fma_rn(-cnt, q0, a);
+            const double q1 = __fma_rn(r0, y, q0);
+            const double r1 = __fma_rn(-cnt, q1, a);
+            return __fma_rn(r1, y, q1);
+        }
+    }
+    return __ddiv_rn(a, cnt);
+}
 
 // Prefix-isotonic PAVA over seq(j) = col[(rev ? n-1-j : j) * ld], j in [0, n); fills rec[0..n).
-template <typename T, int kYRing, int kStack>
+template <typename T, int kYRing, int kStack, bool FAST, class SH>
 __device__ __forceinline__ void pava_prefix(const T* __restrict__ col, long long ld, int n, bool rev, bool nn,
-                                            Rec* __restrict__ rec, SharedState<kYRing, kStack>& sh, int tid) {
+                                            Rec* __restrict__ rec, SH& sh, int tid) {
     const long long step = rev ? -ld : ld;
     const T* p = col + (rev ? (long long)(n - 1) * ld : 0LL);
     // element j lands in ring slot j % kYRing, stored as T in the first sizeof(T) bytes of the slot
@@ -112,26 +154,22 @@ __device__ __forceinline__ void pava_prefix(const T* __restrict__ col, long long
                     top.level = b.x;
                     top.err_after = b.y;
                 } else {  // cascade deeper than the cached window: re-read the recorded block end (rare)
-                    const Rec* r = rec + (cur.start - 1);
-                    top.start = r->start;
-                    top.sy = r->sy;
-                    top.sy2 = r->sy2;
-                    top.err_after = r->err_after;
-                    top.level = __ddiv_rn(top.sy, (double)(cur.start - top.start));
+                    load_rec<FAST>(rec + (cur.start - 1), top.err_after, top.sy, top.sy2, top.start);
+                    top.level = div_count<FAST>(top.sy, (double)(cur.start - top.start));
                 }
             }
             num = cur.sy;
         } else {
             num = __dmul_rn(cur.sy, cur.sy);
         }
-        const double q = __ddiv_rn(num, (double)(i - cur.start + 1));
+        const double q = div_count<FAST>(num, (double)(i - cur.start + 1));
         if (merge) {
             cur.level = q;  // (:21)
         } else {
             const double levelerror = __dsub_rn(cur.sy2, q);  // (:57)
             const double before = has_top ? top.err_after : 0.0;
             cur.err_after = (nn && cur.level < 0.0) ? cum : __dadd_rn(levelerror, before);  // (:58-62)
-            store_rec(rec + i, cur.err_after, cur.sy, cur.sy2, cur.start);
+            store_rec<FAST>(rec + i, cur.err_after, cur.sy, cur.sy2, cur.start);
             if (has_top) {  // push the old top
                 const int d = depth % kStack;
                 sh.sums[d][tid] = make_double2(top.sy, top.sy2);
@@ -157,15 +195,111 @@ __device__ __forceinline__ void pava_prefix(const T* __restrict__ col, long long
     cp_async_wait<0>();
 }
 
+// Same PAVA, two units of work per trip: a lane whose current block must absorb the block below does that merge, and
+// — if the merged block now sits above its new neighbour (or on the floor) — finalises the element in the SAME trip
+// instead of the next one.  The instruction stream of a trip is [merge part | finalise part], which is what a divergent
+// trip of the one-unit loop executes anyway (merging and finalising lanes are serialised), plus the second division;
+// a column that merges once per element (noise-like data) then takes ~n trips instead of ~2 n.  Same operations in the
+// same order per column, so levels, errors and the peak index stay bit-identical.
+template <typename T, int kYRing, int kStack, class SH>
+__device__ __forceinline__ void pava_prefix_dual(const T* __restrict__ col, long long ld, int n, bool rev, bool nn,
+                                                 Rec* __restrict__ rec, SH& sh, int tid) {
+    const long long step = rev ? -ld : ld;
+    const T* p = col + (rev ? (long long)(n - 1) * ld : 0LL);
+#pragma unroll
+    for (int u = 1; u <= kYRing; ++u) {
+        if (u < n) cp_async_elem<T>(&sh.y[u % kYRing][tid], p + (long long)u * step);
+        cp_async_commit();
+    }
+    Block cur, top;
+    bool has_top = false;
+    int depth = 0, cached = 0;
+    top.start = 0;
+    top.sy = top.sy2 = top.level = top.err_after = 0.0;
+    int i = 0;
+    {
+        const double y0 = (double)p[0];
+        cur.start = 0;
+        cur.sy = y0;
+        cur.sy2 = __dmul_rn(y0, y0);
+        cur.level = y0;
+    }
+    double cum = cur.sy2;
+    while (i < n) {
+        bool merge = has_top && cur.level <= top.level;
+        if (merge) {
+            cur.sy = __dadd_rn(cur.sy, top.sy);
+            cur.sy2 = __dadd_rn(cur.sy2, top.sy2);
+            cur.start = top.start;
+            has_top = cur.start > 0;
+            if (has_top) {
+                --depth;
+                if (cached > 0) {
+                    --cached;
+                    const int d = depth % kStack;
+                    const double2 a = sh.sums[d][tid], b = sh.lvl_err[d][tid];
+                    top.start = sh.start[d][tid];
+                    top.sy = a.x;
+                    top.sy2 = a.y;
+                    top.level = b.x;
+                    top.err_after = b.y;
+                } else {
+                    load_rec<true>(rec + (cur.start - 1), top.err_after, top.sy, top.sy2, top.start);
+                    top.level = div_count<true>(top.sy, (double)(cur.start - top.start));
+                }
+            }
+            cur.level = div_count<true>(cur.sy, (double)(i - cur.start + 1));
+            merge = has_top && cur.level <= top.level;  // another merge is due: next trip
+        }
+        if (!merge) {
+            const double q = div_count<true>(__dmul_rn(cur.sy, cur.sy), (double)(i - cur.start + 1));
+            const double levelerror = __dsub_rn(cur.sy2, q);
+            const double before = has_top ? top.err_after : 0.0;
+            cur.err_after = (nn && cur.level < 0.0) ? cum : __dadd_rn(levelerror, before);
+            store_rec<true>(rec + i, cur.err_after, cur.sy, cur.sy2, cur.start);
+            if (has_top) {
+                const int d = depth % kStack;
+                sh.sums[d][tid] = make_double2(top.sy, top.sy2);
+                sh.lvl_err[d][tid] = make_double2(top.level, top.err_after);
+                sh.start[d][tid] = top.start;
+                ++depth;
+                cached = cached < kStack ? cached + 1 : kStack;
+            }
+            top = cur;
+            has_top = true;
+            ++i;
+            cp_async_wait<kYRing - 1>();
+            const double yi = (double)*(const T*)&sh.y[i % kYRing][tid];
+            if (i + kYRing < n) cp_async_elem<T>(&sh.y[i % kYRing][tid], p + (long long)(i + kYRing) * step);
+            cp_async_commit();
+            cur.start = i;
+            cur.sy = yi;
+            cur.sy2 = __dmul_rn(yi, yi);
+            cur.level = yi;
+            cum = __dadd_rn(cum, cur.sy2);
+        }
+    }
+    cp_async_wait<0>();
+}
+
 // Phase 1 of the fit reconstruction (_compute_isotonic_from_index, :72-81): walk the block ends of the length-`len`
 // prefix from the back and write the block list (start, thresholded level :64-67) top-down into rec[len-1-k] — always
 // inside the part of the prefix the walk has already passed.  Returns the number of blocks K; the list, read from
 // rec[len-K] upwards, is sorted by ascending block start.
+template <bool FAST>
 __device__ __forceinline__ int list_blocks(int len, bool nn, Rec* __restrict__ rec) {
     int idx = len - 1, k = 0;
     while (idx >= 0) {
-        const int s = rec[idx].start;
-        const double level = __ddiv_rn(rec[idx].sy, (double)(idx - s + 1));
+        int s;
+        double sy;
+        if constexpr (FAST) {
+            double e_, sy2_;
+            load_rec<true>(rec + idx, e_, sy, sy2_, s);
+        } else {
+            s = rec[idx].start;
+            sy = rec[idx].sy;
+        }
+        const double level = div_count<FAST>(sy, (double)(idx - s + 1));
         Rec* out = rec + (len - 1 - k);
         out->err_after = (nn && level < 0.0) ? 0.0 : level;
         out->start = s;
@@ -216,13 +350,14 @@ __device__ __forceinline__ void fill_prefix(T* __restrict__ aux, T* __restrict__
 // 3.94 ms; 5 CTAs (89 registers, the compiler's own choice) 4.27 ms; 6 CTAs 4.51 ms; 8 CTAs with the maximum
 // shared-memory carve-out 5.50 ms.  The variant (ring depth, stack-cache depth, CTAs per SM) is a template parameter
 // pack selected by B2_OPT_UNIMODAL_VARIANT so that alternatives can be A/B-ed inside one process.
-template <typename T, int YRING, int STACK, int MINCTAS>
-__global__ void __launch_bounds__(kThreads, MINCTAS)
+template <typename T, int YRING, int STACK, int MINCTAS, bool FAST, bool DUAL, int NT = kThreads>
+__global__ void __launch_bounds__(NT, MINCTAS)
 unimodal_kernel(T* __restrict__ aux, T* __restrict__ dual, const int64_t* __restrict__ row_off, int n_groups, int R,
                 int max_rows, int nn_flag, int32_t* __restrict__ peaks, unsigned char* __restrict__ ws,
                 long long ncolslots, size_t thread_bytes) {
     extern __shared__ __align__(16) unsigned char uni_smem[];
-    SharedState<YRING, STACK>& sh = *(SharedState<YRING, STACK>*)uni_smem;
+    using SH = SharedState<YRING, STACK, NT>;
+    SH& sh = *(SH*)uni_smem;
     const int tid = threadIdx.x, lane = tid & 31;
     const int rev = lane >> 4;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -244,7 +379,12 @@ unimodal_kernel(T* __restrict__ aux, T* __restrict__ dual, const int64_t* __rest
             n = (int)(row_off[g + 1] - r0);
             base = r0 * R + c;
         }
-        if (active && n > 0) pava_prefix<T, YRING, STACK>(dual + base, R, n, rev != 0, nn, mine, sh, tid);
+        if (active && n > 0) {
+            if constexpr (DUAL)
+                pava_prefix_dual<T, YRING, STACK, SH>(dual + base, R, n, rev != 0, nn, mine, sh, tid);
+            else
+                pava_prefix<T, YRING, STACK, FAST, SH>(dual + base, R, n, rev != 0, nn, mine, sh, tid);
+        }
         __syncwarp();  // the partner lane's prefix errors are read below
         // peak: first strict minimum of errL[i] + errR[n - i], i = 0..n (:84-92); the pair splits the range.
         // error[0] = 0 is implicit, error[k] = rec[k-1].err_after.
@@ -262,12 +402,13 @@ unimodal_kernel(T* __restrict__ aux, T* __restrict__ dual, const int64_t* __rest
             };
             best = cand_at(lo);
             bidx = lo;
-            for (int i0 = lo + 1; i0 < hi; i0 += 8) {
-                double cand[8];
+            constexpr int PU = FAST ? 16 : 8;  // candidates (2 loads each) in flight per trip
+            for (int i0 = lo + 1; i0 < hi; i0 += PU) {
+                double cand[PU];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) cand[u] = (i0 + u < hi) ? cand_at(i0 + u) : 0.0;
+                for (int u = 0; u < PU; ++u) cand[u] = (i0 + u < hi) ? cand_at(i0 + u) : 0.0;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < PU; ++u) {
                     if (i0 + u < hi && cand[u] < best) {
                         best = cand[u];
                         bidx = i0 + u;
@@ -286,13 +427,52 @@ unimodal_kernel(T* __restrict__ aux, T* __restrict__ dual, const int64_t* __rest
         }
         __syncwarp();  // both lanes are done reading each other's records before they are recycled as block lists
         const int len = (active && n > 0) ? (rev ? n - bidx : bidx) : 0;
-        const int K = list_blocks(len, nn, mine);
+        const int K = list_blocks<FAST>(len, nn, mine);
         if (len > 0) fill_prefix<T>(aux + base, dual + base, R, n, len, rev != 0, mine, K);
         if (active && n > 0 && !rev && peaks) peaks[colid] = bidx;
         __syncwarp();  // scratch is reused by the next round
     }
 }
 
+// self-test of div_count<true> against the IEEE division: pseudo-random numerators over the whole exponent range (and
+// values next to the guard thresholds), every divisor 1..max_cnt
+__global__ void div_selftest_kernel(long long n, unsigned long long seed, int max_cnt, unsigned long long* mismatches) {
+    unsigned long long bad = 0;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        unsigned long long x = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);  // splitmix64
+        x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+        x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+        x ^= x >> 31;
+        unsigned long long y = x * 0xD1342543DE82EF95ull + 1;
+        const int cnt = 1 + (int)(y % (unsigned long long)max_cnt);
+        double a;
+        const int kind = (int)((y >> 40) & 7);
+        if (kind < 5) {  // moderate magnitudes (sums of data values and their squares)
+            const unsigned long long e = 1023 - 40 + ((y >> 20) % 80);
+            a = __longlong_as_double((long long)((x & 0x800FFFFFFFFFFFFFull) | (e << 52)));
+        } else if (kind < 7) {  // any finite bit pattern, zeros and subnormals included
+            a = __longlong_as_double((long long)x);
+            if (!isfinite(a)) a = 0.0;
+        } else {  // exact multiples and near-multiples of the divisor
+            a = (double)cnt * (double)(long long)((x >> 11) & 0xFFFFFFFFFFull) * (1.0 + (double)((y >> 8) & 3) * 0x1p-52);
+        }
+        const double f = div_count<true>(a, (double)cnt), r = __ddiv_rn(a, (double)cnt);
+        if (__double_as_longlong(f) != __double_as_longlong(r) && !(f == 0.0 && r == 0.0)) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+// Measured and rejected (profiles/r2_ab_unimodal_*.log, config-3 size, bit-identical results):
+//  * more resident threads through 64- or 96-thread CTAs (576 / 640 threads per SM instead of 512): 3.8 - 7.5 ms against
+//    3.24 ms — like 5, 6 and 8 CTAs of 128 threads in round 1, every thread beyond ~512 per SM costs more L1 (per-thread
+//    records) than it hides latency;
+//  * the block below the top prefetched into registers (a merge promotes it at once, the next one is requested early):
+//    4.18 ms against 3.34 ms — the extra state and instructions cost more than the hidden round trip;
+//  * a two-pass "replay" formulation (pass 1 writes only the 8-byte prefix errors, the block stack lives in the
+//    shared-memory window and spills when it outgrows it; pass 2 re-runs the PAVA on the winning prefix): less than
+//    half the DRAM bytes, but 4.01 ms against 3.30 ms on noise-like input and the same 4.63 ms on peak-like input — the
+//    kernel is bound by the serial dependency chain per thread, not by DRAM, so a second pass over part of the column
+//    costs more than the traffic it saves.
 size_t per_thread_bytes(int max_rows) {
     return (size_t)max_rows * 32;  // one Rec per element
 }
@@ -309,6 +489,15 @@ size_t b2_unimodal_workspace_bytes(int n_groups, int R, int max_rows) {
     return (size_t)total * 2 * per_thread_bytes(max_rows) + 256;
 }
 
+int b2_selftest_div_count(long long n, unsigned long long seed, int max_cnt, unsigned long long* mismatches_dev,
+                          void* stream) {
+    B2_REQUIRE(n >= 0 && max_cnt >= 1 && mismatches_dev, "bad arguments");
+    B2_CHECK_CUDA(cudaMemsetAsync(mismatches_dev, 0, sizeof(unsigned long long), (cudaStream_t)stream));
+    div_selftest_kernel<<<b2_num_sms() * 8, 256, 0, (cudaStream_t)stream>>>(n, seed, max_cnt, mismatches_dev);
+    B2_LAUNCH_CHECK();
+    return B2_OK;
+}
+
 int b2_prox_unimodal(void* aux, void* dual, const int64_t* row_off, int n_groups, int R, int max_rows,
                      int non_negativity, int32_t* peaks, int dtype, void* ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
@@ -321,28 +510,32 @@ int b2_prox_unimodal(void* aux, void* dual, const int64_t* row_off, int n_groups
     const long long want = (total + 15) / 16 * 16;
     if (ncolslots > want) ncolslots = want;
     B2_REQUIRE(ncolslots >= 16, "b2_prox_unimodal workspace too small (%zu bytes for max_rows=%d)", ws_bytes, max_rows);
-    B2_REQUIRE(((uintptr_t)ws) % 16 == 0, "workspace must be 16-byte aligned");
+    B2_REQUIRE(((uintptr_t)ws) % 32 == 0, "workspace must be 32-byte aligned");
     const long long threads = ncolslots * 2;  // 16 column slots per warp
-    const int grid = (int)((threads + kThreads - 1) / kThreads);
     const int variant = b2_option_value(B2_OPT_UNIMODAL_VARIANT);
-#define B2_UNI_LAUNCH(YR, SK, MC)                                                                                     \
+#define B2_UNI_LAUNCH_NT(YR, SK, MC, FAST, DUAL, NTV)                                                                 \
     B2_DISPATCH_DTYPE(dtype, {                                                                                        \
-        auto kern = unimodal_kernel<T, YR, SK, MC>;                                                                   \
-        const int smem = (int)sizeof(SharedState<YR, SK>);                                                            \
+        auto kern = unimodal_kernel<T, YR, SK, MC, FAST, DUAL, NTV>;                                                  \
+        const int smem = (int)sizeof(SharedState<YR, SK, NTV>);                                                       \
+        const int grid_nt = (int)((threads + NTV - 1) / NTV);                                                         \
         B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                 \
-        kern<<<grid, kThreads, smem, st>>>((T*)aux, (T*)dual, row_off, n_groups, R, max_rows, non_negativity, peaks,  \
-                                           (unsigned char*)ws, ncolslots, tb);                                        \
+        kern<<<grid_nt, NTV, smem, st>>>((T*)aux, (T*)dual, row_off, n_groups, R, max_rows, non_negativity, peaks,    \
+                                         (unsigned char*)ws, ncolslots, tb);                                          \
         B2_LAUNCH_CHECK();                                                                                            \
     })
+#define B2_UNI_LAUNCH(YR, SK, MC, FAST, DUAL) B2_UNI_LAUNCH_NT(YR, SK, MC, FAST, DUAL, kThreads)
     switch (variant) {
-        case 1: B2_UNI_LAUNCH(4, 8, 4); break;    // deeper stack cache, shorter ring: 40 KB per CTA
-        case 2: B2_UNI_LAUNCH(8, 8, 4); break;    // deeper stack cache: 44 KB per CTA
-        case 3: B2_UNI_LAUNCH(4, 16, 3); break;   // stack cache covers noise-like data completely: 76 KB per CTA
-        case 4: B2_UNI_LAUNCH(4, 8, 5); break;
-        case 5: B2_UNI_LAUNCH(4, 12, 4); break;
-        default: B2_UNI_LAUNCH(8, 4, 4); break;   // round-1 configuration
+        case 1: B2_UNI_LAUNCH(4, 8, 4, false, false); break;    // deeper stack cache, shorter ring: 40 KB per CTA
+        case 2: B2_UNI_LAUNCH(8, 8, 4, false, false); break;    // deeper stack cache: 44 KB per CTA
+        case 3: B2_UNI_LAUNCH(4, 16, 3, false, false); break;   // stack cache covers noise-like data completely: 76 KB per CTA
+        case 4: B2_UNI_LAUNCH(4, 8, 5, false, false); break;
+        case 5: B2_UNI_LAUNCH(4, 12, 4, false, false); break;
+        case 6: B2_UNI_LAUNCH(4, 8, 4, true, false); break;     // variant 1 + Markstein division + 256-bit record I/O
+        case 9: B2_UNI_LAUNCH(4, 8, 4, true, true); break;   // variant 6 + merge and finalise in one trip
+        default: B2_UNI_LAUNCH(8, 4, 4, false, false); break;   // round-1 configuration
     }
 #undef B2_UNI_LAUNCH
+#undef B2_UNI_LAUNCH_NT
     return B2_OK;
 }
 

@@ -361,7 +361,32 @@ def test_l2ball_groups():
             np.testing.assert_allclose(dual.cpu().numpy(), V - ref, rtol=1e-12, atol=1e-14)
 
 
-def test_unimodal_golden_bit_exact(golden_dir):
+@pytest.fixture(params=[None, 1, 6], ids=["variant_default", "variant_1", "variant_6"])
+def unimodal_variant(request):
+    """Runs a unimodal test under the default kernel variant, the IEEE-division one (1) and the reciprocal-division /
+    256-bit record one (6): bit-exactness must not depend on the variant."""
+    from matcouply_b200 import _lib
+
+    lib = _lib.load()
+    before = lib.b2_get_option(_lib.OPT_UNIMODAL_VARIANT)
+    if request.param is not None:
+        lib.b2_set_option(_lib.OPT_UNIMODAL_VARIANT, request.param)
+    yield request.param
+    lib.b2_set_option(_lib.OPT_UNIMODAL_VARIANT, before)
+
+
+def test_exact_division_by_counts_selftest():
+    """The division of the unimodal kernel's fast variants (reciprocal + two Markstein corrections) equals the IEEE
+    division bit for bit: 2^28 pseudo-random numerators (all exponents, zeros, subnormals, near-multiples) x divisors
+    1..4096 on the device."""
+    _lib, _ops, O = _imports()
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for seed, max_cnt in ((1, 4096), (2, 17), (3, 1 << 20)):
+        _lib.call("b2_selftest_div_count", 1 << 28, seed, max_cnt, bad.data_ptr(), _ops._stream())
+        assert int(bad.item()) == 0, (seed, max_cnt, int(bad.item()))
+
+
+def test_unimodal_golden_bit_exact(golden_dir, unimodal_variant):
     """Unimodal regression: fits AND peak indices bit-identical to the reference on its own golden vectors."""
     _lib, _ops, O = _imports()
     g = np.load(os.path.join(golden_dir, "operators.npz"))
@@ -378,7 +403,7 @@ def test_unimodal_golden_bit_exact(golden_dir):
         np.testing.assert_array_equal(dual.cpu().numpy(), y - fit)
 
 
-def test_unimodal_ragged_groups_vs_oracle_and_sklearn():
+def test_unimodal_ragged_groups_vs_oracle_and_sklearn(unimodal_variant):
     _lib, _ops, O = _imports()
     from sklearn.isotonic import IsotonicRegression
 
