@@ -374,7 +374,7 @@ class AOADMMEngine:
             want_x1 and self.fuse_local and self.update_B and I > 0 and N > 0 and dt == torch.float64
             and self.n_inner > 0 and len(d1) <= 2 and all(d[0] in (_lib.PEN_NONNEG, _lib.PEN_BOX, _lib.PEN_L1) for d in d1)
             and N >= 4 * R * I and _ops.xstream_fused_supported(K, R, dt, len(d1)))
-        self.z_fresh = self.g_fresh = False
+        self.z_fresh = self.g_fresh = self.ctc_fresh = False
         if self.fused_x1:
             self.G = z(I, K, R)
             self.fws = _ops.FusedWorkspace(packed.row_offsets, K, R, dev)
@@ -416,7 +416,7 @@ class AOADMMEngine:
     def load_state(self, A, B_is, C, auxes, duals):
         """A: I x R, B_is: list of J_i x R (or packed N x R), C: K x R; auxes/duals: 3 lists as in ADMMVars."""
         st = self.modes
-        self.z_fresh = self.g_fresh = False
+        self.z_fresh = self.g_fresh = self.ctc_fresh = False
         st[0].x = self._up(A)
         st[1].x = self._up_rows(B_is)
         st[2].x = self._up(C)
@@ -463,7 +463,7 @@ class AOADMMEngine:
         gen = torch.Generator(device=self.dev).manual_seed(int(seed))
         rnd = lambda *s: torch.rand(s, dtype=self.dtype, device=self.dev, generator=gen)  # noqa: E731
         st, R = self.modes, self.R
-        self.z_fresh = self.g_fresh = False
+        self.z_fresh = self.g_fresh = self.ctc_fresh = False
         st[0].x, st[1].x, st[2].x = rnd(self.I, R), rnd(self.N, R), rnd(self.K, R)
         for m, n in ((0, self.I), (1, self.N), (2, self.K)):
             st[m].aux, st[m].dual = [], []
@@ -683,7 +683,9 @@ class AOADMMEngine:
         """admm_update_B (decomposition.py:222-292); rhs_i = Y_i o a_i with the cached Y = X C."""
         st, R, I = self.modes[1], self.R, self.I
         A, C = self.modes[0].x, self.modes[2].x
-        _ops.gram(C, self.K, self.CtC, self.ws)
+        if not self.ctc_fresh:  # refresh_products() of the previous iteration already left C^T C of this C behind
+            _ops.gram(C, self.K, self.CtC, self.ws)
+            self.ctc_fresh = True
         _ops.scale_gram(self.CtC, A, self.lhsB)
         _ops.rho_from_trace(self.lhsB, I, R, self.scale, self.rhoB, self.rho_max if self.const_B else None)
         if self.const_B:
@@ -811,6 +813,7 @@ class AOADMMEngine:
     def step_C(self):
         """admm_update_C (decomposition.py:295-344); one X pass: Z = X^T (B o a)."""
         st, R, K = self.modes[2], self.R, self.K
+        self.ctc_fresh = False  # C changes below
         if self.z_fresh:  # Z = sum_i G_i diag(a_i) came out of the fused pass (A has not changed since)
             self.z_fresh = False
         else:
@@ -839,6 +842,7 @@ class AOADMMEngine:
         (decomposition.py:138-158).  Also what the fit term needs (:446-449)."""
         C, B = self.modes[2].x, self.modes[1].x
         _ops.gram(C, self.K, self.CtC, self.ws)
+        self.ctc_fresh = True
         _ops.hadamard_bcast(self.BtB, self.CtC, self.I, self.R, self.cross)
         if self.g_fresh:
             # G_i = X_i^T B_i of the current B is at hand (fused pass): diag(B_i^T X_i C) = colsum_k(G_i o C), no X pass.
@@ -1069,14 +1073,14 @@ class AOADMMEngine:
             self._graphs = {}
         entry = self._graphs.get(key)
         if entry is None:
-            flags = (self.w_fresh, self.z_fresh, self.g_fresh, getattr(self, "pf2_deferred", None),
+            flags = (self.w_fresh, self.z_fresh, self.g_fresh, self.ctc_fresh, getattr(self, "pf2_deferred", None),
                      getattr(self, "pf2_fresh", None))
             g = torch.cuda.CUDAGraph()
             torch.cuda.synchronize()
             with torch.cuda.graph(g):
                 self.outer_iteration()
                 launched = self._launch_diagnostics() if with_diagnostics else None
-            after = (self.w_fresh, self.z_fresh, self.g_fresh, getattr(self, "pf2_deferred", None),
+            after = (self.w_fresh, self.z_fresh, self.g_fresh, self.ctc_fresh, getattr(self, "pf2_deferred", None),
                      getattr(self, "pf2_fresh", None))
             if flags != after:
                 raise RuntimeError("graph capture outside the steady state of the engine")
