@@ -463,6 +463,8 @@ __global__ void div_selftest_kernel(long long n, unsigned long long seed, int ma
 }
 
 // Measured and rejected (profiles/r2_ab_unimodal_*.log, config-3 size, bit-identical results):
+//  * the reciprocals 1/count from an L1-resident table instead of __drcp_rn's 6 dependent operations: 3.89 ms against
+//    3.37 ms — one more memory operation per division costs more than the arithmetic it replaces;
 //  * more resident threads through 64- or 96-thread CTAs (576 / 640 threads per SM instead of 512): 3.8 - 7.5 ms against
 //    3.24 ms — like 5, 6 and 8 CTAs of 128 threads in round 1, every thread beyond ~512 per SM costs more L1 (per-thread
 //    records) than it hides latency;
