@@ -179,17 +179,21 @@ __global__ void reduce_stats_final_kernel(const double* __restrict__ part, int b
 template <typename T>
 __global__ void fit_terms_kernel(const T* __restrict__ rhs, const T* __restrict__ cross, const T* __restrict__ A,
                                  int n_groups, int R, double* __restrict__ part) {
+    // one warp per slice: the R x R cross matrix is read with coalesced loads (lane = flat element), a_g is held one
+    // entry per lane and broadcast with shuffles (a thread per slice walked 2 KB-strided rows: 49 us at 4 096 slices)
     __shared__ double scratch[32];
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
     double inner = 0.0, quad = 0.0;
-    for (int g = blockIdx.x * blockDim.x + threadIdx.x; g < n_groups; g += gridDim.x * blockDim.x) {
-        const T* a = A + (size_t)g * R;
+    for (int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; g < n_groups; g += warps) {
+        const double al = lane < R ? (double)A[(size_t)g * R + lane] : 0.0;
+        if (lane < R) inner += (double)rhs[(size_t)g * R + lane] * al;
         const T* cr = cross + (size_t)g * R * R;
-        for (int r = 0; r < R; ++r) {
-            const double ar = (double)a[r];
-            inner += (double)rhs[(size_t)g * R + r] * ar;
-            double s = 0.0;
-            for (int c = 0; c < R; ++c) s += (double)cr[r * R + c] * (double)a[c];
-            quad += ar * s;
+        for (int e0 = 0; e0 < R * R; e0 += 32) {
+            const int e = e0 + lane;
+            const int r = e < R * R ? e / R : 0, c = e < R * R ? e - r * R : 0;
+            const double ar = __shfl_sync(0xffffffffu, al, r), ac = __shfl_sync(0xffffffffu, al, c);
+            if (e < R * R) quad += ar * ((double)cr[e] * ac);
         }
     }
     inner = block_sum(inner, scratch);
@@ -275,7 +279,7 @@ int b2_reduce_stats(const void* x, const void* y, long long n, double* out, int 
 int b2_fit_terms(const void* rhs, const void* cross, const void* A, int n_groups, int R, double* out, int dtype,
                  void* ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
-    int blocks = (n_groups + 127) / 128;
+    int blocks = (n_groups + 3) / 4;  // 4 warps per block, one warp per slice
     if (blocks > b2_num_sms() * 4) blocks = b2_num_sms() * 4;
     if (blocks < 1) blocks = 1;
     B2_REQUIRE(ws_bytes >= (size_t)blocks * 2 * sizeof(double), "b2_fit_terms workspace too small");

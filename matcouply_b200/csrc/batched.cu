@@ -159,72 +159,92 @@ __device__ void eig_inverse_warp(double* __restrict__ G, double* __restrict__ Q,
         }
 }
 
+// Shared-memory layout: row stride LD = R | 1 (odd), so that a warp access to one COLUMN (lane = row) and to one ROW
+// (lane = column) are both bank-conflict free.  The right-looking trailing update runs with lane = column j:
+// L[i][j] -= L[i][k] * L[j][k] for i = k+1..R-1 is one broadcast load + one FMA on a conflict-free row access per i
+// (the first version walked lane = row with a lane-dependent inner loop and a 16-way conflicted stride R).  Every
+// element sees the same operations in the same order as before (k ascending, one FMA each): bit-identical results.
 template <typename T>
 __global__ void factor_batch_kernel(const T* __restrict__ lhs, int n_groups, int R, T* __restrict__ rho,
                                     const T* __restrict__ rho_max, int n_reg, double l2, T* __restrict__ Minv) {
-    extern __shared__ double fsm[];  // per warp: L (R*R) + Z (R*R)
+    extern __shared__ double fsm[];  // per warp: L (R*LD) + Z (R*LD)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = blockIdx.x * kFactorWarps + warp;
     if (g >= n_groups) return;
-    double* L = fsm + (size_t)warp * 2 * R * R;
-    double* Z = L + R * R;
+    const int LD = R | 1;
+    double* L = fsm + (size_t)warp * 2 * R * LD;
+    double* Z = L + R * LD;
     double rho_g = rho_max ? (double)rho_max[0] : (double)rho[g];
     if (rho_max && lane == 0) rho[g] = (T)rho_g;
     const double shift = rho_g * n_reg + l2;
     const T* src = lhs + (size_t)g * R * R;
     for (int e = lane; e < R * R; e += 32) {
         const int r = e / R, c = e - r * R;
-        L[e] = (double)src[e] + (r == c ? shift : 0.0);
+        L[r * LD + c] = (double)src[e] + (r == c ? shift : 0.0);
     }
     __syncwarp();
-    // in-place Cholesky (lower), right-looking; lane owns row `lane`
+    // in-place Cholesky (lower), right-looking
     bool spd = true;
     for (int k = 0; k < R; ++k) {
-        const double dd = L[k * R + k];
+        const double dd = L[k * LD + k];
         if (!(dd > 0.0)) {  // same value in every lane: warp-uniform exit
             spd = false;
             break;
         }
         const double d = sqrt(dd);
         __syncwarp();
-        if (lane == k) L[k * R + k] = d;
-        if (lane > k && lane < R) L[lane * R + k] /= d;
+        if (lane == k) L[k * LD + k] = d;
+        if (lane > k && lane < R) L[lane * LD + k] /= d;  // lane = row: column k
         __syncwarp();
-        if (lane > k && lane < R) {
-            const double lik = L[lane * R + k];
-            for (int j = k + 1; j <= lane; ++j) L[lane * R + j] -= lik * L[j * R + k];
+        const bool upd = lane > k && lane < R;
+        const double ljk = upd ? L[lane * LD + k] : 0.0;  // lane = column j of the trailing block
+        for (int i = k + 1; i < R; ++i) {
+            const double lik = L[i * LD + k];  // broadcast
+            if (upd && lane <= i) L[i * LD + lane] -= lik * ljk;
         }
         __syncwarp();
     }
     if (!spd) {  // not positive definite: inverse through the eigen-decomposition, like the reference's SVD route
         __syncwarp();
-        for (int e = lane; e < R * R; e += 32) {
+        for (int e = lane; e < R * R; e += 32) {  // eig_inverse_warp works on dense R x R scratch
             const int r = e / R, c = e - r * R;
             L[e] = 0.5 * ((double)src[e] + (double)src[c * R + r]) + (r == c ? shift : 0.0);
         }
         __syncwarp();
-        eig_inverse_warp<T>(L, Z, R, lane, Minv + (size_t)g * R * R);
+        eig_inverse_warp<T>(L, L + R * R, R, lane, Minv + (size_t)g * R * R);
         return;
     }
-    // Z = L^-1 (lower): lane = column c, forward substitution
+    // Z = L^-1 (lower): lane = column c, forward substitution in its right-looking form: once Z[i][c] is known, the
+    // R - i - 1 updates Z[i'][c] -= L[i'][i] Z[i][c] (i' > i) are independent of each other (the left-looking form is
+    // one dependent load-FMA chain per entry).  Every entry still receives its subtractions in ascending j, one FMA
+    // each, so the values are those of the left-looking loop bit for bit.
     if (lane < R) {
         const int c = lane;
-        for (int i = 0; i < R; ++i) {
-            double s = (i == c) ? 1.0 : 0.0;
-            for (int j = c; j < i; ++j) s -= L[i * R + j] * Z[j * R + c];
-            Z[i * R + c] = (i < c) ? 0.0 : s / L[i * R + i];
+        for (int i = 0; i < R; ++i) Z[i * LD + c] = (i == c) ? 1.0 : 0.0;
+        for (int i = c; i < R; ++i) {
+            const double zi = Z[i * LD + c] / L[i * LD + i];
+            Z[i * LD + c] = zi;
+            for (int ip = i + 1; ip < R; ++ip) Z[ip * LD + c] -= L[ip * LD + i] * zi;
         }
     }
     __syncwarp();
-    // Minv = Z^T Z ; lane = column s
+    // Minv = Z^T Z ; lane = column s; four rows r at a time (independent accumulator chains).  The sums run over all
+    // k: Z is lower triangular with exact zeros above the diagonal, and an FMA with a zero factor leaves the
+    // accumulator unchanged, so this equals the sum from k = max(r, s).
     if (lane < R) {
         const int s = lane;
         T* dst = Minv + (size_t)g * R * R;
-        for (int r = 0; r < R; ++r) {
-            double acc = 0.0;
-            const int k0 = r > s ? r : s;
-            for (int k = k0; k < R; ++k) acc += Z[k * R + r] * Z[k * R + s];
-            dst[r * R + s] = (T)acc;
+        for (int r0 = 0; r0 < R; r0 += 4) {
+            double acc[4] = {0.0, 0.0, 0.0, 0.0};
+            for (int k = r0; k < R; ++k) {
+                const double zks = Z[k * LD + s];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (r0 + u < R) acc[u] += Z[k * LD + r0 + u] * zks;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (r0 + u < R) dst[(r0 + u) * R + s] = (T)acc[u];
         }
     }
 }
@@ -340,7 +360,7 @@ extern "C" {
 int b2_gram(const void* M, long long n, int R, int ld, void* G, int dtype, void* ws, size_t ws_bytes, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
-    int blocks = (int)((n + 1023) / 1024);
+    int blocks = (int)((n + 63) / 64);  // a factor matrix has few rows (K): spread them instead of walking them in one CTA
     const int cap = b2_num_sms() * 2;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
@@ -397,7 +417,7 @@ int b2_factor_batch(const void* lhs, int n_groups, int R, void* rho, const void*
     cudaStream_t st = (cudaStream_t)stream;
     B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
     if (n_groups == 0) return B2_OK;
-    const size_t smem = (size_t)kFactorWarps * 2 * R * R * sizeof(double);
+    const size_t smem = (size_t)kFactorWarps * 2 * R * (R | 1) * sizeof(double);
     B2_DISPATCH_DTYPE(dtype, {
         auto kern = factor_batch_kernel<T>;
         B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
