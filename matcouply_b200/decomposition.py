@@ -451,9 +451,11 @@ def cmf_aoadmm(
     the global problem, the initial state is drawn for the GLOBAL problem from ``random_state`` (so the run equals the
     unsharded one) and cut to the shard, and a few small all-reduces per outer iteration couple the ranks;
     ``gather_factors`` returns the complete ``A`` / ``B_is`` on every rank instead of the local share.
-    ``use_cuda_graph=True``: replay the steady-state outer iteration as one CUDA graph (single GPU, small problems).
-    Off by default: measured on the README configuration the iteration is bound by the ~90 DEPENDENT tiny kernels
-    (0.76 ms per iteration eager and replayed alike), not by host launch overhead, and the capture costs ~0.15 s.
+    ``use_cuda_graph``: replay the steady-state outer iteration as one CUDA graph.  ``None`` (default) = the engine's
+    policy: on for single-GPU problems without PARAFAC2 whose penalties are single kernels on the main stream and
+    ``n_iter_max >= 16`` (config 1: 2.01 -> 1.91 ms per iteration; with PARAFAC2 the replay does not pay — README
+    configuration 0.76 ms eager and replayed alike, config 3 slower); ``True`` = wherever the engine allows it
+    (single GPU, data <= 1 GB or no PARAFAC2); ``False`` = never.  Same kernels on the same buffers: bit-identical.
     """
     import torch
 
@@ -652,11 +654,22 @@ def _cmf_aoadmm_on_device(
     message = "MAXIMUM NUMBER OF ITERATIONS REACHED"
     it = -1
     want_diag = bool(tol or absolute_tol or return_errors)
-    use_graph = bool(use_cuda_graph) and engine.graph_eligible()
+    # use_cuda_graph: True = where the engine allows it, False = never, None = the engine's own policy (graph_auto:
+    # single-GPU CMF-type problems, and only when the capture can pay for itself)
+    if use_cuda_graph is None:
+        use_graph = n_iter_max >= 16 and engine.graph_auto()
+    else:
+        use_graph = bool(use_cuda_graph) and engine.graph_eligible()
     for it in range(n_iter_max):
         launched = None
         if use_graph and it >= 2:  # steady state: replay the captured launch sequence (see AOADMMEngine.graph_iteration)
-            launched = engine.graph_iteration(want_diag)
+            try:
+                launched = engine.graph_iteration(want_diag)
+            except Exception:
+                if use_cuda_graph:  # asked for explicitly: report
+                    raise
+                engine._graph_failed, use_graph = True, False  # own policy: fall back to issuing the launches one by one
+                engine.outer_iteration()
         else:
             engine.outer_iteration()
 

@@ -121,12 +121,19 @@ def test_fp64_trajectory_config1_single_read_pass(rank, monkeypatch):
         for k, A_o, B_o, C_o in traj:
             calls.update(fused=0, y=0, z=0)
             cmf, diag = cmf_aoadmm(X, rank, n_iter_max=k, tol=None, absolute_tol=None, random_state=0,
-                                   return_errors=True, **cfg["kw"])
+                                   return_errors=True, use_cuda_graph=False, **cfg["kw"])  # eager: the launches are counted
             assert (calls["fused"], calls["y"], calls["z"]) == (k, 1, 0)  # + the Y pass of the initial fit
             _, (A, B_is, C) = cmf
             errs = (rel(A, A_o), rel(np.concatenate(B_is, 0), B_o), rel(C, C_o))
             worst = max(worst, *errs)
             assert max(errs) < 1e-8, (rank, k, errs)
+        # the same 50 iterations with the engine's own launch policy (CUDA-graph replay from the third iteration on):
+        # same kernels on the same buffers, bit-identical to the eager run
+        cmf_g, diag_g = cmf_aoadmm(X, rank, n_iter_max=max(CHECKPOINTS), tol=None, absolute_tol=None, random_state=0,
+                                   return_errors=True, **cfg["kw"])
+        np.testing.assert_array_equal(cmf_g[1][2], cmf[1][2])
+        np.testing.assert_array_equal(np.concatenate(cmf_g[1][1], 0), np.concatenate(cmf[1][1], 0))
+        np.testing.assert_array_equal(diag_g.regularized_loss, diag.regularized_loss)
     finally:
         _engine.FUSION_DEFAULTS.update(x1=default)
     np.testing.assert_allclose(diag.regularized_loss, o["regularized_loss"], rtol=1e-8)
