@@ -12,17 +12,22 @@
 // (b2_slice_gdot).  The reference reads X three times per outer iteration, the two-pass schedule of xstream.cu twice.
 //
 // Work decomposition: persistent grid, one CTA per SM, every slice is owned by ONE CTA (host-side balanced schedule),
-// so G_i and B_i^T B_i need no cross-CTA reduction.  A slice is processed in chunks of 64 rows; per chunk
+// so G_i and B_i^T B_i need no cross-CTA reduction.  A slice is processed in chunks of 128 rows; per chunk
 //   Y-phase  the producer warp streams X[chunk, :] through the TMA ring (stage = 8 swizzled boxes [32 rows x 16
-//            doubles]: 2 row halves x 4 k-quarters); consumer warp (rh, kq) contracts its box with DMMA.8x8x4 against
-//            the factor matrix C resident in shared memory; the 4 k-quarter partials are summed through shared memory
-//   B-update every consumer warp owns 8 rows of the chunk in the MMA accumulator layout and runs the whole inner loop
-//            in registers (same formulation as admm_mma.cu), writes x / aux / dual to HBM and the new rows to shared
-//            memory
-//   Z-phase  the producer re-streams the same 64 rows (stage = 8 boxes [32 rows x 16 doubles] = 128 k's; the chunk is
-//            256 KB at K = 512, so this read is served by L2 — 148 CTAs keep 37 MB live) and consumer warp w
-//            accumulates G_i[k-block + 16 w .. + 16][:] in registers.
-// fp64 only (DMMA); the register-resident G_i / Z accumulators bound K * ceil(R/8) <= 1024.
+//            doubles]: 4 row quarters x 2 k-halves, 32 k's per stage; loads marked L2 evict_last); consumer warp (rq, kh)
+//            contracts its box with DMMA.8x8x4 against the factor matrix C resident in shared memory; the 2 k-half
+//            partials meet in shared memory
+//   B-update every consumer warp owns 2 x 8 rows of the chunk in the MMA accumulator layout and runs the whole inner
+//            loop in registers (same formulation as admm_mma.cu; the two row blocks are independent DMMA chains, the
+//            fragments of Minv_g stay in registers), writes x / aux / dual to HBM and stages the new rows in shared
+//            memory (the tile B_i^T B_i is accumulated from doubles as the operand of the Z-phase)
+//   Z-phase  the producer re-streams the same 128 rows (stage = 8 boxes [32 rows x 16 doubles] = 128 k's, loads marked
+//            evict_first; the chunk is 512 KB at K = 512, so this read is served by L2 — 148 CTAs keep 74 MB live, ncu:
+//            5.0 GB of DRAM reads for 4.29 GB of X) and consumer warp w accumulates G_i[k-block + 16 w .. + 16][:] in
+//            registers.
+// The per-slice operands (Minv_g, a_g, rho_g) of the NEXT slice are fetched with cp.async while the current one runs.
+// fp64 only (DMMA); the register-resident G_i accumulators bound K * ceil(R/8) <= 1024.  Measured and rejected: the
+// B-update on two extra warps next to the contractions.
 #include <stddef.h>
 
 #include "admm_common.cuh"
