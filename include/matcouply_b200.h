@@ -60,8 +60,10 @@ enum { B2_OPT_PF2_ROWPASS_MMA = 0 /* row pass of b2_pf2_rowpass: 0 = shuffle ker
                                      alone or with non-negativity) */,
        B2_OPT_POLAR_WARP = 1 /* polar step of b2_pf2_polar: 2 (default) = warp per slice, Jacobi in registers; 1 = warp per slice in shared memory; 0 = CTA per slice */,
        B2_OPT_ADMM_LOCAL_MMA = 2 /* DMMA formulation of b2_admm_local (CTA-per-slice path) */,
-       B2_OPT_XSTREAM_HYBRID = 3 /* DMMA blocks + DFMA remainder columns in the fp64 X-stream kernels (R = 8b+1..4);
-                                    default OFF: measured 2-6 % slower than padding to a whole block */,
+       B2_OPT_XSTREAM_HYBRID = 3 /* fp64 X-stream kernel variants: 0 (default) = padded DMMA column blocks, Y kernel with 12
+                                    consumer warps from R = 17 on (fp64-pipe-bound ranks) and 8 below; 1 = DMMA blocks +
+                                    DFMA remainder columns (R = 8b+1..4; measured 2-6 % slower than padding); 2 = Y kernel
+                                    always with 12 consumer warps; 3 = always 8 */,
        B2_OPT_UNIMODAL_VARIANT = 4 /* b2_prox_unimodal: (column ring depth, shared-memory stack-cache depth, CTAs per
                                       SM) of the PAVA kernel: 0 = (8, 4, 4) round 1, 1 = (4, 8, 4), 2 = (8, 8, 4), 3 = (4, 16, 3),
                                       4 = (4, 8, 5), 5 = (4, 12, 4); 6 = variant 1 with the exact reciprocal-based division

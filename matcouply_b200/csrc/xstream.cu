@@ -22,10 +22,12 @@ constexpr int kThreads = kConsumerThreads + 32;  // + producer warp
 // Stage layout (1024-byte aligned): NBOX swizzled boxes [TM rows x 128 B] of X, then the C chunk [KC x LDC].
 // FMA path: 128-row tiles, 2 boxes per stage.  DMMA path: 256-row tiles (4 m-blocks = 12..16 independent accumulator
 // chains per warp: the DMMA pipe needs that much ILP with only 8 consumer warps per SM), 1 box per stage.
-template <typename T, bool DMMA>
+template <typename T, bool DMMA, int CW = 8>
 struct YCfg {
-    static constexpr int TM = DMMA ? 256 : 128;       // rows per tile
-    static constexpr int MB = TM / 64;                // 8-row m-blocks per consumer warp (DMMA path)
+    static constexpr int TM = DMMA ? 32 * CW : 128;   // rows per tile (DMMA: 32 rows = 4 m-blocks per consumer warp)
+    static constexpr int RBOX = TM > 256 ? 128 : TM;  // rows per TMA box (a box dimension is limited to 256)
+    static constexpr int NRB = TM / RBOX;             // row boxes per k-box
+    static constexpr int MB = DMMA ? 4 : TM / 64;     // 8-row m-blocks per consumer warp (DMMA path)
     static constexpr int EPB = 128 / (int)sizeof(T);  // elements per 128-byte box row
     static constexpr int NBOX = DMMA ? 1 : 2;
     static constexpr int KC = NBOX * EPB;  // K-chunk per stage
@@ -46,11 +48,13 @@ struct YCfg {
 // C[k(t)][8*NBLK + e], which sits in the 4 pad words of the staged C row) and summed over the 4 t-lanes at the end
 // of the tile.  DMMA and DFMA share the fp64 units (b2_microbench_flops kind 3), so what this buys is the saved
 // padding: R = 20 costs 20 columns of pipe time instead of 24.
-template <typename T, int CT, bool DMMA, int NBLK, int EX>
-__global__ void __launch_bounds__(kThreads, 1)
+// CW = consumer warps (DMMA path only: 8, or 12 = three per SM sub-partition for more issue slack around the DMMAs)
+template <typename T, int CT, bool DMMA, int NBLK, int EX, int CW = 8>
+__global__ void __launch_bounds__((CW + 1) * 32, 1)
 xstream_y_kernel(const __grid_constant__ CUtensorMap tmap_x, const T* __restrict__ Cp, T* __restrict__ Y, long long N,
                  int R, int Kp, int LDC, int num_tiles, int stages) {
-    using Cfg = YCfg<T, DMMA>;
+    using Cfg = YCfg<T, DMMA, CW>;
+    static_assert(DMMA || CW == 8, "the FMA path is laid out for 8 consumer warps");
     constexpr int TM = Cfg::TM, EPB = Cfg::EPB, NBOX = Cfg::NBOX, KC = Cfg::KC, MB = Cfg::MB;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     // carve: [stages x (X boxes | C chunk)] | full[stages] | empty[stages]
@@ -65,14 +69,14 @@ xstream_y_kernel(const __grid_constant__ CUtensorMap tmap_x, const T* __restrict
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kConsumerThreads / 32);
+            mbar_init(&empty[s], CW);
         }
         fence_mbar_init();
     }
     __syncthreads();
     const int kchunks = Kp / KC;
 
-    if (warp == kConsumerThreads / 32) {
+    if (warp == CW) {
         // ===== producer warp: one elected lane issues all TMA traffic =====
         if (lane == 0) {
             prefetch_tmap(&tmap_x);
@@ -86,7 +90,10 @@ xstream_y_kernel(const __grid_constant__ CUtensorMap tmap_x, const T* __restrict
                     mbar_arrive_expect_tx(&full[s], Cfg::X_BYTES + c_bytes);
 #pragma unroll
                     for (int b = 0; b < NBOX; ++b)
-                        tma_load_2d(st + b * Cfg::BOX_BYTES, &tmap_x, kc * KC + b * EPB, row0, &full[s]);
+#pragma unroll
+                        for (int rb = 0; rb < Cfg::NRB; ++rb)  // a k-box of TM rows = NRB TMA boxes of RBOX rows
+                            tma_load_2d(st + b * Cfg::BOX_BYTES + rb * Cfg::RBOX * 128, &tmap_x, kc * KC + b * EPB,
+                                        row0 + rb * Cfg::RBOX, &full[s]);
                     bulk_load_1d(st + Cfg::X_BYTES, Cp + (size_t)kc * KC * LDC, c_bytes, &full[s]);
                     if (++s == stages) {
                         s = 0;
@@ -572,7 +579,7 @@ __global__ void reduce_double_kernel(const double* __restrict__ part, int n, dou
 // otherwise R is padded up to whole tensor-core blocks.
 void y_dmma_split(int R, int* NBLK, int* EX) {
     const int nb = R / 8, rem = R % 8;
-    if (nb >= 1 && rem >= 1 && rem <= 4 && b2_option_value(B2_OPT_XSTREAM_HYBRID)) {
+    if (nb >= 1 && rem >= 1 && rem <= 4 && b2_option_value(B2_OPT_XSTREAM_HYBRID) == 1) {
         *NBLK = nb;
         *EX = rem <= 2 ? 2 : 4;
     } else {
@@ -590,20 +597,20 @@ int launch_y_fma(const CUtensorMap& map, const T* Cp, T* Y, long long N, int R, 
     B2_LAUNCH_CHECK();
     return B2_OK;
 }
-template <int NBLK, int EX>
+template <int NBLK, int EX, int CW = 8>
 int launch_y_dmma(const CUtensorMap& map, const double* Cp, double* Y, long long N, int R, int Kp, int LDC, int num_tiles,
                   int grid, int stages, size_t smem, cudaStream_t st) {
-    auto kern = xstream_y_kernel<double, 1, true, NBLK, EX>;
+    auto kern = xstream_y_kernel<double, 1, true, NBLK, EX, CW>;
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kThreads, smem, st>>>(map, Cp, Y, N, R, Kp, LDC, num_tiles, stages);
+    kern<<<grid, (CW + 1) * 32, smem, st>>>(map, Cp, Y, N, R, Kp, LDC, num_tiles, stages);
     B2_LAUNCH_CHECK();
     return B2_OK;
 }
 
-template <typename T, bool DMMA>
+template <typename T, bool DMMA, int CW = 8>
 int xstream_y_impl(const void* X, long long N, int K, int ldx, const void* C, int R, void* Y, void* ws, size_t ws_bytes,
                    int max_ctas, cudaStream_t st) {
-    using Cfg = YCfg<T, DMMA>;
+    using Cfg = YCfg<T, DMMA, CW>;
     const int dtype = sizeof(T) == 8 ? B2_F64 : B2_F32;
     constexpr bool dmma = DMMA;
     B2_REQUIRE(R >= 1 && R <= B2_MAX_RANK, "rank %d outside [1, %d]", R, B2_MAX_RANK);
@@ -621,7 +628,7 @@ int xstream_y_impl(const void* X, long long N, int K, int ldx, const void* C, in
     B2_LAUNCH_CHECK();
 
     alignas(64) CUtensorMap map;
-    int rc = encode_x_map(&map, X, N, K, ldx, dtype, Cfg::TM);
+    int rc = encode_x_map(&map, X, N, K, ldx, dtype, Cfg::RBOX);
     if (rc != B2_OK) return rc;
     const int num_tiles = (int)((N + Cfg::TM - 1) / Cfg::TM);
     const uint32_t c_bytes = (uint32_t)(Cfg::KC * LDC * sizeof(T));
@@ -638,9 +645,11 @@ int xstream_y_impl(const void* X, long long N, int K, int ldx, const void* C, in
         const double* Cp = (const double*)ws;
         double* Yd = (double*)Y;
 #define B2_Y_CASE(NB, E) \
-    if (NBLK == NB && EX == E) return launch_y_dmma<NB, E>(map, Cp, Yd, N, R, Kp, LDC, num_tiles, grid, stages, smem, st);
+    if (NBLK == NB && EX == E) return launch_y_dmma<NB, E, CW>(map, Cp, Yd, N, R, Kp, LDC, num_tiles, grid, stages, smem, st);
         B2_Y_CASE(1, 0) B2_Y_CASE(2, 0) B2_Y_CASE(3, 0) B2_Y_CASE(4, 0)
-        B2_Y_CASE(1, 2) B2_Y_CASE(1, 4) B2_Y_CASE(2, 2) B2_Y_CASE(2, 4) B2_Y_CASE(3, 2) B2_Y_CASE(3, 4)
+        if constexpr (CW == 8) {
+            B2_Y_CASE(1, 2) B2_Y_CASE(1, 4) B2_Y_CASE(2, 2) B2_Y_CASE(2, 4) B2_Y_CASE(3, 2) B2_Y_CASE(3, 4)
+        }
 #undef B2_Y_CASE
         B2_REQUIRE(false, "xstream_y: no kernel for NBLK=%d EX=%d", NBLK, EX);
     }
@@ -817,6 +826,14 @@ int b2_xstream_y(const void* X, long long n_rows, int K, int ldx, const void* C,
                  size_t ws_bytes, int variant, int max_ctas, void* stream) {
     if (variant == B2_VARIANT_DMMA) {
         B2_REQUIRE(dtype == B2_F64, "the DMMA variant exists for fp64 only");
+        // 12 consumer warps (384-row tiles, three warps per SM sub-partition) where the kernel is bound by the fp64
+        // tensor pipe, i.e. from three column blocks on (R >= 17): the third warp fills issue gaps around the DMMAs
+        // (R = 20: 7.92 -> 7.4-7.6 ms per 39 GB under sustained load, R = 32: 4.03 -> 3.84 ms per 16 GB; bit-identical).
+        // HBM-bound ranks keep 8 warps and 256-row tiles (finer tile granularity over 148 CTAs).
+        const int opt = b2_option_value(B2_OPT_XSTREAM_HYBRID);
+        if (opt == 2 || (opt == 0 && R > 16))
+            return xstream_y_impl<double, true, 12>(X, n_rows, K, ldx, C, R, Y, ws, ws_bytes, max_ctas,
+                                                    (cudaStream_t)stream);
         return xstream_y_impl<double, true>(X, n_rows, K, ldx, C, R, Y, ws, ws_bytes, max_ctas, (cudaStream_t)stream);
     }
     B2_DISPATCH_DTYPE(dtype, return xstream_y_impl<T, false>(X, n_rows, K, ldx, C, R, Y, ws, ws_bytes, max_ctas,

@@ -1149,3 +1149,26 @@ def test_xstream_fused_local_limits():
     assert not _ops.xstream_fused_supported(512, 16, torch.float32, 1)
     assert not _ops.xstream_fused_supported(512, 16, torch.float64, 3)
     assert _ops.xstream_fused_supported(512, 16, torch.float64, 1)
+
+
+@pytest.mark.parametrize("N,K,R", [(1000, 512, 20), (385, 100, 17), (5000, 1030, 32), (777, 64, 24), (383, 33, 8)])
+def test_xstream_y_12_consumer_warps_bit_identical(N, K, R):
+    """The Y kernel with 12 consumer warps / 384-row tiles (the engine's choice from R = 17 on) contracts every row in
+    the same order as the 8-warp kernel: bit-identical results, ragged tails included."""
+    _lib, _ops, O = _imports()
+    lib = _lib.load()
+    rs = np.random.RandomState(N + R)
+    Xh, X = packed_x(N, K, torch.float64, rs)
+    C = dev(rs.standard_normal(size=(K, R)))
+    ws = _ops.Workspace("cuda", K, R, torch.float64)
+    outs = []
+    try:
+        for opt in (3, 2):
+            lib.b2_set_option(_lib.OPT_XSTREAM_HYBRID, opt)
+            Y = torch.full((N, R), np.nan, dtype=torch.float64, device="cuda")
+            _ops.xstream_y(X, N, K, C, Y, ws, _lib.VARIANT_DMMA)
+            outs.append(Y.cpu().numpy())
+    finally:
+        lib.b2_set_option(_lib.OPT_XSTREAM_HYBRID, 0)
+    np.testing.assert_array_equal(outs[0], outs[1])
+    np.testing.assert_allclose(outs[1], Xh @ C.cpu().numpy(), rtol=1e-11, atol=1e-11 * np.abs(outs[1]).max())
