@@ -402,10 +402,16 @@ constexpr int kZdXBytes = (kZdKZ / 16) * kZdBoxBytes;
 // EX: as in xstream_y_kernel — the remainder columns 8*NBLK .. 8*NBLK+EX-1 of W are contracted with DFMAs on the A
 // fragments (lane (g,t) holds X[row(t)][k(g)] and needs W[row(t)][8*NBLK + e]: a broadcast over g) and summed over
 // the 4 t-lanes once, after the last tile.
-template <int NBLK, int EX>
-__global__ void __launch_bounds__(kThreads, 1)
+// CW = consumer warps: 8 (warp w owns the 16 k's of box w over all 32 rows of a stage, two accumulator sets), or 16 for
+// the fp64-pipe-bound ranks: two warps per box, each on 16 of the 32 rows with ONE accumulator set — the same number of
+// DMMA chains per SM on twice as many warps (four per SM sub-partition), and every warp pair writes its own partial.
+template <int NBLK, int EX, int CW = 8>
+__global__ void __launch_bounds__((CW + 1) * 32, 1)
 xstream_z_dmma_kernel(const __grid_constant__ CUtensorMap tmap_x, const double* __restrict__ W, int ldw,
                       double* __restrict__ part, int K, int R, int num_tiles, int stages) {
+    static_assert(CW == 8 || (CW == 16 && EX == 0), "16 consumer warps: padded column blocks only");
+    constexpr int SETS = CW == 8 ? 2 : 1;   // accumulator sets per warp
+    constexpr int RGS = CW == 8 ? 4 : 2;    // 8-row groups of a stage per warp
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     const uint32_t w_bytes = (uint32_t)(kZdTM * ldw * sizeof(double));
     const uint32_t stage_bytes = (kZdXBytes + w_bytes + 1023u) & ~1023u;
@@ -417,13 +423,13 @@ xstream_z_dmma_kernel(const __grid_constant__ CUtensorMap tmap_x, const double* 
     if (tid == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], kConsumerThreads / 32);
+            mbar_init(&empty[s], CW);
         }
         fence_mbar_init();
     }
     __syncthreads();
     const int k_base = blockIdx.y * kZdKZ;
-    if (warp == kConsumerThreads / 32) {
+    if (warp == CW) {
         if (lane == 0) {
             prefetch_tmap(&tmap_x);
             int s = 0;
@@ -446,12 +452,13 @@ xstream_z_dmma_kernel(const __grid_constant__ CUtensorMap tmap_x, const double* 
         return;
     }
     const int g = lane >> 2, t = lane & 3;
-    // Two independent accumulator sets (rows r0+h+2t, h = 0 / 1, summed at the end): 4*NBLK dependent DMMA
+    const int kbox = warp & 7, half = warp >> 3;  // CW == 8: half == 0
+    // CW == 8: two independent accumulator sets (rows r0+h+2t, h = 0 / 1, summed at the end): 4*NBLK dependent DMMA
     // chains per warp instead of 2*NBLK — with 8 consumer warps per SM the DMMA pipe needs that much ILP.
-    double acc[2][2][NBLK][2];
+    double acc[SETS][2][NBLK][2];
     double accx[2][EX > 0 ? EX : 1];  // [m][extra column], summed over this lane's rows
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < SETS; ++u)
 #pragma unroll
         for (int m = 0; m < 2; ++m)
 #pragma unroll
@@ -465,10 +472,11 @@ xstream_z_dmma_kernel(const __grid_constant__ CUtensorMap tmap_x, const double* 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&full[s], ph);
         const uint32_t st = base_s + (uint32_t)s * stage_bytes;
-        const uint32_t box = st + (uint32_t)warp * kZdBoxBytes;
+        const uint32_t box = st + (uint32_t)kbox * kZdBoxBytes;
         const uint32_t Ws = st + kZdXBytes + (uint32_t)(g * sizeof(double));
 #pragma unroll
-        for (int rg = 0; rg < kZdTM / 8; ++rg) {
+        for (int rgi = 0; rgi < RGS; ++rgi) {
+            const int rg = half * RGS + rgi;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const uint32_t row = rg * 8 + h + 2 * t;
@@ -494,12 +502,13 @@ xstream_z_dmma_kernel(const __grid_constant__ CUtensorMap tmap_x, const double* 
 #pragma unroll
                 for (int m = 0; m < 2; ++m)
 #pragma unroll
-                    for (int n = 0; n < NBLK; ++n) dmma884(acc[h][m][n][0], acc[h][m][n][1], a[m], bf[n]);
+                    for (int n = 0; n < NBLK; ++n)
+                        dmma884(acc[h % SETS][m][n][0], acc[h % SETS][m][n][1], a[m], bf[n]);
             }
         }
         int dep = 0;
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
+        for (int u = 0; u < SETS; ++u)
 #pragma unroll
             for (int m = 0; m < 2; ++m)
 #pragma unroll
@@ -516,7 +525,8 @@ xstream_z_dmma_kernel(const __grid_constant__ CUtensorMap tmap_x, const double* 
             ph ^= 1;
         }
     }
-    double* out = part + (size_t)blockIdx.x * K * R;
+    // one partial per (row group, row half): part[(blockIdx.x * (CW / 8) + half)][k][c]
+    double* out = part + ((size_t)blockIdx.x * (CW / 8) + half) * K * R;
     if constexpr (EX > 0) {  // sum the DFMA partials over the 4 lanes (t) that share a k
 #pragma unroll
         for (int m = 0; m < 2; ++m)
@@ -528,13 +538,15 @@ xstream_z_dmma_kernel(const __grid_constant__ CUtensorMap tmap_x, const double* 
     }
 #pragma unroll
     for (int m = 0; m < 2; ++m) {
-        const int k = k_base + warp * 16 + m * 8 + g;
+        const int k = k_base + kbox * 16 + m * 8 + g;
         if (k < K) {
 #pragma unroll
             for (int n = 0; n < NBLK; ++n) {
                 const int col = n * 8 + 2 * t;
-                if (col < R) out[(size_t)k * R + col] = acc[0][m][n][0] + acc[1][m][n][0];
-                if (col + 1 < R) out[(size_t)k * R + col + 1] = acc[0][m][n][1] + acc[1][m][n][1];
+                const double v0 = SETS == 2 ? acc[0][m][n][0] + acc[SETS - 1][m][n][0] : acc[0][m][n][0];
+                const double v1 = SETS == 2 ? acc[0][m][n][1] + acc[SETS - 1][m][n][1] : acc[0][m][n][1];
+                if (col < R) out[(size_t)k * R + col] = v0;
+                if (col + 1 < R) out[(size_t)k * R + col + 1] = v1;
             }
             if constexpr (EX > 0) {  // lane t writes extra column t
 #pragma unroll
@@ -688,12 +700,12 @@ int launch_z(const CUtensorMap& map, const T* W, int ldw, T* part, int K, int R,
     return B2_OK;
 }
 
-template <int NBLK, int EX>
+template <int NBLK, int EX, int CW = 8>
 int launch_z_dmma(const CUtensorMap& map, const double* W, int ldw, double* part, int K, int R, int num_tiles, dim3 grid,
                   int stages, size_t smem, cudaStream_t st) {
-    auto kern = xstream_z_dmma_kernel<NBLK, EX>;
+    auto kern = xstream_z_dmma_kernel<NBLK, EX, CW>;
     B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, kThreads, smem, st>>>(map, W, ldw, part, K, R, num_tiles, stages);
+    kern<<<grid, (CW + 1) * 32, smem, st>>>(map, W, ldw, part, K, R, num_tiles, stages);
     B2_LAUNCH_CHECK();
     return B2_OK;
 }
@@ -718,7 +730,12 @@ int xstream_z_dmma_impl(const void* X, long long N, int K, int ldx, const void* 
     if (max_ctas > 0 && max_ctas / kblocks < groups) groups = max_ctas / kblocks;
     if (groups < 1) groups = 1;
     if (groups > num_tiles) groups = num_tiles;
-    const size_t part_bytes = (size_t)groups * K * R * sizeof(double);
+    // 16 consumer warps (two per 16-k box, one partial per row half) where the kernel is bound by the fp64 tensor pipe
+    // (three column blocks and more), like the Y kernel's 12; 8 warps for the HBM-bound ranks and the DFMA-remainder variant
+    const int opt = b2_option_value(B2_OPT_XSTREAM_HYBRID);
+    const bool wide = EX == 0 && (opt == 2 || (opt == 0 && R > 16));
+    const int halves = wide ? 2 : 1;
+    const size_t part_bytes = (size_t)groups * halves * K * R * sizeof(double);
     B2_REQUIRE(ws_bytes >= part_bytes, "xstream_z workspace too small: need %zu bytes, got %zu", part_bytes, ws_bytes);
     alignas(64) CUtensorMap map;
     int rc = encode_x_map(&map, X, N, K, ldx, B2_F64, kZdTM);
@@ -734,12 +751,19 @@ int xstream_z_dmma_impl(const void* X, long long N, int K, int ldx, const void* 
     rc = B2_ERR_INVALID;
 #define B2_Z_CASE(NB, E) \
     if (NBLK == NB && EX == E) rc = launch_z_dmma<NB, E>(map, Wd, ldw, part, K, R, num_tiles, grid, stages, smem, st);
-    B2_Z_CASE(1, 0) B2_Z_CASE(2, 0) B2_Z_CASE(3, 0) B2_Z_CASE(4, 0)
-    B2_Z_CASE(1, 2) B2_Z_CASE(1, 4) B2_Z_CASE(2, 2) B2_Z_CASE(2, 4) B2_Z_CASE(3, 2) B2_Z_CASE(3, 4)
+#define B2_Z_WIDE(NB) \
+    if (NBLK == NB) rc = launch_z_dmma<NB, 0, 16>(map, Wd, ldw, part, K, R, num_tiles, grid, stages, smem, st);
+    if (wide) {
+        B2_Z_WIDE(1) B2_Z_WIDE(2) B2_Z_WIDE(3) B2_Z_WIDE(4)
+    } else {
+        B2_Z_CASE(1, 0) B2_Z_CASE(2, 0) B2_Z_CASE(3, 0) B2_Z_CASE(4, 0)
+        B2_Z_CASE(1, 2) B2_Z_CASE(1, 4) B2_Z_CASE(2, 2) B2_Z_CASE(2, 4) B2_Z_CASE(3, 2) B2_Z_CASE(3, 4)
+    }
 #undef B2_Z_CASE
+#undef B2_Z_WIDE
     if (rc != B2_OK) return rc;
     const int n = K * R;
-    reduce_partials_kernel<double><<<(n + 255) / 256, 256, 0, st>>>(part, (double*)Z, n, groups);
+    reduce_partials_kernel<double><<<(n + 255) / 256, 256, 0, st>>>(part, (double*)Z, n, groups * halves);
     B2_LAUNCH_CHECK();
     return B2_OK;
 }

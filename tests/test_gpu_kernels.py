@@ -1172,3 +1172,29 @@ def test_xstream_y_12_consumer_warps_bit_identical(N, K, R):
         lib.b2_set_option(_lib.OPT_XSTREAM_HYBRID, 0)
     np.testing.assert_array_equal(outs[0], outs[1])
     np.testing.assert_allclose(outs[1], Xh @ C.cpu().numpy(), rtol=1e-11, atol=1e-11 * np.abs(outs[1]).max())
+
+
+@pytest.mark.parametrize("N,K,R", [(1000, 512, 20), (385, 100, 17), (5000, 1030, 32), (777, 64, 24), (31, 33, 8)])
+def test_xstream_z_16_consumer_warps(N, K, R):
+    """The Z kernel with 16 consumer warps (two per 16-k box, one partial per row half; the engine's choice from R = 17
+    on) against the 8-warp kernel and NumPy (the partial sums are grouped differently: equal to round-off)."""
+    _lib, _ops, O = _imports()
+    lib = _lib.load()
+    rs = np.random.RandomState(N + R + 1)
+    Xh, X = packed_x(N, K, torch.float64, rs)
+    Wh = rs.standard_normal(size=(N, R))
+    W = _ops.alloc_w(N, R, torch.float64, "cuda", _lib.VARIANT_DMMA)
+    W[:N, :R] = dev(Wh)
+    ws = _ops.Workspace("cuda", K, R, torch.float64)
+    outs = []
+    try:
+        for opt in (3, 2):
+            lib.b2_set_option(_lib.OPT_XSTREAM_HYBRID, opt)
+            Z = torch.full((K, R), np.nan, dtype=torch.float64, device="cuda")
+            _ops.xstream_z(X, N, K, W, Z, ws, _lib.VARIANT_DMMA)
+            outs.append(Z.cpu().numpy())
+    finally:
+        lib.b2_set_option(_lib.OPT_XSTREAM_HYBRID, 0)
+    ref = Xh.T @ Wh
+    for z in outs:
+        np.testing.assert_allclose(z, ref, rtol=1e-11, atol=1e-11 * np.abs(ref).max())
