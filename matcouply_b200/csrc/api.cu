@@ -27,7 +27,7 @@ int b2_num_sms() {
     return cached[dev];
 }
 
-static int g_options[B2_OPT_COUNT] = {2, 2, 1, 0, 9};  // XSTREAM_HYBRID measured slower than padded DMMA (profiles/): off
+static int g_options[B2_OPT_COUNT] = {2, 2, 1, 0, 14};  // XSTREAM_HYBRID measured slower than padded DMMA (profiles/): off
 int b2_option_value(int option) { return (option >= 0 && option < B2_OPT_COUNT) ? g_options[option] : 0; }
 
 namespace {

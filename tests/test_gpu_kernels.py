@@ -361,10 +361,13 @@ def test_l2ball_groups():
             np.testing.assert_allclose(dual.cpu().numpy(), V - ref, rtol=1e-12, atol=1e-14)
 
 
-@pytest.fixture(params=[None, 1, 6], ids=["variant_default", "variant_1", "variant_6"])
+@pytest.fixture(params=[None, 1, 6, 9, 10, 11, 12, 14, 15],
+                ids=["variant_default", "variant_1", "variant_6", "variant_9", "variant_10", "variant_11", "variant_12",
+                     "variant_14", "variant_15"])
 def unimodal_variant(request):
-    """Runs a unimodal test under the default kernel variant, the IEEE-division one (1) and the reciprocal-division /
-    256-bit record one (6): bit-exactness must not depend on the variant."""
+    """Runs a unimodal test under the default kernel variant, the IEEE-division one (1), the reciprocal-division /
+    256-bit record one (6), merge + finalisation in one trip (9), the compact-prefix-error variants (10-12) and the deferred-fill ones (14, 15):
+    bit-exactness must not depend on the variant."""
     from matcouply_b200 import _lib
 
     lib = _lib.load()
@@ -432,6 +435,37 @@ def test_unimodal_ragged_groups_vs_oracle_and_sklearn(unimodal_variant):
                      if n - t else np.zeros(0))
             best = min(best, np.sum((np.concatenate([left, right]) - y) ** 2))
         assert abs(np.sum((got[off[g]:off[g + 1], 0] - y) ** 2) - best) < 1e-9 * max(best, 1.0)
+
+
+def test_unimodal_few_long_groups_all_variants_bit_identical():
+    """Few long ragged groups (the deferred fill splits the rows of a slice over several CTAs; block counts and prefix
+    lengths that are not multiples of four): every kernel variant gives the oracle's fit and peaks bit for bit."""
+    _lib, _ops, O = _imports()
+    lib = _lib.load()
+    rs = np.random.RandomState(5)
+    R = 5
+    sizes = np.array([5003, 1, 2998, 7, 4])
+    off = np.concatenate([[0], np.cumsum(sizes)])
+    t = np.arange(off[-1])[:, None]
+    V = np.exp(-0.5 * ((t % 3000 - 1400.0) / 300.0) ** 2) + 0.05 * rs.standard_normal(size=(off[-1], R))
+    before = lib.b2_get_option(_lib.OPT_UNIMODAL_VARIANT)
+    try:
+        for nn in (False, True):
+            refs = [O.unimodal_regression(V[off[g]:off[g + 1]], nn, return_peaks=True) for g in range(len(sizes))]
+            fit = np.concatenate([r[0] for r in refs], 0)
+            peaks = np.concatenate([r[1] for r in refs])
+            for variant in (9, 10, 11, 13, 14, 15):
+                lib.b2_set_option(_lib.OPT_UNIMODAL_VARIANT, variant)
+                ws = _ops.Workspace("cuda", 1, R, torch.float64)
+                aux = torch.empty(V.shape, dtype=torch.float64, device="cuda")
+                dual = dev(V)
+                pk = torch.zeros(len(sizes) * R, dtype=torch.int32, device="cuda")
+                _ops.prox_unimodal(aux, dual, dev(off, torch.int64), len(sizes), R, int(sizes.max()), nn, ws, pk)
+                assert np.array_equal(pk.cpu().numpy(), peaks), variant
+                assert np.array_equal(aux.cpu().numpy(), fit), variant
+                np.testing.assert_array_equal(dual.cpu().numpy(), V - fit)
+    finally:
+        lib.b2_set_option(_lib.OPT_UNIMODAL_VARIANT, before)
 
 
 def test_parafac2_prox_golden(golden_dir):
