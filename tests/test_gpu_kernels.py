@@ -361,12 +361,12 @@ def test_l2ball_groups():
             np.testing.assert_allclose(dual.cpu().numpy(), V - ref, rtol=1e-12, atol=1e-14)
 
 
-@pytest.fixture(params=[None, 1, 6, 9, 10, 11, 12, 14, 15],
+@pytest.fixture(params=[None, 1, 6, 9, 10, 11, 12, 14, 15, 16, 17],
                 ids=["variant_default", "variant_1", "variant_6", "variant_9", "variant_10", "variant_11", "variant_12",
-                     "variant_14", "variant_15"])
+                     "variant_14", "variant_15", "variant_16", "variant_17"])
 def unimodal_variant(request):
     """Runs a unimodal test under the default kernel variant, the IEEE-division one (1), the reciprocal-division /
-    256-bit record one (6), merge + finalisation in one trip (9), the compact-prefix-error variants (10-12) and the deferred-fill ones (14, 15):
+    256-bit record one (6), merge + finalisation in one trip (9), the compact-prefix-error variants (10-12), the deferred-fill ones (14, 15) and the compact-record kernel (16, 17):
     bit-exactness must not depend on the variant."""
     from matcouply_b200 import _lib
 
@@ -454,7 +454,7 @@ def test_unimodal_few_long_groups_all_variants_bit_identical():
             refs = [O.unimodal_regression(V[off[g]:off[g + 1]], nn, return_peaks=True) for g in range(len(sizes))]
             fit = np.concatenate([r[0] for r in refs], 0)
             peaks = np.concatenate([r[1] for r in refs])
-            for variant in (9, 10, 11, 13, 14, 15):
+            for variant in (9, 10, 11, 13, 14, 15, 16, 17):
                 lib.b2_set_option(_lib.OPT_UNIMODAL_VARIANT, variant)
                 ws = _ops.Workspace("cuda", 1, R, torch.float64)
                 aux = torch.empty(V.shape, dtype=torch.float64, device="cuda")
@@ -466,6 +466,36 @@ def test_unimodal_few_long_groups_all_variants_bit_identical():
                 np.testing.assert_array_equal(dual.cpu().numpy(), V - fit)
     finally:
         lib.b2_set_option(_lib.OPT_UNIMODAL_VARIANT, before)
+
+
+def test_unimodal_more_columns_than_scratch_slots():
+    """More columns than scratch slots (148 SMs x 1024): the kernel works in rounds and the deferred-fill variants fall
+    back to the fill inside the PAVA kernel; same bits as the reference order of operations (oracle on a sample)."""
+    _lib, _ops, O = _imports()
+    lib = _lib.load()
+    rs = np.random.RandomState(8)
+    R, G = 8, 148 * 1024 // 8 + 300
+    sizes, off, V = ragged(rs, G, 3, 12, R)
+    before = lib.b2_get_option(_lib.OPT_UNIMODAL_VARIANT)
+    outs = {}
+    try:
+        for variant in (9, 14, 16):
+            lib.b2_set_option(_lib.OPT_UNIMODAL_VARIANT, variant)
+            ws = _ops.Workspace("cuda", 1, R, torch.float64)
+            aux = torch.empty(V.shape, dtype=torch.float64, device="cuda")
+            dual = dev(V)
+            pk = torch.zeros(G * R, dtype=torch.int32, device="cuda")
+            _ops.prox_unimodal(aux, dual, dev(off, torch.int64), G, R, int(sizes.max()), True, ws, pk)
+            outs[variant] = (aux.cpu().numpy(), dual.cpu().numpy(), pk.cpu().numpy())
+    finally:
+        lib.b2_set_option(_lib.OPT_UNIMODAL_VARIANT, before)
+    for variant in (14, 16):
+        for a, b in zip(outs[9], outs[variant]):
+            assert np.array_equal(a, b), variant
+    for g in (0, 1, G // 2, G - 2, G - 1):
+        ref, peaks = O.unimodal_regression(V[off[g]:off[g + 1]], True, return_peaks=True)
+        assert np.array_equal(outs[14][0][off[g]:off[g + 1]], ref)
+        assert np.array_equal(outs[14][2][g * R:(g + 1) * R], peaks)
 
 
 def test_parafac2_prox_golden(golden_dir):
