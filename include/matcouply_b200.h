@@ -67,8 +67,13 @@ enum { B2_OPT_PF2_ROWPASS_MMA = 0 /* row pass of b2_pf2_rowpass: 0 = shuffle ker
        B2_OPT_UNIMODAL_VARIANT = 4 /* b2_prox_unimodal: (column ring depth, shared-memory stack-cache depth, CTAs per
                                       SM) of the PAVA kernel: 0 = (8, 4, 4) round 1, 1 = (4, 8, 4), 2 = (8, 8, 4), 3 = (4, 16, 3),
                                       4 = (4, 8, 5), 5 = (4, 12, 4); 6 = variant 1 with the exact reciprocal-based division
-                                      and 256-bit record loads / stores; 9 (default) = 6 with merge + finalisation in one
-                                      trip; same results, different speed */,
+                                      and 256-bit record loads / stores; 9 = 6 with merge + finalisation in one trip;
+                                      10 / 11 = 9 with a compact copy of the prefix errors for the peak search (staged in
+                                      shared memory / in registers) and one reciprocal per trip; 12 / 13 = 10 / 11 with 16
+                                      loads in flight in the fill pass; 14 (default) / 15 = 11 / 10 with the fill as a
+                                      second, streaming kernel (when every column has a scratch slot, else 11); 16 / 17 =
+                                      20-byte records + spill stack (half the DRAM bytes, measured 2.4x slower);
+                                      same results, different speed */,
        B2_OPT_COUNT = 5 };
 int b2_set_option(int option, int value);
 int b2_get_option(int option);
