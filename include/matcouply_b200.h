@@ -71,8 +71,7 @@ enum { B2_OPT_PF2_ROWPASS_MMA = 0 /* row pass of b2_pf2_rowpass: 0 = shuffle ker
                                       10 / 11 = 9 with a compact copy of the prefix errors for the peak search (staged in
                                       shared memory / in registers) and one reciprocal per trip; 12 / 13 = 10 / 11 with 16
                                       loads in flight in the fill pass; 14 (default) / 15 = 11 / 10 with the fill as a
-                                      second, streaming kernel (when every column has a scratch slot, else 11); 16 / 17 =
-                                      20-byte records + spill stack (half the DRAM bytes, measured 2.4x slower);
+                                      second, streaming kernel (when every column has a scratch slot, else 11);
                                       same results, different speed */,
        B2_OPT_COUNT = 5 };
 int b2_set_option(int option, int value);

@@ -642,253 +642,6 @@ unimodal_kernel(T* __restrict__ aux, T* __restrict__ dual, const int64_t* __rest
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------
-// Compact-record kernel (variant 16).  The 32-byte record per element of the kernels above is a persistent linked
-// list of block stacks: rec[i] = top block at time i, rec[start - 1] the one below, ...  It serves three readers: the
-// peak search (error), the reconstruction of the winning prefix (start, level) and pops that fall below the
-// shared-memory stack cache (sums, error).  Written per element and direction it is 4.3 GB of scattered sector writes
-// at config 3, most of it never read again: with the compact error copy the kernel moves 10.6 GB through DRAM in
-// 2.7 ms (ncu, profiles/r2_ncu_unimodal_v11_full_s36.txt) and its stores back up the LSU (long-scoreboard stalls on the
-// instructions that reuse a store's registers).  Here the per-element record is 20 bytes,
-//     chain[i] = (error[i + 1], level of the top block at time i)      16 B
-//     start[i] = start of that block                                     4 B
-// and the sums a deep pop needs come from a SPILL STACK indexed by stack depth (32 B per entry: sums, error, start; the
-// level is recomputed from its sum and count exactly as the deep-pop path above does): the eight most recent blocks
-// below the top live in the shared-memory ring, four are written out when it is full and four are brought back with
-// asynchronous copies when it runs empty, so a falling flank that eats hundreds of blocks costs one memory round
-// trip per four pops instead of one per pop, and noise-like columns (stack depth hovering) hardly touch the spill.
-// Arithmetic and its order are those of pava_prefix_ec: bit-identical levels, errors and peaks.
-struct __align__(16) ListEnt {  // block list entry of the compact-record kernel (unimodal2_kernel)
-    double level;
-    int start, pad;
-};
-__device__ __forceinline__ double ent_level(const Rec& r) { return r.err_after; }
-__device__ __forceinline__ double ent_level(const ListEnt& e) { return e.level; }
-struct __align__(16) Chain {
-    double err_after, level;
-};
-struct __align__(32) Spill {
-    double sy, sy2, err_after;
-    int start, pad;
-};
-
-template <int YRING, int NT>
-struct Shared2 {
-    double y[YRING][NT];
-    double2 sums[8][NT];     // sy, sy2
-    double2 err_st[8][NT];   // err_after, start (low word)
-    double lvl[8][NT];
-};
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
-}
-
-struct Scratch2 {  // per-thread scratch layout
-    size_t off_start, off_spill, bytes;
-    __host__ __device__ explicit Scratch2(int max_rows) {
-        off_start = ((size_t)max_rows * 16 + 31) / 32 * 32;
-        off_spill = off_start + ((size_t)max_rows * 4 + 31) / 32 * 32;
-        bytes = off_spill + (size_t)max_rows * 32 + 32;  // + header (prefix length, number of blocks)
-    }
-};
-
-template <typename T, int kYRing, class SH>
-__device__ __forceinline__ void pava2(const T* __restrict__ col, long long ld, int n, bool rev, bool nn,
-                                      Chain* __restrict__ ch, int* __restrict__ stv, Spill* __restrict__ sp, SH& sh,
-                                      int tid) {
-    const long long step = rev ? -ld : ld;
-    const T* p = col + (rev ? (long long)(n - 1) * ld : 0LL);
-#pragma unroll
-    for (int u = 1; u <= kYRing; ++u) {
-        if (u < n) cp_async_elem<T>(&sh.y[u % kYRing][tid], p + (long long)u * step);
-        cp_async_commit();
-    }
-    Block cur, top;
-    bool has_top = false;
-    int depth = 0, lo = 0;  // blocks below `top`; entries [lo, depth) of them sit in the shared ring, [0, lo) in the spill
-    top.start = 0;
-    top.sy = top.sy2 = top.level = top.err_after = 0.0;
-    int i = 0;
-    {
-        const double y0 = (double)p[0];
-        cur.start = 0;
-        cur.sy = y0;
-        cur.sy2 = __dmul_rn(y0, y0);
-        cur.level = y0;
-    }
-    double cum = cur.sy2;
-    while (i < n) {
-        bool merge = has_top && cur.level <= top.level;
-        double cnt = 1.0, y = 1.0;
-        if (merge) {
-            cur.sy = __dadd_rn(cur.sy, top.sy);
-            cur.sy2 = __dadd_rn(cur.sy2, top.sy2);
-            cur.start = top.start;
-            cnt = (double)(i - cur.start + 1);
-            y = __drcp_rn(cnt);
-            has_top = cur.start > 0;
-            if (has_top) {
-                if (depth == lo) {  // ring empty: bring the four entries below back (lo is a positive multiple of 4)
-                    const int b = lo - 4;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        cp_async16(&sh.sums[(b + k) & 7][tid], &sp[b + k].sy);
-                        cp_async16(&sh.err_st[(b + k) & 7][tid], &sp[b + k].err_after);
-                    }
-                    cp_async_commit();
-                    cp_async_wait<0>();
-                    int next_start = cur.start;  // the block on top of entry b + 3 is the merged one
-#pragma unroll
-                    for (int k = 3; k >= 0; --k) {
-                        const int s_k = __double2loint(sh.err_st[(b + k) & 7][tid].y);
-                        sh.lvl[(b + k) & 7][tid] = div_count<true>(sh.sums[(b + k) & 7][tid].x, (double)(next_start - s_k));
-                        next_start = s_k;
-                    }
-                    lo = b;
-                }
-                --depth;
-                const int d = depth & 7;
-                const double2 a = sh.sums[d][tid], b2 = sh.err_st[d][tid];
-                top.level = sh.lvl[d][tid];
-                top.sy = a.x;
-                top.sy2 = a.y;
-                top.err_after = b2.x;
-                top.start = __double2loint(b2.y);
-            }
-            cur.level = div_count_y(cur.sy, cnt, y);
-            merge = has_top && cur.level <= top.level;  // another merge is due: next trip
-        }
-        if (!merge) {
-            const double q = div_count_y(__dmul_rn(cur.sy, cur.sy), cnt, y);
-            const double levelerror = __dsub_rn(cur.sy2, q);
-            const double before = has_top ? top.err_after : 0.0;
-            cur.err_after = (nn && cur.level < 0.0) ? cum : __dadd_rn(levelerror, before);
-            asm volatile("st.global.v2.f64 [%0], {%1,%2};" ::"l"(ch + i), "d"(cur.err_after), "d"(cur.level) : "memory");
-            stv[i] = cur.start;
-            if (has_top) {  // push the old top
-                if (depth - lo == 8) {  // ring full: the four oldest entries go to the spill stack
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) {
-                        const double2 a = sh.sums[(lo + k) & 7][tid], b2 = sh.err_st[(lo + k) & 7][tid];
-                        store4((double*)(sp + lo + k), a.x, a.y, b2.x, b2.y);
-                    }
-                    lo += 4;
-                }
-                const int d = depth & 7;
-                sh.sums[d][tid] = make_double2(top.sy, top.sy2);
-                sh.err_st[d][tid] = make_double2(top.err_after, __hiloint2double(0, top.start));
-                sh.lvl[d][tid] = top.level;
-                ++depth;
-            }
-            top = cur;
-            has_top = true;
-            ++i;
-            cp_async_wait<kYRing - 1>();
-            const double yi = (double)*(const T*)&sh.y[i % kYRing][tid];
-            if (i + kYRing < n) cp_async_elem<T>(&sh.y[i % kYRing][tid], p + (long long)(i + kYRing) * step);
-            cp_async_commit();
-            cur.start = i;
-            cur.sy = yi;
-            cur.sy2 = __dmul_rn(yi, yi);
-            cur.level = yi;
-            cum = __dadd_rn(cum, cur.sy2);
-        }
-    }
-    cp_async_wait<0>();
-}
-
-// One round only (a scratch slot per column): PAVA of both directions, peak search on chain[].err_after, block list
-// of the winning prefix into the (now free) spill area, header for unimodal_fill_kernel.
-template <typename T, int YRING, int MINCTAS, int NT = kThreads>
-__global__ void __launch_bounds__(NT, MINCTAS)
-unimodal2_kernel(const T* __restrict__ dual, const int64_t* __restrict__ row_off, int n_groups, int R, int max_rows,
-                 int nn_flag, int32_t* __restrict__ peaks, unsigned char* __restrict__ ws, long long ncolslots,
-                 size_t thread_bytes) {
-    extern __shared__ __align__(16) unsigned char uni_smem[];
-    using SH = Shared2<YRING, NT>;
-    SH& sh = *(SH*)uni_smem;
-    const int tid = threadIdx.x, lane = tid & 31;
-    const int rev = lane >> 4;
-    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const long long slot = warp * 16 + (lane & 15);
-    const bool nn = nn_flag != 0;
-    const Scratch2 lay(max_rows);
-    const long long sl = slot < ncolslots ? slot : 0;
-    unsigned char* mine = ws + (size_t)(2 * sl + rev) * thread_bytes;  // thread_bytes >= lay.bytes
-    const unsigned char* other = ws + (size_t)(2 * sl + (rev ^ 1)) * thread_bytes;
-    Chain* ch = (Chain*)mine;
-    const Chain* och = (const Chain*)other;
-    int* stv = (int*)(mine + lay.off_start);
-    Spill* sp = (Spill*)(mine + lay.off_spill);
-    const long long total = (long long)n_groups * R;
-    const long long colid = slot;
-    const bool active = slot < ncolslots && colid < total;
-    int n = 0;
-    long long base = 0;
-    if (active) {
-        const int g = (int)(colid / R), c = (int)(colid - (long long)g * R);
-        const long long r0 = row_off[g];
-        n = (int)(row_off[g + 1] - r0);
-        base = r0 * R + c;
-    }
-    if (active && n > 0) pava2<T, YRING, SH>(dual + base, R, n, rev != 0, nn, ch, stv, sp, sh, tid);
-    __syncwarp();  // the partner lane's prefix errors are read below
-    // Peak: first strict minimum of errL[i] + errR[n - i], i = 0..n.  Both lanes of a column walk in lockstep: at step i
-    // the forward lane holds errL[i] = chain[i - 1].err_after of ITS OWN chain, the reversed lane errR[n - i] =
-    // chain[n - i - 1].err_after of its own, and hands it over with a shuffle — every lane reads only its own
-    // array, front to back resp. back to front, one 16-byte entry per step (two steps per sector).
-    double best = 0.0;
-    int bidx = 0;
-    {
-        const int nmax = __reduce_max_sync(0xffffffffu, (active && n > 0) ? n : -1);
-        constexpr int PU = 16;
-        bool first = true;
-        for (int i0 = 0; i0 <= nmax; i0 += PU) {
-            double e[PU];
-#pragma unroll
-            for (int u = 0; u < PU; ++u) {
-                const int i = i0 + u;
-                const int k = rev ? n - i - 1 : i - 1;  // own chain entry
-                e[u] = 0.0;
-                if (active && i <= n && k >= 0) {
-                    double lv;
-                    asm volatile("ld.global.v2.f64 {%0,%1}, [%2];" : "=d"(e[u]), "=d"(lv) : "l"(ch + k) : "memory");
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < PU; ++u) {
-                const int i = i0 + u;
-                const double eo = __shfl_xor_sync(0xffffffffu, e[u], 16);
-                if (!rev && active && n > 0 && i <= n) {
-                    const double cand = __dadd_rn(e[u], eo);
-                    if (first || cand < best) {
-                        best = cand;
-                        bidx = i;
-                        first = false;
-                    }
-                }
-            }
-        }
-        bidx = __shfl_sync(0xffffffffu, bidx, lane & 15);  // the reversed lane takes the forward lane's result
-    }
-    // block list of the winning prefix, top-down into list[len - 1 - k] (the spill area is free now)
-    const int len = (active && n > 0) ? (rev ? n - bidx : bidx) : 0;
-    ListEnt* list = (ListEnt*)sp;
-    int idx = len - 1, K = 0;
-    while (idx >= 0) {
-        const int s = stv[idx];
-        const double level = ch[idx].level;
-        ListEnt* out = list + (len - 1 - K);
-        out->level = (nn && level < 0.0) ? 0.0 : level;
-        out->start = s;
-        ++K;
-        idx = s - 1;
-    }
-    if (slot < ncolslots) *(int2*)(mine + thread_bytes - 32) = make_int2(len, K);
-    if (active && n > 0 && !rev && peaks) peaks[colid] = bidx;
-}
-
 // Second kernel of the deferred-fill variants: aux = fitted value, dual = V - aux from the block lists the PAVA kernel
 // left in the scratch area (list_blocks: (start, level) of the blocks of the winning prefix per column and direction).
 // Inside the PAVA kernel this pass costs a quarter of the time (ncu, profiles/r2_ncu_unimodal_v11_full_s36.txt): every lane
@@ -898,10 +651,10 @@ unimodal2_kernel(const T* __restrict__ dual, const int64_t* __restrict__ row_off
 // of column c, so a warp step touches whole rows (R consecutive values) of 32 / R chunks.
 // Rows below the peak t* = len_L come from the forward list at position r, rows from t* on from the reversed list at
 // position n - 1 - r (walked downwards).
-template <typename T, typename LE>
+template <typename T>
 __global__ void __launch_bounds__(256)
 unimodal_fill_kernel(T* __restrict__ aux, T* __restrict__ dual, const int64_t* __restrict__ row_off, int n_groups, int R,
-                     const unsigned char* __restrict__ ws, size_t thread_bytes, size_t list_off) {
+                     const unsigned char* __restrict__ ws, size_t thread_bytes) {
     const int cpb = blockDim.x / R;  // row chunks of a slice in flight
     const int c = threadIdx.x % R, k = threadIdx.x / R;
     if (k >= cpb) return;
@@ -915,8 +668,8 @@ unimodal_fill_kernel(T* __restrict__ aux, T* __restrict__ dual, const int64_t* _
         const unsigned char* bR = bL + thread_bytes;
         const int2 hL = *(const int2*)(bL + thread_bytes - 32), hR = *(const int2*)(bR + thread_bytes - 32);
         const int tstar = hL.x;  // rows [0, t*) forward fit, [t*, n) reversed fit; hR.x == n - t*
-        const LE* lL = (const LE*)(bL + list_off) + (hL.x - hL.y);
-        const LE* lR = (const LE*)(bR + list_off) + (hR.x - hR.y);
+        const Rec* lL = (const Rec*)bL + (hL.x - hL.y);  // (level in err_after, start), ascending block starts
+        const Rec* lR = (const Rec*)bR + (hR.x - hR.y);
         const int nch = cpb * (int)gridDim.y;  // gridDim.y CTAs share a slice when there are few slices
         const int CH = (n + nch - 1) / nch;
         const int ra = min(n, ((int)blockIdx.y * cpb + k) * CH), rb = min(n, ra + CH);
@@ -933,7 +686,7 @@ unimodal_fill_kernel(T* __restrict__ aux, T* __restrict__ dual, const int64_t* _
                 else hi = mid - 1;
             }
             int b = lo;
-            T v = (T)ent_level(lL[b]);
+            T v = (T)lL[b].err_after;
             int next_s = b + 1 < hL.y ? lL[b + 1].start : tstar;
             for (int j0 = r; j0 < re; j0 += U) {
                 T vv[U];
@@ -945,7 +698,7 @@ unimodal_fill_kernel(T* __restrict__ aux, T* __restrict__ dual, const int64_t* _
                     if (j < re) {
                         if (j == next_s) {
                             ++b;
-                            v = (T)ent_level(lL[b]);
+                            v = (T)lL[b].err_after;
                             next_s = b + 1 < hL.y ? lL[b + 1].start : tstar;
                         }
                         ap[(long long)j * R] = v;
@@ -965,7 +718,7 @@ unimodal_fill_kernel(T* __restrict__ aux, T* __restrict__ dual, const int64_t* _
                 else hi = mid - 1;
             }
             int b = lo;
-            T v = (T)ent_level(lR[b]);
+            T v = (T)lR[b].err_after;
             int cur_s = lR[b].start;
             for (int j0 = r; j0 < rb; j0 += U) {
                 T vv[U];
@@ -978,7 +731,7 @@ unimodal_fill_kernel(T* __restrict__ aux, T* __restrict__ dual, const int64_t* _
                         const int q = n - 1 - j;
                         if (q < cur_s) {
                             --b;
-                            v = (T)ent_level(lR[b]);
+                            v = (T)lR[b].err_after;
                             cur_s = lR[b].start;
                         }
                         ap[(long long)j * R] = v;
@@ -1031,12 +784,18 @@ __global__ void div_selftest_kernel(long long n, unsigned long long seed, int ma
 //    half the DRAM bytes, but 4.01 ms against 3.30 ms on noise-like input and the same 4.63 ms on peak-like input — the
 //    kernel is bound by the serial dependency chain per thread, not by DRAM, so a second pass over part of the column
 //    costs more than the traffic it saves.
+//  * (last session, profiles/r2_ab_unimodal_compact_s40.log, r2_ncu_unimodal_v16_full_s39.txt) 20-byte records
+//    (error, level, block start) with the sums of deep pops in a spill stack indexed by stack depth, written / re-read
+//    four entries at a time: DRAM bytes 10.6 -> 7.6 GB, 25 % fewer instructions, 87 registers, bit-identical - and
+//    6.3 ms against 2.69 ms: two scattered store instructions per trip (one sector per lane each) instead of 1.25 back up
+//    the L1 data pipe, and the shared-memory pops behind them wait;
+//  * (profiles/r2_ab_unimodal_inplace_s42.log) the top block updated in place (a pooling element is added to the
+//    register block, only an element that starts a block pushes): half the ring traffic on paper, but three paths per
+//    trip instead of two, which a divergent warp all executes: 3.38 ms against 2.69 ms.
 size_t per_thread_bytes(int max_rows) {
     // one Rec per element + the compact prefix errors E[0..max_rows] in whole 32-byte sectors + a 32-byte header
     // ((prefix length, number of blocks) for the deferred fill)
-    const size_t v1 = (size_t)max_rows * 32 + (size_t)(max_rows / 4 + 1) * 32 + 32;
-    const size_t v2 = Scratch2(max_rows).bytes;  // compact-record kernel
-    return v1 > v2 ? v1 : v2;
+    return (size_t)max_rows * 32 + (size_t)(max_rows / 4 + 1) * 32 + 32;
 }
 
 }  // namespace
@@ -1099,35 +858,6 @@ int b2_prox_unimodal(void* aux, void* dual, const int64_t* row_off, int n_groups
         case 11: B2_UNI_LAUNCH_EC(4, 8, 4, 2, 8); break;     // the same, staged in registers
         case 12: B2_UNI_LAUNCH_EC(4, 8, 4, 1, 16); break;    // variant 10 with 16 loads in flight in the fill pass
         case 13: B2_UNI_LAUNCH_EC(4, 8, 4, 2, 16); break;
-        case 16:  // compact 20-byte records + spill stack (unimodal2_kernel) + streaming fill; one round only
-        case 17:  // the same with the maximum shared-memory carve-out (5 CTAs per SM, ~28 KB of L1)
-            if (ncolslots >= want) {
-                B2_DISPATCH_DTYPE(dtype, {
-                    auto kern = unimodal2_kernel<T, 4, 4>;
-                    const int smem = (int)sizeof(Shared2<4, kThreads>);
-                    const int grid2 = (int)((threads + kThreads - 1) / kThreads);
-                    B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-                    // 196 KB of shared memory per SM: four CTAs (5 would fit the registers) and ~60 KB of L1 for the
-                    // column loads that share sectors between neighbouring lanes
-                    B2_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                                       variant == 17 ? 100 : 86));
-                    kern<<<grid2, kThreads, smem, st>>>((const T*)dual, row_off, n_groups, R, max_rows, non_negativity,
-                                                        peaks, (unsigned char*)ws, ncolslots, tb);
-                    B2_LAUNCH_CHECK();
-                    const int nthr = R <= 256 ? 256 / R * R : R;
-                    const int grid_f = n_groups < b2_num_sms() * 8 ? n_groups : b2_num_sms() * 8;
-                    int parts = (b2_num_sms() * 4 + grid_f - 1) / grid_f;
-                    const int max_parts = (max_rows + (nthr / R) * 8 - 1) / ((nthr / R) * 8);
-                    parts = parts > max_parts ? max_parts : parts;
-                    parts = parts < 1 ? 1 : (parts > 65535 ? 65535 : parts);
-                    unimodal_fill_kernel<T, ListEnt><<<dim3(grid_f, parts), nthr, 0, st>>>(
-                        (T*)aux, (T*)dual, row_off, n_groups, R, (const unsigned char*)ws, tb, Scratch2(max_rows).off_spill);
-                    B2_LAUNCH_CHECK();
-                });
-            } else {
-                B2_UNI_LAUNCH_EC(4, 8, 4, 2, 8);
-            }
-            break;
         case 14:  // variant 11 with the fill as a second, streaming kernel (needs one round: a scratch slot per column)
         case 15:  // variant 10 likewise
             if (ncolslots >= want) {
@@ -1140,8 +870,8 @@ int b2_prox_unimodal(void* aux, void* dual, const int64_t* row_off, int n_groups
                 parts = parts > max_parts ? max_parts : parts;
                 parts = parts < 1 ? 1 : (parts > 65535 ? 65535 : parts);
                 B2_DISPATCH_DTYPE(dtype, {
-                    unimodal_fill_kernel<T, Rec><<<dim3(grid_f, parts), nthr, 0, st>>>(
-                        (T*)aux, (T*)dual, row_off, n_groups, R, (const unsigned char*)ws, tb, (size_t)0);
+                    unimodal_fill_kernel<T><<<dim3(grid_f, parts), nthr, 0, st>>>(
+                        (T*)aux, (T*)dual, row_off, n_groups, R, (const unsigned char*)ws, tb);
                     B2_LAUNCH_CHECK();
                 });
             } else {

@@ -361,12 +361,12 @@ def test_l2ball_groups():
             np.testing.assert_allclose(dual.cpu().numpy(), V - ref, rtol=1e-12, atol=1e-14)
 
 
-@pytest.fixture(params=[None, 1, 6, 9, 10, 11, 12, 14, 15, 16, 17],
+@pytest.fixture(params=[None, 1, 6, 9, 10, 11, 12, 15],
                 ids=["variant_default", "variant_1", "variant_6", "variant_9", "variant_10", "variant_11", "variant_12",
-                     "variant_14", "variant_15", "variant_16", "variant_17"])
+                     "variant_15"])
 def unimodal_variant(request):
     """Runs a unimodal test under the default kernel variant, the IEEE-division one (1), the reciprocal-division /
-    256-bit record one (6), merge + finalisation in one trip (9), the compact-prefix-error variants (10-12), the deferred-fill ones (14, 15) and the compact-record kernel (16, 17):
+    256-bit record one (6), merge + finalisation in one trip (9), the compact-prefix-error variants (10-12) and the deferred-fill ones (14 = default, 15):
     bit-exactness must not depend on the variant."""
     from matcouply_b200 import _lib
 
@@ -454,7 +454,7 @@ def test_unimodal_few_long_groups_all_variants_bit_identical():
             refs = [O.unimodal_regression(V[off[g]:off[g + 1]], nn, return_peaks=True) for g in range(len(sizes))]
             fit = np.concatenate([r[0] for r in refs], 0)
             peaks = np.concatenate([r[1] for r in refs])
-            for variant in (9, 10, 11, 13, 14, 15, 16, 17):
+            for variant in (9, 10, 11, 13, 14, 15):
                 lib.b2_set_option(_lib.OPT_UNIMODAL_VARIANT, variant)
                 ws = _ops.Workspace("cuda", 1, R, torch.float64)
                 aux = torch.empty(V.shape, dtype=torch.float64, device="cuda")
@@ -479,7 +479,7 @@ def test_unimodal_more_columns_than_scratch_slots():
     before = lib.b2_get_option(_lib.OPT_UNIMODAL_VARIANT)
     outs = {}
     try:
-        for variant in (9, 14, 16):
+        for variant in (9, 14):
             lib.b2_set_option(_lib.OPT_UNIMODAL_VARIANT, variant)
             ws = _ops.Workspace("cuda", 1, R, torch.float64)
             aux = torch.empty(V.shape, dtype=torch.float64, device="cuda")
@@ -489,7 +489,7 @@ def test_unimodal_more_columns_than_scratch_slots():
             outs[variant] = (aux.cpu().numpy(), dual.cpu().numpy(), pk.cpu().numpy())
     finally:
         lib.b2_set_option(_lib.OPT_UNIMODAL_VARIANT, before)
-    for variant in (14, 16):
+    for variant in (14,):
         for a, b in zip(outs[9], outs[variant]):
             assert np.array_equal(a, b), variant
     for g in (0, 1, G // 2, G - 2, G - 1):
