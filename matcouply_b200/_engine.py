@@ -363,6 +363,8 @@ class AOADMMEngine:
             self.comp_stats_part = torch.zeros(3 * max(I, 1), dtype=torch.float64, device=dev)
             self.pf2_gap_part = torch.zeros(3 * max(I, 1), dtype=torch.float64, device=dev)
             self.pf2_Q = torch.zeros(I, R, R, dtype=torch.float64, device=dev)  # Jacobi eigenvectors (warm start)
+            self._polar_updates = 0
+            self.polar_cold_every = max(1, int(os.environ.get("B2_POLAR_COLD_EVERY", "1")))
         # Single-read fused pass: applies when the whole B-update is slice-local and row-local.
         # The extra traffic is G (I x K x R, written by the pass and read once by the A-update), 2 R / mean(J_i) of X:
         # not worth it for very short slices.
@@ -798,12 +800,20 @@ class AOADMMEngine:
 
     def _pf2_polar_delta(self, st, I, it):
         """Polar step + coordinate-matrix update of one inner iteration (penalties.py:1229-1245)."""
-        # cold Jacobi start on the first inner iteration (bounds the round-off drift of the accumulated
-        # rotations), warm start from the previous inner iteration's eigenvectors afterwards
+        # warm Jacobi start from the eigenvectors of the previous inner iteration (3-5 sweeps instead of 8-10); the first
+        # inner iteration of every `polar_cold_every`-th B-update starts cold, which bounds the round-off drift of the
+        # accumulated rotations.  Default 1 = every B-update: B2_POLAR_COLD_EVERY=8 saves 11 % of the polar time
+        # (0.8 % of a config-2 step, profiles/r2_ab_polar_warm_s43.txt) but moves the trajectory by ~1e-13 per step,
+        # which one of the 24 random differential configurations (UnitSimplex + PARAFAC2) amplifies to 1.3e-7 > 1e-7
         for sub in range(int(st.regs[0].n_iter)):  # Parafac2(n_iter=...): alternations on the same V
+            # (a captured iteration is replayed as it is: keep its first polar step cold)
+            cold = it == 0 and sub == 0 and (self._polar_updates % self.polar_cold_every == 0
+                                             or torch.cuda.is_current_stream_capturing())
             self._timed("polar", lambda: _ops.pf2_polar(self.S, self.Delta, self.rhoB, I, self.R, self.Wmat,
-                                                        self.num_part, self.pf2_Q, warm=it > 0 or sub > 0))
+                                                        self.num_part, self.pf2_Q, warm=not cold))
             self._pf2_delta_update(self.rhoB, I)
+        if it == 0:
+            self._polar_updates += 1
 
     def _row_local(self, st):
         """True when every penalty of the mode is elementwise (the fused b2_admm_local path applies)."""

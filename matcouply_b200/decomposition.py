@@ -660,6 +660,8 @@ def _cmf_aoadmm_on_device(
         use_graph = n_iter_max >= 16 and engine.graph_auto()
     else:
         use_graph = bool(use_cuda_graph) and engine.graph_eligible()
+    if use_graph and hasattr(engine, "polar_cold_every"):
+        engine.polar_cold_every = 1  # a replayed iteration starts its polar steps cold: the eager iterations do the same
     for it in range(n_iter_max):
         launched = None
         if use_graph and it >= 2:  # steady state: replay the captured launch sequence (see AOADMMEngine.graph_iteration)

@@ -225,10 +225,13 @@ def test_fused_kernels_match_stepwise_kernels(kw, dtype):
 
 
 @pytest.mark.parametrize("name", ["c0_readme", "c1_nn_cmf", "c2_nn_pf2_l1_ragged", "c3_unimodal_l2ball_pf2"])
-def test_cuda_graph_replay_equals_eager_launches(name):
+def test_cuda_graph_replay_equals_eager_launches(name, monkeypatch):
     """The steady-state outer iteration replayed as a CUDA graph launches the same kernels on the same buffers as the
-    eager loop: factors, ADMM variables and diagnostics must be bit-identical."""
+    eager loop: factors, ADMM variables and diagnostics must be bit-identical.  (A replayed PARAFAC2 iteration starts
+    its first polar step cold every time, like the eager loop at its default B2_POLAR_COLD_EVERY=1.)"""
     from matcouply_b200 import cmf_aoadmm
+
+    monkeypatch.setenv("B2_POLAR_COLD_EVERY", "1")
 
     g, X, rank, kw = load_case(name)
     kw = dict(kw)
