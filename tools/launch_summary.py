@@ -16,7 +16,8 @@ def main(path, out=None):
         v = float(r["Metric Value"].replace(",", ""))
         unit = r["Metric Unit"]
         v = v / 1e3 if unit == "ns" else (v * 1e3 if unit == "ms" else v)
-        m = re.search(r"<unnamed>::(\w+)", name) or re.search(r"\(anonymous namespace\)::(\w+)", name)
+        m = (re.search(r"<unnamed>::(\w+)", name) or re.search(r"\(anonymous namespace\)::(\w+)", name)
+             or re.search(r"\brp2::(\w+)", name))
         rows.append((m.group(1) if m and not name.startswith("void at::") and "at::" not in name[:60] else "torch/other", v))
     idx = max((i for i, (n, _) in enumerate(rows) if n == "sumsq_kernel"), default=0)
     body = rows[idx:]
