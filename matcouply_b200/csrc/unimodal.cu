@@ -792,6 +792,9 @@ __global__ void div_selftest_kernel(long long n, unsigned long long seed, int ma
 //  * (profiles/r2_ab_unimodal_inplace_s42.log) the top block updated in place (a pooling element is added to the
 //    register block, only an element that starts a block pushes): half the ring traffic on paper, but three paths per
 //    trip instead of two, which a divergent warp all executes: 3.38 ms against 2.69 ms.
+//  * (profiles/r2_ab_unimodal_pg4_fill64_s48.log) four instead of two groups of peak candidates in flight (spills at
+//    the 128-register cap: 2.93 against 2.69 ms) and >= 64 instead of 32 rows per thread in the fill kernel (fewer
+//    block-list searches, but half the threads per slice: 2.85 ms).
 size_t per_thread_bytes(int max_rows) {
     // one Rec per element + the compact prefix errors E[0..max_rows] in whole 32-byte sectors + a 32-byte header
     // ((prefix length, number of blocks) for the deferred fill)
