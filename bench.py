@@ -643,9 +643,11 @@ def main():
     traffic, traffic_src = None, None
     try:  # DRAM bytes per algorithmic byte from the committed `ncu --set full` capture, scaled to this launch
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj[dom]["ratio"] * algo[dom_key]
-        traffic_src = (f"(dram__bytes_read.sum + dram__bytes_write.sum) / algorithmic bytes = {tj[dom]['ratio']:.4f} in "
-                       f"the {tj.get(dom, {}).get('source', tj.get('source'))}, times this launch's algorithmic bytes")
+        # the capture at the FULL size of the headline config where there is one, else the 2 048-slice capture
+        ent = tj.get(dom + "_fullsize") if (args.config == "c2" and not args.slices and dom + "_fullsize" in tj) else tj[dom]
+        traffic = ent["ratio"] * algo[dom_key]
+        traffic_src = (f"(dram__bytes_read.sum + dram__bytes_write.sum) / algorithmic bytes = {ent['ratio']:.4f} in "
+                       f"the {ent.get('source', tj.get('source'))}, times this launch's algorithmic bytes")
     except Exception:
         pass
     # second roof of the fp64 X-stream kernels: the fp64 tensor pipe (DMMA.8x8x4), measured live (burst, idle GPU)
