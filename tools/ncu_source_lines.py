@@ -1,3 +1,7 @@
+"""Stall samples and executed instructions per SOURCE LINE of one kernel, from the source page of an .ncu-rep:
+    ncu -i report.ncu-rep --page source --csv --print-source cuda,sass > src.csv
+    python tools/ncu_source_lines.py src.csv [N lines, default 40]
+(reports with several kernels / source files: the first section only — see profiles/README.md for the summaries)."""
 import csv, sys
 rows = list(csv.reader(open(sys.argv[1])))
 hdr = rows[2]
